@@ -1,0 +1,135 @@
+/* kamino_b200.h — C ABI of the B200-native kamino front end (libkamino_b200.so).
+ *
+ * Drop-in boundary for kamino's data-parallel front end.  The reference (Rust) has no FFI
+ * layer; the seams this ABI replaces are crate-private functions, cited per entry point as
+ * file:line under /root/reference.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and non-zero on failure; kmn_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure on the calling thread;
+ *   - there is NO CPU fallback: a missing device, a CUDA error or an out-of-memory condition is
+ *     an error return, never a silent host path;
+ *   - one context drives one GPU (one process per GPU); calls on one context must be serialised
+ *     by the caller; buffers passed in stay caller-owned and may be freed after the call returns;
+ *   - "residues" are the bytes seq_io's rec.seq() yields for each FASTA record, concatenated:
+ *     line terminators and other ASCII whitespace {0x20,0x09,0x0A,0x0C,0x0D} may be present and
+ *     are skipped ON THE DEVICE exactly like group_extraction.rs:376-378; any other byte that is
+ *     not one of the 20 amino-acid letters (either case) of the chosen scheme resets the roll
+ *     (group_extraction.rs:380-384).
+ */
+#ifndef KAMINO_B200_H
+#define KAMINO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kmn_ctx kmn_ctx;
+
+/* RecodeScheme (src/recode.rs:9-16) */
+enum { KMN_DAYHOFF6 = 0, KMN_SR6 = 1, KMN_KGB6 = 2 };
+
+/* proba_filter.rs:13-19 — fixed by the reference; exported so hosts can size buffers. */
+#define KMN_BLOOM_BITS  (1u << 25)
+#define KMN_CMS_WIDTH   (1u << 26)
+#define KMN_CMS_DEPTH   4u
+#define KMN_CMS_CELLS   ((uint64_t)KMN_CMS_WIDTH * KMN_CMS_DEPTH)
+
+/* One boundary hit of pass 2 (KmerHit, group_extraction.rs:131-139; end = start + k and
+ * shared == (occ >= min_needed) are implied). */
+typedef struct kmn_hit {
+    uint64_t kmer;       /* packed 3-bit k-mer code                                              */
+    uint32_t rec;        /* record (protein) index inside its species                            */
+    uint32_t seg_start;  /* whitespace-stripped offset, inside the record, of the valid segment   */
+    uint32_t start;      /* k-mer start inside that segment (KmerHit.start)                      */
+    uint32_t occ;        /* CountMinSketch::estimate of the k-mer                                */
+} kmn_hit;
+
+const char* kmn_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+uint32_t kmn_abi_version(void);
+
+/* Context: owns the device, its stream, the count-min accumulators (AtomicCountMinSketch::new,
+ * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.
+ * k in 1..=21 (lib.rs:208-218); scheme = KMN_*.  device = CUDA ordinal. */
+int  kmn_create(kmn_ctx** out, int device, int k, int scheme);
+void kmn_destroy(kmn_ctx* ctx);
+
+/* ---- pass 1: table build ------------------------------------------------------------------
+ * Replaces count_species_kmers (group_extraction.rs:359-395) driven by extract_groups stage 2
+ * (group_extraction.rs:557-567) for a batch of WHOLE species.
+ *   residues      concatenated rec.seq() bytes of all records of the batch (host memory)
+ *   rec_off       [n_rec+1] byte offsets of the records inside `residues`, non-decreasing
+ *   sp_rec_off    [n_sp+1]  record ranges of the species (file order inside a species)
+ *   new_kmers_per_species (optional, [n_sp]) number of k-mers that passed the per-species Bloom
+ *                 filter, i.e. the number of AtomicCountMinSketch::increment calls for it.
+ * The batch stays resident in HBM (recoded, whitespace-free) for pass 2; *batch_id (optional)
+ * receives its handle.  n_residues < 2^31 per batch.
+ */
+int kmn_count_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                    const uint64_t* sp_rec_off, uint32_t n_sp, uint64_t* new_kmers_per_species,
+                    uint32_t* batch_id);
+/* The same in two steps: host->device staging only, then the kernels on the staged batch.
+ * kmn_count_staged may be called repeatedly on one staged batch (benchmarks: inputs resident in
+ * HBM); each call adds the batch to the table again, so pair it with kmn_reset_table. */
+int kmn_stage_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                    const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
+int kmn_count_staged(kmn_ctx* ctx, uint32_t batch_id, uint64_t* new_kmers_per_species);
+/* Zero the accumulators (a fresh AtomicCountMinSketch). */
+int kmn_reset_table(kmn_ctx* ctx);
+/* Drop every staged batch (frees their HBM). */
+int kmn_release_batches(kmn_ctx* ctx);
+
+/* AtomicCountMinSketch::snapshot (proba_filter.rs:171-177): clamp the accumulators to the
+ * saturating u16 table.  After this the table is read-only until kmn_reset_table. */
+int kmn_finalize_table(kmn_ctx* ctx);
+/* Copy the finalized table to host: 4 * 2^26 u16, row-major == CountMinSketch.table. */
+int kmn_table_snapshot(kmn_ctx* ctx, uint16_t* out);
+/* Load a finalized table from host (pass 2 against an externally built table). */
+int kmn_table_load(kmn_ctx* ctx, const uint16_t* table);
+/* Multi-GPU plumbing: device pointer of the u32 accumulators (KMN_CMS_CELLS entries, summable
+ * across ranks because the sketch is linear) and of the finalized u16 table. */
+int kmn_table_accum_device_ptr(kmn_ctx* ctx, void** ptr);
+int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
+/* Block until all work queued on the context's stream has finished. */
+int kmn_synchronize(kmn_ctx* ctx);
+/* CUDA stream of the context (cudaStream_t as void*), for event timing by the caller. */
+int kmn_stream(kmn_ctx* ctx, void** stream);
+
+/* ---- pass 2: occupancy scan ---------------------------------------------------------------
+ * Replaces CountMinSketch::estimate (proba_filter.rs:103-112) per k-mer position plus the
+ * segmentation and boundary rule of extract_species_blocks / extract_from_valid_segment
+ * (group_extraction.rs:446-498, :264-303) for every species of a staged batch.  Results stay on
+ * the device until fetched.  min_needed = ceil(f32(min_freq) * f32(n)) (group_extraction.rs:544).
+ */
+int kmn_scan_batch(kmn_ctx* ctx, uint32_t batch_id, uint32_t min_needed, uint64_t* n_starts,
+                   uint64_t* n_ends);
+/* Start candidates / end anchors of species `sp` (index inside the batch), in reference order
+ * (record, segment, position).  Two-call protocol: with starts == NULL only the counts are set. */
+int kmn_fetch_hits(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_hit* starts, uint64_t cap_starts,
+                   uint64_t* n_starts, kmn_hit* ends, uint64_t cap_ends, uint64_t* n_ends);
+/* Occupancy per whitespace-stripped residue of species `sp` (records concatenated): estimate()
+ * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues. */
+int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap,
+                        uint64_t* n);
+
+/* ---- --nj: pairwise counts ----------------------------------------------------------------
+ * Replaces the integer part of lg_f81_distance (phylo.rs:84-95) for all pairs i<j of
+ * compute_distance_matrix (phylo.rs:114-141).  mapped = n x L codes 0..19, 20 = gap/unknown
+ * (map_sequence, phylo.rs:75-79).  valid / mismatch are n x n row-major u32; the strict upper
+ * triangle is written.  The f64 correction (phylo.rs:96-105) stays on the host (glibc log). */
+int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid,
+                    uint32_t* mismatch);
+
+/* Device time (ms) of the last kmn_count_staged / kmn_scan_batch / kmn_pair_counts call on this
+ * context, per stage, measured with CUDA events on the context's stream.
+ * which: 0 frame, 1 bloom, 2 cms, 3 finalize, 4 scan, 5 pair_counts. */
+int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t kmn_launch_count(kmn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAMINO_B200_H */

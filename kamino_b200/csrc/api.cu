@@ -1,0 +1,555 @@
+// api.cu — context + extern "C" surface of libkamino_b200.so (see include/kamino_b200.h).
+//
+// Host-side orchestration of the sm_100a kernels.  There is deliberately no CPU code path: every
+// entry point either runs the CUDA kernels or fails with an error message.
+#include "../../include/kamino_b200.h"
+#include "count_kernels.cuh"
+#include "frame_kernels.cuh"
+#include "pair_kernels.cuh"
+#include "scan_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace kmn;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define KMN_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +      \
+                            __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        KMN_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+};
+
+// recode.rs:40-80 as a 256-entry table (product-side copy; the oracle has its own).
+RecodeLut make_lut(int scheme) {
+    static const char* classes[3][6] = {
+        {"C", "AGPST", "DENQ", "HKR", "ILMV", "FWY"},      // Dayhoff6  recode.rs:40-51
+        {"APST", "DENG", "QKR", "MIVL", "WC", "FYH"},      // SR6       recode.rs:54-65
+        {"AGPS", "DENQHKRT", "MIL", "W", "FY", "CV"},      // KGB6      recode.rs:68-80
+    };
+    RecodeLut lut;
+    std::memset(lut.v, CODE_INVALID, sizeof lut.v);
+    for (int c = 0; c < 6; c++)
+        for (const char* p = classes[scheme][c]; *p; p++) {
+            lut.v[uint8_t(*p)] = uint8_t(c);
+            lut.v[uint8_t(*p) + 32] = uint8_t(c);  // lower case (to_ascii_uppercase, group_extraction.rs:379)
+        }
+    for (uint8_t ws : {0x20, 0x09, 0x0A, 0x0C, 0x0D}) lut.v[ws] = CODE_SKIP;  // u8::is_ascii_whitespace
+    return lut;
+}
+
+struct Batch {
+    uint64_t n_raw = 0;
+    uint32_t n_rec = 0, n_sp = 0;
+    size_t raw_pad = 0;      // n_raw rounded up to FRAME_TILE
+    size_t codes_cap = 0;    // allocated codes bytes (multiple of WARP_TILE)
+    uint32_t n_codes = 0;    // stripped residues + n_rec separators (known after framing)
+    bool framed = false;
+    DevBuf<uint8_t> raw, codes;
+    DevBuf<uint64_t> rec_off, sp_rec_off;
+    DevBuf<uint32_t> rec_cstart, sp_cstart;
+    DevBuf<uint16_t> flags;
+    std::vector<uint32_t> h_sp_cstart;   // host copy (after framing)
+    std::vector<uint64_t> h_sp_rec_off;
+    // pass 2 results
+    bool scanned = false;
+    DevBuf<uint16_t> occ;
+    DevBuf<uint32_t> inv_pos;
+    uint32_t n_inv = 0;
+    DevBuf<kmn_hit> starts, ends;
+    std::vector<uint32_t> h_sp_starts_off, h_sp_ends_off;
+};
+
+}  // namespace
+
+struct kmn_ctx {
+    int device = 0;
+    int k = 13;
+    int scheme = KMN_SR6;
+    uint64_t k_mask = 0;
+    RecodeLut lut;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    DevBuf<uint32_t> acc;                 // 4 x 2^26 u32 accumulators (1 GiB)
+    DevBuf<uint16_t> cms;                 // finalized table (512 MiB)
+    bool finalized = false;
+    DevBuf<unsigned long long> first;     // MAX_GROUP_SPECIES x 2^25 first-touch tags (4 GiB)
+    uint32_t epoch = 1;                   // next species epoch (0 = never written)
+    DevBuf<unsigned long long> new_counts;
+    DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
+    DevBuf<uint16_t> warp_cnt;
+    std::vector<std::unique_ptr<Batch>> batches;
+    cudaEvent_t ev[8] = {};
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    explicit DeviceGuard(int dev) { KMN_CUDA(cudaSetDevice(dev)); }
+};
+
+void check_launch(kmn_ctx* c) {
+    c->launches++;
+    KMN_CUDA(cudaGetLastError());
+}
+
+int grid_for(kmn_ctx* c, int ctas_per_sm) { return c->sm_count * ctas_per_sm; }
+
+Batch& get_batch(kmn_ctx* c, uint32_t id) {
+    if (id >= c->batches.size() || !c->batches[id]) throw std::runtime_error("unknown batch id");
+    return *c->batches[id];
+}
+
+void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                 const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+    if (!rec_off || !sp_rec_off) throw std::runtime_error("rec_off / sp_rec_off must not be NULL");
+    if (n_rec >= (1ull << 31)) throw std::runtime_error("too many records in one batch");
+    if (n_sp > 65535) throw std::runtime_error("too many species in one batch (maximum 65535)");  // group_extraction.rs:538
+    if (rec_off[0] != 0) throw std::runtime_error("rec_off[0] must be 0");
+    const uint64_t n_raw = rec_off[n_rec];
+    if (n_raw + n_rec >= (1ull << 31)) throw std::runtime_error("batch too large: residues + records must stay below 2^31");
+    if (n_raw && !residues) throw std::runtime_error("residues must not be NULL");
+    for (uint64_t r = 0; r < n_rec; r++)
+        if (rec_off[r + 1] < rec_off[r]) throw std::runtime_error("rec_off must be non-decreasing");
+    if (sp_rec_off[0] != 0 || sp_rec_off[n_sp] != n_rec) throw std::runtime_error("sp_rec_off must span [0, n_rec]");
+    for (uint32_t s = 0; s < n_sp; s++)
+        if (sp_rec_off[s + 1] < sp_rec_off[s]) throw std::runtime_error("sp_rec_off must be non-decreasing");
+
+    auto b = std::make_unique<Batch>();
+    b->n_raw = n_raw;
+    b->n_rec = uint32_t(n_rec);
+    b->n_sp = n_sp;
+    b->raw_pad = (size_t(n_raw) + FRAME_TILE - 1) / FRAME_TILE * FRAME_TILE;
+    if (b->raw_pad == 0) b->raw_pad = FRAME_TILE;
+    b->raw.alloc(b->raw_pad);
+    b->rec_off.alloc(n_rec + 1);
+    b->sp_rec_off.alloc(size_t(n_sp) + 1);
+    b->h_sp_rec_off.assign(sp_rec_off, sp_rec_off + n_sp + 1);
+    if (n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, residues, n_raw, cudaMemcpyHostToDevice, c->stream));
+    if (b->raw_pad > n_raw)  // pad with spaces: skipped like any whitespace
+        KMN_CUDA(cudaMemsetAsync(b->raw.p + n_raw, 0x20, b->raw_pad - n_raw, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(b->rec_off.p, rec_off, (n_rec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    // worst case: every raw byte is a residue, plus one separator per record
+    b->codes_cap = (size_t(n_raw) + n_rec + WARP_TILE - 1) / WARP_TILE * WARP_TILE + WARP_TILE;
+    b->codes.alloc(b->codes_cap);
+    b->rec_cstart.alloc(n_rec + 1);
+    b->sp_cstart.alloc(size_t(n_sp) + 1);
+    b->flags.alloc(b->codes_cap / CHUNK);
+    KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
+    c->batches.push_back(std::move(b));
+    if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
+}
+
+// K0 on a staged batch.
+void frame_batch(kmn_ctx* c, Batch& b) {
+    KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));
+    const uint32_t n_tiles = uint32_t(b.raw_pad / FRAME_TILE);
+    c->tile_cnt.ensure(n_tiles + 1);
+    c->tile_base.ensure(n_tiles + 2);
+    c->warp_cnt.ensure(size_t(n_tiles) * FRAME_WARPS);
+    if (b.n_rec > 0) {
+        frame_count_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, c->lut, c->tile_cnt.p, c->warp_cnt.p);
+        check_launch(c);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_tiles);
+        check_launch(c);
+        if (b.n_raw > 0) {
+            frame_scatter_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p,
+                                                                       b.rec_off.p, b.n_rec, b.codes.p);
+            check_launch(c);
+        }
+        frame_records_kernel<<<(b.n_rec + 1 + 255) / 256, 256, 0, c->stream>>>(
+            b.raw.p, c->lut, c->tile_base.p, c->warp_cnt.p, b.rec_off.p, b.n_rec, b.rec_cstart.p, b.codes.p);
+        check_launch(c);
+    } else {
+        KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));
+    }
+    species_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_cstart.p, b.sp_rec_off.p, b.n_sp, b.sp_cstart.p);
+    check_launch(c);
+    b.h_sp_cstart.resize(size_t(b.n_sp) + 1);
+    KMN_CUDA(cudaMemcpyAsync(b.h_sp_cstart.data(), b.sp_cstart.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    b.n_codes = b.h_sp_cstart[b.n_sp];
+    b.framed = true;
+    b.scanned = false;
+}
+
+void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
+    if (c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    frame_batch(c, b);
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaMemsetAsync(b.flags.p, 0, (b.codes_cap / CHUNK) * sizeof(uint16_t), c->stream));
+    c->new_counts.ensure(size_t(b.n_sp) + 1);
+    KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
+    const int grid = grid_for(c, 8);
+    for (uint32_t s0 = 0; s0 < b.n_sp; s0 += MAX_GROUP_SPECIES) {
+        GroupBounds g;
+        g.n = std::min<uint32_t>(MAX_GROUP_SPECIES, b.n_sp - s0);
+        g.first_species = s0;
+        if (c->epoch > 0xFFFFFFFFu - MAX_GROUP_SPECIES) {  // epoch wrap: start over with clean slots
+            KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
+            c->epoch = 1;
+        }
+        g.epoch0 = c->epoch;
+        c->epoch += g.n;
+        if (b.h_sp_cstart[s0 + g.n] == b.h_sp_cstart[s0]) continue;  // no residues in this group
+        bloom_mark_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, c->first.p);
+        check_launch(c);
+        bloom_resolve_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask,
+                                                                   c->first.p, b.flags.p, c->new_counts.p);
+        check_launch(c);
+    }
+    KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (b.n_codes > 0) {
+        cms_update_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.flags.p, 0u, b.n_codes, c->k, c->k_mask, c->acc.p);
+        check_launch(c);
+    }
+    KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    std::vector<unsigned long long> h(b.n_sp);
+    if (new_kmers_per_species && b.n_sp)
+        KMN_CUDA(cudaMemcpyAsync(h.data(), c->new_counts.p, size_t(b.n_sp) * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    if (new_kmers_per_species)
+        for (uint32_t s = 0; s < b.n_sp; s++) new_kmers_per_species[s] = h[s];
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[2], c->ev[2], c->ev[3]));
+}
+
+void finalize_table(kmn_ctx* c) {
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    cms_finalize_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->acc.p),
+                                                             reinterpret_cast<uint2*>(c->cms.p), CMS_CELLS / 4);
+    check_launch(c);
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
+    c->finalized = true;
+}
+
+void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, uint64_t* n_ends) {
+    if (!c->finalized) throw std::runtime_error("kmn_scan_batch needs a finalized table (kmn_finalize_table / kmn_table_load)");
+    if (!b.framed) frame_batch(c, b);
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const uint32_t n_tiles = uint32_t((size_t(b.n_codes) + WARP_TILE - 1) / WARP_TILE);
+    b.occ.ensure(size_t(n_tiles + 1) * WARP_TILE);
+    const int grid = grid_for(c, 8);
+    if (n_tiles) {
+        occupancy_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(b.codes.p, n_tiles, c->k, c->k_mask, c->cms.p, b.occ.p);
+        check_launch(c);
+    }
+    // reset positions -> segments
+    const uint32_t n_ctiles = (b.n_codes + 4095) / 4096;
+    c->tile_cnt.ensure(n_ctiles + 1);
+    c->tile_base.ensure(n_ctiles + 2);
+    uint32_t n_inv = 0;
+    if (n_ctiles) {
+        invalid_count_kernel<<<n_ctiles, 256, 0, c->stream>>>(b.codes.p, b.n_codes, c->tile_cnt.p);
+        check_launch(c);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_ctiles);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(&n_inv, c->tile_base.p + n_ctiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        b.inv_pos.ensure(n_inv);
+        invalid_scatter_kernel<<<n_ctiles, 256, 0, c->stream>>>(b.codes.p, b.n_codes, c->tile_base.p, b.inv_pos.p);
+        check_launch(c);
+    }
+    b.n_inv = n_inv;
+    c->seg_s_cnt.ensure(size_t(n_inv) + 1);
+    c->seg_e_cnt.ensure(size_t(n_inv) + 1);
+    c->seg_s_off.ensure(size_t(n_inv) + 2);
+    c->seg_e_off.ensure(size_t(n_inv) + 2);
+    c->sp_s_off.ensure(size_t(b.n_sp) + 1);
+    c->sp_e_off.ensure(size_t(b.n_sp) + 1);
+    uint32_t tot_s = 0, tot_e = 0;
+    if (n_inv) {
+        segment_boundary_kernel<false><<<grid, SCAN_THREADS, 0, c->stream>>>(
+            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr,
+            b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, nullptr, nullptr);
+        check_launch(c);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_s_cnt.p, c->seg_s_off.p, n_inv);
+        check_launch(c);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_e_cnt.p, c->seg_e_off.p, n_inv);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(&tot_s, c->seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(&tot_e, c->seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        b.starts.ensure(tot_s);
+        b.ends.ensure(tot_e);
+        segment_boundary_kernel<true><<<grid, SCAN_THREADS, 0, c->stream>>>(
+            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, nullptr, nullptr, c->seg_s_off.p, c->seg_e_off.p,
+            b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, b.starts.p, b.ends.p);
+        check_launch(c);
+        species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
+            b.inv_pos.p, n_inv, b.sp_cstart.p, b.n_sp, c->seg_s_off.p, c->seg_e_off.p, c->sp_s_off.p, c->sp_e_off.p);
+        check_launch(c);
+        b.h_sp_starts_off.resize(size_t(b.n_sp) + 1);
+        b.h_sp_ends_off.resize(size_t(b.n_sp) + 1);
+        KMN_CUDA(cudaMemcpyAsync(b.h_sp_starts_off.data(), c->sp_s_off.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(b.h_sp_ends_off.data(), c->sp_e_off.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        b.h_sp_starts_off.assign(size_t(b.n_sp) + 1, 0);
+        b.h_sp_ends_off.assign(size_t(b.n_sp) + 1, 0);
+    }
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[4], c->ev[0], c->ev[1]));
+    b.scanned = true;
+    if (n_starts) *n_starts = tot_s;
+    if (n_ends) *n_ends = tot_e;
+}
+
+void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
+    if (n < 2) return;
+    if (L >= (1ull << 32)) throw std::runtime_error("alignment too long for u32 counts");
+    const uint32_t n_tiles = (n + PAIR_TILE - 1) / PAIR_TILE;
+    const uint32_t n_pad = n_tiles * PAIR_TILE;
+    const uint32_t W = uint32_t((L + 31) / 32);
+    DevBuf<uint8_t> d_mapped;
+    DevBuf<uint32_t> d_planes, d_valid, d_mism;
+    d_mapped.alloc(size_t(n) * L);
+    d_planes.alloc(size_t(n_pad) * std::max<uint32_t>(W, 1) * PAIR_PLANES);
+    d_valid.alloc(size_t(n) * n);
+    d_mism.alloc(size_t(n) * n);
+    if (L) KMN_CUDA(cudaMemcpyAsync(d_mapped.p, mapped, size_t(n) * L, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemsetAsync(d_valid.p, 0, size_t(n) * n * sizeof(uint32_t), c->stream));
+    KMN_CUDA(cudaMemsetAsync(d_mism.p, 0, size_t(n) * n * sizeof(uint32_t), c->stream));
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (W) {
+        const uint64_t items = uint64_t(n_pad) * W;
+        pair_pack_kernel<<<uint32_t((items + 255) / 256), 256, 0, c->stream>>>(d_mapped.p, n, L, n_pad, W, d_planes.p);
+        check_launch(c);
+        const uint32_t n_blocks = n_tiles * (n_tiles + 1) / 2;
+        pair_count_kernel<<<n_blocks, PAIR_THREADS, 0, c->stream>>>(d_planes.p, n, W, n_tiles, d_valid.p, d_mism.p);
+        check_launch(c);
+    }
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaMemcpyAsync(valid, d_valid.p, size_t(n) * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(mismatch, d_mism.p, size_t(n) * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[1]));
+}
+
+template <typename F>
+int guarded(kmn_ctx* c, F&& f) {
+    try {
+        if (!c) throw std::runtime_error("NULL context");
+        DeviceGuard dg(c->device);
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    } catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kmn_last_error(void) { return g_err.c_str(); }
+uint32_t kmn_abi_version(void) { return 1; }
+
+int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
+    try {
+        if (!out) throw std::runtime_error("out must not be NULL");
+        *out = nullptr;
+        if (k < 1 || k > 21) throw std::runtime_error("invalid k");  // lib.rs:218
+        if (scheme < 0 || scheme > 2) throw std::runtime_error("invalid recode scheme");
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e != cudaSuccess || n_dev == 0)
+            throw std::runtime_error(std::string("no CUDA device available (there is no CPU fallback): ") +
+                                     cudaGetErrorString(e));
+        if (device < 0 || device >= n_dev) throw std::runtime_error("invalid device ordinal");
+        KMN_CUDA(cudaSetDevice(device));
+        auto c = std::make_unique<kmn_ctx>();
+        c->device = device;
+        c->k = k;
+        c->scheme = scheme;
+        c->k_mask = (3 * k >= 64) ? ~0ull : ((1ull << (3 * k)) - 1);  // group_extraction.rs:545-549
+        c->lut = make_lut(scheme);
+        KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
+        c->acc.alloc(CMS_CELLS);
+        c->cms.alloc(CMS_CELLS);
+        c->first.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_BITS_LOG2);
+        KMN_CUDA(cudaMemsetAsync(c->acc.p, 0, CMS_CELLS * sizeof(uint32_t), c->stream));
+        KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        *out = c.release();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+void kmn_destroy(kmn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->batches.clear();
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int kmn_stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                    const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+    return guarded(c, [&] { stage_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, batch_id); });
+}
+
+int kmn_count_staged(kmn_ctx* c, uint32_t batch_id, uint64_t* new_kmers_per_species) {
+    return guarded(c, [&] { count_staged(c, get_batch(c, batch_id), new_kmers_per_species); });
+}
+
+int kmn_count_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                    const uint64_t* sp_rec_off, uint32_t n_sp, uint64_t* new_kmers_per_species,
+                    uint32_t* batch_id) {
+    return guarded(c, [&] {
+        uint32_t id = 0;
+        stage_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, &id);
+        if (batch_id) *batch_id = id;
+        count_staged(c, get_batch(c, id), new_kmers_per_species);
+    });
+}
+
+int kmn_reset_table(kmn_ctx* c) {
+    return guarded(c, [&] {
+        KMN_CUDA(cudaMemsetAsync(c->acc.p, 0, CMS_CELLS * sizeof(uint32_t), c->stream));
+        c->finalized = false;
+    });
+}
+
+int kmn_release_batches(kmn_ctx* c) {
+    return guarded(c, [&] {
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->batches.clear();
+    });
+}
+
+int kmn_finalize_table(kmn_ctx* c) { return guarded(c, [&] { finalize_table(c); }); }
+
+int kmn_table_snapshot(kmn_ctx* c, uint16_t* out) {
+    return guarded(c, [&] {
+        if (!out) throw std::runtime_error("out must not be NULL");
+        if (!c->finalized) throw std::runtime_error("table not finalized");
+        KMN_CUDA(cudaMemcpyAsync(out, c->cms.p, CMS_CELLS * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kmn_table_load(kmn_ctx* c, const uint16_t* table) {
+    return guarded(c, [&] {
+        if (!table) throw std::runtime_error("table must not be NULL");
+        KMN_CUDA(cudaMemcpyAsync(c->cms.p, table, CMS_CELLS * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->finalized = true;
+    });
+}
+
+int kmn_table_accum_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->acc.p; }); }
+int kmn_table_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->cms.p; }); }
+int kmn_synchronize(kmn_ctx* c) { return guarded(c, [&] { KMN_CUDA(cudaStreamSynchronize(c->stream)); }); }
+int kmn_stream(kmn_ctx* c, void** stream) { return guarded(c, [&] { *stream = c->stream; }); }
+
+int kmn_scan_batch(kmn_ctx* c, uint32_t batch_id, uint32_t min_needed, uint64_t* n_starts, uint64_t* n_ends) {
+    return guarded(c, [&] { scan_batch(c, get_batch(c, batch_id), min_needed, n_starts, n_ends); });
+}
+
+int kmn_fetch_hits(kmn_ctx* c, uint32_t batch_id, uint32_t sp, kmn_hit* starts, uint64_t cap_starts,
+                   uint64_t* n_starts, kmn_hit* ends, uint64_t cap_ends, uint64_t* n_ends) {
+    return guarded(c, [&] {
+        Batch& b = get_batch(c, batch_id);
+        if (!b.scanned) throw std::runtime_error("batch has not been scanned (kmn_scan_batch)");
+        if (sp >= b.n_sp) throw std::runtime_error("species index out of range");
+        const uint64_t s0 = b.h_sp_starts_off[sp], s1 = b.h_sp_starts_off[sp + 1];
+        const uint64_t e0 = b.h_sp_ends_off[sp], e1 = b.h_sp_ends_off[sp + 1];
+        if (n_starts) *n_starts = s1 - s0;
+        if (n_ends) *n_ends = e1 - e0;
+        if (!starts && !ends) return;
+        if ((starts && cap_starts < s1 - s0) || (ends && cap_ends < e1 - e0)) throw std::runtime_error("hit buffers too small");
+        if (starts && s1 > s0)
+            KMN_CUDA(cudaMemcpyAsync(starts, b.starts.p + s0, (s1 - s0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
+        if (ends && e1 > e0)
+            KMN_CUDA(cudaMemcpyAsync(ends, b.ends.p + e0, (e1 - e0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap, uint64_t* n) {
+    return guarded(c, [&] {
+        Batch& b = get_batch(c, batch_id);
+        if (!b.scanned) throw std::runtime_error("batch has not been scanned (kmn_scan_batch)");
+        if (sp >= b.n_sp) throw std::runtime_error("species index out of range");
+        const uint32_t r0 = uint32_t(b.h_sp_rec_off[sp]), r1 = uint32_t(b.h_sp_rec_off[sp + 1]);
+        const uint64_t n_res = uint64_t(b.h_sp_cstart[sp + 1] - b.h_sp_cstart[sp]) - (r1 - r0);
+        if (n) *n = n_res;
+        if (!occ || n_res == 0) return;
+        if (cap < n_res) throw std::runtime_error("occupancy buffer too small");
+        DevBuf<uint16_t> tmp;
+        tmp.alloc(n_res);
+        occupancy_gather_kernel<<<std::min<uint32_t>(r1 - r0, 4096u), 128, 0, c->stream>>>(b.occ.p, b.rec_cstart.p, r0, r1, tmp.p);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(occ, tmp.p, n_res * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kmn_pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
+    return guarded(c, [&] {
+        if (!mapped || !valid || !mismatch) throw std::runtime_error("NULL argument");
+        pair_counts(c, mapped, n, L, valid, mismatch);
+    });
+}
+
+int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
+    return guarded(c, [&] {
+        if (which < 0 || which > 5 || !ms) throw std::runtime_error("invalid stage index");
+        *ms = c->stage_ms[which];
+    });
+}
+
+uint64_t kmn_launch_count(kmn_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

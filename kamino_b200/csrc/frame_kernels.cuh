@@ -1,0 +1,190 @@
+// frame_kernels.cuh — K0: raw seq() bytes -> whitespace-free recoded stream with record separators.
+//
+// Replaces, for a whole batch at once, the per-byte front of count_species_kmers
+// (/root/reference/src/group_extraction.rs:375-384): skip ASCII whitespace, upper-case, recode
+// (src/recode.rs:31-80) -> class 0..5 or 255.  Memory-bound streaming: 1 B read + 1 B written per
+// raw byte, 16-byte vector loads, 256-entry recode LUT in shared memory.
+#pragma once
+#include "kmn_device.cuh"
+
+namespace kmn {
+
+constexpr int FRAME_THREADS = 256;
+constexpr int FRAME_TILE = FRAME_THREADS * CHUNK;  // 4096 raw bytes per CTA
+constexpr int FRAME_WARPS = FRAME_THREADS / 32;
+
+struct RecodeLut { uint8_t v[256]; };  // passed by value as a kernel parameter (256 B)
+
+__device__ __forceinline__ void load_lut(uint8_t* s_lut, const RecodeLut& lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut.v[i];
+    __syncthreads();
+}
+
+// number of non-whitespace bytes among the 16 bytes of v
+__device__ __forceinline__ uint32_t count_kept(const uint4& v, const uint8_t* s_lut) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t n = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) n += s_lut[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu] != CODE_SKIP;
+    return n;
+}
+
+// Pass A: kept-byte counts per CTA tile (4096 B) and per warp sub-tile (512 B).
+// raw is padded with spaces to a multiple of FRAME_TILE, so no tail guard is needed.
+__global__ void __launch_bounds__(FRAME_THREADS)
+frame_count_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, uint32_t* __restrict__ tile_cnt,
+                   uint16_t* __restrict__ warp_cnt) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_w[FRAME_WARPS];
+    load_lut(s_lut, lut);
+    const size_t base = size_t(blockIdx.x) * FRAME_TILE + size_t(threadIdx.x) * CHUNK;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + base));
+    uint32_t n = count_kept(v, s_lut);
+    n = __reduce_add_sync(0xffffffffu, n);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_w[warp] = n;
+        warp_cnt[size_t(blockIdx.x) * FRAME_WARPS + warp] = uint16_t(n);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < FRAME_WARPS; i++) t += s_w[i];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+// Single-CTA exclusive scan of n u32 values (n <= a few 10^5 tiles); total -> out[n].
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __restrict__ in,
+                                                              uint32_t* __restrict__ out, uint32_t n) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < n ? in[i] : 0u;
+        uint32_t incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= unsigned(d)) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= unsigned(d)) wi += y;
+            }
+            s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < n) out[i] = carry + s_warp[warp] + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// index of the record that contains raw byte offset x: largest r with rec_off[r] <= x, skipping
+// empty records (rec_off[r] == rec_off[r+1]); search window [lo, hi].
+__device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_off, uint32_t lo,
+                                              uint32_t hi, uint64_t x) {
+    // find the largest r in [lo, hi] with rec_off[r] <= x
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (rec_off[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Pass B: scatter recoded residues.  Output index of a kept raw byte i =
+//   (#kept bytes before i) + (index of the record containing i)      [one separator per earlier record]
+__global__ void __launch_bounds__(FRAME_THREADS)
+frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut,
+                     const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ rec_off,
+                     uint32_t n_rec, uint8_t* __restrict__ codes) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_w[FRAME_WARPS];
+    __shared__ uint32_t s_rlo, s_rhi;
+    load_lut(s_lut, lut);
+    const uint64_t tile0 = uint64_t(blockIdx.x) * FRAME_TILE;
+    if (threadIdx.x == 0) s_rlo = record_of(rec_off, 0, n_rec - 1, tile0);
+    if (threadIdx.x == 32) {
+        uint64_t last = tile0 + FRAME_TILE - 1;
+        if (last >= n_raw) last = n_raw - 1;
+        s_rhi = record_of(rec_off, 0, n_rec - 1, last);
+    }
+    const uint64_t i0 = tile0 + uint64_t(threadIdx.x) * CHUNK;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + i0));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t n = count_kept(v, s_lut);
+    // exclusive scan of n over the CTA
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= unsigned(d)) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int i = 0; i < FRAME_WARPS; i++) woff += (i < int(warp)) ? s_w[i] : 0u;
+    uint32_t out = tile_base[blockIdx.x] + woff + incl - n;
+    if (i0 >= n_raw || n == 0) return;
+    uint32_t r = record_of(rec_off, s_rlo, s_rhi, i0);
+    uint64_t r_end = rec_off[r + 1];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint64_t i = i0 + j;
+        const uint8_t c = s_lut[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+        if (i < n_raw && c != CODE_SKIP) {
+            while (i >= r_end) { r++; r_end = rec_off[r + 1]; }
+            codes[size_t(out) + r] = c;
+            out++;
+        }
+    }
+}
+
+// Pass C: one thread per record boundary b in 0..n_rec: S(b) = #kept bytes before rec_off[b];
+// rec_cstart[b] = S(b) + b; and record b-1's separator (0xFF) is written at rec_cstart[b]-1.
+__global__ void __launch_bounds__(256)
+frame_records_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, const uint32_t* __restrict__ tile_base,
+                     const uint16_t* __restrict__ warp_cnt, const uint64_t* __restrict__ rec_off,
+                     uint32_t n_rec, uint32_t* __restrict__ rec_cstart, uint8_t* __restrict__ codes) {
+    __shared__ uint8_t s_lut[256];
+    load_lut(s_lut, lut);
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_rec) return;
+    const uint64_t x = rec_off[b];
+    const uint64_t tile = x / FRAME_TILE;
+    uint32_t s = tile_base[tile];
+    const uint32_t in_tile = uint32_t(x - tile * FRAME_TILE);
+    const uint32_t wfull = in_tile / WARP_TILE;
+    for (uint32_t wi = 0; wi < wfull; wi++) s += warp_cnt[tile * FRAME_WARPS + wi];
+    const uint64_t p0 = tile * FRAME_TILE + uint64_t(wfull) * WARP_TILE;
+    for (uint64_t p = p0; p < x; p++) s += s_lut[raw[p]] != CODE_SKIP;
+    const uint32_t cs = s + b;
+    rec_cstart[b] = cs;
+    if (b > 0) codes[cs - 1] = CODE_INVALID;
+}
+
+// species -> codes[] offsets: sp_cstart[s] = rec_cstart[sp_rec_off[s]]
+__global__ void species_offsets_kernel(const uint32_t* __restrict__ rec_cstart,
+                                       const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp,
+                                       uint32_t* __restrict__ sp_cstart) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= n_sp) sp_cstart[s] = rec_cstart[sp_rec_off[s]];
+}
+
+}  // namespace kmn

@@ -1,0 +1,128 @@
+// kmn_device.cuh — device-side building blocks shared by the sm_100a kernels.
+//
+// HBM layout of a staged batch:
+//   codes[n_codes]   one byte per whitespace-stripped residue: class 0..5 (recode.rs:40-80) or
+//                    0xFF for a residue that resets the roll; ONE extra 0xFF separator after the
+//                    last residue of every record (group_extraction.rs:373-374 resets roll/have
+//                    per record, so a separator is exactly a reset).  Padded with 0xFF to a
+//                    multiple of 512 bytes so a warp always loads 32 aligned 16-byte chunks.
+//   rec_cstart[n_rec+1]  index in codes[] of the first residue of each record
+//                    (rec_cstart[r+1]-1 is record r's separator).
+//   sp_cstart[n_sp+1]    index in codes[] where each species starts.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kmn {
+
+constexpr uint32_t BLOOM_BITS_LOG2 = 25;                 // proba_filter.rs:13
+constexpr uint32_t BLOOM_MASK = (1u << BLOOM_BITS_LOG2) - 1;
+constexpr uint32_t CMS_WIDTH_LOG2 = 26;                  // proba_filter.rs:17
+constexpr uint32_t CMS_MASK = (1u << CMS_WIDTH_LOG2) - 1;
+constexpr uint32_t CMS_DEPTH = 4;                        // proba_filter.rs:19
+constexpr uint64_t CMS_CELLS = uint64_t(CMS_DEPTH) << CMS_WIDTH_LOG2;
+
+// proba_filter.rs:21-28
+constexpr uint64_t SEED_BLOOM_1 = 0x9e3779b97f4a7c15ull;
+constexpr uint64_t SEED_BLOOM_2 = 0xbf58476d1ce4e5b9ull;
+constexpr uint64_t SEED_CMS_0 = 0x94d049bb133111ebull;
+constexpr uint64_t SEED_CMS_1 = 0x3c79ac492ba7b653ull;
+constexpr uint64_t SEED_CMS_2 = 0x1c69b3f74ac4ae35ull;
+constexpr uint64_t SEED_CMS_3 = 0x6a09e667f3bcc909ull;
+
+constexpr uint8_t CODE_INVALID = 0xFF;  // resets roll/have
+constexpr uint8_t CODE_SKIP = 0xFE;     // ASCII whitespace: skipped without a reset (LUT only)
+
+constexpr int CHUNK = 16;               // residues per thread (one 16-byte vector load)
+constexpr int WARP_TILE = 32 * CHUNK;   // residues per warp iteration
+
+// SplitMix64 finalizer (proba_filter.rs:30-37)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+// Bloom probe indices (proba_filter.rs:60-64): idx_i = (h1 + i*h2) & mask, h2 forced odd.
+__device__ __forceinline__ void bloom_indices(uint64_t kmer, uint32_t& i0, uint32_t& i1) {
+    uint64_t h1 = mix64(kmer ^ SEED_BLOOM_1);
+    uint64_t h2 = mix64(kmer ^ SEED_BLOOM_2) | 1ull;
+    i0 = uint32_t(h1) & BLOOM_MASK;
+    i1 = uint32_t(h1 + h2) & BLOOM_MASK;
+}
+
+// CMS cell index of row r (proba_filter.rs:107,148); flat offset = r * 2^26 + idx.
+__device__ __forceinline__ uint32_t cms_index(uint64_t kmer, uint64_t seed) {
+    return uint32_t(mix64(kmer ^ seed)) & CMS_MASK;
+}
+
+// Pack one 16-code chunk: symbol j (memory order) lands at bits [3*(15-j), 3*(15-j)+3) of P, so
+// P equals the reference's roll after shifting in the 16 symbols.  last_inv = index of the last
+// 0xFF in the chunk, -1 if none.
+__device__ __forceinline__ void pack_chunk(const uint4& v, uint64_t& P, int& last_inv) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint64_t p = 0;
+    int li = -1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t x = w[i];
+        // bytes b0..b3 (little endian) -> 12 bits, b0 most significant
+        uint32_t t = ((x & 7u) << 9) | (((x >> 8) & 7u) << 6) | (((x >> 16) & 7u) << 3) | ((x >> 24) & 7u);
+        p = (p << 12) | t;
+        uint32_t inv = x & 0x80808080u;  // only 0xFF has bit 7 set
+        if (inv) li = 4 * i + ((31 - __clz(inv)) >> 3);
+    }
+    P = p;
+    last_inv = li;
+}
+
+// Warp-cooperative rolling k-mer enumeration over one warp tile (32 lanes x 16 codes).
+// Every lane owns codes [c0, c0+16), c0 = tile_base + 16*lane; the (k-1)-symbol history comes from
+// the two previous lanes by warp shuffle (lanes 0/1 fetch the two chunks before the tile).
+// Calls f(c, kmer) for every position c whose k-mer is valid under group_extraction.rs:373-388
+// (have == k, no reset inside the window).  ALL 32 lanes must call this (shuffles inside).
+template <typename F>
+__device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __restrict__ codes,
+                                                           uint32_t tile_base, int k, uint64_t k_mask,
+                                                           F&& f) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t c0 = tile_base + lane * CHUNK;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes + c0));
+    uint64_t P;
+    int li;
+    pack_chunk(v, P, li);
+    // history chunks for lanes 0 and 1: chunk (tile-2) on lane 0, chunk (tile-1) on lane 1
+    uint64_t E = 0;
+    int eli = 15;  // "before the buffer" behaves like a reset
+    if (lane < 2 && tile_base >= (2 - lane) * CHUNK) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4*>(codes + tile_base - (2 - lane) * CHUNK));
+        pack_chunk(e, E, eli);
+    }
+    uint64_t P1 = __shfl_up_sync(0xffffffffu, P, 1), P2 = __shfl_up_sync(0xffffffffu, P, 2);
+    int li1 = __shfl_up_sync(0xffffffffu, li, 1), li2 = __shfl_up_sync(0xffffffffu, li, 2);
+    const uint64_t E0 = __shfl_sync(0xffffffffu, E, 0), E1 = __shfl_sync(0xffffffffu, E, 1);
+    const int el0 = __shfl_sync(0xffffffffu, eli, 0), el1 = __shfl_sync(0xffffffffu, eli, 1);
+    if (lane == 0) { P1 = E1; li1 = el1; P2 = E0; li2 = el0; }
+    if (lane == 1) { P2 = E1; li2 = el1; }
+    // roll/have as they stand after the previous chunk
+    uint64_t roll = (((P2 & 0x7FFFull) << 48) | P1) & k_mask;
+    int have = li1 >= 0 ? 15 - li1 : (li2 >= 0 ? 31 - li2 : 32);
+    if (have > k) have = k;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        if (code == CODE_INVALID) {
+            roll = 0;
+            have = 0;
+        } else {
+            roll = ((roll << 3) | uint64_t(code)) & k_mask;
+            if (have < k) have++;
+            if (have == k) f(c0 + j, roll);
+        }
+    }
+}
+
+}  // namespace kmn

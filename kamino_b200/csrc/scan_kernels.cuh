@@ -1,0 +1,218 @@
+// scan_kernels.cuh — pass 2: per-position occupancy + segment boundary rule.
+//
+// Replaces CountMinSketch::estimate (/root/reference/src/proba_filter.rs:103-112) evaluated at every
+// k-mer position, the segmentation of extract_species_blocks (group_extraction.rs:455-498: split at
+// residues that recode to 255, keep segments >= 2k+1) and the boundary rule of
+// extract_from_valid_segment (group_extraction.rs:292-299).
+#pragma once
+#include "kmn_device.cuh"
+#include "../../include/kamino_b200.h"
+
+namespace kmn {
+
+constexpr int SCAN_THREADS = 256;
+
+// K5a: occ[c] = min over the 4 CMS rows for every valid k-mer END position c; 0 elsewhere.
+__global__ void __launch_bounds__(SCAN_THREADS)
+occupancy_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int k, uint64_t k_mask,
+                 const uint16_t* __restrict__ cms, uint16_t* __restrict__ occ) {
+    const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
+    const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
+        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
+        uint32_t o[CHUNK / 2];
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; i++) o[i] = 0;
+        for_each_kmer_in_warp_tile(codes, t * WARP_TILE, k, k_mask, [&](uint32_t c, uint64_t kmer) {
+            const uint32_t a = __ldg(cms + (size_t(0) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_0));
+            const uint32_t b = __ldg(cms + (size_t(1) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_1));
+            const uint32_t d = __ldg(cms + (size_t(2) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_2));
+            const uint32_t e = __ldg(cms + (size_t(3) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_3));
+            const uint32_t m = min(min(a, b), min(d, e));
+            const uint32_t j = c - c0;
+            o[j >> 1] |= m << (16 * (j & 1));
+        });
+        uint4* dst = reinterpret_cast<uint4*>(occ + c0);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ---- list of reset positions (0xFF codes) of a batch: count / scatter around exclusive_scan_kernel
+__global__ void __launch_bounds__(256)
+invalid_count_kernel(const uint8_t* __restrict__ codes, uint32_t n_codes, uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t c0 = (blockIdx.x * 256u + threadIdx.x) * CHUNK;
+    uint32_t n = 0;
+    if (c0 < n_codes) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes + c0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            n += (c0 + j < n_codes) && (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == CODE_INVALID);
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s_w[i];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+invalid_scatter_kernel(const uint8_t* __restrict__ codes, uint32_t n_codes, const uint32_t* __restrict__ tile_base,
+                       uint32_t* __restrict__ inv_pos) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t c0 = (blockIdx.x * 256u + threadIdx.x) * CHUNK;
+    uint32_t mask = 0;
+    if (c0 < n_codes) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes + c0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if ((c0 + j < n_codes) && (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == CODE_INVALID)) mask |= 1u << j;
+    }
+    const uint32_t n = __popc(mask);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= unsigned(d)) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int i = 0; i < 8; i++) woff += (i < int(warp)) ? s_w[i] : 0u;
+    uint32_t out = tile_base[blockIdx.x] + woff + incl - n;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        inv_pos[out++] = c0 + j;
+    }
+}
+
+__device__ __forceinline__ uint32_t upper_index_le(const uint32_t* __restrict__ a, uint32_t n, uint32_t x) {
+    // largest i in [0, n) with a[i] <= x   (a non-decreasing, a[0] <= x guaranteed)
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (a[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// The k-mer that ENDS at position c (all k codes are known to be valid).
+__device__ __forceinline__ uint64_t kmer_ending_at(const uint8_t* __restrict__ codes, uint32_t c, int k) {
+    uint64_t r = 0;
+    for (int i = k - 1; i >= 0; i--) r = (r << 3) | uint64_t(codes[c - i]);
+    return r;
+}
+
+// K5b/K5c: one warp per valid segment (the codes strictly between two consecutive resets).
+// EMIT == false: count start candidates / end anchors per segment.
+// EMIT == true : write them, in position order, at the scanned offsets.
+template <bool EMIT>
+__global__ void __launch_bounds__(SCAN_THREADS)
+segment_boundary_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ occ,
+                        const uint32_t* __restrict__ inv_pos, uint32_t n_inv, int k, uint32_t min_needed,
+                        uint32_t* __restrict__ seg_starts_cnt, uint32_t* __restrict__ seg_ends_cnt,
+                        const uint32_t* __restrict__ seg_starts_off, const uint32_t* __restrict__ seg_ends_off,
+                        const uint32_t* __restrict__ rec_cstart, uint32_t n_rec,
+                        const uint32_t* __restrict__ sp_cstart, const uint64_t* __restrict__ sp_rec_off,
+                        uint32_t n_sp, kmn_hit* __restrict__ starts, kmn_hit* __restrict__ ends) {
+    const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
+    const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (uint32_t j = warp_id; j < n_inv; j += warps_per_grid) {
+        const uint32_t seg_lo = j == 0 ? 0u : inv_pos[j - 1] + 1;  // first code of the segment
+        const uint32_t seg_hi = inv_pos[j];                        // one past its last code
+        const uint32_t len = seg_hi - seg_lo;
+        uint32_t ns = 0, ne = 0;
+        uint32_t rec = 0, seg_start = 0, os = 0, oe = 0;
+        if (len >= uint32_t(2 * k + 1)) {   // group_extraction.rs:424,462,484
+            if (EMIT) {
+                const uint32_t r = upper_index_le(rec_cstart, n_rec, seg_lo);
+                const uint32_t s = upper_index_le(sp_cstart, n_sp, seg_lo);
+                rec = r - uint32_t(sp_rec_off[s]);
+                seg_start = seg_lo - rec_cstart[r];
+                os = seg_starts_off[j];
+                oe = seg_ends_off[j];
+            }
+            // hit h (h >= 1) ends at c = seg_lo + k - 1 + h; compare with hit h-1 (group_extraction.rs:292-299)
+            for (uint32_t base = seg_lo + k; base < seg_hi; base += 32) {
+                const uint32_t c = base + lane;
+                bool is_s = false, is_e = false;
+                uint32_t prev = 0, cur = 0;
+                if (c < seg_hi) {
+                    prev = occ[c - 1];
+                    cur = occ[c];
+                    is_s = prev >= min_needed && prev > cur;   // previous hit becomes a start candidate
+                    is_e = cur >= min_needed && prev < cur;    // current hit becomes an end anchor
+                }
+                const unsigned bs = __ballot_sync(0xffffffffu, is_s), be = __ballot_sync(0xffffffffu, is_e);
+                if (EMIT) {
+                    if (is_s) {
+                        kmn_hit h;
+                        h.kmer = kmer_ending_at(codes, c - 1, k);
+                        h.rec = rec;
+                        h.seg_start = seg_start;
+                        h.start = (c - 1) - (k - 1) - seg_lo;
+                        h.occ = prev;
+                        starts[os + ns + __popc(bs & lt_mask)] = h;
+                    }
+                    if (is_e) {
+                        kmn_hit h;
+                        h.kmer = kmer_ending_at(codes, c, k);
+                        h.rec = rec;
+                        h.seg_start = seg_start;
+                        h.start = c - (k - 1) - seg_lo;
+                        h.occ = cur;
+                        ends[oe + ne + __popc(be & lt_mask)] = h;
+                    }
+                }
+                ns += __popc(bs);
+                ne += __popc(be);
+            }
+        }
+        if (!EMIT && lane == 0) {
+            seg_starts_cnt[j] = ns;
+            seg_ends_cnt[j] = ne;
+        }
+    }
+}
+
+// hit-list offsets per species: first segment of species s is the first reset position >= sp_cstart[s]
+__global__ void species_hit_offsets_kernel(const uint32_t* __restrict__ inv_pos, uint32_t n_inv,
+                                           const uint32_t* __restrict__ sp_cstart, uint32_t n_sp,
+                                           const uint32_t* __restrict__ seg_starts_off,
+                                           const uint32_t* __restrict__ seg_ends_off,
+                                           uint32_t* __restrict__ sp_starts_off, uint32_t* __restrict__ sp_ends_off) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_sp) return;
+    const uint32_t x = sp_cstart[s];
+    uint32_t lo = 0, hi = n_inv;  // first j with inv_pos[j] >= x
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (inv_pos[mid] >= x) hi = mid; else lo = mid + 1;
+    }
+    sp_starts_off[s] = seg_starts_off[lo];
+    sp_ends_off[s] = seg_ends_off[lo];
+}
+
+// Parity helper: occupancy per stripped residue of one species (separators removed).
+__global__ void occupancy_gather_kernel(const uint16_t* __restrict__ occ, const uint32_t* __restrict__ rec_cstart,
+                                        uint32_t r0, uint32_t r1, uint16_t* __restrict__ out) {
+    // one CTA per record (grid-stride); out index = c - rec_cstart[r0] - (r - r0)
+    for (uint32_t r = r0 + blockIdx.x; r < r1; r += gridDim.x) {
+        const uint32_t lo = rec_cstart[r], hi = rec_cstart[r + 1] - 1;
+        const uint32_t shift = rec_cstart[r0] + (r - r0);
+        for (uint32_t c = lo + threadIdx.x; c < hi; c += blockDim.x) out[c - shift] = occ[c];
+    }
+}
+
+}  // namespace kmn

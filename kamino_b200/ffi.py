@@ -1,0 +1,226 @@
+"""ctypes binding of libkamino_b200.so (C ABI in include/kamino_b200.h).
+
+Thin plumbing only: numpy arrays in, numpy arrays out.  There is no CPU fallback — if the CUDA
+library is missing or no GPU is present, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+DAYHOFF6, SR6, KGB6 = 0, 1, 2
+SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
+CMS_CELLS = 4 << 26
+STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5}
+
+HIT_DTYPE = np.dtype(
+    [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
+)
+
+# every symbol declared in include/kamino_b200.h
+ABI_SYMBOLS = [
+    "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_count_batch",
+    "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
+    "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
+    "kmn_table_device_ptr", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
+    "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
+]
+
+
+class KaminoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Load libkamino_b200.so (must have been built: `python -m kamino_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise KaminoError(
+            f"{path} is missing: build it with `python -m kamino_b200.build` (no CPU fallback exists)"
+        )
+    lib = C.CDLL(str(path))
+    u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    lib.kmn_last_error.restype = C.c_char_p
+    lib.kmn_abi_version.restype = C.c_uint32
+    lib.kmn_create.argtypes = [vpp, C.c_int, C.c_int, C.c_int]
+    lib.kmn_destroy.argtypes = [vp]
+    lib.kmn_destroy.restype = None
+    lib.kmn_count_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, vp, u32p]
+    lib.kmn_stage_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, u32p]
+    lib.kmn_count_staged.argtypes = [vp, C.c_uint32, vp]
+    lib.kmn_reset_table.argtypes = [vp]
+    lib.kmn_release_batches.argtypes = [vp]
+    lib.kmn_finalize_table.argtypes = [vp]
+    lib.kmn_table_snapshot.argtypes = [vp, vp]
+    lib.kmn_table_load.argtypes = [vp, vp]
+    lib.kmn_table_accum_device_ptr.argtypes = [vp, vpp]
+    lib.kmn_table_device_ptr.argtypes = [vp, vpp]
+    lib.kmn_synchronize.argtypes = [vp]
+    lib.kmn_stream.argtypes = [vp, vpp]
+    lib.kmn_scan_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
+    lib.kmn_fetch_hits.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p, vp, C.c_uint64, u64p]
+    lib.kmn_fetch_occupancy.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
+    lib.kmn_last_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.kmn_launch_count.argtypes = [vp]
+    lib.kmn_launch_count.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One kmn_ctx: one GPU, one table (mirrors AtomicCountMinSketch + CountMinSketch ownership)."""
+
+    def __init__(self, k: int = 13, scheme: int | str = SR6, device: int = 0):
+        self.lib = load_library()
+        if isinstance(scheme, str):
+            scheme = SCHEMES[scheme.lower()]
+        self.k, self.scheme, self.device = k, scheme, device
+        h = C.c_void_p()
+        self._check(self.lib.kmn_create(C.byref(h), device, k, scheme))
+        self._h = h
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KaminoError(self.lib.kmn_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.kmn_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pass 1
+    def stage_batch(self, residues, rec_off, sp_rec_off) -> int:
+        residues = _as(residues, np.uint8)
+        rec_off, sp_rec_off = _as(rec_off, np.uint64), _as(sp_rec_off, np.uint64)
+        bid = C.c_uint32()
+        self._check(self.lib.kmn_stage_batch(self._h, _ptr(residues), _ptr(rec_off), len(rec_off) - 1,
+                                             _ptr(sp_rec_off), len(sp_rec_off) - 1, C.byref(bid)))
+        return bid.value
+
+    def count_staged(self, batch_id: int, n_sp: int | None = None) -> np.ndarray | None:
+        out = np.zeros(n_sp, dtype=np.uint64) if n_sp is not None else None
+        self._check(self.lib.kmn_count_staged(self._h, batch_id, _ptr(out)))
+        return out
+
+    def count_batch(self, residues, rec_off, sp_rec_off, want_counts: bool = True):
+        residues = _as(residues, np.uint8)
+        rec_off, sp_rec_off = _as(rec_off, np.uint64), _as(sp_rec_off, np.uint64)
+        n_sp = len(sp_rec_off) - 1
+        out = np.zeros(n_sp, dtype=np.uint64) if want_counts else None
+        bid = C.c_uint32()
+        self._check(self.lib.kmn_count_batch(self._h, _ptr(residues), _ptr(rec_off), len(rec_off) - 1,
+                                             _ptr(sp_rec_off), n_sp, _ptr(out), C.byref(bid)))
+        return bid.value, out
+
+    def reset_table(self):
+        self._check(self.lib.kmn_reset_table(self._h))
+
+    def release_batches(self):
+        self._check(self.lib.kmn_release_batches(self._h))
+
+    def finalize_table(self):
+        self._check(self.lib.kmn_finalize_table(self._h))
+
+    def table_snapshot(self) -> np.ndarray:
+        out = np.empty(CMS_CELLS, dtype=np.uint16)
+        self._check(self.lib.kmn_table_snapshot(self._h, _ptr(out)))
+        return out
+
+    def table_load(self, table):
+        table = _as(table, np.uint16)
+        assert table.size == CMS_CELLS
+        self._check(self.lib.kmn_table_load(self._h, _ptr(table)))
+
+    def accum_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.kmn_table_accum_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def table_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.kmn_table_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.kmn_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def synchronize(self):
+        self._check(self.lib.kmn_synchronize(self._h))
+
+    # ---- pass 2
+    def scan_batch(self, batch_id: int, min_needed: int) -> tuple[int, int]:
+        ns, ne = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kmn_scan_batch(self._h, batch_id, min_needed, C.byref(ns), C.byref(ne)))
+        return ns.value, ne.value
+
+    def fetch_hits(self, batch_id: int, sp: int) -> tuple[np.ndarray, np.ndarray]:
+        ns, ne = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kmn_fetch_hits(self._h, batch_id, sp, None, 0, C.byref(ns), None, 0, C.byref(ne)))
+        starts = np.zeros(ns.value, dtype=HIT_DTYPE)
+        ends = np.zeros(ne.value, dtype=HIT_DTYPE)
+        self._check(self.lib.kmn_fetch_hits(self._h, batch_id, sp, _ptr(starts), ns.value, C.byref(ns),
+                                            _ptr(ends), ne.value, C.byref(ne)))
+        return starts, ends
+
+    def fetch_occupancy(self, batch_id: int, sp: int) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self.lib.kmn_fetch_occupancy(self._h, batch_id, sp, None, 0, C.byref(n)))
+        occ = np.zeros(n.value, dtype=np.uint16)
+        self._check(self.lib.kmn_fetch_occupancy(self._h, batch_id, sp, _ptr(occ), n.value, C.byref(n)))
+        return occ
+
+    # ---- --nj
+    def pair_counts(self, mapped: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        mapped = _as(mapped, np.uint8)
+        n, L = mapped.shape
+        valid = np.zeros((n, n), dtype=np.uint32)
+        mism = np.zeros((n, n), dtype=np.uint32)
+        self._check(self.lib.kmn_pair_counts(self._h, _ptr(mapped), n, L, _ptr(valid), _ptr(mism)))
+        return valid, mism
+
+    # ---- instrumentation
+    def stage_ms(self, name: str) -> float:
+        ms = C.c_float()
+        self._check(self.lib.kmn_last_stage_ms(self._h, STAGES[name], C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.kmn_launch_count(self._h))

@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bit-exact: table, per-species new-k-mer counts, occupancies, start/end hit lists, pair counts."""
+import numpy as np
+import pytest
+
+from kamino_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DAYHOFF6, SR6, KGB6 = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def ffi():
+    from kamino_b200 import build, ffi as _ffi
+    build.build()
+    return _ffi
+
+
+def _batch_from_records(species_records):
+    """species_records: list (species) of list (records) of bytes."""
+    res, rec_off, sp = [], [0], [0]
+    for recs in species_records:
+        for r in recs:
+            res.append(np.frombuffer(r, dtype=np.uint8))
+            rec_off.append(rec_off[-1] + len(r))
+        sp.append(len(rec_off) - 1)
+    residues = np.concatenate(res) if res else np.zeros(0, np.uint8)
+    return residues, np.array(rec_off, np.uint64), np.array(sp, np.uint64)
+
+
+def _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, min_needed, scan_species=None,
+                           threads=8):
+    n_sp = len(sp) - 1
+    h = oracle.cmsa_new()
+    try:
+        want_new = oracle.count_batch(h, residues, rec_off, sp, k, scheme, threads=threads)
+        want_table = oracle.cmsa_table(h)
+        with ffi.Context(k, scheme) as ctx:
+            bid, got_new = ctx.count_batch(residues, rec_off, sp)
+            assert got_new.tolist() == want_new.tolist()
+            ctx.finalize_table()
+            got_table = ctx.table_snapshot()
+            assert np.array_equal(got_table, want_table), "count-min table differs from the oracle"
+            ctx.scan_batch(bid, min_needed)
+            cms = oracle.cms_from_table(want_table)
+            try:
+                for s in (range(n_sp) if scan_species is None else scan_species):
+                    ws, we, wocc = oracle.scan_species(cms, residues, rec_off, int(sp[s]), int(sp[s + 1]), k,
+                                                       scheme, min_needed)
+                    gs, ge = ctx.fetch_hits(bid, s)
+                    gocc = ctx.fetch_occupancy(bid, s)
+                    assert np.array_equal(gocc, wocc[:len(gocc)]), f"occupancy differs (species {s})"
+                    assert np.array_equal(gs, ws), f"start candidates differ (species {s})"
+                    assert np.array_equal(ge, we), f"end anchors differ (species {s})"
+            finally:
+                oracle.cms_free(cms)
+        return want_new, want_table
+    finally:
+        oracle.cmsa_free(h)
+
+
+def _load_3diff(oracle, golden_dir):
+    names = ["A.fas.gz", "B.fas", "C.fas", "D1.fas", "D2.fas", "E1.fas", "E2.fas", "E3.fas"]
+    recs = []
+    for n in names:
+        r, o = oracle.read_fasta(golden_dir / "test_3diff" / "input" / n)
+        recs.append([r[int(o[i]):int(o[i + 1])].tobytes() for i in range(len(o) - 1)])
+    return _batch_from_records(recs)
+
+
+@pytest.mark.parametrize("scheme", [DAYHOFF6, SR6, KGB6])
+def test_3diff_golden_inputs(ffi, oracle, golden_dir, scheme):
+    residues, rec_off, sp = _load_3diff(oracle, golden_dir)
+    new, table = _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, scheme, 7)
+    assert new.tolist() == [84] * 8
+    if scheme == DAYHOFF6:  # SURVEY.md §8c known answers
+        nz = table[table != 0]
+        assert nz.size == 440 and int(nz.sum()) == 2688
+
+
+def test_3diff_known_anchors(ffi, oracle, golden_dir):
+    residues, rec_off, sp = _load_3diff(oracle, golden_dir)
+    with ffi.Context(13, DAYHOFF6) as ctx:
+        bid, _ = ctx.count_batch(residues, rec_off, sp)
+        ctx.finalize_table()
+        ns, ne = ctx.scan_batch(bid, 7)
+        starts, ends = ctx.fetch_hits(bid, 0)
+        assert [(int(h["start"]), int(h["occ"]), int(h["kmer"])) for h in starts] == [(17, 8, 313726741273)]
+        assert [(int(h["start"]), int(h["occ"]), int(h["kmer"])) for h in ends] == [(36, 8, 78946387236)]
+
+
+@pytest.mark.parametrize("k,scheme", [(13, SR6), (1, SR6), (2, DAYHOFF6), (7, KGB6), (16, SR6), (21, DAYHOFF6)])
+def test_synthetic_small(ffi, oracle, k, scheme):
+    species = synth.bacterial(5, seed=11 + k, n_prot=300, mean_len=200.0)
+    b = synth.stage(species)
+    _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, k, scheme,
+                           oracle.min_needed(0.85, 5))
+
+
+def test_edge_cases_ragged(ffi, oracle):
+    recs = [
+        [b"", b"ACDEFGHIKLMNPQRSTVWY" * 3, b"", b""],                      # empty records around one
+        [b"acdefghiklmnpqrstvwy\nACDEFGHIKLMNPQRSTVWYACDEFG\r\nHIKL \t MNPQ\x0cRSTVWY"],  # case + whitespace
+        [],                                                                 # species without records
+        [b"ACDEFGHIKLMN", b"ACDEFGHIKLMNP", b"ACDEFGHIKLMNPQ"],            # k-1, k, k+1 residues
+        [b"ACDEFGHIKLMNPQRSTVWYACDEFGHXIKLMNPQRSTVWYACDEFGHIKLMNPQRSTVWY" * 2],  # X resets
+        [b"ACD*EFG-HIK.LMNBPQRZSTVJWYUACDOEFG\x0bHIKLMNPQRSTVWY1ACDEFGHIKLMNPQRSTVWY\xffAC\x80DE"],
+        [b"\n\n\n", b"   ", b"X", b"XXXXXXXXXXXXXXXXXXXXXXXXXXXX"],        # nothing countable
+        [b"MVLFFQILGFALFIFWLLLIARVVVEFIRSFSRDWHPTGITVVVLEIIMSITDPPVKLLRRLIPQLTIGAVRFDLSIMVLLLVAFIGMQLAFGAAA"] * 3,
+        [b"A" * 5000],                                                     # one k-mer repeated
+    ]
+    residues, rec_off, sp = _batch_from_records(recs)
+    for k, scheme in [(13, SR6), (3, KGB6), (21, DAYHOFF6)]:
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, 1)
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, 2)
+
+
+def test_empty_batches(ffi, oracle):
+    with ffi.Context(13, SR6) as ctx:
+        bid, new = ctx.count_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint64))
+        assert new.size == 0
+        bid, new = ctx.count_batch(np.zeros(0, np.uint8), np.zeros(3, np.uint64), np.array([0, 1, 1, 2], np.uint64))
+        assert new.tolist() == [0, 0, 0]
+        ctx.finalize_table()
+        assert not ctx.table_snapshot().any()
+        assert ctx.scan_batch(bid, 1) == (0, 0)
+        s, e = ctx.fetch_hits(bid, 1)
+        assert len(s) == 0 and len(e) == 0
+
+
+def test_argument_errors(ffi):
+    with pytest.raises(ffi.KaminoError):
+        ffi.Context(22, SR6)
+    with pytest.raises(ffi.KaminoError):
+        ffi.Context(0, SR6)
+    with ffi.Context(13, SR6) as ctx:
+        with pytest.raises(ffi.KaminoError):
+            ctx.count_batch(np.zeros(4, np.uint8), np.array([0, 5, 3], np.uint64), np.array([0, 2], np.uint64))
+        with pytest.raises(ffi.KaminoError):
+            ctx.scan_batch(0, 1)   # no such batch / table not finalized
+        with pytest.raises(ffi.KaminoError):
+            ctx.table_snapshot()
+
+
+def test_many_small_species_cross_groups(ffi, oracle):
+    """More species than first-touch slots, species boundaries inside 16-residue chunks."""
+    rng = np.random.default_rng(3)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    recs = []
+    for s in range(53):
+        n_rec = int(rng.integers(0, 4))
+        recs.append([aa[rng.integers(0, 20, int(rng.integers(0, 70)))].tobytes() for _ in range(n_rec)])
+    residues, rec_off, sp = _batch_from_records(recs)
+    _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 5, SR6, 2)
+
+
+def test_bloom_order_dependence_large_species(ffi, oracle):
+    """One 12 M-residue species: ~24 M probes into 2^25 bits, so a large share of the occurrences
+    are Bloom false positives whose outcome depends on file order (proba_filter.rs:59-74)."""
+    rng = np.random.default_rng(7)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    seq = aa[rng.integers(0, 20, 12_000_000)]
+    lens = np.full(12_000, 1000)
+    b = synth.stage([synth.Species(seq, lens), synth.Species(seq[:2_000_000].copy(), lens[:2000])])
+    new, _ = _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, 2,
+                                    scan_species=[1])
+    n_kmers = 12_000 * (1000 - 12)
+    assert new[0] < n_kmers * 0.97, "expected a visible Bloom false-positive rate"
+
+
+def test_cms_saturation_and_repeat_calls(ffi, oracle):
+    """70 000 species holding the same single k-mer: cells saturate at 65 535 (proba_filter.rs:152-156)."""
+    one = b"ACDEFGHIKLMNP"
+    recs = [[one] for _ in range(35_000)]
+    residues, rec_off, sp = _batch_from_records(recs)
+    key = int(oracle.roll_kmers(one, 13, SR6)[0])
+    idx = oracle.cms_indices(key)
+    with ffi.Context(13, SR6) as ctx:
+        ctx.count_batch(residues, rec_off, sp, want_counts=False)
+        ctx.finalize_table()
+        t = ctx.table_snapshot()
+        assert [int(t[r * (1 << 26) + idx[r]]) for r in range(4)] == [35_000] * 4
+        ctx.reset_table()
+        for _ in range(2):
+            ctx.count_batch(residues, rec_off, sp, want_counts=False)
+        ctx.finalize_table()
+        t = ctx.table_snapshot()
+        assert [int(t[r * (1 << 26) + idx[r]]) for r in range(4)] == [65_535] * 4
+        assert int(t.astype(np.uint64).sum()) == 4 * 65_535
+
+
+def test_staged_recount_is_idempotent_after_reset(ffi, oracle):
+    species = synth.bacterial(3, seed=5, n_prot=200, mean_len=150.0)
+    b = synth.stage(species)
+    with ffi.Context(13, SR6) as ctx:
+        bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+        a = ctx.count_staged(bid, b.n_sp)
+        ctx.finalize_table()
+        t1 = ctx.table_snapshot()
+        ctx.reset_table()
+        a2 = ctx.count_staged(bid, b.n_sp)
+        ctx.finalize_table()
+        t2 = ctx.table_snapshot()
+        assert a.tolist() == a2.tolist() and np.array_equal(t1, t2)
+        # linearity of the sketch: counting twice doubles every (unsaturated) cell
+        ctx.reset_table()
+        ctx.count_staged(bid)
+        ctx.count_staged(bid)
+        ctx.finalize_table()
+        assert np.array_equal(ctx.table_snapshot(), (t1.astype(np.uint32) * 2).astype(np.uint16))
+
+
+def test_table_load_roundtrip(ffi, oracle):
+    rng = np.random.default_rng(9)
+    table = np.zeros(4 << 26, np.uint16)
+    table[rng.integers(0, table.size, 100_000)] = rng.integers(1, 65535, 100_000)
+    with ffi.Context(13, SR6) as ctx:
+        ctx.table_load(table)
+        assert np.array_equal(ctx.table_snapshot(), table)
+
+
+@pytest.mark.parametrize("n,L", [(2, 1), (7, 131), (70, 1000), (130, 77), (65, 4097)])
+def test_pair_counts(ffi, oracle, n, L):
+    rng = np.random.default_rng(n * 1000 + L)
+    m = rng.integers(0, 20, size=(n, L), dtype=np.uint8)
+    m[rng.random((n, L)) < 0.07] = 20
+    m[1:, :] = np.where(rng.random((n - 1, L)) < 0.8, m[0], m[1:, :])   # related rows
+    wv, wm = oracle.pair_counts(m, threads=4)
+    with ffi.Context(13, SR6) as ctx:
+        gv, gm = ctx.pair_counts(m)
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(gv[iu], wv[iu]) and np.array_equal(gm[iu], wm[iu])
