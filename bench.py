@@ -262,15 +262,17 @@ def run_gpu(args):
 
     # ---- timed: end to end from pinned host buffers
     ctx.release_batches()
-    step_e2e(); ctx.release_batches()
+    e2e_steps = 0 if args.profile else args.steps
+    if e2e_steps:
+        step_e2e(); ctx.release_batches()
     barrier()
     ev0.record(lib_stream)
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_e2e()
         ctx.release_batches()
     ev1.record(lib_stream)
     barrier()
-    e2e_elapsed = ev0.elapsed_time(ev1) * 1e-3
+    e2e_elapsed = max(ev0.elapsed_time(ev1) * 1e-3, 1e-9)
     if world > 1:
         t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,7 +298,7 @@ def run_gpu(args):
     }
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
         threads = host_threads()
         n_res, dt, _, n_sp = cpu_pass1(batch, threads, n_species=8)
         n_sample = int(max(8, min(N_SPECIES, 15.0 / max(dt / n_sp, 1e-6))))
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -54,7 +54,7 @@ def _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, min_ne
                     assert np.array_equal(ge, we), f"end anchors differ (species {s})"
             finally:
                 oracle.cms_free(cms)
-        return want_new, want_table
+        return want_new, got_table   # owned copy, verified equal to the oracle's (freed below)
     finally:
         oracle.cmsa_free(h)
 
