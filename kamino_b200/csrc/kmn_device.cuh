@@ -83,13 +83,15 @@ __device__ __forceinline__ void pack_chunk(const uint4& v, uint64_t& P, int& las
 // the two previous lanes by warp shuffle (lanes 0/1 fetch the two chunks before the tile).
 // Calls f(c, kmer) for every position c whose k-mer is valid under group_extraction.rs:373-388
 // (have == k, no reset inside the window).  ALL 32 lanes must call this (shuffles inside).
-template <typename F>
+template <bool STREAM = false, typename F>
 __device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __restrict__ codes,
                                                            uint32_t tile_base, int k, uint64_t k_mask,
                                                            F&& f) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t c0 = tile_base + lane * CHUNK;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes + c0));
+    // STREAM: evict-first loads, so re-streamed codes do not displace an L2-resident table slice
+    const uint4 v = STREAM ? __ldcs(reinterpret_cast<const uint4*>(codes + c0))
+                           : __ldg(reinterpret_cast<const uint4*>(codes + c0));
     uint64_t P;
     int li;
     pack_chunk(v, P, li);
