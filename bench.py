@@ -212,10 +212,12 @@ def run_gpu(args):
 
     bid = ctx.stage_batch(h_res, h_rec, h_sp)
 
+    from kamino_b200 import sharding
+
     def exchange():
         if world > 1:
             ctx.synchronize()
-            dist.all_reduce(acc_t)  # the sketch is linear: sum of per-rank accumulators
+            sharding.exchange_accumulators(acc_t)  # the sketch is linear: sum of per-rank accumulators
             torch.cuda.synchronize()
 
     def step_resident():
@@ -282,19 +284,30 @@ def run_gpu(args):
     d2h = int(batch.n_sp * 8 + (batch.n_sp + 1) * 4)
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream)
+    # The CMS build is the dominant stage: `sweeps` launches of cms_sweep_kernel per step, each applying
+    # 1/sweeps of the table updates.  SURVEY.md 8d: B1 = 1 + 16u algorithmic bytes per residue for pass 1,
+    # so one launch carries (1 + 16u)/sweeps bytes per residue of the batch and lasts cms_ms/sweeps.
     peak, peak_src = measured_peaks()
     stage_ms = {s: v / args.steps for s, v in stage_acc.items()}
-    dominant = max(("bloom", "cms"), key=lambda s: stage_ms[s])
-    alg_bytes = (1.0 + 16.0 * u) * batch.n_residues        # B1 = 1 + 16u bytes / residue
+    sweeps = 4 * int(os.environ.get("KMN_CMS_SLICES_PER_ROW", "4"))
+    alg_bytes = (1.0 + 16.0 * u) * batch.n_residues
     dom_ms = stage_ms["cms"]
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    achieved = (alg_bytes / sweeps) / (dom_ms / sweeps * 1e-3) / 1e9
     pass1_ms = sum(stage_ms.values())
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text())["cms_sweep_kernel"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "cms_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "new_kmer_fraction_u": u,
-        "kernel_ms": dom_ms, "stage_ms": stage_ms, "slowest_stage": dominant,
+        "bound": "hbm", "kernel": "cms_sweep_kernel", "launches_per_step": sweeps, "achieved": achieved,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "algorithmic_bytes_per_launch": alg_bytes / sweeps,
+        "new_kmer_fraction_u": u, "kernel_ms_per_launch": dom_ms / sweeps, "stage_ms": stage_ms,
         "whole_pass1_frac": alg_bytes / (pass1_ms * 1e-3) / 1e9 / peak,
+        "note": "integer/atomic path: the binding resource is L2 atomic throughput, not HBM bytes (DESIGN.md 4)",
     }
 
     cpu_baseline = None

@@ -114,10 +114,10 @@ struct kmn_ctx {
     cudaEvent_t ev[8] = {};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
-    int bloom_mode = 1;                   // 1: L2-resident bitsets (+ first[] for contended bits); 0: first[] for every probe
     uint32_t bloom_group = 8;             // species per Bloom launch (bitsets of a group stay in L2)
     DevBuf<uint32_t> bl_bits, bl_multi, bl_fw, late_list, late_count;
-    uint32_t cms_slices_per_row = 4;      // L2-sliced CMS sweep: 4 rows x N slices; 0 = single scattered pass
+    DevBuf<uint32_t> idx[CMS_DEPTH];      // per-row CMS cell index streams (scratch of count_staged)
+    uint32_t cms_slices_per_row = 4;      // L2-sliced CMS sweep: 4 rows x N slices
 };
 
 namespace {
@@ -223,28 +223,27 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     c->new_counts.ensure(size_t(b.n_sp) + 1);
     KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
     const int grid = grid_for(c, 8);
-    const uint32_t group = c->bloom_mode == 0 ? MAX_GROUP_SPECIES : c->bloom_group;
-    if (c->bloom_mode) KMN_CUDA(cudaMemsetAsync(b.wf.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
+    const uint32_t group = c->bloom_group;
+    // index streams (scratch): 4 rows x 4 B per codes[] position; the tail of the last vector is "none"
+    const size_t n_idx = (size_t(b.n_codes) + 63) / 64 * 64 + 64;
+    IndexStreams ix;
+    for (uint32_t r = 0; r < CMS_DEPTH; r++) {
+        c->idx[r].ensure(n_idx);
+        ix.row[r] = c->idx[r].p;
+        KMN_CUDA(cudaMemsetAsync(c->idx[r].p + (b.n_codes / CHUNK) * CHUNK, 0xFF, 2 * CHUNK * sizeof(uint32_t), c->stream));
+    }
+    KMN_CUDA(cudaMemsetAsync(b.wf.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
     for (uint32_t s0 = 0; s0 < b.n_sp; s0 += group) {
         GroupBounds g;
         g.n = std::min<uint32_t>(group, b.n_sp - s0);
         g.first_species = s0;
-        if (c->epoch > 0xFFFFFFFFu - MAX_GROUP_SPECIES) {  // epoch wrap: start over with clean slots
+        if (c->epoch > 0xFFFFFFFFu - MAX_GROUP_SPECIES) {  // epoch wrap: start over with clean tags
             KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
             c->epoch = 1;
         }
         g.epoch0 = c->epoch;
         c->epoch += g.n;
         if (b.h_sp_cstart[s0 + g.n] == b.h_sp_cstart[s0]) continue;  // no residues in this group
-        if (c->bloom_mode == 0) {   // v1: every probe goes through the 64-bit first[] array (DRAM-random)
-            bloom_mark_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, c->first.p);
-            check_launch(c);
-            bloom_resolve_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask,
-                                                                       c->first.p, b.flags.p, c->new_counts.p);
-            check_launch(c);
-            continue;
-        }
-        // L2-resident bitsets; first[] only for contended bits
         const size_t words = size_t(g.n) << BLOOM_WORDS_LOG2;
         KMN_CUDA(cudaMemsetAsync(c->bl_bits.p, 0, words * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(c->bl_multi.p, 0, words * sizeof(uint32_t), c->stream));
@@ -257,31 +256,27 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
                                                                  b.wf.p, c->late_list.p, c->late_count.p);
         check_launch(c);
         bloom_settle_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, bs,
-                                                                  b.wf.p, b.flags.p, c->new_counts.p);
+                                                                  b.wf.p, b.flags.p, ix, c->new_counts.p);
         check_launch(c);
         bloom_late_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, bs, c->late_list.p,
                                                                 c->late_count.p, reinterpret_cast<uint32_t*>(b.flags.p),
-                                                                c->new_counts.p);
+                                                                ix, c->new_counts.p);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (b.n_codes > 0) {
-        if (c->cms_slices_per_row == 0) {  // single pass, scattered DRAM atomics
-            cms_update_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.flags.p, 0u, b.n_codes, c->k, c->k_mask, c->acc.p);
-            check_launch(c);
-        } else {                           // L2-sliced sweep: rows x slices launches
-            static const uint64_t seeds[4] = {SEED_CMS_0, SEED_CMS_1, SEED_CMS_2, SEED_CMS_3};
-            uint32_t log2s = 0;
-            while ((1u << log2s) < c->cms_slices_per_row) log2s++;
-            const uint32_t slice_shift = CMS_WIDTH_LOG2 - log2s;
-            for (uint32_t r = 0; r < CMS_DEPTH; r++)
-                for (uint32_t q = 0; q < (1u << log2s); q++) {
-                    cms_sweep_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(
-                        b.codes.p, b.flags.p, 0u, b.n_codes, c->k, c->k_mask, seeds[r], slice_shift, q,
-                        c->acc.p + (size_t(r) << CMS_WIDTH_LOG2));
-                    check_launch(c);
-                }
-        }
+        // L2-sliced sweep: rows x slices launches over the per-row index streams
+        uint32_t log2s = 0;
+        while ((1u << log2s) < c->cms_slices_per_row) log2s++;
+        const uint32_t slice_shift = CMS_WIDTH_LOG2 - log2s;
+        const uint32_t n_vec = (b.n_codes + 3) / 4;
+        for (uint32_t r = 0; r < CMS_DEPTH; r++)
+            for (uint32_t q = 0; q < (1u << log2s); q++) {
+                cms_sweep_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(
+                    reinterpret_cast<const uint4*>(c->idx[r].p), n_vec, slice_shift, q,
+                    c->acc.p + (size_t(r) << CMS_WIDTH_LOG2));
+                check_launch(c);
+            }
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
     std::vector<unsigned long long> h(b.n_sp);
@@ -454,13 +449,12 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         c->lut = make_lut(scheme);
         if (const char* e = std::getenv("KMN_CMS_SLICES_PER_ROW")) {  // tuning knob (power of two, 0 = off)
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 0 || v > 64 || (v & (v - 1))) throw std::runtime_error("KMN_CMS_SLICES_PER_ROW must be 0 or a power of two <= 64");
+            if (v < 1 || v > 64 || (v & (v - 1))) throw std::runtime_error("KMN_CMS_SLICES_PER_ROW must be a power of two in 1..64");
             c->cms_slices_per_row = uint32_t(v);
         }
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
-        if (const char* e = std::getenv("KMN_BLOOM_MODE")) c->bloom_mode = std::atoi(e) ? 1 : 0;
         if (const char* e = std::getenv("KMN_BLOOM_GROUP")) {
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > MAX_GROUP_SPECIES) throw std::runtime_error("KMN_BLOOM_GROUP must be in 1..16");

@@ -78,20 +78,19 @@ __device__ __forceinline__ void pack_chunk(const uint4& v, uint64_t& P, int& las
     last_inv = li;
 }
 
-// Warp-cooperative rolling k-mer enumeration over one warp tile (32 lanes x 16 codes).
-// Every lane owns codes [c0, c0+16), c0 = tile_base + 16*lane; the (k-1)-symbol history comes from
-// the two previous lanes by warp shuffle (lanes 0/1 fetch the two chunks before the tile).
-// Calls f(c, kmer) for every position c whose k-mer is valid under group_extraction.rs:373-388
-// (have == k, no reset inside the window).  ALL 32 lanes must call this (shuffles inside).
-template <bool STREAM = false, typename F>
-__device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __restrict__ codes,
-                                                           uint32_t tile_base, int k, uint64_t k_mask,
-                                                           F&& f) {
+// Warp-cooperative load of one warp tile (32 lanes x 16 codes).  Every lane owns codes [c0, c0+16),
+// c0 = tile_base + 16*lane, and receives the roll / have state of the reference's loop
+// (group_extraction.rs:373-388) as it stands just BEFORE c0: the (k-1)-symbol history comes from the
+// two previous lanes by warp shuffle (lanes 0/1 fetch the two chunks before the tile).
+// ALL 32 lanes must call this (shuffles inside).
+// STREAM: evict-first loads, so re-streamed codes do not displace an L2-resident table slice.
+template <bool STREAM>
+__device__ __forceinline__ void warp_tile_seed(const uint8_t* __restrict__ codes, uint32_t tile_base, int k,
+                                               uint64_t k_mask, uint4& v, uint64_t& roll, int& have) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t c0 = tile_base + lane * CHUNK;
-    // STREAM: evict-first loads, so re-streamed codes do not displace an L2-resident table slice
-    const uint4 v = STREAM ? __ldcs(reinterpret_cast<const uint4*>(codes + c0))
-                           : __ldg(reinterpret_cast<const uint4*>(codes + c0));
+    v = STREAM ? __ldcs(reinterpret_cast<const uint4*>(codes + c0))
+               : __ldg(reinterpret_cast<const uint4*>(codes + c0));
     uint64_t P;
     int li;
     pack_chunk(v, P, li);
@@ -108,10 +107,22 @@ __device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __rest
     const int el0 = __shfl_sync(0xffffffffu, eli, 0), el1 = __shfl_sync(0xffffffffu, eli, 1);
     if (lane == 0) { P1 = E1; li1 = el1; P2 = E0; li2 = el0; }
     if (lane == 1) { P2 = E1; li2 = el1; }
-    // roll/have as they stand after the previous chunk
-    uint64_t roll = (((P2 & 0x7FFFull) << 48) | P1) & k_mask;
-    int have = li1 >= 0 ? 15 - li1 : (li2 >= 0 ? 31 - li2 : 32);
+    roll = (((P2 & 0x7FFFull) << 48) | P1) & k_mask;
+    have = li1 >= 0 ? 15 - li1 : (li2 >= 0 ? 31 - li2 : 32);
     if (have > k) have = k;
+}
+
+// Calls f(c, kmer) for every position c of the lane's chunk whose k-mer is valid (have == k, no
+// reset inside the window).
+template <bool STREAM = false, typename F>
+__device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __restrict__ codes,
+                                                           uint32_t tile_base, int k, uint64_t k_mask,
+                                                           F&& f) {
+    uint4 v;
+    uint64_t roll;
+    int have;
+    warp_tile_seed<STREAM>(codes, tile_base, k, k_mask, v, roll, have);
+    const uint32_t c0 = tile_base + (threadIdx.x & 31u) * CHUNK;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < CHUNK; j++) {
@@ -125,6 +136,35 @@ __device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __rest
             if (have == k) f(c0 + j, roll);
         }
     }
+}
+
+// Register-resident variant: the lane ends up with the k-mers ENDING at its 16 positions (kmer[j],
+// garbage where invalid) and returns the validity mask (bit j: position c0+j carries a valid k-mer).
+// Lets the caller issue all of a chunk's memory operations before consuming any result
+// (memory-level parallelism instead of one exposed round trip per position).
+template <bool STREAM = false>
+__device__ __forceinline__ uint32_t load_chunk_kmers(const uint8_t* __restrict__ codes, uint32_t tile_base,
+                                                     int k, uint64_t k_mask, uint64_t (&kmer)[CHUNK]) {
+    uint4 v;
+    uint64_t roll;
+    int have;
+    warp_tile_seed<STREAM>(codes, tile_base, k, k_mask, v, roll, have);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        if (code == CODE_INVALID) {
+            roll = 0;
+            have = 0;
+        } else {
+            roll = ((roll << 3) | uint64_t(code)) & k_mask;
+            if (have < k) have++;
+            if (have == k) valid |= 1u << j;
+        }
+        kmer[j] = roll;
+    }
+    return valid;
 }
 
 }  // namespace kmn

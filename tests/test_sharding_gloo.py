@@ -1,0 +1,101 @@
+"""CPU tests of the N>1 path: world_size-2 gloo processes shard the species, build their partial
+tables with the oracle, exchange them like the GPU path does (sum of u32 accumulators, then clamp)
+and must reproduce the single-process table."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import oracle_ffi
+    from kamino_b200 import sharding, synth
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = oracle_ffi.load()
+        species = synth.bacterial(6, seed=77, n_prot=60, mean_len=120.0)
+        b = synth.stage(species)
+        mine = sharding.shard_species(b.n_sp, world, rank)
+        res, rec, sp = sharding.select_species(b.residues, b.rec_off, b.sp_rec_off, mine)
+        h = orc.cmsa_new()
+        try:
+            new = orc.count_batch(h, res, rec, sp, 13, 1, threads=2)
+            table = orc.cmsa_table(h)
+            nz = np.flatnonzero(table)
+            # sparse exchange keeps the CPU test light: all-gather (index, value) pairs and sum
+            acc = torch.zeros(4 << 26, dtype=torch.int32)
+            acc[torch.from_numpy(nz)] = torch.from_numpy(table[nz].astype(np.int32))
+        finally:
+            orc.cmsa_free(h)
+        sharding.exchange_accumulators(acc)
+        merged = sharding.clamp_u16(acc.numpy())
+        counts = [None] * world
+        dist.all_gather_object(counts, (mine.tolist(), new.tolist()))
+        if rank == 0:
+            h = orc.cmsa_new()
+            try:
+                want_new = orc.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, 13, 1, threads=2)
+                want = np.array(orc.cmsa_table(h))
+            finally:
+                orc.cmsa_free(h)
+            got_new = np.zeros(b.n_sp, dtype=np.uint64)
+            for ids, vals in counts:
+                got_new[ids] = vals
+            ok = bool(np.array_equal(merged, want)) and got_new.tolist() == want_new.tolist()
+            Path(out_dir, "result.txt").write_text("ok" if ok else "mismatch")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_round_robin_shards_cover_everything():
+    from kamino_b200 import sharding
+    for n, w in [(0, 2), (1, 2), (7, 2), (100, 8), (1000, 8), (5, 8)]:
+        seen = np.concatenate([sharding.shard_species(n, w, r) for r in range(w)])
+        assert sorted(seen.tolist()) == list(range(n))
+        sizes = [len(sharding.shard_species(n, w, r)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_select_species_roundtrip():
+    from kamino_b200 import sharding, synth
+    b = synth.stage(synth.bacterial(5, seed=3, n_prot=20, mean_len=80.0))
+    res, rec, sp = sharding.select_species(b.residues, b.rec_off, b.sp_rec_off, np.arange(b.n_sp))
+    assert np.array_equal(res, b.residues) and np.array_equal(rec, b.rec_off) and np.array_equal(sp, b.sp_rec_off)
+    res, rec, sp = sharding.select_species(b.residues, b.rec_off, b.sp_rec_off, np.array([3, 1]))
+    r0, r1 = int(b.sp_rec_off[3]), int(b.sp_rec_off[4])
+    assert np.array_equal(res[:int(rec[int(sp[1])])], b.residues[int(b.rec_off[r0]):int(b.rec_off[r1])])
+
+
+def test_two_rank_gloo_exchange_matches_single_process(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "result.txt").read_text() == "ok"
+
+
+def test_clamp_is_exact_under_saturation():
+    from kamino_b200 import sharding
+    a = np.array([0, 1, 65534, 65535, 65536, 70000, 2**31 - 1], dtype=np.int64).astype(np.int32)
+    assert sharding.clamp_u16(a).tolist() == [0, 1, 65534, 65535, 65535, 65535, 65535]
+    # min(sum(min(a_r, M)), M) == min(sum(a_r), M): partial clamping commutes with the exchange
+    rng = np.random.default_rng(0)
+    parts = rng.integers(0, 50000, size=(4, 1000))
+    assert np.array_equal(np.minimum(np.minimum(parts, 65535).sum(0), 65535), np.minimum(parts.sum(0), 65535))
