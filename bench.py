@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -196,7 +196,11 @@ def run_gpu(args):
     batch = make_batch(rank)
     log(f"[rank {rank}] synthetic batch: {batch.n_sp} species, {batch.n_residues} residues, "
         f"{batch.residues.size} bytes staged ({time.time() - t0:.1f}s)")
-    n_res_total = batch.n_residues * world
+    n_res_total = batch.n_residues
+    if world > 1:   # every rank stages its own proteomes: the job's residue count is the sum over ranks
+        t = torch.tensor([batch.n_residues], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        n_res_total = int(t.item())
 
     ctx = ffi.Context(K, SCHEME, device=local_rank)
     acc_t = None
@@ -345,7 +349,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

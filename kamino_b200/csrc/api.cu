@@ -111,10 +111,11 @@ struct kmn_ctx {
     DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
     DevBuf<uint16_t> warp_cnt;
     std::vector<std::unique_ptr<Batch>> batches;
+    std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
     cudaEvent_t ev[8] = {};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
-    uint32_t bloom_group = 8;             // species per Bloom launch (bitsets of a group stay in L2)
+    uint32_t bloom_group = 16;            // species per Bloom launch (bitsets of a group stay in L2)
     DevBuf<uint32_t> bl_bits, bl_multi, bl_fw, late_list, late_count;
     DevBuf<uint32_t> idx[CMS_DEPTH];      // per-row CMS cell index streams (scratch of count_staged)
     uint32_t cms_slices_per_row = 4;      // L2-sliced CMS sweep: 4 rows x N slices
@@ -153,15 +154,25 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     for (uint32_t s = 0; s < n_sp; s++)
         if (sp_rec_off[s + 1] < sp_rec_off[s]) throw std::runtime_error("sp_rec_off must be non-decreasing");
 
-    auto b = std::make_unique<Batch>();
+    // staged batches recycle the device buffers of released ones (cudaMalloc/cudaFree of ~1 GB per
+    // batch would otherwise dominate the host-to-table path)
+    std::unique_ptr<Batch> b;
+    if (!c->spare.empty()) {
+        b = std::move(c->spare.back());
+        c->spare.pop_back();
+        b->framed = b->scanned = false;
+        b->n_codes = b->n_inv = 0;
+    } else {
+        b = std::make_unique<Batch>();
+    }
     b->n_raw = n_raw;
     b->n_rec = uint32_t(n_rec);
     b->n_sp = n_sp;
     b->raw_pad = (size_t(n_raw) + FRAME_TILE - 1) / FRAME_TILE * FRAME_TILE;
     if (b->raw_pad == 0) b->raw_pad = FRAME_TILE;
-    b->raw.alloc(b->raw_pad);
-    b->rec_off.alloc(n_rec + 1);
-    b->sp_rec_off.alloc(size_t(n_sp) + 1);
+    b->raw.ensure(b->raw_pad);
+    b->rec_off.ensure(n_rec + 1);
+    b->sp_rec_off.ensure(size_t(n_sp) + 1);
     b->h_sp_rec_off.assign(sp_rec_off, sp_rec_off + n_sp + 1);
     if (n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, residues, n_raw, cudaMemcpyHostToDevice, c->stream));
     if (b->raw_pad > n_raw)  // pad with spaces: skipped like any whitespace
@@ -170,11 +181,11 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     // worst case: every raw byte is a residue, plus one separator per record
     b->codes_cap = (size_t(n_raw) + n_rec + WARP_TILE - 1) / WARP_TILE * WARP_TILE + WARP_TILE;
-    b->codes.alloc(b->codes_cap);
-    b->rec_cstart.alloc(n_rec + 1);
-    b->sp_cstart.alloc(size_t(n_sp) + 1);
-    b->flags.alloc(b->codes_cap / CHUNK + 2);   // +2: viewed as u32 words by bloom_late_kernel
-    b->wf.alloc(b->codes_cap / CHUNK);
+    b->codes.ensure(b->codes_cap);
+    b->rec_cstart.ensure(n_rec + 1);
+    b->sp_cstart.ensure(size_t(n_sp) + 1);
+    b->flags.ensure(b->codes_cap / CHUNK + 2);   // +2: viewed as u32 words by bloom_late_kernel
+    b->wf.ensure(b->codes_cap / CHUNK);
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
@@ -224,14 +235,6 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
     const int grid = grid_for(c, 8);
     const uint32_t group = c->bloom_group;
-    // index streams (scratch): 4 rows x 4 B per codes[] position; the tail of the last vector is "none"
-    const size_t n_idx = (size_t(b.n_codes) + 63) / 64 * 64 + 64;
-    IndexStreams ix;
-    for (uint32_t r = 0; r < CMS_DEPTH; r++) {
-        c->idx[r].ensure(n_idx);
-        ix.row[r] = c->idx[r].p;
-        KMN_CUDA(cudaMemsetAsync(c->idx[r].p + (b.n_codes / CHUNK) * CHUNK, 0xFF, 2 * CHUNK * sizeof(uint32_t), c->stream));
-    }
     KMN_CUDA(cudaMemsetAsync(b.wf.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
     for (uint32_t s0 = 0; s0 < b.n_sp; s0 += group) {
         GroupBounds g;
@@ -244,11 +247,11 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         g.epoch0 = c->epoch;
         c->epoch += g.n;
         if (b.h_sp_cstart[s0 + g.n] == b.h_sp_cstart[s0]) continue;  // no residues in this group
-        const size_t words = size_t(g.n) << BLOOM_WORDS_LOG2;
-        KMN_CUDA(cudaMemsetAsync(c->bl_bits.p, 0, words * sizeof(uint32_t), c->stream));
-        KMN_CUDA(cudaMemsetAsync(c->bl_multi.p, 0, words * sizeof(uint32_t), c->stream));
-        KMN_CUDA(cudaMemsetAsync(c->bl_fw.p, 0, words * sizeof(uint32_t), c->stream));
-        KMN_CUDA(cudaMemsetAsync(c->late_count.p, 0, sizeof(uint32_t), c->stream));
+        const uint32_t clear_vec = uint32_t((size_t(g.n) << BLOOM_WORDS_LOG2) / 4);
+        bloom_clear_kernel<<<grid_for(c, 4), 256, 0, c->stream>>>(
+            reinterpret_cast<uint4*>(c->bl_bits.p), reinterpret_cast<uint4*>(c->bl_multi.p),
+            reinterpret_cast<uint4*>(c->bl_fw.p), clear_vec, c->late_count.p);
+        check_launch(c);
         const size_t group_positions = b.h_sp_cstart[s0 + g.n] - b.h_sp_cstart[s0];
         c->late_list.ensure(2 * group_positions + 64);
         BloomSlots bs{c->bl_bits.p, c->bl_multi.p, c->bl_fw.p, c->first.p};
@@ -256,15 +259,24 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
                                                                  b.wf.p, c->late_list.p, c->late_count.p);
         check_launch(c);
         bloom_settle_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, bs,
-                                                                  b.wf.p, b.flags.p, ix, c->new_counts.p);
+                                                                  b.wf.p, b.flags.p, c->new_counts.p);
         check_launch(c);
         bloom_late_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, bs, c->late_list.p,
                                                                 c->late_count.p, reinterpret_cast<uint32_t*>(b.flags.p),
-                                                                ix, c->new_counts.p);
+                                                                c->new_counts.p);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (b.n_codes > 0) {
+        // hash once: 4 index streams (scratch, 16 B per codes[] position, whole warp tiles)
+        const uint32_t n_wtiles = (b.n_codes + WARP_TILE - 1) / WARP_TILE;
+        IndexStreams ix;
+        for (uint32_t r = 0; r < CMS_DEPTH; r++) {
+            c->idx[r].ensure(size_t(n_wtiles) * WARP_TILE);
+            ix.row[r] = c->idx[r].p;
+        }
+        cms_index_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, ix);
+        check_launch(c);
         // L2-sliced sweep: rows x slices launches over the per-row index streams
         uint32_t log2s = 0;
         while ((1u << log2s) < c->cms_slices_per_row) log2s++;
@@ -483,6 +495,7 @@ void kmn_destroy(kmn_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->batches.clear();
+    c->spare.clear();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -518,6 +531,8 @@ int kmn_reset_table(kmn_ctx* c) {
 int kmn_release_batches(kmn_ctx* c) {
     return guarded(c, [&] {
         KMN_CUDA(cudaStreamSynchronize(c->stream));
+        for (auto& b : c->batches)
+            if (b && c->spare.size() < 2) c->spare.push_back(std::move(b));
         c->batches.clear();
     });
 }

@@ -24,7 +24,7 @@
 // ---- CMS (proba_filter.rs:146-168) -------------------------------------------------------------
 // All updates are +1 and saturation is monotone, so accumulating in u32 and clamping to 65535 at
 // snapshot time is bit-identical to saturating u16.  The four cell indices of every new k-mer are
-// hashed ONCE (in settle / late) into four index streams; the 1 GiB accumulator table is then swept
+// hashed ONCE (cms_index_kernel) into four index streams; the 1 GiB accumulator table is then swept
 // in L2-resident slices: one launch per (row, slice) streams 4 B per position and applies only the
 // increments that land inside the slice, so the scattered red.add hits L2 instead of paying a 64 B
 // DRAM read + 32 B write-back per 4-byte update.
@@ -65,18 +65,86 @@ __device__ __forceinline__ uint32_t range_mask16(uint32_t c0, uint32_t cb, uint3
     return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
-// slot (species index inside the group) of each of the 16 positions, 4 bits each
-__device__ __forceinline__ uint64_t slots16(const uint32_t* s_b, uint32_t c0, uint32_t valid) {
-    uint64_t packed = 0;
-    uint32_t sl = 0;
+// Rare path of pass A, kept out of line: a probe found its bit already set.
+__device__ __noinline__ void bloom_mark_late(BloomSlots bs, uint32_t sl, uint32_t bit, unsigned long long tag) {
+    atomicOr(bs.multi + (size_t(sl) << BLOOM_WORDS_LOG2) + (bit >> 5), 1u << (bit & 31u));
+    atomicMax(bs.first + (size_t(sl) << BLOOM_BITS_LOG2) + bit, tag);
+}
+
+// Rare path of pass B, kept out of line: a was_first probe of a contended bit.
+__device__ __noinline__ bool bloom_first_wins(BloomSlots bs, uint32_t sl, uint32_t bit, unsigned long long tag) {
+    if (tag > bs.first[(size_t(sl) << BLOOM_BITS_LOG2) + bit]) {   // earlier than every late toucher
+        atomicOr(bs.fw + (size_t(sl) << BLOOM_WORDS_LOG2) + (bit >> 5), 1u << (bit & 31u));
+        return true;
+    }
+    return false;
+}
+
+// One lane's 16-position chunk of pass A.  UNIFORM: the whole chunk lies inside species slot `sl`
+// and inside the launch's range (the common case) — no per-position range / slot bookkeeping.
+// Two half chunks: 16 atomicOr in flight per thread before any result is consumed.
+template <bool UNIFORM>
+__device__ __forceinline__ void bloom_touch_chunk(const uint4& v, uint64_t roll, int have, int k, uint64_t k_mask,
+                                                  uint32_t c0, uint32_t range, const uint32_t* s_b, uint32_t sl,
+                                                  const GroupBounds& g, const BloomSlots& bs,
+                                                  uint32_t& first_bits, uint32_t& late_bits) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < CHUNK; j++) {
-        if ((valid >> j) & 1u) {
-            while (c0 + j >= s_b[sl + 1]) sl++;
-            packed |= uint64_t(sl) << (4 * j);
+    for (int h = 0; h < 2; h++) {
+        uint32_t idx[8][2], old[8][2];
+        uint32_t vmask = 0, slots = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = 8 * h + q;
+            const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (code == CODE_INVALID) {
+                roll = 0;
+                have = 0;
+            } else {
+                roll = ((roll << 3) | uint64_t(code)) & k_mask;
+                if (have < k) have++;
+                if (have == k && (UNIFORM || ((range >> j) & 1u))) vmask |= 1u << q;
+            }
+            bloom_indices(roll, idx[q][0], idx[q][1]);
+            if (!UNIFORM) {
+                if ((vmask >> q) & 1u)
+                    while (c0 + j >= s_b[sl + 1]) sl++;
+                slots |= sl << (4 * q);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
+            uint32_t* words = bs.bits + (size_t(s) << BLOOM_WORDS_LOG2);
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                old[q][pr] = 0;
+                if ((vmask >> q) & 1u) old[q][pr] = atomicOr(words + (idx[q][pr] >> 5), 1u << (idx[q][pr] & 31u));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (!((vmask >> q) & 1u)) continue;
+            const int j = 8 * h + q;
+            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                if (old[q][pr] & (1u << (idx[q][pr] & 31u))) {   // late toucher of this bit
+                    bloom_mark_late(bs, s, idx[q][pr], bloom_tag(g.epoch0 + s, c0 + j - s_b[s]));
+                    late_bits |= 1u << (2 * j + pr);
+                } else {
+                    first_bits |= 1u << (2 * j + pr);
+                }
+            }
         }
     }
-    return packed;
+}
+
+// slot of position c (c inside the launch's range)
+__device__ __forceinline__ uint32_t slot_of(const uint32_t* s_b, uint32_t n, uint32_t c) {
+    uint32_t sl = 0;
+    while (sl + 1 < n && c >= s_b[sl + 1]) sl++;
+    return sl;
 }
 
 // Pass A: touch.
@@ -94,51 +162,21 @@ bloom_touch_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
     const uint32_t tile_lo = cb / WARP_TILE, tile_hi = (ce + WARP_TILE - 1) / WARP_TILE;
     for (uint32_t t = tile_lo + warp_id; t < tile_hi; t += warps_per_grid) {
         const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint64_t kmer[CHUNK];
-        uint32_t valid = load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
-        valid &= range_mask16(c0, cb, ce);
-        const uint64_t slots = slots16(s_b, c0, valid);
+        uint4 v;
+        uint64_t roll;
+        int have;
+        warp_tile_seed<true>(codes, t * WARP_TILE, k, k_mask, v, roll, have);
+        const uint32_t range = range_mask16(c0, cb, ce);
         uint32_t first_bits = 0;  // bit 2j / 2j+1: probe 0 / 1 of position c0+j saw its bit clear
         uint32_t late_bits = 0;   // same indexing: the probe found its bit already set
-#pragma unroll
-        for (int h = 0; h < 2; h++) {   // two half chunks: 16 atomics in flight per thread
-            uint32_t idx[8][2], old[8][2];
-#pragma unroll
-            for (int q = 0; q < 8; q++) bloom_indices(kmer[8 * h + q], idx[q][0], idx[q][1]);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int j = 8 * h + q;
-                const size_t wbase = size_t((slots >> (4 * j)) & 15u) << BLOOM_WORDS_LOG2;
-#pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                    old[q][pr] = 0;
-                    if ((valid >> j) & 1u)
-                        old[q][pr] = atomicOr(bs.bits + wbase + (idx[q][pr] >> 5), 1u << (idx[q][pr] & 31u));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int j = 8 * h + q;
-                if (!((valid >> j) & 1u)) continue;
-                const uint32_t sl = uint32_t(slots >> (4 * j)) & 15u;
-#pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                    const uint32_t m = 1u << (idx[q][pr] & 31u);
-                    if (old[q][pr] & m) {  // late toucher of this bit
-                        atomicOr(bs.multi + (size_t(sl) << BLOOM_WORDS_LOG2) + (idx[q][pr] >> 5), m);
-                        atomicMax(bs.first + (size_t(sl) << BLOOM_BITS_LOG2) + idx[q][pr],
-                                  bloom_tag(g.epoch0 + sl, c0 + j - s_b[sl]));
-                        late_bits |= 1u << (2 * j + pr);
-                    } else {
-                        first_bits |= 1u << (2 * j + pr);
-                    }
-                }
-            }
-        }
-        if (c0 + CHUNK > cb && c0 < ce) {
+        if (range) {
+            const uint32_t sl0 = slot_of(s_b, g.n, max(c0, cb));
+            if (range == 0xFFFFu && c0 + CHUNK <= s_b[sl0 + 1])
+                bloom_touch_chunk<true>(v, roll, have, k, k_mask, c0, range, s_b, sl0, g, bs, first_bits, late_bits);
+            else
+                bloom_touch_chunk<false>(v, roll, have, k, k_mask, c0, range, s_b, sl0, g, bs, first_bits, late_bits);
             // chunks straddling a group boundary are shared by two stream-ordered launches
-            const bool whole = c0 >= cb && c0 + CHUNK <= ce;
-            wf[c0 / CHUNK] = whole ? first_bits : (wf[c0 / CHUNK] | first_bits);
+            wf[c0 / CHUNK] = range == 0xFFFFu ? first_bits : (wf[c0 / CHUNK] | first_bits);
         }
         // warp-aggregated append of the late probes: one global atomic per warp tile
         const uint32_t n_late = __popc(late_bits);
@@ -162,12 +200,77 @@ bloom_touch_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
     }
 }
 
-// Pass B: settle every was_first probe; hash the four CMS cell indices of every new k-mer.
+// One lane's chunk of pass B: all multi[] loads of a half chunk are in flight together.
+template <bool UNIFORM>
+__device__ __forceinline__ uint32_t bloom_settle_chunk(const uint4& v, uint64_t roll, int have, int k, uint64_t k_mask,
+                                                       uint32_t c0, uint32_t range, uint32_t first_bits,
+                                                       const uint32_t* s_b, uint32_t sl, const GroupBounds& g,
+                                                       const BloomSlots& bs, uint32_t* s_cnt) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t new_bits = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t idx[8][2], mw[8][2];
+        uint32_t vmask = 0, slots = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = 8 * h + q;
+            const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (code == CODE_INVALID) {
+                roll = 0;
+                have = 0;
+            } else {
+                roll = ((roll << 3) | uint64_t(code)) & k_mask;
+                if (have < k) have++;
+                if (have == k && (UNIFORM || ((range >> j) & 1u))) vmask |= 1u << q;
+            }
+            bloom_indices(roll, idx[q][0], idx[q][1]);
+            if (!UNIFORM) {
+                if ((vmask >> q) & 1u)
+                    while (c0 + j >= s_b[sl + 1]) sl++;
+                slots |= sl << (4 * q);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = 8 * h + q;
+            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
+            const uint32_t* words = bs.multi + (size_t(s) << BLOOM_WORDS_LOG2);
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                mw[q][pr] = 0;
+                if (((vmask >> q) & 1u) && ((first_bits >> (2 * j + pr)) & 1u)) mw[q][pr] = words[idx[q][pr] >> 5];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (!((vmask >> q) & 1u)) continue;
+            const int j = 8 * h + q;
+            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
+            bool is_new = false;
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                if (!((first_bits >> (2 * j + pr)) & 1u)) continue;   // late probes: bloom_late_kernel
+                if (!(mw[q][pr] & (1u << (idx[q][pr] & 31u))))
+                    is_new = true;                                     // only toucher of this bit
+                else if (bloom_first_wins(bs, s, idx[q][pr], bloom_tag(g.epoch0 + s, c0 + j - s_b[s])))
+                    is_new = true;
+            }
+            if (is_new) {
+                new_bits |= 1u << j;
+                if (!UNIFORM) atomicAdd(&s_cnt[s], 1u);
+            }
+        }
+    }
+    if (UNIFORM && new_bits) atomicAdd(&s_cnt[sl], uint32_t(__popc(new_bits)));
+    return new_bits;
+}
+
+// Pass B: settle every was_first probe.
 __global__ void __launch_bounds__(COUNT_THREADS)
 bloom_settle_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, GroupBounds g,
                     int k, uint64_t k_mask, BloomSlots bs, const uint32_t* __restrict__ wf,
-                    uint16_t* __restrict__ flags, IndexStreams ix,
-                    unsigned long long* __restrict__ new_per_species) {
+                    uint16_t* __restrict__ flags, unsigned long long* __restrict__ new_per_species) {
     __shared__ uint32_t s_b[MAX_GROUP_SPECIES + 1];
     __shared__ uint32_t s_cnt[MAX_GROUP_SPECIES];
     if (threadIdx.x <= g.n) s_b[threadIdx.x] = sp_cstart[g.first_species + threadIdx.x];
@@ -180,91 +283,22 @@ bloom_settle_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restric
     const uint32_t tile_lo = cb / WARP_TILE, tile_hi = (ce + WARP_TILE - 1) / WARP_TILE;
     for (uint32_t t = tile_lo + warp_id; t < tile_hi; t += warps_per_grid) {
         const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint64_t kmer[CHUNK];
-        uint32_t valid = load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
-        const uint32_t in_range = range_mask16(c0, cb, ce);
-        valid &= in_range;
-        const uint64_t slots = slots16(s_b, c0, valid);
+        uint4 v;
+        uint64_t roll;
+        int have;
+        warp_tile_seed<true>(codes, t * WARP_TILE, k, k_mask, v, roll, have);
+        const uint32_t range = range_mask16(c0, cb, ce);
+        if (!range) continue;
         const uint32_t first_bits = __ldcs(wf + c0 / CHUNK);
-        uint32_t new_bits = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t idx[8][2], mw[8][2];
-#pragma unroll
-            for (int q = 0; q < 8; q++) bloom_indices(kmer[8 * h + q], idx[q][0], idx[q][1]);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {          // all multi[] loads of the half chunk in flight
-                const int j = 8 * h + q;
-                const size_t wbase = size_t((slots >> (4 * j)) & 15u) << BLOOM_WORDS_LOG2;
-#pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                    mw[q][pr] = 0;
-                    if (((valid >> j) & 1u) && ((first_bits >> (2 * j + pr)) & 1u))
-                        mw[q][pr] = bs.multi[wbase + (idx[q][pr] >> 5)];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int j = 8 * h + q;
-                if (!((valid >> j) & 1u)) continue;
-                const uint32_t sl = uint32_t(slots >> (4 * j)) & 15u;
-                bool is_new = false;
-#pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                    if (!((first_bits >> (2 * j + pr)) & 1u)) continue;  // late probes: bloom_late_kernel
-                    const uint32_t m = 1u << (idx[q][pr] & 31u);
-                    if (!(mw[q][pr] & m)) {
-                        is_new = true;          // only toucher of this bit
-                    } else {
-                        const unsigned long long tag = bloom_tag(g.epoch0 + sl, c0 + j - s_b[sl]);
-                        if (tag > bs.first[(size_t(sl) << BLOOM_BITS_LOG2) + idx[q][pr]]) {  // before every late toucher
-                            atomicOr(bs.fw + (size_t(sl) << BLOOM_WORDS_LOG2) + (idx[q][pr] >> 5), m);
-                            is_new = true;
-                        }
-                    }
-                }
-                if (is_new) new_bits |= 1u << j;
-            }
-        }
-        // per-species counts (a chunk rarely spans species)
+        const uint32_t sl0 = slot_of(s_b, g.n, max(c0, cb));
+        uint32_t new_bits;
+        if (range == 0xFFFFu && c0 + CHUNK <= s_b[sl0 + 1])
+            new_bits = bloom_settle_chunk<true>(v, roll, have, k, k_mask, c0, range, first_bits, s_b, sl0, g, bs, s_cnt);
+        else
+            new_bits = bloom_settle_chunk<false>(v, roll, have, k, k_mask, c0, range, first_bits, s_b, sl0, g, bs, s_cnt);
         if (new_bits) {
-            uint32_t rest = new_bits;
-            while (rest) {
-                const int j = __ffs(rest) - 1;
-                const uint32_t sl = uint32_t(slots >> (4 * j)) & 15u;
-                uint32_t same = 0;
-#pragma unroll
-                for (int q = 0; q < CHUNK; q++)
-                    if (((rest >> q) & 1u) && (uint32_t(slots >> (4 * q)) & 15u) == sl) same |= 1u << q;
-                atomicAdd(&s_cnt[sl], uint32_t(__popc(same)));
-                rest &= ~same;
-            }
             uint16_t* f = flags + (c0 / CHUNK);
             *f = uint16_t(*f | new_bits);   // merge: a straddling chunk is shared by two launches
-        }
-        // CMS cell indices, hashed once, one stream per row
-        if (in_range) {
-            const bool whole = in_range == 0xFFFFu;
-#pragma unroll
-            for (int r = 0; r < int(CMS_DEPTH); r++) {
-                const uint64_t seed = r == 0 ? SEED_CMS_0 : r == 1 ? SEED_CMS_1 : r == 2 ? SEED_CMS_2 : SEED_CMS_3;
-                uint32_t v[CHUNK];
-#pragma unroll
-                for (int j = 0; j < CHUNK; j++)
-                    v[j] = ((new_bits >> j) & 1u) ? cms_index(kmer[j], seed) : IDX_NONE;
-                uint32_t* dst = ix.row[r] + c0;
-                if (whole) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-                    d4[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                    d4[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                    d4[2] = make_uint4(v[8], v[9], v[10], v[11]);
-                    d4[3] = make_uint4(v[12], v[13], v[14], v[15]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CHUNK; j++)
-                        if ((in_range >> j) & 1u) dst[j] = v[j];
-                }
-            }
         }
     }
     __syncthreads();
@@ -277,7 +311,7 @@ bloom_settle_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restric
 __global__ void __launch_bounds__(COUNT_THREADS)
 bloom_late_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, GroupBounds g,
                   int k, BloomSlots bs, const uint32_t* __restrict__ late_list,
-                  const uint32_t* __restrict__ late_count, uint32_t* __restrict__ flags32, IndexStreams ix,
+                  const uint32_t* __restrict__ late_count, uint32_t* __restrict__ flags32,
                   unsigned long long* __restrict__ new_per_species) {
     __shared__ uint32_t s_b[MAX_GROUP_SPECIES + 1];
     __shared__ uint32_t s_cnt[MAX_GROUP_SPECIES];
@@ -300,19 +334,55 @@ bloom_late_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
             !(bs.fw[(size_t(sl) << BLOOM_WORDS_LOG2) + w] & m)) {
             const uint32_t fm = 1u << (c & 31u);
             const uint32_t old = atomicOr(flags32 + (c >> 5), fm);
-            if (!(old & fm)) {   // not already new through its other probe
-                atomicAdd(&s_cnt[sl], 1u);
-                ix.row[0][c] = cms_index(kmer, SEED_CMS_0);
-                ix.row[1][c] = cms_index(kmer, SEED_CMS_1);
-                ix.row[2][c] = cms_index(kmer, SEED_CMS_2);
-                ix.row[3][c] = cms_index(kmer, SEED_CMS_3);
-            }
+            if (!(old & fm)) atomicAdd(&s_cnt[sl], 1u);   // not already new through its other probe
         }
     }
     __syncthreads();
     if (threadIdx.x < g.n && s_cnt[threadIdx.x])
         atomicAdd(new_per_species + g.first_species + threadIdx.x,
                   static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+// Clears the bitsets of a group's slots and the late counter in ONE launch.
+__global__ void __launch_bounds__(256)
+bloom_clear_kernel(uint4* __restrict__ bits, uint4* __restrict__ multi, uint4* __restrict__ fw, uint32_t n_vec,
+                   uint32_t* __restrict__ late_count) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x) {
+        bits[i] = z;
+        multi[i] = z;
+        fw[i] = z;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *late_count = 0;
+}
+
+// Hash-once: the four CMS cell indices of every flagged (new) k-mer, one 4 B stream per row.
+// Pure ALU + streaming stores: 4 x mix64 per new k-mer, IDX_NONE elsewhere.
+__global__ void __launch_bounds__(COUNT_THREADS)
+cms_index_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_tiles,
+                 int k, uint64_t k_mask, IndexStreams ix) {
+    const uint32_t warps_per_grid = gridDim.x * (COUNT_THREADS / 32);
+    const uint32_t warp_id = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
+        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
+        uint64_t kmer[CHUNK];
+        load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);   // a flag implies a valid k-mer
+        const uint32_t new_bits = __ldcs(flags + c0 / CHUNK);
+#pragma unroll
+        for (int r = 0; r < int(CMS_DEPTH); r++) {
+            const uint64_t seed = r == 0 ? SEED_CMS_0 : r == 1 ? SEED_CMS_1 : r == 2 ? SEED_CMS_2 : SEED_CMS_3;
+            uint32_t v[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++)
+                v[j] = ((new_bits >> j) & 1u) ? cms_index(kmer[j], seed) : IDX_NONE;
+            uint4* d4 = reinterpret_cast<uint4*>(ix.row[r] + c0);
+            __stcs(d4 + 0, make_uint4(v[0], v[1], v[2], v[3]));
+            __stcs(d4 + 1, make_uint4(v[4], v[5], v[6], v[7]));
+            __stcs(d4 + 2, make_uint4(v[8], v[9], v[10], v[11]));
+            __stcs(d4 + 3, make_uint4(v[12], v[13], v[14], v[15]));
+        }
+    }
 }
 
 // K3: one launch per (row, slice): stream the row's index stream (evict-first) and apply the

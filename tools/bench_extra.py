@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Secondary measurements: pass-2 occupancy scan and the --nj pair-count kernel, each
+next to the CPU oracle on a bounded sample.  Writes one JSON object per line to stdout."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--species", type=int, default=100)
+    ap.add_argument("--nj-n", type=int, default=2000)
+    ap.add_argument("--nj-l", type=int, default=100_000)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import oracle_ffi
+    from kamino_b200 import ffi, synth
+    orc = oracle_ffi.load()
+    threads = len(os.sched_getaffinity(0))
+
+    # ---- pass 2 on the bacterial config
+    species = synth.bacterial(args.species)
+    b = synth.stage(species)
+    min_needed = orc.min_needed(0.85, b.n_sp)
+    with ffi.Context(13, "sr6") as ctx:
+        bid, new = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+        ctx.finalize_table()
+        table = ctx.table_snapshot()
+        for _ in range(2):
+            ns, ne = ctx.scan_batch(bid, min_needed)
+        ms = []
+        for _ in range(args.reps):
+            ctx.scan_batch(bid, min_needed)
+            ms.append(ctx.stage_ms("scan"))
+        scan_ms = float(np.median(ms))
+        # CPU: oracle scan of a few species (single thread per species, run sequentially)
+        cms = orc.cms_from_table(table)
+        n_cpu = min(4, b.n_sp)
+        t0 = time.perf_counter()
+        res_cpu = 0
+        for s in range(n_cpu):
+            ws, we, _ = orc.scan_species(cms, b.residues, b.rec_off, int(b.sp_rec_off[s]), int(b.sp_rec_off[s + 1]),
+                                         13, 1, min_needed, want_occ=False)
+            res_cpu += int(species[s].lens.sum())
+            gs, ge = ctx.fetch_hits(bid, s)
+            assert np.array_equal(gs, ws) and np.array_equal(ge, we)
+        cpu_dt = time.perf_counter() - t0
+        orc.cms_free(cms)
+        print(json.dumps({"what": "pass2_scan", "species": b.n_sp, "residues": b.n_residues, "ms": scan_ms,
+                          "residues_per_s": b.n_residues / (scan_ms * 1e-3), "starts": ns, "ends": ne,
+                          "cpu_single_thread_residues_per_s": res_cpu / cpu_dt, "parity_species_checked": n_cpu}))
+
+    # ---- --nj pair counts
+    rng = np.random.default_rng(1)
+    n, L = args.nj_n, args.nj_l
+    base = rng.choice(20, size=L, p=synth.LG_PI).astype(np.uint8)
+    m = np.tile(base, (n, 1))
+    mut = rng.random((n, L)) < 0.05
+    m[mut] = rng.integers(0, 20, int(mut.sum()), dtype=np.uint8)
+    m[rng.random((n, L)) < 0.05] = 20
+    with ffi.Context(13, "sr6") as ctx:
+        ctx.pair_counts(m[:64])
+        ms = []
+        for _ in range(args.reps):
+            v, mm = ctx.pair_counts(m)
+            ms.append(ctx.stage_ms("pair_counts"))
+        k_ms = float(np.median(ms))
+    n_cpu = 48
+    t0 = time.perf_counter()
+    wv, wm = orc.pair_counts(m[:n_cpu], threads=threads)
+    cpu_dt = time.perf_counter() - t0
+    iu = np.triu_indices(n_cpu, 1)
+    assert np.array_equal(v[:n_cpu, :n_cpu][iu], wv[iu]) and np.array_equal(mm[:n_cpu, :n_cpu][iu], wm[iu])
+    pairs = n * (n - 1) // 2
+    print(json.dumps({"what": "pair_counts", "n": n, "L": L, "kernel_ms": k_ms,
+                      "pair_columns_per_s": pairs * L / (k_ms * 1e-3),
+                      "cpu_pair_columns_per_s": (n_cpu * (n_cpu - 1) // 2) * L / cpu_dt, "cpu_threads": threads}))
+
+
+if __name__ == "__main__":
+    main()
