@@ -218,24 +218,32 @@ def run_gpu(args):
 
     from kamino_b200 import sharding
 
-    def exchange():
-        if world > 1:
+    fused = False
+    if world > 1 and os.environ.get("KMN_EXCHANGE", "fused") == "fused":
+        fused = sharding.setup_fused_exchange(ctx)       # CUDA IPC peer mapping over NVLink
+        log(f"[rank {rank}] fused NVLink exchange: {'on' if fused else 'unavailable, using NCCL all-reduce'}")
+
+    def exchange_and_finalize():
+        if world == 1:
+            ctx.finalize_table()
+        elif fused:
+            sharding.fused_exchange(ctx)                 # one kernel: P2P reduce + clamp + all-gather
+        else:
             ctx.synchronize()
-            sharding.exchange_accumulators(acc_t)  # the sketch is linear: sum of per-rank accumulators
+            sharding.exchange_accumulators(acc_t)        # the sketch is linear: sum of per-rank accumulators
             torch.cuda.synchronize()
+            ctx.finalize_table()
 
     def step_resident():
         ctx.reset_table()
         new = ctx.count_staged(bid, batch.n_sp)
-        exchange()
-        ctx.finalize_table()
+        exchange_and_finalize()
         return new
 
     def step_e2e():
         ctx.reset_table()
         _, new = ctx.count_batch(h_res, h_rec, h_sp)   # H2D of residues + offsets inside
-        exchange()
-        ctx.finalize_table()
+        exchange_and_finalize()
         return new                                       # D2H: per-species counts
 
     for _ in range(args.warmup):
@@ -332,7 +340,9 @@ def run_gpu(args):
             "config": {"workload": f"{N_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa) per GPU, k={K}, {SCHEME_NAME}",
                        "residues_per_gpu": batch.n_residues, "species_per_gpu": batch.n_sp,
                        "l2": "inputs (132 MB residues + 1 GiB accumulators) exceed the 126 MB L2; no explicit flush",
-                       "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the u32 accumulators"},
+                       "exchange": "none (1 GPU)" if world == 1 else (
+                           "fused NVLink peer kernel: reduce-scatter + clamp + all-gather" if fused
+                           else "NCCL all-reduce of the u32 accumulators")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_elapsed / args.steps},
             "gpu_launches": int(launches),

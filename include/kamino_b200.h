@@ -92,6 +92,16 @@ int kmn_table_load(kmn_ctx* ctx, const uint16_t* table);
  * across ranks because the sketch is linear) and of the finalized u16 table. */
 int kmn_table_accum_device_ptr(kmn_ctx* ctx, void** ptr);
 int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
+/* Fused NVLink exchange (one process per GPU): every rank exports CUDA IPC handles of its accumulators
+ * and of its finalized table (64 bytes each); after an all-gather of the handles by the caller,
+ * kmn_exchange_setup maps the peers' buffers.  kmn_exchange_reduce then runs ONE kernel per rank that
+ * loads this rank's 1/world cell range from every peer over NVLink, sums, clamps to u16
+ * (== snapshot of the summed sketch, proba_filter.rs:171-177) and stores the result into EVERY peer's
+ * table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The caller must
+ * barrier across ranks after counting (before the call) and after kmn_synchronize (after the call). */
+int kmn_exchange_export(kmn_ctx* ctx, uint8_t* acc_handle64, uint8_t* table_handle64);
+int kmn_exchange_setup(kmn_ctx* ctx, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles);
+int kmn_exchange_reduce(kmn_ctx* ctx);
 /* Block until all work queued on the context's stream has finished. */
 int kmn_synchronize(kmn_ctx* ctx);
 /* CUDA stream of the context (cudaStream_t as void*), for event timing by the caller. */
@@ -124,7 +134,7 @@ int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L,
 
 /* Device time (ms) of the last kmn_count_staged / kmn_scan_batch / kmn_pair_counts call on this
  * context, per stage, measured with CUDA events on the context's stream.
- * which: 0 frame, 1 bloom, 2 cms, 3 finalize, 4 scan, 5 pair_counts. */
+ * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts. */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

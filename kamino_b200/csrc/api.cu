@@ -111,6 +111,9 @@ struct kmn_ctx {
     DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
     DevBuf<uint16_t> warp_cnt;
     std::vector<std::unique_ptr<Batch>> batches;
+    PeerTables peers{};                   // mapped peer buffers of the fused exchange
+    bool peers_ready = false;
+    std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
     cudaEvent_t ev[8] = {};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -496,6 +499,7 @@ void kmn_destroy(kmn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->batches.clear();
     c->spare.clear();
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -559,6 +563,61 @@ int kmn_table_load(kmn_ctx* c, const uint16_t* table) {
 
 int kmn_table_accum_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->acc.p; }); }
 int kmn_table_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->cms.p; }); }
+int kmn_exchange_export(kmn_ctx* c, uint8_t* acc_handle64, uint8_t* table_handle64) {
+    return guarded(c, [&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        KMN_CUDA(cudaIpcGetMemHandle(&h, c->acc.p));
+        std::memcpy(acc_handle64, &h, 64);
+        KMN_CUDA(cudaIpcGetMemHandle(&h, c->cms.p));
+        std::memcpy(table_handle64, &h, 64);
+    });
+}
+
+int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles) {
+    return guarded(c, [&] {
+        if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) throw std::runtime_error("invalid world / rank");
+        if (CMS_CELLS / 4 % uint64_t(world)) throw std::runtime_error("world size must divide the table");
+        for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+        c->ipc_opened.clear();
+        c->peers = PeerTables{};
+        c->peers.world = world;
+        c->peers.rank = rank;
+        for (int p = 0; p < world; p++) {
+            if (p == rank) {
+                c->peers.acc[p] = reinterpret_cast<const uint4*>(c->acc.p);
+                c->peers.cms[p] = reinterpret_cast<uint2*>(c->cms.p);
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            void* ptr = nullptr;
+            std::memcpy(&h, acc_handles + 64 * p, 64);
+            KMN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(ptr);
+            c->peers.acc[p] = reinterpret_cast<const uint4*>(ptr);
+            std::memcpy(&h, table_handles + 64 * p, 64);
+            KMN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(ptr);
+            c->peers.cms[p] = reinterpret_cast<uint2*>(ptr);
+        }
+        c->peers_ready = true;
+    });
+}
+
+int kmn_exchange_reduce(kmn_ctx* c) {
+    return guarded(c, [&] {
+        if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
+        const uint64_t n_vec = CMS_CELLS / 4, per = n_vec / uint64_t(c->peers.world);
+        KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        exchange_reduce_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(c->peers, per * c->peers.rank, per * (c->peers.rank + 1));
+        check_launch(c);
+        KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
+        c->finalized = true;   // valid once every rank's kernel has finished (caller barriers)
+    });
+}
+
 int kmn_synchronize(kmn_ctx* c) { return guarded(c, [&] { KMN_CUDA(cudaStreamSynchronize(c->stream)); }); }
 int kmn_stream(kmn_ctx* c, void** stream) { return guarded(c, [&] { *stream = c->stream; }); }
 

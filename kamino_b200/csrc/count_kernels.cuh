@@ -410,4 +410,30 @@ cms_finalize_kernel(const uint4* __restrict__ acc4, uint2* __restrict__ out2, ui
     }
 }
 
+// Fused exchange over NVLink peer memory: reduce-scatter of the u32 accumulators + clamp + all-gather
+// of the u16 table, one launch per rank (see kmn_exchange_reduce).
+constexpr int MAX_PEERS = 16;
+struct PeerTables {
+    const uint4* acc[MAX_PEERS];   // every rank's accumulators (peer-mapped; acc[rank] is local)
+    uint2* cms[MAX_PEERS];         // every rank's finalized table
+    int world, rank;
+};
+
+__global__ void __launch_bounds__(256)
+exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end) {
+    for (uint64_t i = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_end;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        uint4 s = pt.acc[pt.rank][i];
+#pragma unroll 1
+        for (int p = 1; p < pt.world; p++) {
+            const int peer = (pt.rank + p) % pt.world;   // stagger the peers across ranks
+            const uint4 a = pt.acc[peer][i];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+        const uint2 o = make_uint2(min(s.x, 65535u) | (min(s.y, 65535u) << 16),
+                                   min(s.z, 65535u) | (min(s.w, 65535u) << 16));
+        for (int p = 0; p < pt.world; p++) pt.cms[(pt.rank + p) % pt.world][i] = o;
+    }
+}
+
 }  // namespace kmn

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
-    "kmn_table_device_ptr", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
+    "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
@@ -70,6 +70,9 @@ def load_library() -> C.CDLL:
     lib.kmn_table_load.argtypes = [vp, vp]
     lib.kmn_table_accum_device_ptr.argtypes = [vp, vpp]
     lib.kmn_table_device_ptr.argtypes = [vp, vpp]
+    lib.kmn_exchange_export.argtypes = [vp, vp, vp]
+    lib.kmn_exchange_setup.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    lib.kmn_exchange_reduce.argtypes = [vp]
     lib.kmn_synchronize.argtypes = [vp]
     lib.kmn_stream.argtypes = [vp, vpp]
     lib.kmn_scan_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
@@ -176,6 +179,20 @@ class Context:
         p = C.c_void_p()
         self._check(self.lib.kmn_table_device_ptr(self._h, C.byref(p)))
         return p.value
+
+    def exchange_export(self) -> tuple[bytes, bytes]:
+        a, t = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        self._check(self.lib.kmn_exchange_export(self._h, _ptr(a), _ptr(t)))
+        return a.tobytes(), t.tobytes()
+
+    def exchange_setup(self, world: int, rank: int, acc_handles: list[bytes], table_handles: list[bytes]):
+        a = np.frombuffer(b"".join(acc_handles), dtype=np.uint8).copy()
+        t = np.frombuffer(b"".join(table_handles), dtype=np.uint8).copy()
+        assert a.size == 64 * world and t.size == 64 * world
+        self._check(self.lib.kmn_exchange_setup(self._h, world, rank, _ptr(a), _ptr(t)))
+
+    def exchange_reduce(self):
+        self._check(self.lib.kmn_exchange_reduce(self._h))
 
     def stream(self) -> int:
         p = C.c_void_p()

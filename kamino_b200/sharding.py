@@ -43,6 +43,32 @@ def exchange_accumulators(acc, group=None):
     return acc
 
 
+def setup_fused_exchange(ctx, group=None) -> bool:
+    """All-gather the CUDA IPC handles and map the peers' tables (once per context).  Returns False
+    when peer mapping is unavailable (the caller then uses exchange_accumulators + finalize)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.exchange_export(), group=group)
+    ok = True
+    try:
+        ctx.exchange_setup(world, rank, [h[0] for h in handles], [h[1] for h in handles])
+    except Exception:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)
+    return all(flags)
+
+
+def fused_exchange(ctx, group=None):
+    """reduce-scatter + snapshot + all-gather in one kernel per rank over NVLink peer memory."""
+    import torch.distributed as dist
+    ctx.synchronize()
+    dist.barrier(group=group)      # every rank's accumulators are complete
+    ctx.exchange_reduce()          # synchronizes its own stream before returning
+    dist.barrier(group=group)      # every rank's table has been written by all peers
+
+
 def clamp_u16(acc: np.ndarray) -> np.ndarray:
     """Host restatement of the finalize kernel (tests only)."""
     return np.minimum(acc.astype(np.int64) & 0xFFFFFFFF, 65535).astype(np.uint16)

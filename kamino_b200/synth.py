@@ -100,7 +100,7 @@ def evolve(rng, sp: Species, p_sub: float, indel_rate=1 / 2000, p_loss=0.02, x_r
 
 
 def species_set(n_species: int, n_prot: int, mean_len: float, seed: int = SEED0,
-                p_sub_range=(0.002, 0.06), max_len=3000) -> list[Species]:
+                p_sub_range=(0.0005, 0.01), max_len=3000) -> list[Species]:
     """Random tree: every new species branches off a uniformly chosen earlier one."""
     rng = np.random.default_rng(seed)
     root = root_proteome(rng, n_prot, mean_len, hi=max_len)
@@ -116,7 +116,7 @@ def bacterial(n_species: int, seed: int = SEED0 + 1, n_prot=4000, mean_len=330.0
 
 
 def eukaryotic(n_species: int, seed: int = SEED0 + 3, n_prot=20000, mean_len=500.0) -> list[Species]:
-    return species_set(n_species, n_prot, mean_len, seed, p_sub_range=(0.01, 0.15), max_len=6000)
+    return species_set(n_species, n_prot, mean_len, seed, p_sub_range=(0.002, 0.03), max_len=6000)
 
 
 def _wrap_species(sp: Species, width: int) -> tuple[np.ndarray, np.ndarray]:

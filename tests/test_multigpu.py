@@ -1,0 +1,83 @@
+"""2-GPU parity (skipped unless >= 2 CUDA devices): species sharded over two ranks, tables merged by
+the fused NVLink exchange kernel and by the NCCL all-reduce path; both must equal the single-process
+oracle table bit for bit."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import oracle_ffi
+    from kamino_b200 import ffi, sharding, synth
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        b = synth.stage(synth.bacterial(7, seed=99, n_prot=200, mean_len=150.0))
+        mine = sharding.shard_species(b.n_sp, world, rank)
+        res, rec, sp = sharding.select_species(b.residues, b.rec_off, b.sp_rec_off, mine)
+        results = {}
+        with ffi.Context(13, "sr6", device=rank) as ctx:
+            fused_ok = sharding.setup_fused_exchange(ctx)
+            for mode in (["fused"] if fused_ok else []) + ["nccl"]:
+                ctx.reset_table()
+                ctx.count_batch(res, rec, sp)
+                if mode == "fused":
+                    sharding.fused_exchange(ctx)
+                else:
+                    acc = torch.as_tensor(_DevArray(ctx.accum_device_ptr(), ffi.CMS_CELLS, "<i4"), device=f"cuda:{rank}")
+                    ctx.synchronize()
+                    sharding.exchange_accumulators(acc)
+                    torch.cuda.synchronize()
+                    ctx.finalize_table()
+                results[mode] = ctx.table_snapshot()
+                ctx.release_batches()
+                dist.barrier()
+        orc = oracle_ffi.load()
+        h = orc.cmsa_new()
+        try:
+            orc.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, 13, 1, threads=4)
+            want = orc.cmsa_table(h)
+            ok = all(np.array_equal(t, want) for t in results.values())
+        finally:
+            orc.cmsa_free(h)
+        Path(out_dir, f"rank{rank}.txt").write_text(("ok " if ok else "mismatch ") + ",".join(results))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_exchange_matches_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        txt = (tmp_path / f"rank{r}.txt").read_text()
+        assert txt.startswith("ok"), txt
+        print("rank", r, txt)
