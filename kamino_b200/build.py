@@ -62,5 +62,30 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+HOST_BIN = LIB_DIR / "kamino-b200"
+HOST_SRC = CSRC / "host"
+
+
+def build_host(force: bool = False) -> Path:
+    """`kamino-b200`: the C++ host pipeline (kamino's CLI) linked against libkamino_b200.so."""
+    lib = build(force=False)
+    srcs = sorted(HOST_SRC.glob("*.cpp"))
+    deps = srcs + list(HOST_SRC.glob("*.hpp")) + [lib]
+    if not force and HOST_BIN.exists() and all(p.stat().st_mtime <= HOST_BIN.stat().st_mtime for p in deps):
+        return HOST_BIN
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-pthread", "-I", str(INCLUDE),
+           "-o", str(HOST_BIN), *map(str, srcs), "-L", str(LIB_DIR), "-lkamino_b200", "-lz",
+           "-Wl,-rpath,$ORIGIN"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed building kamino-b200")
+    if proc.stderr.strip():
+        sys.stderr.write(proc.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,249 @@
+// extraction.cpp — stage driver of the B200 pipeline: both passes run on the GPU through the C ABI,
+// the host only pairs the boundary hits the device returns and books the resulting blocks.
+// Equivalent to /root/reference/src/group_extraction.rs:146-242 (anchor selection / pairing),
+// :397-404 (protein names) and :527-660 (stage order, limits, deterministic sid-ordered merge).
+#include "../../../include/kamino_b200.h"
+#include "kamino_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+namespace kh {
+
+namespace {
+
+struct Ctx {   // RAII over kmn_ctx
+    kmn_ctx* p = nullptr;
+    Ctx(int device, int k, int scheme) {
+        if (kmn_create(&p, device, k, scheme) != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error());
+    }
+    ~Ctx() { kmn_destroy(p); }
+    void ok(int rc) const { if (rc != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error()); }
+};
+
+bool valid_utf8(const std::string& s) {   // rec.id()? / rec.desc() fail on invalid UTF-8 (group_extraction.rs:429-430)
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(s.data());
+    size_t i = 0, n = s.size();
+    while (i < n) {
+        const unsigned c = p[i];
+        if (c < 0x80) { i++; continue; }
+        int need;
+        unsigned cp;
+        if (c >= 0xC2 && c <= 0xDF) { need = 1; cp = c & 0x1F; }
+        else if (c >= 0xE0 && c <= 0xEF) { need = 2; cp = c & 0x0F; }
+        else if (c >= 0xF0 && c <= 0xF4) { need = 3; cp = c & 0x07; }
+        else return false;
+        if (i + size_t(need) >= n) return false;
+        for (int j = 1; j <= need; j++) {
+            const unsigned d = p[i + j];
+            if ((d & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (d & 0x3F);
+        }
+        if (need == 2 && (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF))) return false;
+        if (need == 3 && (cp < 0x10000 || cp > 0x10FFFF)) return false;
+        i += size_t(need) + 1;
+    }
+    return true;
+}
+
+bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+std::string trim(const std::string& s) {
+    size_t b = 0, e = s.size();
+    while (b < e && is_ws((unsigned char)s[b])) b++;
+    while (e > b && is_ws((unsigned char)s[e - 1])) e--;
+    return s.substr(b, e - b);
+}
+
+// "id desc" with both parts trimmed, cut at the first " [" (group_extraction.rs:397-404, :429-436)
+std::string protein_name_of(const std::string& head) {
+    const size_t sp = head.find(' ');
+    const std::string id = trim(sp == std::string::npos ? head : head.substr(0, sp));
+    const std::string desc = sp == std::string::npos ? std::string() : trim(head.substr(sp + 1));
+    std::string name = trim(desc.empty() ? id : id + " " + desc);
+    const size_t cut = name.find(" [");
+    if (cut != std::string::npos) {
+        name.resize(cut);
+        while (!name.empty() && is_ws((unsigned char)name.back())) name.pop_back();
+    }
+    return name;
+}
+
+// Best start candidate of every local cluster: a cluster spans [first.start, first.start + 10);
+// better = higher occupancy, then smaller start (group_extraction.rs:21, :146-175).
+void pick_cluster_starts(const kmn_hit* s, size_t n, std::vector<kmn_hit>& out) {
+    out.clear();
+    if (n == 0) return;
+    uint32_t cluster_at = s[0].start;
+    kmn_hit best = s[0];
+    for (size_t i = 1; i < n; i++) {
+        if (s[i].start < cluster_at + 10) {
+            if (s[i].occ > best.occ || (s[i].occ == best.occ && s[i].start < best.start)) best = s[i];
+        } else {
+            out.push_back(best);
+            cluster_at = s[i].start;
+            best = s[i];
+        }
+    }
+    out.push_back(best);
+}
+
+}  // namespace
+
+Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
+                          Scheme scheme, const Options& opt) {
+    const size_t n = inputs.size();
+    if (n > 0xFFFF)   // group_extraction.rs:538-543
+        throw std::runtime_error("too many species (" + std::to_string(n) + ") for compact direct block observations; maximum is 65535");
+    const float nf = float(n < 1 ? size_t(1) : n);
+    volatile float prod = min_freq * nf;                       // f32 arithmetic, group_extraction.rs:544
+    const uint32_t min_needed = uint32_t(std::ceil(float(prod)));
+    Ctx gpu(opt.device, int(k), int(scheme));
+
+    // ---- load every proteome (host threads; gunzip + framing only)
+    if (!opt.quiet) std::fprintf(stderr, " . pass 1: estimate k-mer occupancies\n");
+    std::vector<Proteome> prot(n);
+    std::vector<std::string> errs(n);
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t i; (i = next.fetch_add(1)) < n;) {
+                try { prot[i] = load_proteome(inputs[i].path); }
+                catch (const std::exception& e) { errs[i] = *e.what() ? e.what() : "error"; }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, n)); t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);   // first error in species order (:569-571)
+
+    // ---- pass 1: batches of whole species through kmn_count_batch
+    struct BatchRef { uint32_t id; size_t sp0, sp1; };
+    std::vector<BatchRef> batches;
+    std::vector<uint8_t> buf;
+    std::vector<uint64_t> rec_off, sp_rec_off;
+    for (size_t s0 = 0; s0 < n;) {
+        size_t s1 = s0, bytes = 0, recs = 0;
+        while (s1 < n && (s1 == s0 || bytes + prot[s1].seq.size() <= opt.batch_bytes)) {
+            bytes += prot[s1].seq.size();
+            recs += prot[s1].rec_off.size() - 1;
+            s1++;
+        }
+        if (bytes + recs >= (uint64_t(1) << 31)) throw std::runtime_error("species " + inputs[s0].name + " is too large for one GPU batch");
+        buf.resize(bytes);
+        rec_off.assign(1, 0);
+        sp_rec_off.assign(1, 0);
+        size_t at = 0;
+        for (size_t s = s0; s < s1; s++) {
+            std::memcpy(buf.data() + at, prot[s].seq.data(), prot[s].seq.size());
+            for (size_t r = 1; r < prot[s].rec_off.size(); r++) rec_off.push_back(at + prot[s].rec_off[r]);
+            at += prot[s].seq.size();
+            sp_rec_off.push_back(rec_off.size() - 1);
+        }
+        uint32_t id = 0;
+        gpu.ok(kmn_count_batch(gpu.p, buf.data(), rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
+                               uint32_t(s1 - s0), nullptr, &id));
+        batches.push_back({id, s0, s1});
+        s0 = s1;
+    }
+    gpu.ok(kmn_finalize_table(gpu.p));   // snapshot (:576)
+
+    // ---- pass 2: boundary hits from the device, pairing on the host, merged in sid order (:611-636)
+    if (!opt.quiet) std::fprintf(stderr, " . pass 2: extract sequences\n");
+    Extraction ex;
+    ex.k = k;
+    ex.min_needed = min_needed;
+    ex.n_species = n;
+    for (auto& in : inputs) ex.species_names.push_back(in.name);
+    std::vector<kmn_hit> starts, ends, picked;
+    std::vector<uint8_t> aa;     // whitespace-stripped, upper-cased residues of the current record
+    uint64_t order = 0;
+    for (const BatchRef& b : batches) {
+        uint64_t ts = 0, te = 0;
+        gpu.ok(kmn_scan_batch(gpu.p, b.id, min_needed, &ts, &te));
+        for (size_t sid = b.sp0; sid < b.sp1; sid++) {
+            const Proteome& pr = prot[sid];
+            const size_t n_rec = pr.rec_off.size() - 1;
+            for (const std::string& h : pr.heads) {   // id()/desc() are validated for every record (:429-430)
+                const size_t sp = h.find(' ');
+                if (!valid_utf8(sp == std::string::npos ? h : h.substr(0, sp)) ||
+                    (sp != std::string::npos && !valid_utf8(h.substr(sp + 1))))
+                    throw std::runtime_error("invalid UTF-8 in FASTA header of species " + inputs[sid].name);
+            }
+            const size_t protein_base = ex.protein_names.size();
+            if (protein_base + n_rec > 0xFFFFFFFFull)   // :342-344
+                throw std::runtime_error("too many protein records across all species to index with u32");
+            for (const std::string& h : pr.heads) ex.protein_names.push_back(protein_name_of(h));
+            uint64_t ns = 0, ne = 0;
+            gpu.ok(kmn_fetch_hits(gpu.p, b.id, uint32_t(sid - b.sp0), nullptr, 0, &ns, nullptr, 0, &ne));
+            starts.resize(ns);
+            ends.resize(ne);
+            if (ns == 0 || ne == 0) continue;
+            gpu.ok(kmn_fetch_hits(gpu.p, b.id, uint32_t(sid - b.sp0), starts.data(), ns, &ns, ends.data(), ne, &ne));
+            size_t ei = 0;
+            uint32_t aa_rec = 0xFFFFFFFFu;
+            for (size_t si = 0; si < ns;) {
+                const uint32_t rec = starts[si].rec, seg = starts[si].seg_start;
+                size_t sj = si;
+                while (sj < ns && starts[sj].rec == rec && starts[sj].seg_start == seg) sj++;
+                while (ei < ne && (ends[ei].rec < rec || (ends[ei].rec == rec && ends[ei].seg_start < seg))) ei++;
+                size_t ej = ei;
+                while (ej < ne && ends[ej].rec == rec && ends[ej].seg_start == seg) ej++;
+                pick_cluster_starts(starts.data() + si, sj - si, picked);
+                // right anchor of every selected start (group_extraction.rs:178-242)
+                size_t first_end = ei;
+                for (const kmn_hit& left : picked) {
+                    const uint32_t left_end = left.start + uint32_t(k);
+                    while (first_end < ej && ends[first_end].start <= left_end) first_end++;
+                    const kmn_hit* best = nullptr;
+                    for (size_t j = first_end; j < ej; j++) {
+                        const kmn_hit& right = ends[j];
+                        if (right.start <= left_end) continue;
+                        if (right.start - left_end > length_middle) break;
+                        if (!best || right.occ > best->occ || (right.occ == best->occ && right.start < best->start)) best = &right;
+                    }
+                    if (!best) continue;
+                    if (aa_rec != rec) {   // strip + upper-case the record once (group_extraction.rs:455-482)
+                        aa.clear();
+                        for (uint64_t i = pr.rec_off[rec]; i < pr.rec_off[rec + 1]; i++) {
+                            const uint8_t c = pr.seq[i];
+                            if (c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0C || c == 0x0D) continue;
+                            aa.push_back((c >= 'a' && c <= 'z') ? uint8_t(c - 32) : c);
+                        }
+                        aa_rec = rec;
+                    }
+                    const size_t lo = size_t(seg) + left.start, hi = size_t(seg) + best->start + k;
+                    if (hi - lo > 0xFFFF)   // :92-94
+                        throw std::runtime_error("amino-acid block length " + std::to_string(hi - lo) + " exceeds u16::MAX");
+                    Observation o;
+                    o.left = left.kmer;
+                    o.right = best->kmer;
+                    o.sid = uint32_t(sid);
+                    o.protein = uint32_t(protein_base + rec);
+                    o.aa_off = ex.arena.size();
+                    o.len = uint32_t(hi - lo);
+                    o.order = order++;
+                    ex.arena.insert(ex.arena.end(), aa.begin() + lo, aa.begin() + hi);
+                    ex.obs.push_back(o);
+                }
+                si = sj;
+                ei = ej;
+            }
+        }
+    }
+    // group by anchor pair; inside a group keep emission order == the reference's Vec order (sid, then file order)
+    std::sort(ex.obs.begin(), ex.obs.end(), [](const Observation& a, const Observation& b) {
+        if (a.left != b.left) return a.left < b.left;
+        if (a.right != b.right) return a.right < b.right;
+        return a.order < b.order;
+    });
+    for (size_t i = 0; i < ex.obs.size(); i++)
+        if (i == 0 || ex.obs[i].left != ex.obs[i - 1].left || ex.obs[i].right != ex.obs[i - 1].right) ex.n_groups++;
+    return ex;
+}
+
+}  // namespace kh

@@ -1,0 +1,291 @@
+// groups.cpp — candidate selection, non-overlap filter, column filtering and alignment assembly on
+// the flat observation table.  Equivalent to /root/reference/src/group_sorting.rs:10-380 and
+// /root/reference/src/group_filtering.rs:32-363.
+#include "kamino_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace kh {
+
+uint8_t recode(uint8_t b, Scheme s) {   // recode.rs:31-80
+    static const char* classes[3][6] = {
+        {"C", "AGPST", "DENQ", "HKR", "ILMV", "FWY"},
+        {"APST", "DENG", "QKR", "MIVL", "WC", "FYH"},
+        {"AGPS", "DENQHKRT", "MIL", "W", "FY", "CV"},
+    };
+    static uint8_t lut[3][256];
+    static const bool init = [] {
+        std::memset(lut, 255, sizeof lut);
+        for (int sc = 0; sc < 3; sc++)
+            for (int c = 0; c < 6; c++)
+                for (const char* p = classes[sc][c]; *p; p++) {
+                    lut[sc][uint8_t(*p)] = uint8_t(c);
+                    lut[sc][uint8_t(*p) + 32] = uint8_t(c);
+                }
+        return true;
+    }();
+    (void)init;
+    return lut[int(s)][b];
+}
+
+namespace {
+
+inline bool gap_or_x(uint8_t b) { return b == '-' || b == 'X'; }   // group_filtering.rs:32-35
+
+// Rolling recoded k-mers of a block (group_sorting.rs:155-244); f returns true to stop early.
+template <typename F>
+bool roll_block(const uint8_t* aa, size_t len, size_t k, Scheme scheme, F&& f) {
+    if (len < k) return false;
+    const uint64_t mask = 3 * k >= 64 ? ~0ull : ((1ull << (3 * k)) - 1);
+    uint64_t val = 0;
+    size_t have = 0;
+    for (size_t i = 0; i < len; i++) {
+        const uint8_t c = recode(aa[i], scheme);
+        if (c == 255) { val = 0; have = 0; continue; }
+        val = ((val << 3) | c) & mask;
+        if (have < k) have++;
+        if (have == k && f(val)) return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme scheme) {   // group_sorting.rs:329-380
+    std::vector<Candidate> cands;
+    const auto& obs = ex.obs;
+    std::vector<std::pair<uint32_t, uint32_t>> len_sid;
+    for (size_t g0 = 0; g0 < obs.size();) {
+        size_t g1 = g0;
+        while (g1 < obs.size() && obs[g1].left == obs[g0].left && obs[g1].right == obs[g0].right) g1++;
+        // support of every block length = number of DISTINCT species (group_sorting.rs:90-143);
+        // buckets are visited in first-appearance order, ties reject the group
+        len_sid.clear();
+        std::vector<uint32_t> lens_in_order;
+        for (size_t i = g0; i < g1; i++) {
+            len_sid.emplace_back(obs[i].len, obs[i].sid);
+            if (std::find(lens_in_order.begin(), lens_in_order.end(), obs[i].len) == lens_in_order.end())
+                lens_in_order.push_back(obs[i].len);
+        }
+        std::sort(len_sid.begin(), len_sid.end());
+        len_sid.erase(std::unique(len_sid.begin(), len_sid.end()), len_sid.end());
+        size_t best_len = 0, best_c = 0;
+        bool tie = false;
+        for (uint32_t len : lens_in_order) {
+            const size_t c = size_t(std::count_if(len_sid.begin(), len_sid.end(), [len](const auto& p) { return p.first == len; }));
+            if (c > best_c) { best_len = len; best_c = c; tie = false; }
+            else if (c == best_c) tie = true;
+        }
+        if (!tie && best_c >= ex.min_needed && best_len >= 2 * ex.k + 1) {
+            Candidate c;
+            c.left = obs[g0].left;
+            c.right = obs[g0].right;
+            c.coverage = best_c;
+            c.raw_len = best_len;
+            for (size_t i = g0; i < g1; i++) if (obs[i].len == best_len) c.rows.push_back(uint32_t(i));
+            cands.push_back(std::move(c));
+        }
+        g0 = g1;
+    }
+    // strongest first: coverage desc, length desc, key asc (group_sorting.rs:252-258)
+    std::sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) {
+        if (a.coverage != b.coverage) return a.coverage > b.coverage;
+        if (a.raw_len != b.raw_len) return a.raw_len > b.raw_len;
+        if (a.left != b.left) return a.left < b.left;
+        return a.right < b.right;
+    });
+    // greedy non-overlap on recoded overlap_k-mers (group_sorting.rs:12-22, :246-286)
+    const size_t overlap_k = ex.k < 10 ? 2 * ex.k + 1 : 21;
+    std::unordered_set<uint64_t> used;
+    std::vector<Candidate> kept;
+    for (Candidate& c : cands) {
+        bool clash = false;
+        for (uint32_t r : c.rows) {
+            const Observation& o = obs[r];
+            if (roll_block(ex.arena.data() + o.aa_off, o.len, overlap_k, scheme, [&](uint64_t v) { return used.count(v) != 0; })) {
+                clash = true;
+                break;
+            }
+        }
+        if (clash) continue;
+        for (uint32_t r : c.rows) {
+            const Observation& o = obs[r];
+            roll_block(ex.arena.data() + o.aa_off, o.len, overlap_k, scheme, [&](uint64_t v) { used.insert(v); return false; });
+        }
+        kept.push_back(std::move(c));
+    }
+    return kept;
+}
+
+namespace {
+
+inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+std::string trim(const std::string& s) {
+    size_t b = 0, e = s.size();
+    while (b < e && is_ws((unsigned char)s[b])) b++;
+    while (e > b && is_ws((unsigned char)s[e - 1])) e--;
+    return s.substr(b, e - b);
+}
+
+// Majority-rule label over the descriptions of the supporting proteins (group_filtering.rs:143-221).
+std::string consensus_protein_name(const Extraction& ex, const Candidate& c) {
+    std::vector<std::string> names;
+    for (uint32_t r : c.rows) {
+        const uint32_t pid = ex.obs[r].protein;
+        if (pid >= ex.protein_names.size()) continue;
+        const std::string t = trim(ex.protein_names[pid]);
+        size_t p = 0;
+        while (p < t.size() && !is_ws((unsigned char)t[p])) p++;
+        if (p >= t.size()) continue;
+        std::string d = trim(t.substr(p + 1));
+        if (!d.empty()) names.push_back(std::move(d));
+    }
+    if (names.empty()) return "";
+    struct Stat { size_t count, pos_sum, first_seen; };
+    std::unordered_map<std::string, Stat> stats;
+    size_t seen_order = 0;
+    for (const std::string& nm : names) {
+        std::unordered_set<std::string> in_name;
+        size_t pos = 0;
+        for (size_t i = 0; i < nm.size();) {
+            while (i < nm.size() && is_ws((unsigned char)nm[i])) i++;
+            if (i >= nm.size()) break;
+            size_t j = i;
+            while (j < nm.size() && !is_ws((unsigned char)nm[j])) j++;
+            std::string w = nm.substr(i, j - i);
+            i = j;
+            const size_t at = pos++;
+            if (!in_name.insert(w).second) continue;
+            auto it = stats.find(w);
+            if (it == stats.end()) stats.emplace(std::move(w), Stat{1, at, seen_order++});
+            else { it->second.count++; it->second.pos_sum += at; }
+        }
+    }
+    std::vector<std::pair<std::string, Stat>> maj;
+    for (auto& kv : stats) if (kv.second.count * 2 >= names.size()) maj.push_back(kv);
+    std::sort(maj.begin(), maj.end(), [](const auto& a, const auto& b) {
+        const size_t l = a.second.pos_sum * b.second.count, r = b.second.pos_sum * a.second.count;
+        if (l != r) return l < r;
+        if (a.second.first_seen != b.second.first_seen) return a.second.first_seen < b.second.first_seen;
+        return a.first < b.first;
+    });
+    std::string out;
+    for (size_t i = 0; i < maj.size(); i++) out += (i ? " " : "") + maj[i].first;
+    return out;
+}
+
+struct Built { std::vector<uint8_t> rows; size_t kept = 0; std::string name; bool ok = false; };
+
+Built build_group(const Extraction& ex, const Candidate& c, size_t n, size_t k, size_t constant, float min_freq,
+                  size_t mask, Scheme scheme) {   // group_filtering.rs:224-290
+    Built out;
+    out.name = consensus_protein_name(ex, c);
+    const size_t L = c.raw_len;
+    // one consensus row per isolate: '-' -> first aa; equal -> keep; different -> sticky 'X' (group_sorting.rs:288-308)
+    std::vector<uint8_t> rows(n * L, '-');
+    for (uint32_t r : c.rows) {
+        const Observation& o = ex.obs[r];
+        uint8_t* row = rows.data() + size_t(o.sid) * L;
+        const uint8_t* aa = ex.arena.data() + o.aa_off;
+        for (size_t i = 0; i < std::min<size_t>(L, o.len); i++) {
+            if (row[i] == '-') row[i] = aa[i];
+            else if (row[i] != aa[i]) row[i] = 'X';
+        }
+    }
+    if (L < k || L - k <= k) return out;
+    const size_t mid0 = k, mid1 = L - k;
+    if (mask > 0) {
+        // majority recoded state per column, lowest state wins ties (group_filtering.rs:37-67)
+        std::vector<int> cons(L, -1);
+        for (size_t col = 0; col < L; col++) {
+            size_t cnt[6] = {0, 0, 0, 0, 0, 0};
+            for (size_t s = 0; s < n; s++) {
+                const uint8_t b = rows[s * L + col];
+                if (gap_or_x(b)) continue;
+                const uint8_t rc = recode(b, scheme);
+                if (rc != 255) cnt[rc]++;
+            }
+            size_t best = 0;
+            for (int st = 0; st < 6; st++) if (cnt[st] > best) { best = cnt[st]; cons[col] = st; }
+        }
+        // rows with >= mask consecutive recoded mismatches are blanked with 'X' (group_filtering.rs:69-113)
+        for (size_t s = 0; s < n; s++) {
+            uint8_t* row = rows.data() + s * L;
+            size_t run = 0;
+            bool hit = false;
+            for (size_t col = 0; col < L; col++) {
+                if (cons[col] < 0 || gap_or_x(row[col])) { run = 0; continue; }
+                const uint8_t rc = recode(row[col], scheme);
+                if (rc == 255 || int(rc) == cons[col]) { run = 0; continue; }
+                if (++run >= mask) { hit = true; break; }
+            }
+            if (hit) std::memset(row, 'X', L);
+        }
+    }
+    const float thresh = 1.0f - min_freq;   // f32 (group_filtering.rs:254,274)
+    auto missing_ok = [&](size_t col) {
+        size_t miss = 0;
+        for (size_t s = 0; s < n; s++) miss += gap_or_x(rows[s * L + col]);
+        return float(miss) / float(n) <= thresh;
+    };
+    auto polymorphic = [&](size_t col) {   // group_filtering.rs:115-133
+        int first = -1;
+        for (size_t s = 0; s < n; s++) {
+            const uint8_t b = rows[s * L + col];
+            if (gap_or_x(b)) continue;
+            const uint8_t rc = recode(b, scheme);
+            if (rc == 255) continue;
+            if (first < 0) first = rc;
+            else if (first != int(rc)) return true;
+        }
+        return false;
+    };
+    std::vector<size_t> mid;
+    for (size_t col = mid0; col < mid1; col++) if (missing_ok(col)) mid.push_back(col);
+    if (mid.empty()) return out;
+    long p0 = -1, p1 = -1;
+    for (size_t i = 0; i < mid.size(); i++) if (polymorphic(mid[i])) { if (p0 < 0) p0 = long(i); p1 = long(i); }
+    if (p0 < 0) return out;
+    std::vector<size_t> keep(mid.begin() + p0, mid.begin() + p1 + 1);
+    for (size_t col = mid1; col < std::min(mid1 + std::min(constant, k), L); col++) if (missing_ok(col)) keep.push_back(col);
+    out.kept = keep.size();
+    out.rows.reserve(n * out.kept);
+    for (size_t s = 0; s < n; s++) for (size_t col : keep) out.rows.push_back(rows[s * L + col]);
+    out.ok = true;
+    return out;
+}
+
+}  // namespace
+
+Alignment filter_groups(const Extraction& ex, const std::vector<Candidate>& cands, float min_freq, size_t constant,
+                        size_t mask, Scheme scheme, size_t threads) {   // group_filtering.rs:292-363
+    const size_t n = ex.n_species, m = cands.size();
+    std::vector<Built> built(m);
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        for (size_t i; (i = next.fetch_add(1)) < m;) built[i] = build_group(ex, cands[i], n, ex.k, constant, min_freq, mask, scheme);
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < std::max<size_t>(1, std::min(threads, std::max<size_t>(m, 1))); t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    Alignment al;
+    al.species_names = ex.species_names;
+    al.concat.assign(n, {});
+    size_t pos = 0;
+    for (const Built& b : built) {   // candidate order == raw-candidate order (:339)
+        if (!b.ok) continue;
+        for (size_t s = 0; s < n; s++)
+            al.concat[s].insert(al.concat[s].end(), b.rows.begin() + s * b.kept, b.rows.begin() + (s + 1) * b.kept);
+        al.partitions.push_back({pos, pos + b.kept - 1, b.kept});
+        al.partition_names.push_back(b.name);
+        pos += b.kept;
+    }
+    return al;
+}
+
+}  // namespace kh

@@ -1,0 +1,96 @@
+// kamino_host.hpp — host side of the B200 pipeline (C++ above the C ABI of include/kamino_b200.h).
+//
+// kamino's CLI, input discovery, extraction bookkeeping, group sorting / filtering and output writers
+// stay host logic (north_star: "reference-equivalent host logic over the GPU-produced tables"); the
+// data-parallel front end (recode, k-mers, Bloom, count-min table, occupancy scan, pair counts) is
+// only ever computed by libkamino_b200.so — there is no host implementation of it in this tree.
+// Names mirror the reference's modules; each function cites the reference lines it is equivalent to
+// (paths under /root/reference).  Data structures are deliberately flat (sorted observation tables
+// instead of hash maps) so the grouping can later move to the device.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace kh {
+
+enum Scheme : int { Dayhoff6 = 0, SR6 = 1, KGB6 = 2 };
+
+struct Options {                     // src/lib.rs:119-175
+    std::string input_dir, input_file, output = "kamino";
+    bool has_dir = false, has_file = false, genomes = false, nj = false;
+    long k = -1, constant = -1;
+    float min_freq = 0.85f;
+    size_t length_middle = 35, mask = 5, threads = 1;
+    Scheme recode = SR6;
+    int device = 0;                  // new, non-breaking: CUDA ordinal (env KAMINO_DEVICE)
+    size_t batch_bytes = size_t(1) << 30;   // residues per kmn_count_batch call
+    bool quiet = false;
+};
+
+struct SpeciesFile { std::string name, path; };      // src/io.rs:51-58
+
+// io.rs
+std::vector<SpeciesFile> inputs_from_directory(const std::string& dir);   // io.rs:16-79
+std::vector<SpeciesFile> inputs_from_table(const std::string& tsv);       // io.rs:82-162
+std::string species_name_of(const std::string& path);                      // io.rs:164-183
+
+// One proteome as the front end wants it: all rec.seq() bytes back to back + record offsets,
+// plus the raw header lines (needed only when a record contributes a block).
+struct Proteome {
+    std::vector<uint8_t> seq;          // concatenated seq() bytes (line terminators included)
+    std::vector<uint64_t> rec_off;     // [n_rec + 1]
+    std::vector<std::string> heads;    // header line without '>' / CR
+};
+Proteome load_proteome(const std::string& path);      // io.rs:185-200 + seq_io::fasta::Reader
+
+// One observed block between an anchor pair (group_extraction.rs:118-127), flat form.
+struct Observation {
+    uint64_t left, right;              // anchor pair (group_extraction.rs:117)
+    uint32_t sid;                      // species index
+    uint32_t protein;                  // index into Extraction::protein_names
+    uint64_t aa_off;                   // offset into Extraction::arena
+    uint32_t len;                      // block length (<= u16::MAX enforced)
+    uint64_t order;                    // emission order (stable tie-break == reference Vec order)
+};
+
+struct Extraction {                    // RawExtractedGroups, group_extraction.rs:510-525
+    std::vector<std::string> species_names, protein_names;
+    std::vector<uint8_t> arena;
+    std::vector<Observation> obs;      // sorted by (left, right, order) once extraction is finished
+    size_t k = 0, min_needed = 0, n_species = 0, n_groups = 0;
+};
+
+struct Candidate {                     // RawDirectCandidate, group_sorting.rs:79-88
+    uint64_t left, right;
+    size_t coverage, raw_len;
+    std::vector<uint32_t> rows;        // indices into Extraction::obs with the selected length
+};
+
+struct Alignment {                     // AlignmentResult, group_filtering.rs:12-21
+    std::vector<std::string> species_names, partition_names;
+    std::vector<std::vector<uint8_t>> concat;
+    struct Part { size_t start, end, len; };
+    std::vector<Part> partitions;
+};
+
+// group_extraction.rs:527-660 with both passes on the GPU (kmn_count_batch / kmn_scan_batch).
+Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
+                          Scheme scheme, const Options& opt);
+// group_sorting.rs:329-380
+std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme scheme);
+// group_filtering.rs:292-363
+Alignment filter_groups(const Extraction& ex, const std::vector<Candidate>& cands, float min_freq, size_t constant,
+                        size_t mask, Scheme scheme, size_t threads);
+// output.rs:32-95 (+ phylo.rs:274-301 with the pair counts from kmn_pair_counts)
+void write_outputs(const std::string& out_base, const Alignment& al, bool nj, int device, size_t* total_len,
+                   double* pct_missing);
+// lib.rs:206-298
+void run(const Options& opt);
+int cli(int argc, char** argv);
+
+uint8_t recode(uint8_t b, Scheme s);   // recode.rs:31-80 (host copy for the column filters of group_filtering.rs)
+
+}  // namespace kh

@@ -1,0 +1,67 @@
+"""End-to-end parity of the product pipeline (`kamino-b200`: C++ host + CUDA front end) against the
+reference's goldens and against the oracle CLI on synthetic proteome sets: alignment, missing-data
+table, partitions and NJ tree must be byte-identical."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from kamino_b200 import synth
+
+pytestmark = pytest.mark.gpu
+FILES = ["kamino_alignment.fas", "kamino_missing.tsv", "kamino_partitions.tsv", "kamino_NJ.tree"]
+
+
+@pytest.fixture(scope="module")
+def product_cli():
+    from kamino_b200 import build
+    return build.build_host()
+
+
+def _run(cli, args):
+    r = subprocess.run([str(cli), *map(str, args)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+@pytest.mark.parametrize("mode,scheme", [("dir", "dayhoff6"), ("tsv", "kgb6")])
+def test_golden_3diff_through_gpu(product_cli, golden_dir, tmp_path, mode, scheme):
+    """tests/golden.rs:96-124 with both passes and the --nj counts on the GPU."""
+    src = golden_dir / "test_3diff"
+    args = ["-i", src / "input"] if mode == "dir" else ["-I", src / "input.tsv"]
+    _run(product_cli, [*args, "--length-middle", 35, "--recode", scheme, "--nj", "-t", 2, "-o", tmp_path / "kamino"])
+    for f in FILES:
+        assert (tmp_path / f).read_text() == (src / "expected" / f).read_text(), f
+
+
+@pytest.fixture(scope="module")
+def synthetic_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synth")
+    species = synth.species_set(24, 500, 300.0, seed=21)
+    synth.write_fasta_dir(species, d / "in")
+    return d
+
+
+@pytest.mark.parametrize("extra", [
+    [], ["-r", "dayhoff6", "-k", 11], ["-r", "kgb6", "-f", 0.7, "-l", 50], ["-k", 8, "-c", 2, "-m", 3],
+    ["-k", 21, "-f", 0.6], ["--batch-bytes", 700000],
+])
+def test_synthetic_matches_oracle_cli(product_cli, oracle, synthetic_dir, tmp_path, extra):
+    want, got = tmp_path / "want", tmp_path / "got"
+    want.mkdir(); got.mkdir()
+    common = ["-i", synthetic_dir / "in", "--nj", "-t", 4, *extra]
+    r = oracle.run_cli([*common, "-o", want / "kamino"])
+    assert r.returncode == 0, r.stderr
+    _run(product_cli, [*common, "-o", got / "kamino"])
+    for f in FILES:
+        assert (got / f).read_bytes() == (want / f).read_bytes(), (f, extra)
+    aln = (got / "kamino_alignment.fas").read_text().splitlines()
+    assert len(aln) >= 48 and len(aln[1]) > 0, "expected a non-empty alignment on related proteomes"
+
+
+def test_cli_errors(product_cli, golden_dir, tmp_path):
+    src = golden_dir / "test_3diff" / "input"
+    for bad in (["-k", 22], ["-f", 0.5], ["-t", 0], ["-c", 14], ["--genomes"], ["--frobnicate"]):
+        r = subprocess.run([str(product_cli), "-i", str(src), "-o", str(tmp_path / "x"), *map(str, bad)],
+                           capture_output=True, text=True)
+        assert r.returncode != 0, bad
