@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 namespace kh {
@@ -101,13 +102,16 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     const float nf = float(n < 1 ? size_t(1) : n);
     volatile float prod = min_freq * nf;                       // f32 arithmetic, group_extraction.rs:544
     const uint32_t min_needed = uint32_t(std::ceil(float(prod)));
-    Ctx gpu(opt.device, int(k), int(scheme));
+    std::unique_ptr<Ctx> gpu_holder;
+    { StageTimer t("kmn_create"); gpu_holder = std::make_unique<Ctx>(opt.device, int(k), int(scheme)); }
+    Ctx& gpu = *gpu_holder;
 
     // ---- load every proteome (host threads; gunzip + framing only)
     if (!opt.quiet) std::fprintf(stderr, " . pass 1: estimate k-mer occupancies\n");
     std::vector<Proteome> prot(n);
     std::vector<std::string> errs(n);
     {
+        StageTimer t("load proteomes");
         std::atomic<size_t> next{0};
         auto work = [&] {
             for (size_t i; (i = next.fetch_add(1)) < n;) {
@@ -122,6 +126,7 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);   // first error in species order (:569-571)
 
     // ---- pass 1: batches of whole species through kmn_count_batch
+    auto t_p1 = std::make_unique<StageTimer>("pass 1 (stage + count + finalize)");
     struct BatchRef { uint32_t id; size_t sp0, sp1; };
     std::vector<BatchRef> batches;
     std::vector<uint8_t> buf;
@@ -151,6 +156,8 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         s0 = s1;
     }
     gpu.ok(kmn_finalize_table(gpu.p));   // snapshot (:576)
+    t_p1.reset();
+    auto t_p2 = std::make_unique<StageTimer>("pass 2 (scan + pairing)");
 
     // ---- pass 2: boundary hits from the device, pairing on the host, merged in sid order (:611-636)
     if (!opt.quiet) std::fprintf(stderr, " . pass 2: extract sequences\n");
@@ -235,6 +242,8 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
             }
         }
     }
+    t_p2.reset();
+    StageTimer t_sort("group observations");
     // group by anchor pair; inside a group keep emission order == the reference's Vec order (sid, then file order)
     std::sort(ex.obs.begin(), ex.obs.end(), [](const Observation& a, const Observation& b) {
         if (a.left != b.left) return a.left < b.left;

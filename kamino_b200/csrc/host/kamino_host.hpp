@@ -91,6 +91,14 @@ void write_outputs(const std::string& out_base, const Alignment& al, bool nj, in
 void run(const Options& opt);
 int cli(int argc, char** argv);
 
-uint8_t recode(uint8_t b, Scheme s);   // recode.rs:31-80 (host copy for the column filters of group_filtering.rs)
+uint8_t recode(uint8_t b, Scheme s);
+
+// Wall-clock stage timer: prints "[time] <what>: <s>" to stderr when KAMINO_TIMING is set.
+struct StageTimer {
+    const char* what;
+    double t0;
+    explicit StageTimer(const char* w);
+    ~StageTimer();
+};   // recode.rs:31-80 (host copy for the column filters of group_filtering.rs)
 
 }  // namespace kh

@@ -11,11 +11,22 @@
 #include <cstring>
 #include <filesystem>
 #include <limits>
+#include <ctime>
 #include <set>
 
 namespace fs = std::filesystem;
 
 namespace kh {
+
+static double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+}
+StageTimer::StageTimer(const char* w) : what(w), t0(now_s()) {}
+StageTimer::~StageTimer() {
+    if (std::getenv("KAMINO_TIMING")) std::fprintf(stderr, "[time] %s: %.3f s\n", what, now_s() - t0);
+}
 
 namespace {
 
@@ -213,15 +224,18 @@ void run(const Options& o) {   // lib.rs:206-298
     if (!o.quiet) std::fprintf(stderr, "# process input files\n");
     if (o.genomes) throw std::runtime_error("--genomes (protein prediction) is not part of the GPU front end");
     if (inputs.empty()) throw std::runtime_error("At least one input source with files must be provided.");
+    StageTimer t_all("total");
     Extraction ex = extract_groups(inputs, k, o.min_freq, o.length_middle, o.recode, o);
     if (!o.quiet) std::fprintf(stderr, "# analyse variant groups\n . raw variant groups: %zu\n", ex.n_groups);
-    std::vector<Candidate> cands = sort_and_deduplicate_groups(ex, o.recode);
+    std::vector<Candidate> cands;
+    { StageTimer t("sort_and_deduplicate_groups"); cands = sort_and_deduplicate_groups(ex, o.recode); }
     if (!o.quiet) std::fprintf(stderr, " . sorted variant groups: %zu\n", cands.size());
-    Alignment al = filter_groups(ex, cands, o.min_freq, constant, o.mask, o.recode, o.threads);
+    Alignment al;
+    { StageTimer t("filter_groups"); al = filter_groups(ex, cands, o.min_freq, constant, o.mask, o.recode, o.threads); }
     if (!o.quiet) std::fprintf(stderr, " . filtered variant groups: %zu\n", al.partitions.size());
     size_t alen = 0;
     double amiss = 0;
-    write_outputs(o.output, al, o.nj, o.device, &alen, &amiss);
+    { StageTimer t("write_outputs (+NJ)"); write_outputs(o.output, al, o.nj, o.device, &alen, &amiss); }
     if (!o.quiet) std::fprintf(stderr, "# output files\n . alignment: length=%zu missing=%.1f%%\n", alen, amiss);
     if (o.nj && !o.quiet) std::fprintf(stderr, " . NJ tree\n");
 }
