@@ -229,8 +229,8 @@ def run_gpu(args):
         elif fused:
             sharding.fused_exchange(ctx)                 # one kernel: P2P reduce + clamp + all-gather
         else:
-            ctx.synchronize()
-            sharding.exchange_accumulators(acc_t)        # the sketch is linear: sum of per-rank accumulators
+            ctx.table_widen()                            # u16 cells -> summable u32 copy
+            sharding.exchange_accumulators(acc_t)        # the sketch is linear: sum of the per-rank tables
             torch.cuda.synchronize()
             ctx.finalize_table()
 

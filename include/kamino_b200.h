@@ -48,9 +48,9 @@ typedef struct kmn_hit {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);
+uint32_t kmn_abi_version(void);   /* currently 2 */
 
-/* Context: owns the device, its stream, the count-min accumulators (AtomicCountMinSketch::new,
+/* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
  * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.
  * k in 1..=21 (lib.rs:208-218); scheme = KMN_*.  device = CUDA ordinal. */
 int  kmn_create(kmn_ctx** out, int device, int k, int scheme);
@@ -76,29 +76,37 @@ int kmn_count_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_o
 int kmn_stage_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
 int kmn_count_staged(kmn_ctx* ctx, uint32_t batch_id, uint64_t* new_kmers_per_species);
-/* Zero the accumulators (a fresh AtomicCountMinSketch). */
+/* Zero the table (a fresh AtomicCountMinSketch). */
 int kmn_reset_table(kmn_ctx* ctx);
 /* Drop every staged batch (frees their HBM). */
 int kmn_release_batches(kmn_ctx* ctx);
 
-/* AtomicCountMinSketch::snapshot (proba_filter.rs:171-177): clamp the accumulators to the
- * saturating u16 table.  After this the table is read-only until kmn_reset_table. */
+/* AtomicCountMinSketch::snapshot (proba_filter.rs:171-177).  The device table is kept as the
+ * reference's saturating u16 table at all times (every update is +1, so adding a batch's exact
+ * per-cell count with a clamp at 65535 equals the CAS loop of proba_filter.rs:151-166): on one GPU
+ * this only marks the table read-only until kmn_reset_table; after kmn_table_widen + an external sum
+ * it clamps the summed u32 cells back into the table. */
 int kmn_finalize_table(kmn_ctx* ctx);
 /* Copy the finalized table to host: 4 * 2^26 u16, row-major == CountMinSketch.table. */
 int kmn_table_snapshot(kmn_ctx* ctx, uint16_t* out);
 /* Load a finalized table from host (pass 2 against an externally built table). */
 int kmn_table_load(kmn_ctx* ctx, const uint16_t* table);
-/* Multi-GPU plumbing: device pointer of the u32 accumulators (KMN_CMS_CELLS entries, summable
- * across ranks because the sketch is linear) and of the finalized u16 table. */
+/* Multi-GPU plumbing, NCCL variant.  Partial tables of several GPUs combine exactly as
+ * min(sum over ranks, 65535) (a clamped partial only ever replaces a value >= 65535).
+ * kmn_table_widen copies this rank's u16 cells into a u32 buffer (KMN_CMS_CELLS entries) whose device
+ * pointer kmn_table_accum_device_ptr returns (stable for the context's life); the caller sums that
+ * buffer across ranks (ncclSum on u32) and then calls kmn_finalize_table.
+ * kmn_table_device_ptr: the u16 table (the finalized one once finalized / exchanged). */
 int kmn_table_accum_device_ptr(kmn_ctx* ctx, void** ptr);
+int kmn_table_widen(kmn_ctx* ctx);
 int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
-/* Fused NVLink exchange (one process per GPU): every rank exports CUDA IPC handles of its accumulators
- * and of its finalized table (64 bytes each); after an all-gather of the handles by the caller,
+/* Fused NVLink exchange (one process per GPU): every rank exports CUDA IPC handles of its own table
+ * and of its exchanged table (64 bytes each); after an all-gather of the handles by the caller,
  * kmn_exchange_setup maps the peers' buffers.  kmn_exchange_reduce then runs ONE kernel per rank that
- * loads this rank's 1/world cell range from every peer over NVLink, sums, clamps to u16
+ * loads this rank's 1/world cell range from every peer over NVLink, adds with saturation
  * (== snapshot of the summed sketch, proba_filter.rs:171-177) and stores the result into EVERY peer's
- * table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The caller must
- * barrier across ranks after counting (before the call) and after kmn_synchronize (after the call). */
+ * exchanged table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The caller
+ * must barrier across ranks after counting (before the call) and after kmn_synchronize (after the call). */
 int kmn_exchange_export(kmn_ctx* ctx, uint8_t* acc_handle64, uint8_t* table_handle64);
 int kmn_exchange_setup(kmn_ctx* ctx, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles);
 int kmn_exchange_reduce(kmn_ctx* ctx);

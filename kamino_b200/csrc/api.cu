@@ -3,6 +3,7 @@
 // Host-side orchestration of the sm_100a kernels.  There is deliberately no CPU code path: every
 // entry point either runs the CUDA kernels or fails with an error message.
 #include "../../include/kamino_b200.h"
+#include "cms_kernels.cuh"
 #include "count_kernels.cuh"
 #include "frame_kernels.cuh"
 #include "pair_kernels.cuh"
@@ -102,8 +103,11 @@ struct kmn_ctx {
     RecodeLut lut;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    DevBuf<uint32_t> acc;                 // 4 x 2^26 u32 accumulators (1 GiB)
-    DevBuf<uint16_t> cms;                 // finalized table (512 MiB)
+    DevBuf<uint16_t> tab;                 // 4 x 2^26 saturating u16 cells (512 MiB): THE count-min table
+    DevBuf<uint16_t> xtab;                // table after the fused multi-GPU exchange (allocated on setup)
+    DevBuf<uint32_t> wide;                // u32 widening of the table for the NCCL variant (allocated on demand)
+    bool widened = false;
+    const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
     bool finalized = false;
     DevBuf<unsigned long long> first;     // MAX_GROUP_SPECIES x 2^25 first-touch tags (4 GiB)
     uint32_t epoch = 1;                   // next species epoch (0 = never written)
@@ -120,8 +124,11 @@ struct kmn_ctx {
     uint64_t launches = 0;
     uint32_t bloom_group = 16;            // species per Bloom launch (bitsets of a group stay in L2)
     DevBuf<uint32_t> bl_bits, bl_multi, bl_fw, late_list, late_count;
-    DevBuf<uint32_t> idx[CMS_DEPTH];      // per-row CMS cell index streams (scratch of count_staged)
-    uint32_t cms_slices_per_row = 4;      // L2-sliced CMS sweep: 4 rows x N slices
+    DevBuf<uint16_t> cms_ent;             // bucket lists of the CMS partition (scratch of count_staged)
+    DevBuf<uint32_t> cms_cursor, cms_spill, cms_state;
+    int cms_force = 0;                    // test knob: 1 = exact (u32) redo in every bucket, 2 = direct fallback
+    uint32_t cms_cap_override = 0;        // test knob: bucket list capacity (forces the list-full fallback)
+    uint32_t cms_slot_limit = PART_SLOT;  // test knob: staged entries per bucket and tile (forces spills)
 };
 
 namespace {
@@ -271,27 +278,37 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     }
     KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (b.n_codes > 0) {
-        // hash once: 4 index streams (scratch, 16 B per codes[] position, whole warp tiles)
         const uint32_t n_wtiles = (b.n_codes + WARP_TILE - 1) / WARP_TILE;
-        IndexStreams ix;
-        for (uint32_t r = 0; r < CMS_DEPTH; r++) {
-            c->idx[r].ensure(size_t(n_wtiles) * WARP_TILE);
-            ix.row[r] = c->idx[r].p;
+        CmsLists L;
+        // expected list length <= n_codes / 1024 (every position new, uniform hashing); +25 % and a constant
+        // cover the correlation between species that share k-mers.  A full list is not an error: the batch
+        // then takes the exact direct path (cms_direct_kernel).
+        L.cap = c->cms_cap_override ? c->cms_cap_override
+                                    : uint32_t((uint64_t(b.n_codes) / CMS_BUCKETS_PER_ROW * 5 / 4 + 4096 + 7) / 8 * 8);
+        L.spill_cap = b.n_codes / 64 + 65536;
+        c->cms_ent.ensure(size_t(CMS_BUCKETS) * L.cap);
+        c->cms_spill.ensure(L.spill_cap);
+        L.ent = c->cms_ent.p;
+        L.cursor = c->cms_cursor.p;
+        L.spill = c->cms_spill.p;
+        L.state = c->cms_state.p;
+        KMN_CUDA(cudaMemsetAsync(L.cursor, 0, CMS_BUCKETS * sizeof(uint32_t), c->stream));
+        KMN_CUDA(cudaMemsetAsync(L.state, 0, 2 * sizeof(uint32_t), c->stream));
+        if (c->cms_force == 2) {
+            const uint32_t one = 1;
+            KMN_CUDA(cudaMemcpyAsync(L.state, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            const uint32_t n_ptiles = (n_wtiles + PART_WTILES - 1) / PART_WTILES;
+            cms_partition_kernel<<<std::min<uint32_t>(n_ptiles, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
+                b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, L, c->cms_slot_limit);
+            check_launch(c);
+            cms_apply_kernel<<<CMS_BUCKETS, APPLY_THREADS, APPLY_SMEM, c->stream>>>(L, c->tab.p, c->cms_force == 1);
+            check_launch(c);
+            cms_spill_kernel<<<grid_for(c, 2), 256, 0, c->stream>>>(L, c->tab.p);
+            check_launch(c);
         }
-        cms_index_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, ix);
+        cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, c->tab.p, L.state);
         check_launch(c);
-        // L2-sliced sweep: rows x slices launches over the per-row index streams
-        uint32_t log2s = 0;
-        while ((1u << log2s) < c->cms_slices_per_row) log2s++;
-        const uint32_t slice_shift = CMS_WIDTH_LOG2 - log2s;
-        const uint32_t n_vec = (b.n_codes + 3) / 4;
-        for (uint32_t r = 0; r < CMS_DEPTH; r++)
-            for (uint32_t q = 0; q < (1u << log2s); q++) {
-                cms_sweep_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(
-                    reinterpret_cast<const uint4*>(c->idx[r].p), n_vec, slice_shift, q,
-                    c->acc.p + (size_t(r) << CMS_WIDTH_LOG2));
-                check_launch(c);
-            }
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
     std::vector<unsigned long long> h(b.n_sp);
@@ -307,13 +324,19 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
 }
 
 void finalize_table(kmn_ctx* c) {
+    // The table is the saturating u16 snapshot at all times (cms_kernels.cuh); only the NCCL variant,
+    // which summed a widened copy across ranks, has something to clamp back.
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    cms_finalize_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->acc.p),
-                                                             reinterpret_cast<uint2*>(c->cms.p), CMS_CELLS / 4);
-    check_launch(c);
+    if (c->widened) {
+        cms_narrow_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->wide.p),
+                                                               reinterpret_cast<uint2*>(c->tab.p), CMS_CELLS / 4);
+        check_launch(c);
+        c->widened = false;
+    }
     KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
+    c->final_tab = c->tab.p;
     c->finalized = true;
 }
 
@@ -325,7 +348,7 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     b.occ.ensure(size_t(n_tiles + 1) * WARP_TILE);
     const int grid = grid_for(c, 8);
     if (n_tiles) {
-        occupancy_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(b.codes.p, n_tiles, c->k, c->k_mask, c->cms.p, b.occ.p);
+        occupancy_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(b.codes.p, n_tiles, c->k, c->k_mask, c->final_tab, b.occ.p);
         check_launch(c);
     }
     // reset positions -> segments
@@ -441,7 +464,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 1; }
+uint32_t kmn_abi_version(void) { return 2; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
@@ -462,10 +485,20 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         c->scheme = scheme;
         c->k_mask = (3 * k >= 64) ? ~0ull : ((1ull << (3 * k)) - 1);  // group_extraction.rs:545-549
         c->lut = make_lut(scheme);
-        if (const char* e = std::getenv("KMN_CMS_SLICES_PER_ROW")) {  // tuning knob (power of two, 0 = off)
+        if (const char* e = std::getenv("KMN_CMS_FORCE")) {   // test knob: exercise the rare exact paths
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 1 || v > 64 || (v & (v - 1))) throw std::runtime_error("KMN_CMS_SLICES_PER_ROW must be a power of two in 1..64");
-            c->cms_slices_per_row = uint32_t(v);
+            if (v < 0 || v > 2) throw std::runtime_error("KMN_CMS_FORCE must be 0, 1 or 2");
+            c->cms_force = int(v);
+        }
+        if (const char* e = std::getenv("KMN_CMS_SLOT")) {    // test knob: small slots -> many spills
+            const long v = std::strtol(e, nullptr, 10);
+            if (v < 1 || v > PART_SLOT) throw std::runtime_error("KMN_CMS_SLOT must be in 1..32");
+            c->cms_slot_limit = uint32_t(v);
+        }
+        if (const char* e = std::getenv("KMN_CMS_CAP")) {     // test knob: tiny bucket lists
+            const long v = std::strtol(e, nullptr, 10);
+            if (v < 8 || v > (1l << 30) || v % 8) throw std::runtime_error("KMN_CMS_CAP must be a multiple of 8");
+            c->cms_cap_override = uint32_t(v);
         }
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -479,10 +512,13 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         c->bl_multi.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_WORDS_LOG2);
         c->bl_fw.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_WORDS_LOG2);
         c->late_count.alloc(1);
-        c->acc.alloc(CMS_CELLS);
-        c->cms.alloc(CMS_CELLS);
+        c->tab.alloc(CMS_CELLS);
+        c->cms_cursor.alloc(CMS_BUCKETS);
+        c->cms_state.alloc(2);
+        KMN_CUDA(cudaFuncSetAttribute(cms_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PART_SMEM)));
+        KMN_CUDA(cudaFuncSetAttribute(cms_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(APPLY_SMEM)));
         c->first.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_BITS_LOG2);
-        KMN_CUDA(cudaMemsetAsync(c->acc.p, 0, CMS_CELLS * sizeof(uint32_t), c->stream));
+        KMN_CUDA(cudaMemsetAsync(c->tab.p, 0, CMS_CELLS * sizeof(uint16_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         *out = c.release();
@@ -527,8 +563,10 @@ int kmn_count_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off
 
 int kmn_reset_table(kmn_ctx* c) {
     return guarded(c, [&] {
-        KMN_CUDA(cudaMemsetAsync(c->acc.p, 0, CMS_CELLS * sizeof(uint32_t), c->stream));
+        KMN_CUDA(cudaMemsetAsync(c->tab.p, 0, CMS_CELLS * sizeof(uint16_t), c->stream));
         c->finalized = false;
+        c->widened = false;
+        c->final_tab = nullptr;
     });
 }
 
@@ -547,7 +585,7 @@ int kmn_table_snapshot(kmn_ctx* c, uint16_t* out) {
     return guarded(c, [&] {
         if (!out) throw std::runtime_error("out must not be NULL");
         if (!c->finalized) throw std::runtime_error("table not finalized");
-        KMN_CUDA(cudaMemcpyAsync(out, c->cms.p, CMS_CELLS * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(out, c->final_tab, CMS_CELLS * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
     });
 }
@@ -555,21 +593,46 @@ int kmn_table_snapshot(kmn_ctx* c, uint16_t* out) {
 int kmn_table_load(kmn_ctx* c, const uint16_t* table) {
     return guarded(c, [&] {
         if (!table) throw std::runtime_error("table must not be NULL");
-        KMN_CUDA(cudaMemcpyAsync(c->cms.p, table, CMS_CELLS * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(c->tab.p, table, CMS_CELLS * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->widened = false;
+        c->final_tab = c->tab.p;
         c->finalized = true;
     });
 }
 
-int kmn_table_accum_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->acc.p; }); }
-int kmn_table_device_ptr(kmn_ctx* c, void** ptr) { return guarded(c, [&] { *ptr = c->cms.p; }); }
+int kmn_table_accum_device_ptr(kmn_ctx* c, void** ptr) {
+    return guarded(c, [&] {
+        if (!ptr) throw std::runtime_error("ptr must not be NULL");
+        if (!c->wide.p) c->wide.alloc(CMS_CELLS);
+        *ptr = c->wide.p;
+    });
+}
+int kmn_table_widen(kmn_ctx* c) {
+    return guarded(c, [&] {
+        if (c->finalized) throw std::runtime_error("table is finalized");
+        if (!c->wide.p) c->wide.alloc(CMS_CELLS);
+        cms_widen_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint2*>(c->tab.p),
+                                                              reinterpret_cast<uint4*>(c->wide.p), CMS_CELLS / 4);
+        check_launch(c);
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->widened = true;
+    });
+}
+int kmn_table_device_ptr(kmn_ctx* c, void** ptr) {
+    return guarded(c, [&] {
+        if (!ptr) throw std::runtime_error("ptr must not be NULL");
+        *ptr = const_cast<uint16_t*>(c->finalized ? c->final_tab : c->tab.p);
+    });
+}
 int kmn_exchange_export(kmn_ctx* c, uint8_t* acc_handle64, uint8_t* table_handle64) {
     return guarded(c, [&] {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        if (!c->xtab.p) c->xtab.alloc(CMS_CELLS);
         cudaIpcMemHandle_t h;
-        KMN_CUDA(cudaIpcGetMemHandle(&h, c->acc.p));
+        KMN_CUDA(cudaIpcGetMemHandle(&h, c->tab.p));
         std::memcpy(acc_handle64, &h, 64);
-        KMN_CUDA(cudaIpcGetMemHandle(&h, c->cms.p));
+        KMN_CUDA(cudaIpcGetMemHandle(&h, c->xtab.p));
         std::memcpy(table_handle64, &h, 64);
     });
 }
@@ -577,7 +640,8 @@ int kmn_exchange_export(kmn_ctx* c, uint8_t* acc_handle64, uint8_t* table_handle
 int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles) {
     return guarded(c, [&] {
         if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) throw std::runtime_error("invalid world / rank");
-        if (CMS_CELLS / 4 % uint64_t(world)) throw std::runtime_error("world size must divide the table");
+        if (CMS_CELLS / 8 % uint64_t(world)) throw std::runtime_error("world size must divide the table");
+        if (!c->xtab.p) c->xtab.alloc(CMS_CELLS);
         for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
         c->ipc_opened.clear();
         c->peers = PeerTables{};
@@ -585,8 +649,8 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
         c->peers.rank = rank;
         for (int p = 0; p < world; p++) {
             if (p == rank) {
-                c->peers.acc[p] = reinterpret_cast<const uint4*>(c->acc.p);
-                c->peers.cms[p] = reinterpret_cast<uint2*>(c->cms.p);
+                c->peers.part[p] = reinterpret_cast<const uint4*>(c->tab.p);
+                c->peers.full[p] = reinterpret_cast<uint4*>(c->xtab.p);
                 continue;
             }
             cudaIpcMemHandle_t h;
@@ -594,11 +658,11 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
             std::memcpy(&h, acc_handles + 64 * p, 64);
             KMN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(ptr);
-            c->peers.acc[p] = reinterpret_cast<const uint4*>(ptr);
+            c->peers.part[p] = reinterpret_cast<const uint4*>(ptr);
             std::memcpy(&h, table_handles + 64 * p, 64);
             KMN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(ptr);
-            c->peers.cms[p] = reinterpret_cast<uint2*>(ptr);
+            c->peers.full[p] = reinterpret_cast<uint4*>(ptr);
         }
         c->peers_ready = true;
     });
@@ -607,13 +671,14 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
 int kmn_exchange_reduce(kmn_ctx* c) {
     return guarded(c, [&] {
         if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
-        const uint64_t n_vec = CMS_CELLS / 4, per = n_vec / uint64_t(c->peers.world);
+        const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(c->peers.world);   // uint4 = 8 cells
         KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
         exchange_reduce_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(c->peers, per * c->peers.rank, per * (c->peers.rank + 1));
         check_launch(c);
         KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
+        c->final_tab = c->xtab.p;
         c->finalized = true;   // valid once every rank's kernel has finished (caller barriers)
     });
 }

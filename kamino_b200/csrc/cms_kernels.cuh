@@ -1,0 +1,275 @@
+// cms_kernels.cuh — count-min build of pass 1 (AtomicCountMinSketch::increment / snapshot,
+// /root/reference/src/proba_filter.rs:146-177) as partition -> shared-memory histogram -> merge.
+//
+// Measured on B200 (tools/microbench/l2_atomics.cu): scattered RED.add into an L2-resident slice
+// runs at ~190 Gop/s chip-wide, into HBM at ~23-34 Gop/s, while shared-memory atomics run at
+// ~1000 Gop/s.  So the 4 x (new k-mers) increments never touch global memory as atomics:
+//
+//   cms_partition_kernel  each CTA hashes a tile of 16 Ki positions ONCE (k-mers stay in registers for
+//                         the four rows) and splits the cell indices of one row at a time over the
+//                         row's 1024 buckets of 2^16 cells: rank = shared atomicAdd on the bucket's
+//                         fill counter, the low 16 index bits go to a fixed 32-entry slot in shared
+//                         memory, and each bucket's slot is appended to its global list as one run
+//                         (one global atomicAdd per bucket and tile reserves the space).
+//   cms_apply_kernel      one CTA per bucket: a 128 KiB shared-memory histogram (two u16 counters per
+//                         word) of the bucket's list, then  cell = min(cell + count, 65535)  on the
+//                         u16 table by the bucket's only owner — no global atomics, no u32
+//                         accumulators, no separate snapshot pass.
+//
+// The table itself is the reference's saturating u16 table at all times: every update is +1 and
+// saturation is monotone, so adding a batch's exact per-cell count with a clamp is bit-identical to
+// the CAS loop of proba_filter.rs:151-166, and partial tables of several GPUs combine as
+// min(sum_of_clamped, 65535) == min(sum, 65535).
+//
+// Rare paths, all exact: a slot that overflows inside a tile spills single entries to a global list
+// (cms_spill_kernel, CAS loop on the u16 cell); a shared counter that would pass 65535 inside one
+// batch makes the CTA redo its bucket with u32 counters in two halves; a bucket list or spill list
+// that runs out of space raises a flag that disables apply/spill and enables cms_direct_kernel,
+// which rebuilds the batch's increments with global CAS loops straight from codes[] + flags.
+#pragma once
+#include "kmn_device.cuh"
+
+namespace kmn {
+
+constexpr uint32_t CMS_BUCKET_LOG2 = 16;                                             // cells per bucket
+constexpr uint32_t CMS_BUCKETS_PER_ROW = 1u << (CMS_WIDTH_LOG2 - CMS_BUCKET_LOG2);    // 1024
+constexpr uint32_t CMS_BUCKETS = CMS_DEPTH * CMS_BUCKETS_PER_ROW;                     // 4096
+constexpr int PART_THREADS = 1024;                   // == CMS_BUCKETS_PER_ROW: thread t reserves bucket t
+constexpr int PART_TILE = PART_THREADS * CHUNK;      // 16384 positions per CTA tile
+constexpr int PART_WTILES = PART_TILE / WARP_TILE;   // one warp tile per warp
+constexpr int PART_SLOT = 32;                        // staged entries per bucket and tile (mean 16)
+constexpr size_t PART_SMEM = size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * sizeof(uint16_t) +
+                             size_t(CMS_BUCKETS_PER_ROW) * sizeof(uint32_t);
+constexpr int APPLY_THREADS = 1024;
+constexpr uint32_t APPLY_WORDS = 1u << (CMS_BUCKET_LOG2 - 1);   // 32768 u32 words = 2^16 u16 counters
+constexpr size_t APPLY_SMEM = size_t(APPLY_WORDS) * sizeof(uint32_t);
+static_assert(PART_THREADS == int(CMS_BUCKETS_PER_ROW), "one reserving thread per bucket");
+static_assert(PART_SLOT == 32, "copy-out moves one slot per warp instruction");
+
+struct CmsLists {
+    uint16_t* ent;      // [CMS_BUCKETS][cap]  low 16 bits of the cell index, in arrival order
+    uint32_t* cursor;   // [CMS_BUCKETS]       entries appended so far
+    uint32_t* spill;    // [spill_cap]         flat cell offsets (row << 26 | idx) of slot overflows
+    uint32_t* state;    // [0] fallback flag, [1] spill entries
+    uint32_t cap, spill_cap;
+};
+
+__device__ __forceinline__ uint64_t cms_seed(int r) {
+    return r == 0 ? SEED_CMS_0 : r == 1 ? SEED_CMS_1 : r == 2 ? SEED_CMS_2 : SEED_CMS_3;
+}
+
+// saturating +1 on one u16 cell of the global table (the CAS loop of proba_filter.rs:151-166)
+__device__ __forceinline__ void cms_cell_increment(uint16_t* __restrict__ tab, uint32_t cell) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(tab) + (cell >> 1);
+    const uint32_t sh = (cell & 1u) * 16u;
+    uint32_t old = *w;
+    for (;;) {
+        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) return;
+        const uint32_t seen = atomicCAS(w, old, old + (1u << sh));
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
+__global__ void __launch_bounds__(PART_THREADS, 1)
+cms_partition_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_wtiles,
+                     int k, uint64_t k_mask, CmsLists L, uint32_t slot_limit) {
+    extern __shared__ __align__(16) uint8_t part_smem[];
+    uint16_t* stage = reinterpret_cast<uint16_t*>(part_smem);                                   // [1024][32]
+    uint32_t* fill = reinterpret_cast<uint32_t*>(part_smem + size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * 2);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = (n_wtiles + PART_WTILES - 1) / PART_WTILES;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t wt = t * PART_WTILES + warp;
+        uint64_t kmer[CHUNK];
+        uint32_t new_bits = 0;
+        if (wt < n_wtiles) {   // warp-uniform
+            load_chunk_kmers<true>(codes, wt * WARP_TILE, k, k_mask, kmer);   // a flag implies a valid k-mer
+            new_bits = __ldcs(flags + (size_t(wt) * WARP_TILE) / CHUNK + lane);
+        }
+#pragma unroll 1
+        for (int r = 0; r < int(CMS_DEPTH); r++) {
+            fill[threadIdx.x] = 0;
+            __syncthreads();
+            const uint64_t seed = cms_seed(r);
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                if (!((new_bits >> j) & 1u)) continue;
+                const uint32_t idx = cms_index(kmer[j], seed);
+                const uint32_t b = idx >> CMS_BUCKET_LOG2;
+                const uint32_t rank = atomicAdd(&fill[b], 1u);
+                if (rank < slot_limit) {
+                    stage[b * PART_SLOT + rank] = uint16_t(idx);
+                } else {   // slot full: rare single-entry spill
+                    const uint32_t s = atomicAdd(L.state + 1, 1u);
+                    if (s < L.spill_cap) L.spill[s] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
+                    else L.state[0] = 1u;
+                }
+            }
+            __syncthreads();
+            // thread b reserves the run of bucket b; warp w then copies the slots of buckets 32w..32w+31
+            uint32_t n = min(fill[threadIdx.x], slot_limit), base = 0;
+            const uint32_t gb = uint32_t(r) * CMS_BUCKETS_PER_ROW + threadIdx.x;
+            if (n) {
+                base = atomicAdd(L.cursor + gb, n);
+                if (base + n > L.cap) { L.state[0] = 1u; n = 0; }   // list full: the batch falls back
+            }
+#pragma unroll 4
+            for (int q = 0; q < 32; q++) {
+                const uint32_t nb = __shfl_sync(0xffffffffu, n, q);
+                const uint32_t bb = __shfl_sync(0xffffffffu, base, q);
+                if (lane < nb) {
+                    const uint32_t b = warp * 32u + uint32_t(q);
+                    L.ent[size_t(uint32_t(r) * CMS_BUCKETS_PER_ROW + b) * L.cap + bb + lane] = stage[b * PART_SLOT + lane];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t sat_add_u16x2(uint32_t g, uint32_t d) {
+    const uint32_t lo = min((g & 0xFFFFu) + (d & 0xFFFFu), 0xFFFFu);
+    const uint32_t hi = min((g >> 16) + (d >> 16), 0xFFFFu);
+    return lo | (hi << 16);
+}
+
+__global__ void __launch_bounds__(APPLY_THREADS, 1)
+cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact) {
+    extern __shared__ __align__(16) uint32_t s_cnt[];   // APPLY_WORDS words
+    if (L.state[0]) return;                             // fallback: cms_direct_kernel owns this batch
+    const uint32_t B = blockIdx.x;
+    const uint32_t n = min(L.cursor[B], L.cap);
+    if (n == 0) return;
+    uint4* s4 = reinterpret_cast<uint4*>(s_cnt);
+    for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint16_t* __restrict__ e = L.ent + size_t(B) * L.cap;   // cap is a multiple of 8: 16-byte aligned
+    bool ovf = force_exact != 0;
+    auto bump = [&](uint32_t c) {
+        const uint32_t sh = (c & 1u) * 16u;
+        const uint32_t old = atomicAdd(&s_cnt[c >> 1], 1u << sh);
+        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) ovf = true;       // the counter wrapped / carried: redo exactly
+    };
+    const uint32_t n8 = n / 8;
+    for (uint32_t i = threadIdx.x; i < n8; i += APPLY_THREADS) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(e) + i);
+        bump(v.x & 0xFFFFu); bump(v.x >> 16);
+        bump(v.y & 0xFFFFu); bump(v.y >> 16);
+        bump(v.z & 0xFFFFu); bump(v.z >> 16);
+        bump(v.w & 0xFFFFu); bump(v.w >> 16);
+    }
+    for (uint32_t i = n8 * 8 + threadIdx.x; i < n; i += APPLY_THREADS) bump(e[i]);
+    uint16_t* __restrict__ cells = tab + (size_t(B) << CMS_BUCKET_LOG2);   // B = row * 1024 + bucket
+    if (!__syncthreads_or(ovf)) {
+        uint4* g4 = reinterpret_cast<uint4*>(cells);
+        for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) {
+            const uint4 d = s4[i];
+            if (!(d.x | d.y | d.z | d.w)) continue;
+            uint4 g = g4[i];
+            g.x = sat_add_u16x2(g.x, d.x);
+            g.y = sat_add_u16x2(g.y, d.y);
+            g.z = sat_add_u16x2(g.z, d.z);
+            g.w = sat_add_u16x2(g.w, d.w);
+            g4[i] = g;
+        }
+        return;
+    }
+    // exact redo: u32 counters, the bucket's two halves one after the other
+    for (uint32_t half = 0; half < 2; half++) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < APPLY_WORDS; i += APPLY_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += APPLY_THREADS) {
+            const uint32_t c = e[i];
+            if ((c >> 15) == half) atomicAdd(&s_cnt[c & 0x7FFFu], 1u);
+        }
+        __syncthreads();
+        uint32_t* g32 = reinterpret_cast<uint32_t*>(cells + half * APPLY_WORDS);
+        for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 2; i += APPLY_THREADS) {
+            const uint32_t d0 = s_cnt[2 * i], d1 = s_cnt[2 * i + 1];
+            if (!(d0 | d1)) continue;
+            const uint32_t g = g32[i];
+            const uint32_t lo = min((g & 0xFFFFu) + min(d0, 0xFFFFu), 0xFFFFu);
+            const uint32_t hi = min((g >> 16) + min(d1, 0xFFFFu), 0xFFFFu);
+            g32[i] = lo | (hi << 16);
+        }
+    }
+}
+
+// slot overflows of the partition (after cms_apply_kernel in stream order)
+__global__ void __launch_bounds__(256)
+cms_spill_kernel(CmsLists L, uint16_t* __restrict__ tab) {
+    if (L.state[0]) return;
+    const uint32_t n = min(L.state[1], L.spill_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        cms_cell_increment(tab, L.spill[i]);
+}
+
+// Exact slow path straight from codes[] + flags: runs only when the partition raised the fallback flag
+// (or when forced, for the parity tests).
+__global__ void __launch_bounds__(256)
+cms_direct_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_wtiles,
+                  int k, uint64_t k_mask, uint16_t* __restrict__ tab, const uint32_t* __restrict__ state) {
+    if (!state[0]) return;
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x / 32);
+    const uint32_t warp_id = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t t = warp_id; t < n_wtiles; t += warps_per_grid) {
+        uint64_t kmer[CHUNK];
+        load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
+        const uint32_t new_bits = flags[(size_t(t) * WARP_TILE) / CHUNK + lane];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            if (!((new_bits >> j) & 1u)) continue;
+#pragma unroll
+            for (int r = 0; r < int(CMS_DEPTH); r++)
+                cms_cell_increment(tab, (uint32_t(r) << CMS_WIDTH_LOG2) | cms_index(kmer[j], cms_seed(r)));
+        }
+    }
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+// NCCL variant: widen the u16 table to u32 (summable with ncclSum), then clamp the sum back.
+__global__ void __launch_bounds__(256)
+cms_widen_kernel(const uint2* __restrict__ tab2, uint4* __restrict__ wide4, uint64_t n_vec) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint2 v = tab2[i];
+        wide4[i] = make_uint4(v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16);
+    }
+}
+__global__ void __launch_bounds__(256)
+cms_narrow_kernel(const uint4* __restrict__ wide4, uint2* __restrict__ tab2, uint64_t n_vec) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 a = wide4[i];
+        tab2[i] = make_uint2(min(a.x, 65535u) | (min(a.y, 65535u) << 16), min(a.z, 65535u) | (min(a.w, 65535u) << 16));
+    }
+}
+
+// Fused exchange over NVLink peer memory: this rank sums its 1/world cell range of every rank's u16
+// table (saturating), and stores the result into EVERY rank's exchanged table — reduce-scatter +
+// snapshot + all-gather in one launch per rank (see kmn_exchange_reduce).
+constexpr int MAX_PEERS = 16;
+struct PeerTables {
+    const uint4* part[MAX_PEERS];   // every rank's own table (peer-mapped; part[rank] is local)
+    uint4* full[MAX_PEERS];         // every rank's exchanged table
+    int world, rank;
+};
+
+__global__ void __launch_bounds__(256)
+exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end) {
+    for (uint64_t i = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_end;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        uint4 s = pt.part[pt.rank][i];
+#pragma unroll 1
+        for (int p = 1; p < pt.world; p++) {
+            const int peer = (pt.rank + p) % pt.world;   // stagger the peers across ranks
+            const uint4 a = pt.part[peer][i];
+            s.x = sat_add_u16x2(s.x, a.x); s.y = sat_add_u16x2(s.y, a.y);
+            s.z = sat_add_u16x2(s.z, a.z); s.w = sat_add_u16x2(s.w, a.w);
+        }
+        for (int p = 0; p < pt.world; p++) pt.full[(pt.rank + p) % pt.world][i] = s;
+    }
+}
+
+}  // namespace kmn

@@ -21,13 +21,7 @@
 // first[] array is never cleared and only contended bits (a few % of the probes on bacterial
 // proteomes) ever touch it.  False positives AND their order dependence are reproduced exactly.
 //
-// ---- CMS (proba_filter.rs:146-168) -------------------------------------------------------------
-// All updates are +1 and saturation is monotone, so accumulating in u32 and clamping to 65535 at
-// snapshot time is bit-identical to saturating u16.  The four cell indices of every new k-mer are
-// hashed ONCE (cms_index_kernel) into four index streams; the 1 GiB accumulator table is then swept
-// in L2-resident slices: one launch per (row, slice) streams 4 B per position and applies only the
-// increments that land inside the slice, so the scattered red.add hits L2 instead of paying a 64 B
-// DRAM read + 32 B write-back per 4-byte update.
+// The flags (one bit per codes[] position: this occurrence passed the filter) feed cms_kernels.cuh.
 #pragma once
 #include "kmn_device.cuh"
 
@@ -35,7 +29,6 @@ namespace kmn {
 
 constexpr int COUNT_THREADS = 256;
 constexpr int MAX_GROUP_SPECIES = 16;  // species per launch == number of Bloom slots
-constexpr uint32_t IDX_NONE = 0xFFFFFFFFu;   // index-stream sentinel: no increment for this position
 
 struct GroupBounds {                   // codes[] boundaries of the species of one launch
     uint32_t n;                        // species in the group (<= MAX_GROUP_SPECIES)
@@ -50,8 +43,6 @@ struct BloomSlots {
     unsigned long long* first;      // [slots][2^25] tags of the earliest LATE toucher
 };
 constexpr uint32_t BLOOM_WORDS_LOG2 = BLOOM_BITS_LOG2 - 5;
-
-struct IndexStreams { uint32_t* row[CMS_DEPTH]; };   // [n_codes] cell index per position, IDX_NONE = none
 
 __device__ __forceinline__ unsigned long long bloom_tag(uint32_t epoch, uint32_t p) {
     return (static_cast<unsigned long long>(epoch) << 32) | (0xFFFFFFFFu - p);
@@ -354,86 +345,6 @@ bloom_clear_kernel(uint4* __restrict__ bits, uint4* __restrict__ multi, uint4* _
         fw[i] = z;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *late_count = 0;
-}
-
-// Hash-once: the four CMS cell indices of every flagged (new) k-mer, one 4 B stream per row.
-// Pure ALU + streaming stores: 4 x mix64 per new k-mer, IDX_NONE elsewhere.
-__global__ void __launch_bounds__(COUNT_THREADS)
-cms_index_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_tiles,
-                 int k, uint64_t k_mask, IndexStreams ix) {
-    const uint32_t warps_per_grid = gridDim.x * (COUNT_THREADS / 32);
-    const uint32_t warp_id = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5);
-    const unsigned lane = threadIdx.x & 31u;
-    for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
-        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint64_t kmer[CHUNK];
-        load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);   // a flag implies a valid k-mer
-        const uint32_t new_bits = __ldcs(flags + c0 / CHUNK);
-#pragma unroll
-        for (int r = 0; r < int(CMS_DEPTH); r++) {
-            const uint64_t seed = r == 0 ? SEED_CMS_0 : r == 1 ? SEED_CMS_1 : r == 2 ? SEED_CMS_2 : SEED_CMS_3;
-            uint32_t v[CHUNK];
-#pragma unroll
-            for (int j = 0; j < CHUNK; j++)
-                v[j] = ((new_bits >> j) & 1u) ? cms_index(kmer[j], seed) : IDX_NONE;
-            uint4* d4 = reinterpret_cast<uint4*>(ix.row[r] + c0);
-            __stcs(d4 + 0, make_uint4(v[0], v[1], v[2], v[3]));
-            __stcs(d4 + 1, make_uint4(v[4], v[5], v[6], v[7]));
-            __stcs(d4 + 2, make_uint4(v[8], v[9], v[10], v[11]));
-            __stcs(d4 + 3, make_uint4(v[12], v[13], v[14], v[15]));
-        }
-    }
-}
-
-// K3: one launch per (row, slice): stream the row's index stream (evict-first) and apply the
-// increments that fall inside the L2-resident slice [slice << shift, (slice+1) << shift).
-__global__ void __launch_bounds__(COUNT_THREADS)
-cms_sweep_kernel(const uint4* __restrict__ idx_row, uint32_t n_vec, uint32_t slice_shift, uint32_t slice,
-                 uint32_t* __restrict__ acc_row) {
-    for (uint32_t i = blockIdx.x * COUNT_THREADS + threadIdx.x; i < n_vec; i += gridDim.x * COUNT_THREADS) {
-        const uint4 v = __ldcs(idx_row + i);
-        if ((v.x >> slice_shift) == slice) atomicAdd(acc_row + v.x, 1u);
-        if ((v.y >> slice_shift) == slice) atomicAdd(acc_row + v.y, 1u);
-        if ((v.z >> slice_shift) == slice) atomicAdd(acc_row + v.z, 1u);
-        if ((v.w >> slice_shift) == slice) atomicAdd(acc_row + v.w, 1u);
-    }
-}
-
-// AtomicCountMinSketch::snapshot (proba_filter.rs:171-177) on u32 accumulators: clamp to u16.
-__global__ void __launch_bounds__(256)
-cms_finalize_kernel(const uint4* __restrict__ acc4, uint2* __restrict__ out2, uint64_t n_vec) {
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
-         i += uint64_t(gridDim.x) * blockDim.x) {
-        const uint4 a = acc4[i];
-        const uint32_t x = min(a.x, 65535u), y = min(a.y, 65535u), z = min(a.z, 65535u), w = min(a.w, 65535u);
-        out2[i] = make_uint2(x | (y << 16), z | (w << 16));
-    }
-}
-
-// Fused exchange over NVLink peer memory: reduce-scatter of the u32 accumulators + clamp + all-gather
-// of the u16 table, one launch per rank (see kmn_exchange_reduce).
-constexpr int MAX_PEERS = 16;
-struct PeerTables {
-    const uint4* acc[MAX_PEERS];   // every rank's accumulators (peer-mapped; acc[rank] is local)
-    uint2* cms[MAX_PEERS];         // every rank's finalized table
-    int world, rank;
-};
-
-__global__ void __launch_bounds__(256)
-exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end) {
-    for (uint64_t i = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_end;
-         i += uint64_t(gridDim.x) * blockDim.x) {
-        uint4 s = pt.acc[pt.rank][i];
-#pragma unroll 1
-        for (int p = 1; p < pt.world; p++) {
-            const int peer = (pt.rank + p) % pt.world;   // stagger the peers across ranks
-            const uint4 a = pt.acc[peer][i];
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-        }
-        const uint2 o = make_uint2(min(s.x, 65535u) | (min(s.y, 65535u) << 16),
-                                   min(s.z, 65535u) | (min(s.w, 65535u) << 16));
-        for (int p = 0; p < pt.world; p++) pt.cms[(pt.rank + p) % pt.world][i] = o;
-    }
 }
 
 }  // namespace kmn

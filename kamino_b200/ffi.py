@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
-    "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
+    "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
@@ -69,6 +69,7 @@ def load_library() -> C.CDLL:
     lib.kmn_table_snapshot.argtypes = [vp, vp]
     lib.kmn_table_load.argtypes = [vp, vp]
     lib.kmn_table_accum_device_ptr.argtypes = [vp, vpp]
+    lib.kmn_table_widen.argtypes = [vp]
     lib.kmn_table_device_ptr.argtypes = [vp, vpp]
     lib.kmn_exchange_export.argtypes = [vp, vp, vp]
     lib.kmn_exchange_setup.argtypes = [vp, C.c_int, C.c_int, vp, vp]
@@ -174,6 +175,9 @@ class Context:
         p = C.c_void_p()
         self._check(self.lib.kmn_table_accum_device_ptr(self._h, C.byref(p)))
         return p.value
+
+    def table_widen(self):
+        self._check(self.lib.kmn_table_widen(self._h))
 
     def table_device_ptr(self) -> int:
         p = C.c_void_p()

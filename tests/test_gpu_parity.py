@@ -230,3 +230,34 @@ def test_pair_counts(ffi, oracle, n, L):
         gv, gm = ctx.pair_counts(m)
     iu = np.triu_indices(n, 1)
     assert np.array_equal(gv[iu], wv[iu]) and np.array_equal(gm[iu], wm[iu])
+
+
+@pytest.mark.parametrize("knobs", [
+    {"KMN_CMS_FORCE": "1"},                      # every bucket redone with u32 counters
+    {"KMN_CMS_FORCE": "2"},                      # direct CAS path only
+    {"KMN_CMS_CAP": "8"},                        # bucket lists overflow -> fallback flag -> direct path
+    {"KMN_CMS_SLOT": "1"},                       # almost every staged entry spills
+    {"KMN_CMS_SLOT": "1", "KMN_CMS_FORCE": "1"},
+])
+def test_cms_rare_paths(ffi, oracle, knobs, monkeypatch):
+    """The exact rare paths of the count-min build (cms_kernels.cuh) against the oracle."""
+    for key, v in knobs.items():
+        monkeypatch.setenv(key, v)
+    species = synth.bacterial(6, seed=21, n_prot=400, mean_len=220.0)
+    b = synth.stage(species)
+    _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, oracle.min_needed(0.85, 6),
+                           scan_species=[0])
+    # twice into the same table: merge on top of non-zero cells
+    h = oracle.cmsa_new()
+    try:
+        for _ in range(2):
+            oracle.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, threads=8)
+        want = oracle.cmsa_table(h)
+        with ffi.Context(13, SR6) as ctx:
+            bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+            ctx.count_staged(bid)
+            ctx.count_staged(bid)
+            ctx.finalize_table()
+            assert np.array_equal(ctx.table_snapshot(), want)
+    finally:
+        oracle.cmsa_free(h)

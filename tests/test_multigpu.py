@@ -50,7 +50,7 @@ def _worker(rank, world, port, out_dir):
                     sharding.fused_exchange(ctx)
                 else:
                     acc = torch.as_tensor(_DevArray(ctx.accum_device_ptr(), ffi.CMS_CELLS, "<i4"), device=f"cuda:{rank}")
-                    ctx.synchronize()
+                    ctx.table_widen()                      # u16 cells -> summable u32 copy
                     sharding.exchange_accumulators(acc)
                     torch.cuda.synchronize()
                     ctx.finalize_table()
