@@ -81,7 +81,6 @@ struct Batch {
     DevBuf<uint64_t> rec_off, sp_rec_off;
     DevBuf<uint32_t> rec_cstart, sp_cstart;
     DevBuf<uint16_t> flags;
-    DevBuf<uint32_t> wf;                 // 2 bits per codes[] position: probe saw its Bloom bit clear
     std::vector<uint32_t> h_sp_cstart;   // host copy (after framing)
     std::vector<uint64_t> h_sp_rec_off;
     // pass 2 results
@@ -109,8 +108,6 @@ struct kmn_ctx {
     bool widened = false;
     const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
     bool finalized = false;
-    DevBuf<unsigned long long> first;     // MAX_GROUP_SPECIES x 2^25 first-touch tags (4 GiB)
-    uint32_t epoch = 1;                   // next species epoch (0 = never written)
     DevBuf<unsigned long long> new_counts;
     DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
     DevBuf<uint16_t> warp_cnt;
@@ -122,8 +119,10 @@ struct kmn_ctx {
     cudaEvent_t ev[8] = {};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
-    uint32_t bloom_group = 16;            // species per Bloom launch (bitsets of a group stay in L2)
-    DevBuf<uint32_t> bl_bits, bl_multi, bl_fw, late_list, late_count;
+    // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
+    DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
+    DevBuf<uint16_t> bl_cnt;
+    uint32_t bloom_run_cap = RUN_CAP;     // test knob KMN_BLOOM_RUN_CAP: small slots force the slow exact path
     DevBuf<uint16_t> cms_ent;             // bucket lists of the CMS partition (scratch of count_staged)
     DevBuf<uint32_t> cms_cursor, cms_spill, cms_state;
     int cms_force = 0;                    // test knob: 1 = exact (u32) redo in every bucket, 2 = direct fallback
@@ -194,8 +193,7 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     b->codes.ensure(b->codes_cap);
     b->rec_cstart.ensure(n_rec + 1);
     b->sp_cstart.ensure(size_t(n_sp) + 1);
-    b->flags.ensure(b->codes_cap / CHUNK + 2);   // +2: viewed as u32 words by bloom_late_kernel
-    b->wf.ensure(b->codes_cap / CHUNK);
+    b->flags.ensure(b->codes_cap / CHUNK + 2);   // +2: viewed as u32 words by bloom_flags_kernel
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
@@ -244,37 +242,49 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     c->new_counts.ensure(size_t(b.n_sp) + 1);
     KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
     const int grid = grid_for(c, 8);
-    const uint32_t group = c->bloom_group;
-    KMN_CUDA(cudaMemsetAsync(b.wf.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
-    for (uint32_t s0 = 0; s0 < b.n_sp; s0 += group) {
-        GroupBounds g;
-        g.n = std::min<uint32_t>(group, b.n_sp - s0);
-        g.first_species = s0;
-        if (c->epoch > 0xFFFFFFFFu - MAX_GROUP_SPECIES) {  // epoch wrap: start over with clean tags
-            KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
-            c->epoch = 1;
+    if (b.n_codes > 0) {
+        // source tiles: 8 Ki positions of one species each, on the warp-tile grid (count_kernels.cuh)
+        std::vector<uint32_t> h_tile0(size_t(b.n_sp) + 1, 0), h_tile_sp;
+        for (uint32_t s = 0; s < b.n_sp; s++) {
+            const uint32_t cb = b.h_sp_cstart[s], ce = b.h_sp_cstart[s + 1];
+            uint32_t nt = 0;
+            if (ce > cb) nt = ((ce + WARP_TILE - 1) / WARP_TILE - cb / WARP_TILE + BP_TILE_WT - 1) / BP_TILE_WT;
+            h_tile0[s + 1] = h_tile0[s] + nt;
+            h_tile_sp.insert(h_tile_sp.end(), nt, s);
         }
-        g.epoch0 = c->epoch;
-        c->epoch += g.n;
-        if (b.h_sp_cstart[s0 + g.n] == b.h_sp_cstart[s0]) continue;  // no residues in this group
-        const uint32_t clear_vec = uint32_t((size_t(g.n) << BLOOM_WORDS_LOG2) / 4);
-        bloom_clear_kernel<<<grid_for(c, 4), 256, 0, c->stream>>>(
-            reinterpret_cast<uint4*>(c->bl_bits.p), reinterpret_cast<uint4*>(c->bl_multi.p),
-            reinterpret_cast<uint4*>(c->bl_fw.p), clear_vec, c->late_count.p);
-        check_launch(c);
-        const size_t group_positions = b.h_sp_cstart[s0 + g.n] - b.h_sp_cstart[s0];
-        c->late_list.ensure(2 * group_positions + 64);
-        BloomSlots bs{c->bl_bits.p, c->bl_multi.p, c->bl_fw.p, c->first.p};
-        bloom_touch_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, bs,
-                                                                 b.wf.p, c->late_list.p, c->late_count.p);
-        check_launch(c);
-        bloom_settle_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, c->k_mask, bs,
-                                                                  b.wf.p, b.flags.p, c->new_counts.p);
-        check_launch(c);
-        bloom_late_kernel<<<grid, COUNT_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, g, c->k, bs, c->late_list.p,
-                                                                c->late_count.p, reinterpret_cast<uint32_t*>(b.flags.p),
-                                                                c->new_counts.p);
-        check_launch(c);
+        const uint32_t n_tiles = h_tile0[b.n_sp];
+        BloomRuns R;
+        R.cap = c->bloom_run_cap;
+        c->bl_tile_sp.ensure(n_tiles);
+        c->bl_tile0.ensure(size_t(b.n_sp) + 1);
+        c->bl_slow.ensure(b.n_sp);
+        c->bl_ent.ensure(size_t(n_tiles) * BB_BUCKETS * R.cap);
+        c->bl_cnt.ensure(size_t(n_tiles) * BB_BUCKETS);
+        c->bl_lost2.ensure(b.codes_cap / CHUNK);
+        KMN_CUDA(cudaMemcpyAsync(c->bl_tile_sp.p, h_tile_sp.data(), size_t(n_tiles) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(c->bl_tile0.p, h_tile0.data(), h_tile0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaMemsetAsync(c->bl_slow.p, 0, size_t(b.n_sp) * sizeof(uint32_t), c->stream));
+        KMN_CUDA(cudaMemsetAsync(c->bl_lost2.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
+        R.ent = c->bl_ent.p;
+        R.cnt = c->bl_cnt.p;
+        R.tile_sp = c->bl_tile_sp.p;
+        R.sp_tile0 = c->bl_tile0.p;
+        R.slow = c->bl_slow.p;
+        R.lost2 = c->bl_lost2.p;
+        if (n_tiles) {
+            bloom_partition_kernel<<<n_tiles, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+            check_launch(c);
+            KMN_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors above back the async copies
+            // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
+            bloom_bucket_kernel<<<b.n_sp * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, R);
+            check_launch(c);
+            bloom_slow_kernel<<<std::min<uint32_t>(b.n_sp, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
+                b.codes.p, b.sp_cstart.p, b.n_sp, c->k, c->k_mask, R, c->bl_scratch.p);
+            check_launch(c);
+            bloom_flags_kernel<<<n_tiles, BP_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R,
+                                                                     reinterpret_cast<uint32_t*>(b.flags.p), c->new_counts.p);
+            check_launch(c);
+        }
     }
     KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (b.n_codes > 0) {
@@ -503,23 +513,21 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
-        if (const char* e = std::getenv("KMN_BLOOM_GROUP")) {
+        if (const char* e = std::getenv("KMN_BLOOM_RUN_CAP")) {   // test knob
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 1 || v > MAX_GROUP_SPECIES) throw std::runtime_error("KMN_BLOOM_GROUP must be in 1..16");
-            c->bloom_group = uint32_t(v);
+            if (v < 1 || v > long(RUN_CAP)) throw std::runtime_error("KMN_BLOOM_RUN_CAP must be in 1..208");
+            c->bloom_run_cap = uint32_t(v);
         }
-        c->bl_bits.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_WORDS_LOG2);
-        c->bl_multi.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_WORDS_LOG2);
-        c->bl_fw.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_WORDS_LOG2);
-        c->late_count.alloc(1);
+        c->bl_scratch.alloc(size_t(BS_MAX_CTAS) << (BLOOM_BITS_LOG2 - 5));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BB_SMEM)));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BS_SMEM)));
         c->tab.alloc(CMS_CELLS);
         c->cms_cursor.alloc(CMS_BUCKETS);
         c->cms_state.alloc(2);
         KMN_CUDA(cudaFuncSetAttribute(cms_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PART_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(cms_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(APPLY_SMEM)));
-        c->first.alloc(size_t(MAX_GROUP_SPECIES) << BLOOM_BITS_LOG2);
         KMN_CUDA(cudaMemsetAsync(c->tab.p, 0, CMS_CELLS * sizeof(uint16_t), c->stream));
-        KMN_CUDA(cudaMemsetAsync(c->first.p, 0, c->first.n * sizeof(unsigned long long), c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         *out = c.release();
         return 0;

@@ -1,52 +1,79 @@
-// count_kernels.cuh — pass 1 on the recoded stream: exact per-species Bloom semantics + CMS build.
+// count_kernels.cuh — pass 1 on the recoded stream: exact per-species Bloom semantics.
 //
-// Replaces the hot loop of count_species_kmers (/root/reference/src/group_extraction.rs:385-391):
+// Replaces the filter half of the hot loop of count_species_kmers
+// (/root/reference/src/group_extraction.rs:385-391):
 //     if have == k && !bloom.test_and_set(roll) { cmsa.increment(roll) }
+// and produces one flag bit per codes[] position ("this occurrence passed the filter"), which
+// cms_kernels.cuh turns into count-min increments.
 //
-// ---- Bloom (proba_filter.rs:59-74) -------------------------------------------------------------
-// test_and_set is sequential per species: an occurrence is "new" iff at least one of its two probe
+// ---- exact semantics, order-free (proba_filter.rs:59-74) ---------------------------------------
+// test_and_set is sequential per species: an occurrence passes iff at least one of its two probe
 // bits was still clear, i.e. iff it is the FIRST occurrence (in file order) touching one of its two
-// bits (i0 != i1 always because h2 is forced odd).  Order-free restatement:
-//     new(p) <=> p is the file-order-first toucher of bit i0(p) or of bit i1(p).
-// The dense traffic goes to per-species BITSETS (2^25 bits = 4 MiB each, like the reference's
-// filter) that stay resident in the 126 MB L2 for a group of species:
-//   pass A  touch : old = atomicOr(bits[bit]).  The temporally-first toucher of a bit sees it clear
-//                   ("was_first").  A LATE toucher marks multi[bit], publishes its file-order index
-//                   with atomicMax(first[bit], tag(p)) and appends itself to a compact late list.
-//   pass B  settle: a was_first probe whose bit is not in multi[] is the only toucher -> first.
-//                   A was_first probe of a contended bit is first iff its p is smaller than the
-//                   smallest late p (first[bit]); if so it sets fw[bit] ("first toucher wins").
-//   pass C  late  : (late list only) a late probe is first iff it holds first[bit] and !fw[bit].
-// tag(p) = (species_epoch << 32) | ~p with a per-species epoch that only grows, so the 64-bit
-// first[] array is never cleared and only contended bits (a few % of the probes on bacterial
-// proteomes) ever touch it.  False positives AND their order dependence are reproduced exactly.
+// bits (i0 != i1 always because h2 is forced odd).  Call a probe LOST when an earlier position of
+// the species touches the same bit:
+//     passes(p) <=> not (probe 0 of p lost and probe 1 of p lost).
+// False positives AND their dependence on file order are reproduced exactly.
 //
-// The flags (one bit per codes[] position: this occurrence passed the filter) feed cms_kernels.cuh.
+// ---- machine mapping ----------------------------------------------------------------------------
+// Measured on B200 (tools/microbench/l2_atomics.cu): scattered atomicOr-with-result on an L2-resident
+// bitset tops out at 128 Gop/s chip-wide (the first CUDA path of this repo: 2 x 120 M probes -> a
+// 1.9 ms floor per 100 proteomes, ~5 ms achieved), shared-memory atomics run at ~900 Gop/s.  So the
+// filter bits never live in global memory:
+//
+//   bloom_partition_kernel  one CTA per source tile (8 Ki positions of ONE species): hashes every
+//                           k-mer once and splits its two probes over the 128 buckets of 2^18 filter
+//                           bits; entry = (bit inside the bucket, position inside the tile).  Each
+//                           (tile, bucket) run has a FIXED slot in global memory, so there are no
+//                           global atomics and the runs of a bucket are ordered by tile = by file
+//                           position.  A position whose k-mer equals the previous position's (a
+//                           homopolymer run) can never pass and is marked without probing.
+//   bloom_bucket_kernel     one CTA per (species, bucket): the bucket's 2^18 bits in shared memory,
+//                           runs consumed in file order, 16 tiles per step.  A probe whose bit was set
+//                           by an earlier step is lost.  Inside a step: every probe sets its bit with a
+//                           shared-memory atomicOr; a probe that finds the bit set by a probe of the
+//                           same step joins a small conflict list (and marks a 2048-bit mini filter);
+//                           the probes that set a marked bit join it too; inside the list the smallest
+//                           file position wins.  Lost probes add 1 to the 2-bit counter of their position.
+//   bloom_slow_kernel       same step logic on a 4 MiB global bitset, one CTA per species, straight from
+//                           codes[]: only for species whose probes overflow a run slot (massively
+//                           repeated k-mers) — exact for every input, fast for natural ones.
+//   bloom_flags_kernel      flag = valid k-mer and lost counter < 2; per-species counts of passes.
 #pragma once
 #include "kmn_device.cuh"
 
 namespace kmn {
 
-constexpr int COUNT_THREADS = 256;
-constexpr int MAX_GROUP_SPECIES = 16;  // species per launch == number of Bloom slots
-
-struct GroupBounds {                   // codes[] boundaries of the species of one launch
-    uint32_t n;                        // species in the group (<= MAX_GROUP_SPECIES)
-    uint32_t first_species;            // index of the first species inside the batch
-    uint32_t epoch0;                   // epoch of the first species (monotone over the context's life)
-};
-
-struct BloomSlots {
-    uint32_t* bits;                 // [slots][2^20] touched bits
-    uint32_t* multi;                // [slots][2^20] bits touched more than once
-    uint32_t* fw;                   // [slots][2^20] contended bits won by their temporally-first toucher
-    unsigned long long* first;      // [slots][2^25] tags of the earliest LATE toucher
-};
-constexpr uint32_t BLOOM_WORDS_LOG2 = BLOOM_BITS_LOG2 - 5;
-
-__device__ __forceinline__ unsigned long long bloom_tag(uint32_t epoch, uint32_t p) {
-    return (static_cast<unsigned long long>(epoch) << 32) | (0xFFFFFFFFu - p);
+constexpr int BP_THREADS = 512;
+constexpr uint32_t BP_TILE_WT = BP_THREADS / 32;          // warp tiles per source tile (one per warp)
+constexpr uint32_t BP_TILE = BP_TILE_WT * WARP_TILE;       // 8192 positions
+constexpr uint32_t BP_POS_BITS = 13;
+constexpr uint32_t BB_LOG2 = 18;                           // filter bits per bucket (32 KiB of shared memory)
+constexpr uint32_t BB_BUCKETS = 1u << (BLOOM_BITS_LOG2 - BB_LOG2);   // 128
+constexpr uint32_t BB_WORDS = 1u << (BB_LOG2 - 5);
+constexpr uint32_t BB_MASK = (1u << BB_LOG2) - 1;
+constexpr uint32_t RUN_CAP = 208;                          // slots per (tile, bucket): mean 128, sigma 11
+constexpr uint32_t RUN_Q = (RUN_CAP + 31) / 32;            // entries per lane when a warp reads one run
+constexpr int BB_THREADS = 512;
+constexpr uint32_t BB_STEP_RUNS = BB_THREADS / 32;         // runs (source tiles) per step: one per warp
+constexpr uint32_t BB_LIST_CAP = BB_STEP_RUNS * RUN_CAP;   // every entry of a step may conflict
+constexpr uint32_t MF_WORDS = 64;                          // 2048-bit mini filter of a step's conflicting bits
+constexpr size_t BB_SMEM = size_t(BB_LIST_CAP) * sizeof(unsigned long long) + size_t(BB_WORDS) * sizeof(uint32_t);
+static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
+static_assert(BB_LOG2 + BP_POS_BITS <= 32, "entry layout");
+static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
+constexpr size_t bp_smem_for(uint32_t cap) {
+    return size_t(BB_BUCKETS) * cap * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
 }
+
+struct BloomRuns {
+    uint32_t* ent;              // [n_tiles][BB_BUCKETS][cap] (bit_in_bucket << 13) | pos_in_tile
+    uint16_t* cnt;              // [n_tiles][BB_BUCKETS]
+    uint32_t cap;               // RUN_CAP (smaller only under the test knob)
+    const uint32_t* tile_sp;    // [n_tiles] species (index inside the batch) of every source tile
+    const uint32_t* sp_tile0;   // [n_sp + 1] first source tile of every species
+    uint32_t* slow;             // [n_sp] != 0: a run slot overflowed, bloom_slow_kernel owns the species
+    uint32_t* lost2;            // 2-bit lost counters, 16 positions per word (word = codes index / 16)
+};
 
 // bit j set <=> position c0+j lies inside [cb, ce)
 __device__ __forceinline__ uint32_t range_mask16(uint32_t c0, uint32_t cb, uint32_t ce) {
@@ -56,295 +83,305 @@ __device__ __forceinline__ uint32_t range_mask16(uint32_t c0, uint32_t cb, uint3
     return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
-// Rare path of pass A, kept out of line: a probe found its bit already set.
-__device__ __noinline__ void bloom_mark_late(BloomSlots bs, uint32_t sl, uint32_t bit, unsigned long long tag) {
-    atomicOr(bs.multi + (size_t(sl) << BLOOM_WORDS_LOG2) + (bit >> 5), 1u << (bit & 31u));
-    atomicMax(bs.first + (size_t(sl) << BLOOM_BITS_LOG2) + bit, tag);
+// Positions whose k-mer equals the k-mer of the previous position (both valid): the earlier one set
+// both filter bits, so these can never pass (proba_filter.rs:59-74) and are not probed at all.
+// All 32 lanes must call this.
+__device__ __forceinline__ uint32_t dup_mask16(const uint64_t (&kmer)[CHUNK], uint32_t valid) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t prev_k = __shfl_up_sync(0xffffffffu, kmer[CHUNK - 1], 1);
+    const uint32_t prev_v = __shfl_up_sync(0xffffffffu, valid >> (CHUNK - 1), 1) & 1u;
+    uint32_t dup = 0;
+    if (lane > 0 && prev_v && (valid & 1u) && kmer[0] == prev_k) dup |= 1u;   // lane 0: not checked across warp tiles
+#pragma unroll
+    for (int j = 1; j < CHUNK; j++)
+        if (((valid >> (j - 1)) & 3u) == 3u && kmer[j] == kmer[j - 1]) dup |= 1u << j;
+    return dup;
 }
 
-// Rare path of pass B, kept out of line: a was_first probe of a contended bit.
-__device__ __noinline__ bool bloom_first_wins(BloomSlots bs, uint32_t sl, uint32_t bit, unsigned long long tag) {
-    if (tag > bs.first[(size_t(sl) << BLOOM_BITS_LOG2) + bit]) {   // earlier than every late toucher
-        atomicOr(bs.fw + (size_t(sl) << BLOOM_WORDS_LOG2) + (bit >> 5), 1u << (bit & 31u));
-        return true;
+// bit j of m -> value v in the 2-bit field j: the counter word of a 16-position chunk
+__device__ __forceinline__ uint32_t spread2(uint32_t m, uint32_t v) {
+    uint32_t x = m & 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x * v;
+}
+
+// first codes[] index of source tile t of a species that starts at cb (tiles sit on the warp-tile grid)
+__device__ __forceinline__ uint32_t tile_c0(uint32_t cb, uint32_t t) {
+    return (cb / WARP_TILE + t * BP_TILE_WT) * WARP_TILE;
+}
+
+__global__ void __launch_bounds__(BP_THREADS, 2)
+bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k,
+                       uint64_t k_mask, BloomRuns R) {
+    extern __shared__ __align__(16) uint32_t bp_smem[];
+    uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap]
+    uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * R.cap;   // [BB_BUCKETS]
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tg = blockIdx.x;
+    const uint32_t s = R.tile_sp[tg];
+    const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+    const uint32_t base = tile_c0(cb, tg - R.sp_tile0[s]);
+    if (threadIdx.x < BB_BUCKETS) fill[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
+    if (base + warp * WARP_TILE < ce) {   // warp-uniform
+        uint64_t kmer[CHUNK];
+        const uint32_t valid_all = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer);
+        const uint32_t valid = valid_all & range_mask16(c0, cb, ce);
+        const uint32_t dup = dup_mask16(kmer, valid_all) & valid;
+        if (dup) atomicAdd(R.lost2 + c0 / CHUNK, spread2(dup, 2u));
+        const uint32_t todo = valid & ~dup;
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            if (!((todo >> j) & 1u)) continue;
+            uint32_t idx[2];
+            bloom_indices(kmer[j], idx[0], idx[1]);
+            const uint32_t pos = warp * WARP_TILE + lane * CHUNK + j;
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                const uint32_t b = idx[pr] >> BB_LOG2;
+                const uint32_t rank = atomicAdd(&fill[b], 1u);
+                if (rank < R.cap) stage[b * R.cap + rank] = ((idx[pr] & BB_MASK) << BP_POS_BITS) | pos;
+                else ovf = true;
+            }
+        }
+        if (ovf) R.slow[s] = 1u;
     }
-    return false;
+    __syncthreads();
+    if (threadIdx.x < BB_BUCKETS)
+        R.cnt[size_t(tg) * BB_BUCKETS + threadIdx.x] = uint16_t(min(fill[threadIdx.x], R.cap));
+    // warp w copies the runs of buckets 8w .. 8w+7 to their fixed slots
+#pragma unroll 1
+    for (uint32_t q = 0; q < BB_BUCKETS / BP_TILE_WT; q++) {
+        const uint32_t b = warp * (BB_BUCKETS / BP_TILE_WT) + q;
+        const uint32_t n = min(fill[b], R.cap);
+        uint32_t* dst = R.ent + (size_t(tg) * BB_BUCKETS + b) * R.cap;
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = stage[b * R.cap + i];
+    }
 }
 
-// One lane's 16-position chunk of pass A.  UNIFORM: the whole chunk lies inside species slot `sl`
-// and inside the launch's range (the common case) — no per-position range / slot bookkeeping.
-// Two half chunks: 16 atomicOr in flight per thread before any result is consumed.
-template <bool UNIFORM>
-__device__ __forceinline__ void bloom_touch_chunk(const uint4& v, uint64_t roll, int have, int k, uint64_t k_mask,
-                                                  uint32_t c0, uint32_t range, const uint32_t* s_b, uint32_t sl,
-                                                  const GroupBounds& g, const BloomSlots& bs,
-                                                  uint32_t& first_bits, uint32_t& late_bits) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// ---- one step of exact first-touch resolution on a set of probes -----------------------------------
+// Shared by bloom_bucket_kernel (bitset in shared memory) and bloom_slow_kernel (bitset in global
+// memory, GLOBAL_BITS: loads go past L1 because the bits are set by L2 atomics).  Every thread owns up
+// to NE probes of the step: bit[e] (index into the bitset) and p[e] (file order inside the step; unique
+// among the probes of one bit), bit e of `live` set.  Returns the mask of the probes that are NOT the
+// file-order-first toucher of their bit.  All threads of the CTA must call it (barriers inside);
+// `par` alternates 0/1 between consecutive steps.
+struct StepShared {
+    unsigned long long* list;    // [every probe of a step] (bit << 32) | p
+    uint32_t* mf;                // [2][MF_WORDS]
+    uint32_t* n_list;            // [2]
+};
+
+template <int NE, bool GLOBAL_BITS>
+__device__ __forceinline__ uint32_t bloom_step(uint32_t* bitset, const StepShared& S, uint32_t par,
+                                               const uint32_t (&bit)[NE], const uint32_t (&p)[NE], uint32_t live) {
+    // phase 1: bits set by earlier steps (= by smaller file positions)
+    uint32_t pre = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t idx[8][2], old[8][2];
-        uint32_t vmask = 0, slots = 0;
+    for (int e = 0; e < NE; e++) {
+        if (!((live >> e) & 1u)) continue;
+        const uint32_t w = GLOBAL_BITS ? __ldcg(bitset + (bit[e] >> 5)) : bitset[bit[e] >> 5];
+        if (w & (1u << (bit[e] & 31u))) pre |= 1u << e;
+    }
+    __syncthreads();
+    // the other parity's list counter and mini filter were last read in the previous step
+    if (threadIdx.x < MF_WORDS) S.mf[(par ^ 1u) * MF_WORDS + threadIdx.x] = 0;
+    if (threadIdx.x == MF_WORDS) S.n_list[par ^ 1u] = 0;
+    // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
+    uint32_t won = 0, member = 0;
+    uint32_t* mf = S.mf + par * MF_WORDS;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = 8 * h + q;
-            const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (code == CODE_INVALID) {
-                roll = 0;
-                have = 0;
-            } else {
-                roll = ((roll << 3) | uint64_t(code)) & k_mask;
-                if (have < k) have++;
-                if (have == k && (UNIFORM || ((range >> j) & 1u))) vmask |= 1u << q;
-            }
-            bloom_indices(roll, idx[q][0], idx[q][1]);
-            if (!UNIFORM) {
-                if ((vmask >> q) & 1u)
-                    while (c0 + j >= s_b[sl + 1]) sl++;
-                slots |= sl << (4 * q);
-            }
+    for (int e = 0; e < NE; e++) {
+        if (!((live >> e) & 1u) || ((pre >> e) & 1u)) continue;
+        const uint32_t m = 1u << (bit[e] & 31u);
+        const uint32_t old = atomicOr(&bitset[bit[e] >> 5], m);
+        if (old & m) {
+            member |= 1u << e;
+            S.list[atomicAdd(&S.n_list[par], 1u)] = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
+            atomicOr(&mf[(bit[e] >> 5) & (MF_WORDS - 1)], m);
+        } else {
+            won |= 1u << e;
         }
+    }
+    __syncthreads();
+    uint32_t lost = pre;
+    if (S.n_list[par] == 0) return lost;   // CTA-uniform: no same-step conflicts
+    // phase 3a: the probes that set a marked bit join the list
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
-            uint32_t* words = bs.bits + (size_t(s) << BLOOM_WORDS_LOG2);
-#pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                old[q][pr] = 0;
-                if ((vmask >> q) & 1u) old[q][pr] = atomicOr(words + (idx[q][pr] >> 5), 1u << (idx[q][pr] & 31u));
-            }
+    for (int e = 0; e < NE; e++) {
+        if (!((won >> e) & 1u)) continue;
+        if (mf[(bit[e] >> 5) & (MF_WORDS - 1)] & (1u << (bit[e] & 31u))) {
+            member |= 1u << e;
+            S.list[atomicAdd(&S.n_list[par], 1u)] = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
         }
+    }
+    __syncthreads();
+    // phase 3b: inside the list the smallest file position of a bit wins
+    const uint32_t n = S.n_list[par];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (!((vmask >> q) & 1u)) continue;
-            const int j = 8 * h + q;
-            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
+    for (int e = 0; e < NE; e++) {
+        if (!((member >> e) & 1u)) continue;
+        const unsigned long long lo = static_cast<unsigned long long>(bit[e]) << 32, me = lo | p[e];
+        bool l = false;
+        for (uint32_t i = 0; i < n; i++) {
+            const unsigned long long o = S.list[i];
+            l |= (o >= lo) && (o < me);   // same bit, smaller position
+        }
+        if (l) lost |= 1u << e;
+    }
+    return lost;
+}
+
+__global__ void __launch_bounds__(BB_THREADS, 3)
+bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, BloomRuns R) {
+    extern __shared__ __align__(16) unsigned long long bb_smem[];
+    unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(bb_smem + BB_LIST_CAP);       // BB_WORDS
+    __shared__ uint32_t s_mf[2 * MF_WORDS];
+    __shared__ uint32_t s_n[2];
+    const uint32_t s = blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
+    if (R.slow[s]) return;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tg0 = R.sp_tile0[s], n_tiles = R.sp_tile0[s + 1] - tg0;
+    if (n_tiles == 0) return;
+    const uint32_t cb = sp_cstart[s];
+    for (uint32_t i = threadIdx.x; i < BB_WORDS; i += BB_THREADS) s_bits[i] = 0;
+    if (threadIdx.x < 2 * MF_WORDS) s_mf[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+    __syncthreads();
+    const StepShared S{s_list, s_mf, s_n};
+    uint32_t par = 0;
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += BB_STEP_RUNS, par ^= 1u) {
+        const uint32_t t = t0 + warp;   // this warp's run
+        uint32_t bit[RUN_Q], p[RUN_Q], live = 0;
 #pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                if (old[q][pr] & (1u << (idx[q][pr] & 31u))) {   // late toucher of this bit
-                    bloom_mark_late(bs, s, idx[q][pr], bloom_tag(g.epoch0 + s, c0 + j - s_b[s]));
-                    late_bits |= 1u << (2 * j + pr);
-                } else {
-                    first_bits |= 1u << (2 * j + pr);
+        for (int q = 0; q < int(RUN_Q); q++) bit[q] = p[q] = 0;
+        if (t < n_tiles) {
+            const size_t run = size_t(tg0 + t) * BB_BUCKETS + beta;
+            const uint32_t n = R.cnt[run];
+            const uint32_t* __restrict__ e = R.ent + run * R.cap;
+#pragma unroll
+            for (int q = 0; q < int(RUN_Q); q++) {
+                const uint32_t i = lane + 32u * q;
+                if (i < n) {
+                    const uint32_t v = __ldcs(e + i);
+                    bit[q] = v >> BP_POS_BITS;
+                    p[q] = (warp << BP_POS_BITS) | (v & (BP_TILE - 1));
+                    live |= 1u << q;
                 }
             }
         }
-    }
-}
-
-// slot of position c (c inside the launch's range)
-__device__ __forceinline__ uint32_t slot_of(const uint32_t* s_b, uint32_t n, uint32_t c) {
-    uint32_t sl = 0;
-    while (sl + 1 < n && c >= s_b[sl + 1]) sl++;
-    return sl;
-}
-
-// Pass A: touch.
-__global__ void __launch_bounds__(COUNT_THREADS)
-bloom_touch_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, GroupBounds g,
-                   int k, uint64_t k_mask, BloomSlots bs, uint32_t* __restrict__ wf,
-                   uint32_t* __restrict__ late_list, uint32_t* __restrict__ late_count) {
-    __shared__ uint32_t s_b[MAX_GROUP_SPECIES + 1];
-    if (threadIdx.x <= g.n) s_b[threadIdx.x] = sp_cstart[g.first_species + threadIdx.x];
-    __syncthreads();
-    const uint32_t cb = s_b[0], ce = s_b[g.n];
-    const uint32_t warps_per_grid = gridDim.x * (COUNT_THREADS / 32);
-    const uint32_t warp_id = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5);
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t tile_lo = cb / WARP_TILE, tile_hi = (ce + WARP_TILE - 1) / WARP_TILE;
-    for (uint32_t t = tile_lo + warp_id; t < tile_hi; t += warps_per_grid) {
-        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint4 v;
-        uint64_t roll;
-        int have;
-        warp_tile_seed<true>(codes, t * WARP_TILE, k, k_mask, v, roll, have);
-        const uint32_t range = range_mask16(c0, cb, ce);
-        uint32_t first_bits = 0;  // bit 2j / 2j+1: probe 0 / 1 of position c0+j saw its bit clear
-        uint32_t late_bits = 0;   // same indexing: the probe found its bit already set
-        if (range) {
-            const uint32_t sl0 = slot_of(s_b, g.n, max(c0, cb));
-            if (range == 0xFFFFu && c0 + CHUNK <= s_b[sl0 + 1])
-                bloom_touch_chunk<true>(v, roll, have, k, k_mask, c0, range, s_b, sl0, g, bs, first_bits, late_bits);
-            else
-                bloom_touch_chunk<false>(v, roll, have, k, k_mask, c0, range, s_b, sl0, g, bs, first_bits, late_bits);
-            // chunks straddling a group boundary are shared by two stream-ordered launches
-            wf[c0 / CHUNK] = range == 0xFFFFu ? first_bits : (wf[c0 / CHUNK] | first_bits);
-        }
-        // warp-aggregated append of the late probes: one global atomic per warp tile
-        const uint32_t n_late = __popc(late_bits);
-        uint32_t incl = n_late;
+        const uint32_t lost = bloom_step<int(RUN_Q), false>(s_bits, S, par, bit, p, live);
+        // lost probes: +1 on the 2-bit counter of their position
+        const uint32_t c_tile = tile_c0(cb, t);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= unsigned(d)) incl += y;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(late_count, total);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - n_late;
-            while (late_bits) {
-                const int b = __ffs(late_bits) - 1;
-                late_bits &= late_bits - 1;
-                late_list[base++] = (c0 + (b >> 1)) | (uint32_t(b & 1) << 31);
+        for (int q = 0; q < int(RUN_Q); q++)
+            if ((lost >> q) & 1u) {
+                const uint32_t c = c_tile + (p[q] & (BP_TILE - 1));
+                atomicAdd(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK)));
             }
+    }
+}
+
+// Exact path for species with a run-slot overflow: one CTA per species, bitset in global memory
+// (4 MiB per CTA, L2-resident), one source tile per step straight from codes[].
+constexpr int BS_THREADS = BP_THREADS;
+constexpr uint32_t BS_NE = 2 * CHUNK;                       // probes per thread and step
+constexpr uint32_t BS_LIST_CAP = BP_TILE * 2;
+constexpr size_t BS_SMEM = size_t(BS_LIST_CAP) * sizeof(unsigned long long);
+constexpr uint32_t BS_MAX_CTAS = 32;                        // 4 MiB of scratch bits each
+
+__global__ void __launch_bounds__(BS_THREADS, 1)
+bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, uint32_t n_sp, int k,
+                  uint64_t k_mask, BloomRuns R, uint32_t* __restrict__ scratch_bits) {
+    extern __shared__ __align__(16) unsigned long long bs_list[];   // BS_LIST_CAP
+    __shared__ uint32_t s_mf[2 * MF_WORDS];
+    __shared__ uint32_t s_n[2];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t* bitset = scratch_bits + (size_t(blockIdx.x) << (BLOOM_BITS_LOG2 - 5));
+    const StepShared S{bs_list, s_mf, s_n};
+    for (uint32_t s = blockIdx.x; s < n_sp; s += gridDim.x) {
+        if (!R.slow[s]) continue;   // CTA-uniform
+        const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+        const uint32_t n_tiles = R.sp_tile0[s + 1] - R.sp_tile0[s];
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < (1u << (BLOOM_BITS_LOG2 - 5)); i += BS_THREADS) bitset[i] = 0;
+        if (threadIdx.x < 2 * MF_WORDS) s_mf[threadIdx.x] = 0;
+        if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+        __threadfence();
+        __syncthreads();
+        uint32_t par = 0;
+        for (uint32_t t = 0; t < n_tiles; t++, par ^= 1u) {
+            const uint32_t base = tile_c0(cb, t);
+            const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
+            uint32_t bit[BS_NE], p[BS_NE], live = 0;
+#pragma unroll
+            for (int e = 0; e < int(BS_NE); e++) bit[e] = p[e] = 0;
+            if (base + warp * WARP_TILE < ce) {   // warp-uniform
+                uint64_t kmer[CHUNK];
+                const uint32_t valid_all = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer);
+                const uint32_t valid = valid_all & range_mask16(c0, cb, ce);
+                const uint32_t todo = valid & ~dup_mask16(kmer, valid_all);   // duplicates: marked by bloom_partition_kernel
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) {
+                    if (!((todo >> j) & 1u)) continue;
+                    bloom_indices(kmer[j], bit[2 * j], bit[2 * j + 1]);
+                    p[2 * j] = p[2 * j + 1] = warp * WARP_TILE + lane * CHUNK + j;
+                    live |= 3u << (2 * j);
+                }
+            }
+            const uint32_t lost = bloom_step<int(BS_NE), true>(bitset, S, par, bit, p, live);
+            if (lost) {
+                // probes 2j and 2j+1 belong to position j: counter += number of lost probes
+                const uint32_t both = lost & (lost >> 1) & 0x55555555u, one = (lost ^ (lost >> 1)) & 0x55555555u;
+                atomicAdd(R.lost2 + c0 / CHUNK, (both << 1) | one);
+            }
+            __threadfence();   // the bits live in global memory: order this step's atomics before the next step's loads
         }
     }
 }
 
-// One lane's chunk of pass B: all multi[] loads of a half chunk are in flight together.
-template <bool UNIFORM>
-__device__ __forceinline__ uint32_t bloom_settle_chunk(const uint4& v, uint64_t roll, int have, int k, uint64_t k_mask,
-                                                       uint32_t c0, uint32_t range, uint32_t first_bits,
-                                                       const uint32_t* s_b, uint32_t sl, const GroupBounds& g,
-                                                       const BloomSlots& bs, uint32_t* s_cnt) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// flag = valid k-mer that did not lose both probes; per-species count of flags.
+__global__ void __launch_bounds__(BP_THREADS)
+bloom_flags_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k, uint64_t k_mask,
+                   BloomRuns R, uint32_t* __restrict__ flags32, unsigned long long* __restrict__ new_per_species) {
+    __shared__ uint32_t s_new;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tg = blockIdx.x;
+    const uint32_t s = R.tile_sp[tg];
+    const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+    const uint32_t base = tile_c0(cb, tg - R.sp_tile0[s]);
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
     uint32_t new_bits = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t idx[8][2], mw[8][2];
-        uint32_t vmask = 0, slots = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = 8 * h + q;
-            const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (code == CODE_INVALID) {
-                roll = 0;
-                have = 0;
-            } else {
-                roll = ((roll << 3) | uint64_t(code)) & k_mask;
-                if (have < k) have++;
-                if (have == k && (UNIFORM || ((range >> j) & 1u))) vmask |= 1u << q;
-            }
-            bloom_indices(roll, idx[q][0], idx[q][1]);
-            if (!UNIFORM) {
-                if ((vmask >> q) & 1u)
-                    while (c0 + j >= s_b[sl + 1]) sl++;
-                slots |= sl << (4 * q);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = 8 * h + q;
-            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
-            const uint32_t* words = bs.multi + (size_t(s) << BLOOM_WORDS_LOG2);
-#pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                mw[q][pr] = 0;
-                if (((vmask >> q) & 1u) && ((first_bits >> (2 * j + pr)) & 1u)) mw[q][pr] = words[idx[q][pr] >> 5];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (!((vmask >> q) & 1u)) continue;
-            const int j = 8 * h + q;
-            const uint32_t s = UNIFORM ? sl : ((slots >> (4 * q)) & 15u);
-            bool is_new = false;
-#pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                if (!((first_bits >> (2 * j + pr)) & 1u)) continue;   // late probes: bloom_late_kernel
-                if (!(mw[q][pr] & (1u << (idx[q][pr] & 31u))))
-                    is_new = true;                                     // only toucher of this bit
-                else if (bloom_first_wins(bs, s, idx[q][pr], bloom_tag(g.epoch0 + s, c0 + j - s_b[s])))
-                    is_new = true;
-            }
-            if (is_new) {
-                new_bits |= 1u << j;
-                if (!UNIFORM) atomicAdd(&s_cnt[s], 1u);
-            }
-        }
-    }
-    if (UNIFORM && new_bits) atomicAdd(&s_cnt[sl], uint32_t(__popc(new_bits)));
-    return new_bits;
-}
-
-// Pass B: settle every was_first probe.
-__global__ void __launch_bounds__(COUNT_THREADS)
-bloom_settle_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, GroupBounds g,
-                    int k, uint64_t k_mask, BloomSlots bs, const uint32_t* __restrict__ wf,
-                    uint16_t* __restrict__ flags, unsigned long long* __restrict__ new_per_species) {
-    __shared__ uint32_t s_b[MAX_GROUP_SPECIES + 1];
-    __shared__ uint32_t s_cnt[MAX_GROUP_SPECIES];
-    if (threadIdx.x <= g.n) s_b[threadIdx.x] = sp_cstart[g.first_species + threadIdx.x];
-    if (threadIdx.x < MAX_GROUP_SPECIES) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t cb = s_b[0], ce = s_b[g.n];
-    const uint32_t warps_per_grid = gridDim.x * (COUNT_THREADS / 32);
-    const uint32_t warp_id = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5);
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t tile_lo = cb / WARP_TILE, tile_hi = (ce + WARP_TILE - 1) / WARP_TILE;
-    for (uint32_t t = tile_lo + warp_id; t < tile_hi; t += warps_per_grid) {
-        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint4 v;
-        uint64_t roll;
-        int have;
-        warp_tile_seed<true>(codes, t * WARP_TILE, k, k_mask, v, roll, have);
+    if (base + warp * WARP_TILE < ce) {   // warp-uniform
+        uint64_t kmer[CHUNK];
         const uint32_t range = range_mask16(c0, cb, ce);
-        if (!range) continue;
-        const uint32_t first_bits = __ldcs(wf + c0 / CHUNK);
-        const uint32_t sl0 = slot_of(s_b, g.n, max(c0, cb));
-        uint32_t new_bits;
-        if (range == 0xFFFFu && c0 + CHUNK <= s_b[sl0 + 1])
-            new_bits = bloom_settle_chunk<true>(v, roll, have, k, k_mask, c0, range, first_bits, s_b, sl0, g, bs, s_cnt);
-        else
-            new_bits = bloom_settle_chunk<false>(v, roll, have, k, k_mask, c0, range, first_bits, s_b, sl0, g, bs, s_cnt);
+        const uint32_t valid = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer) & range;
+        if (valid) {
+            uint32_t x = (__ldcs(R.lost2 + c0 / CHUNK) >> 1) & 0x55555555u;   // bit 2j: counter of position j is 2
+            x = (x | (x >> 1)) & 0x33333333u;
+            x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+            x = (x | (x >> 4)) & 0x00FF00FFu;
+            x = (x | (x >> 8)) & 0x0000FFFFu;
+            new_bits = valid & ~x;
+        }
         if (new_bits) {
-            uint16_t* f = flags + (c0 / CHUNK);
-            *f = uint16_t(*f | new_bits);   // merge: a straddling chunk is shared by two launches
+            // a chunk straddling a species boundary is shared by two CTAs: merge atomically
+            if (range == 0xFFFFu) reinterpret_cast<uint16_t*>(flags32)[c0 / CHUNK] = uint16_t(new_bits);
+            else atomicOr(flags32 + c0 / (2 * CHUNK), new_bits << (16u * ((c0 / CHUNK) & 1u)));
         }
     }
+    const uint32_t wn = __reduce_add_sync(0xffffffffu, uint32_t(__popc(new_bits)));
+    if (lane == 0 && wn) atomicAdd(&s_new, wn);
     __syncthreads();
-    if (threadIdx.x < g.n && s_cnt[threadIdx.x])
-        atomicAdd(new_per_species + g.first_species + threadIdx.x,
-                  static_cast<unsigned long long>(s_cnt[threadIdx.x]));
-}
-
-// Pass C: late probes only.
-__global__ void __launch_bounds__(COUNT_THREADS)
-bloom_late_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, GroupBounds g,
-                  int k, BloomSlots bs, const uint32_t* __restrict__ late_list,
-                  const uint32_t* __restrict__ late_count, uint32_t* __restrict__ flags32,
-                  unsigned long long* __restrict__ new_per_species) {
-    __shared__ uint32_t s_b[MAX_GROUP_SPECIES + 1];
-    __shared__ uint32_t s_cnt[MAX_GROUP_SPECIES];
-    if (threadIdx.x <= g.n) s_b[threadIdx.x] = sp_cstart[g.first_species + threadIdx.x];
-    if (threadIdx.x < MAX_GROUP_SPECIES) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t n = *late_count;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const uint32_t v = late_list[e];
-        const uint32_t c = v & 0x7FFFFFFFu, j = v >> 31;
-        uint32_t sl = 0;
-        while (c >= s_b[sl + 1]) sl++;
-        uint64_t kmer = 0;
-        for (int i = k - 1; i >= 0; i--) kmer = (kmer << 3) | uint64_t(codes[c - i]);
-        uint32_t idx[2];
-        bloom_indices(kmer, idx[0], idx[1]);
-        const uint32_t bit = idx[j], w = bit >> 5, m = 1u << (bit & 31u);
-        const unsigned long long tag = bloom_tag(g.epoch0 + sl, c - s_b[sl]);
-        if (bs.first[(size_t(sl) << BLOOM_BITS_LOG2) + bit] == tag &&
-            !(bs.fw[(size_t(sl) << BLOOM_WORDS_LOG2) + w] & m)) {
-            const uint32_t fm = 1u << (c & 31u);
-            const uint32_t old = atomicOr(flags32 + (c >> 5), fm);
-            if (!(old & fm)) atomicAdd(&s_cnt[sl], 1u);   // not already new through its other probe
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < g.n && s_cnt[threadIdx.x])
-        atomicAdd(new_per_species + g.first_species + threadIdx.x,
-                  static_cast<unsigned long long>(s_cnt[threadIdx.x]));
-}
-
-// Clears the bitsets of a group's slots and the late counter in ONE launch.
-__global__ void __launch_bounds__(256)
-bloom_clear_kernel(uint4* __restrict__ bits, uint4* __restrict__ multi, uint4* __restrict__ fw, uint32_t n_vec,
-                   uint32_t* __restrict__ late_count) {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x) {
-        bits[i] = z;
-        multi[i] = z;
-        fw[i] = z;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *late_count = 0;
+    if (threadIdx.x == 0 && s_new) atomicAdd(new_per_species + s, static_cast<unsigned long long>(s_new));
 }
 
 }  // namespace kmn

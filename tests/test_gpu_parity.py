@@ -261,3 +261,50 @@ def test_cms_rare_paths(ffi, oracle, knobs, monkeypatch):
             assert np.array_equal(ctx.table_snapshot(), want)
     finally:
         oracle.cmsa_free(h)
+
+
+def _repeat_heavy_species(rng):
+    """Tandem repeats (period 1..7), a duplicated gene family and random proteins: many positions repeat
+    a k-mer seen a few residues earlier, which stresses the same-step conflict list of the Bloom stage."""
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    recs = []
+    for period in (1, 2, 3, 5, 7):
+        unit = aa[rng.integers(0, 20, period)].tobytes()
+        recs.append(unit * (4000 // period))
+    gene = aa[rng.integers(0, 20, 400)].tobytes()
+    recs += [gene] * 30
+    recs += [aa[rng.integers(0, 20, int(rng.integers(30, 900)))].tobytes() for _ in range(200)]
+    rng.shuffle(recs)
+    return recs
+
+
+def test_bloom_repeats_and_conflicts(ffi, oracle):
+    rng = np.random.default_rng(17)
+    residues, rec_off, sp = _batch_from_records([_repeat_heavy_species(rng) for _ in range(3)])
+    for k in (13, 4):
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 2, scan_species=[0])
+
+
+@pytest.mark.parametrize("cap", ["1", "16", "120"])
+def test_bloom_slow_path(ffi, oracle, cap, monkeypatch):
+    """Run slots too small for the probes of a tile: the species take bloom_slow_kernel (global bitset)."""
+    monkeypatch.setenv("KMN_BLOOM_RUN_CAP", cap)
+    rng = np.random.default_rng(23)
+    species = synth.bacterial(4, seed=31, n_prot=300, mean_len=250.0)
+    b = synth.stage(species)
+    _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, oracle.min_needed(0.85, 4),
+                           scan_species=[1])
+    residues, rec_off, sp = _batch_from_records([_repeat_heavy_species(rng) for _ in range(2)])
+    _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, KGB6, 2, scan_species=[0])
+
+
+def test_bloom_natural_overflow_takes_slow_path(ffi, oracle):
+    """A period-5 tandem repeat of 40 000 residues: 5 k-mers, 8 000 occurrences each, far more than a run
+    slot holds, next to ordinary species in the same batch."""
+    rng = np.random.default_rng(29)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    rep = [(b"ACDEW" * 8000)] + [aa[rng.integers(0, 20, 300)].tobytes() for _ in range(50)]
+    normal = [aa[rng.integers(0, 20, int(rng.integers(50, 600)))].tobytes() for _ in range(300)]
+    residues, rec_off, sp = _batch_from_records([normal, rep, normal[:100]])
+    new, _ = _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, SR6, 2)
+    assert new[1] > 0
