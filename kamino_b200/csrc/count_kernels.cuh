@@ -33,11 +33,12 @@
 //                           shared-memory atomicOr; a probe that finds the bit set by a probe of the
 //                           same step joins a small conflict list (and marks a 2048-bit mini filter);
 //                           the probes that set a marked bit join it too; inside the list the smallest
-//                           file position wins.  Lost probes add 1 to the 2-bit counter of their position.
+//                           file position wins.  A lost probe sets its bit (2 per position) in the lost map.
 //   bloom_slow_kernel       same step logic on a 4 MiB global bitset, one CTA per species, straight from
 //                           codes[]: only for species whose probes overflow a run slot (massively
 //                           repeated k-mers) — exact for every input, fast for natural ones.
-//   bloom_flags_kernel      flag = valid k-mer and lost counter < 2; per-species counts of passes.
+//   bloom_flags_kernel      flag = valid k-mer and not both probes lost; per-species counts of passes.
+// The lost map is written with atomicOr only, so redoing a species on the slow path is idempotent.
 #pragma once
 #include "kmn_device.cuh"
 
@@ -55,24 +56,26 @@ constexpr uint32_t RUN_CAP = 208;                          // slots per (tile, b
 constexpr uint32_t RUN_Q = (RUN_CAP + 31) / 32;            // entries per lane when a warp reads one run
 constexpr int BB_THREADS = 512;
 constexpr uint32_t BB_STEP_RUNS = BB_THREADS / 32;         // runs (source tiles) per step: one per warp
-constexpr uint32_t BB_LIST_CAP = BB_STEP_RUNS * RUN_CAP;   // every entry of a step may conflict
-constexpr uint32_t MF_WORDS = 64;                          // 2048-bit mini filter of a step's conflicting bits
+constexpr uint32_t BB_LIST_CAP = 2048;                     // conflict list of a step; overflow -> slow path (exact)
+constexpr uint32_t ENT_BIT_SHIFT = BP_POS_BITS + 1;         // entry = bit_in_bucket << 14 | pos_in_tile << 1 | probe
+constexpr uint32_t MF_WORDS = 256;                         // 8192-bit mini filter of a step's conflicting bits
+constexpr uint32_t MT_SLOTS = 256;                         // hashed min table of a step's conflict list
 constexpr size_t BB_SMEM = size_t(BB_LIST_CAP) * sizeof(unsigned long long) + size_t(BB_WORDS) * sizeof(uint32_t);
 static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
-static_assert(BB_LOG2 + BP_POS_BITS <= 32, "entry layout");
+static_assert(BB_LOG2 + ENT_BIT_SHIFT <= 32, "entry layout");
 static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
 constexpr size_t bp_smem_for(uint32_t cap) {
     return size_t(BB_BUCKETS) * cap * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
 }
 
 struct BloomRuns {
-    uint32_t* ent;              // [n_tiles][BB_BUCKETS][cap] (bit_in_bucket << 13) | pos_in_tile
-    uint16_t* cnt;              // [n_tiles][BB_BUCKETS]
+    uint32_t* ent;              // [n_tiles][BB_BUCKETS][cap] bit_in_bucket << 14 | pos_in_tile << 1 | probe
+    uint16_t* cnt;              // per species: [BB_BUCKETS][tiles of the species] (a bucket's counts are contiguous)
     uint32_t cap;               // RUN_CAP (smaller only under the test knob)
     const uint32_t* tile_sp;    // [n_tiles] species (index inside the batch) of every source tile
     const uint32_t* sp_tile0;   // [n_sp + 1] first source tile of every species
-    uint32_t* slow;             // [n_sp] != 0: a run slot overflowed, bloom_slow_kernel owns the species
-    uint32_t* lost2;            // 2-bit lost counters, 16 positions per word (word = codes index / 16)
+    uint32_t* slow;             // [n_sp] != 0: a run slot / conflict list overflowed, bloom_slow_kernel owns the species
+    uint32_t* lost2;            // lost map: bit 2j+pr of word c/16 <=> probe pr of position c+j lost
 };
 
 // bit j set <=> position c0+j lies inside [cb, ce)
@@ -98,7 +101,7 @@ __device__ __forceinline__ uint32_t dup_mask16(const uint64_t (&kmer)[CHUNK], ui
     return dup;
 }
 
-// bit j of m -> value v in the 2-bit field j: the counter word of a 16-position chunk
+// bit j of m -> value v in the 2-bit field j of a chunk's lost-map word
 __device__ __forceinline__ uint32_t spread2(uint32_t m, uint32_t v) {
     uint32_t x = m & 0xFFFFu;
     x = (x | (x << 8)) & 0x00FF00FFu;
@@ -123,7 +126,8 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
     const uint32_t tg = blockIdx.x;
     const uint32_t s = R.tile_sp[tg];
     const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
-    const uint32_t base = tile_c0(cb, tg - R.sp_tile0[s]);
+    const uint32_t tg0 = R.sp_tile0[s], nt = R.sp_tile0[s + 1] - tg0;
+    const uint32_t base = tile_c0(cb, tg - tg0);
     if (threadIdx.x < BB_BUCKETS) fill[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
@@ -132,7 +136,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
         const uint32_t valid_all = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer);
         const uint32_t valid = valid_all & range_mask16(c0, cb, ce);
         const uint32_t dup = dup_mask16(kmer, valid_all) & valid;
-        if (dup) atomicAdd(R.lost2 + c0 / CHUNK, spread2(dup, 2u));
+        if (dup) atomicOr(R.lost2 + c0 / CHUNK, spread2(dup, 3u));
         const uint32_t todo = valid & ~dup;
         bool ovf = false;
 #pragma unroll
@@ -145,7 +149,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
             for (int pr = 0; pr < 2; pr++) {
                 const uint32_t b = idx[pr] >> BB_LOG2;
                 const uint32_t rank = atomicAdd(&fill[b], 1u);
-                if (rank < R.cap) stage[b * R.cap + rank] = ((idx[pr] & BB_MASK) << BP_POS_BITS) | pos;
+                if (rank < R.cap) stage[b * R.cap + rank] = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
                 else ovf = true;
             }
         }
@@ -153,7 +157,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
     }
     __syncthreads();
     if (threadIdx.x < BB_BUCKETS)
-        R.cnt[size_t(tg) * BB_BUCKETS + threadIdx.x] = uint16_t(min(fill[threadIdx.x], R.cap));
+        R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(min(fill[threadIdx.x], R.cap));
     // warp w copies the runs of buckets 8w .. 8w+7 to their fixed slots
 #pragma unroll 1
     for (uint32_t q = 0; q < BB_BUCKETS / BP_TILE_WT; q++) {
@@ -168,73 +172,140 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
 // Shared by bloom_bucket_kernel (bitset in shared memory) and bloom_slow_kernel (bitset in global
 // memory, GLOBAL_BITS: loads go past L1 because the bits are set by L2 atomics).  Every thread owns up
 // to NE probes of the step: bit[e] (index into the bitset) and p[e] (file order inside the step; unique
-// among the probes of one bit), bit e of `live` set.  Returns the mask of the probes that are NOT the
-// file-order-first toucher of their bit.  All threads of the CTA must call it (barriers inside);
-// `par` alternates 0/1 between consecutive steps.
+// among the probes of one bit), bit e of `live` set.  `lost` receives the mask of the probes that are
+// NOT the file-order-first toucher of their bit.  Returns false (CTA-uniform, nothing decided) when the
+// conflict list is too small.  All threads of the CTA must call it (barriers inside); `par` alternates
+// 0/1 between consecutive steps.
 struct StepShared {
-    unsigned long long* list;    // [every probe of a step] (bit << 32) | p
-    uint32_t* mf;                // [2][MF_WORDS]
+    unsigned long long* list;    // [list_cap] (bit << 32) | p
+    uint32_t list_cap;
+    uint32_t* mf;                // [2][MF_WORDS] mini filter: bits that saw a same-step race
+    unsigned long long* mt;      // [2][MT_SLOTS] min key per hash slot of the conflict list
     uint32_t* n_list;            // [2]
 };
+constexpr size_t STEP_STATIC_SMEM = 2 * MF_WORDS * 4 + 2 * MT_SLOTS * 8 + 8;
 
+__device__ __forceinline__ uint32_t mt_slot(uint32_t bit) { return (bit ^ (bit >> 8) ^ (bit >> 16)) & (MT_SLOTS - 1); }
+
+// NQ_GUARD: probes e >= nq are known dead for the whole WARP (warp-uniform skip of unrolled slots).
 template <int NE, bool GLOBAL_BITS>
-__device__ __forceinline__ uint32_t bloom_step(uint32_t* bitset, const StepShared& S, uint32_t par,
-                                               const uint32_t (&bit)[NE], const uint32_t (&p)[NE], uint32_t live) {
+__device__ __forceinline__ bool bloom_step(uint32_t* bitset, const StepShared& S, uint32_t par, const uint32_t (&bit)[NE],
+                                           const uint32_t (&p)[NE], uint32_t live, int nq, uint32_t& lost) {
     // phase 1: bits set by earlier steps (= by smaller file positions)
     uint32_t pre = 0;
 #pragma unroll
     for (int e = 0; e < NE; e++) {
+        if (e >= nq) break;
         if (!((live >> e) & 1u)) continue;
         const uint32_t w = GLOBAL_BITS ? __ldcg(bitset + (bit[e] >> 5)) : bitset[bit[e] >> 5];
         if (w & (1u << (bit[e] & 31u))) pre |= 1u << e;
     }
     __syncthreads();
-    // the other parity's list counter and mini filter were last read in the previous step
-    if (threadIdx.x < MF_WORDS) S.mf[(par ^ 1u) * MF_WORDS + threadIdx.x] = 0;
-    if (threadIdx.x == MF_WORDS) S.n_list[par ^ 1u] = 0;
+    // the other parity's scratch was last read in the previous step
+    for (uint32_t i = threadIdx.x; i < MF_WORDS; i += blockDim.x) S.mf[(par ^ 1u) * MF_WORDS + i] = 0;
+    for (uint32_t i = threadIdx.x; i < MT_SLOTS; i += blockDim.x) S.mt[(par ^ 1u) * MT_SLOTS + i] = ~0ull;
+    if (threadIdx.x == 0) S.n_list[par ^ 1u] = 0;
     // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
     uint32_t won = 0, member = 0;
     uint32_t* mf = S.mf + par * MF_WORDS;
+    unsigned long long* mt = S.mt + par * MT_SLOTS;
 #pragma unroll
     for (int e = 0; e < NE; e++) {
+        if (e >= nq) break;
         if (!((live >> e) & 1u) || ((pre >> e) & 1u)) continue;
         const uint32_t m = 1u << (bit[e] & 31u);
         const uint32_t old = atomicOr(&bitset[bit[e] >> 5], m);
         if (old & m) {
             member |= 1u << e;
-            S.list[atomicAdd(&S.n_list[par], 1u)] = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
+            const unsigned long long key = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
+            const uint32_t slot = atomicAdd(&S.n_list[par], 1u);
+            if (slot < S.list_cap) S.list[slot] = key;
+            atomicMin(&mt[mt_slot(bit[e])], key);
             atomicOr(&mf[(bit[e] >> 5) & (MF_WORDS - 1)], m);
         } else {
             won |= 1u << e;
         }
     }
     __syncthreads();
-    uint32_t lost = pre;
-    if (S.n_list[par] == 0) return lost;   // CTA-uniform: no same-step conflicts
+    lost = pre;
+    if (S.n_list[par] == 0) return true;   // CTA-uniform: no same-step conflicts
     // phase 3a: the probes that set a marked bit join the list
 #pragma unroll
     for (int e = 0; e < NE; e++) {
+        if (e >= nq) break;
         if (!((won >> e) & 1u)) continue;
         if (mf[(bit[e] >> 5) & (MF_WORDS - 1)] & (1u << (bit[e] & 31u))) {
             member |= 1u << e;
-            S.list[atomicAdd(&S.n_list[par], 1u)] = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
+            const unsigned long long key = (static_cast<unsigned long long>(bit[e]) << 32) | p[e];
+            const uint32_t slot = atomicAdd(&S.n_list[par], 1u);
+            if (slot < S.list_cap) S.list[slot] = key;
+            atomicMin(&mt[mt_slot(bit[e])], key);
         }
     }
     __syncthreads();
-    // phase 3b: inside the list the smallest file position of a bit wins
+    // phase 3b: inside the list the smallest file position of a bit wins.  The hashed min table answers
+    // directly when its slot holds this probe's bit; a slot taken by a smaller bit falls back to the list.
     const uint32_t n = S.n_list[par];
+    if (n > S.list_cap) return false;
+    if (member) {
 #pragma unroll
-    for (int e = 0; e < NE; e++) {
-        if (!((member >> e) & 1u)) continue;
-        const unsigned long long lo = static_cast<unsigned long long>(bit[e]) << 32, me = lo | p[e];
-        bool l = false;
-        for (uint32_t i = 0; i < n; i++) {
-            const unsigned long long o = S.list[i];
-            l |= (o >= lo) && (o < me);   // same bit, smaller position
+        for (int e = 0; e < NE; e++) {
+            if (!((member >> e) & 1u)) continue;
+            const unsigned long long lo = static_cast<unsigned long long>(bit[e]) << 32, me = lo | p[e];
+            const unsigned long long best = mt[mt_slot(bit[e])];
+            bool l;
+            if ((best >> 32) == bit[e]) {
+                l = best != me;
+            } else {
+                l = false;
+                for (uint32_t i = 0; i < n; i++) {
+                    const unsigned long long o = S.list[i];
+                    l |= (o >= lo) && (o < me);   // same bit, smaller position
+                }
+            }
+            if (l) lost |= 1u << e;
         }
-        if (l) lost |= 1u << e;
     }
-    return lost;
+    return true;
+}
+
+// ---- bloom_bucket_kernel: the same step, hand-scheduled for shared memory ---------------------------
+// (32-bit shared addresses and explicit ld/atom.shared keep the per-probe instruction count low: this
+// kernel is bound by instruction issue, not by memory.)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atoms_or_u32(uint32_t a, uint32_t v) {
+    uint32_t o;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    return o;
+}
+
+// rare: a probe of this step found its bit set by another probe of the same step
+__device__ __noinline__ void bucket_conflict_join(unsigned long long* list, unsigned long long* mt, uint32_t* mf,
+                                                  uint32_t* n_list, uint32_t bit, uint32_t p, bool mark) {
+    const unsigned long long key = (static_cast<unsigned long long>(bit) << 32) | p;
+    const uint32_t slot = atomicAdd(n_list, 1u);
+    if (slot < BB_LIST_CAP) list[slot] = key;
+    atomicMin(&mt[mt_slot(bit)], key);
+    if (mark) atomicOr(&mf[(bit >> 5) & (MF_WORDS - 1)], 1u << (bit & 31u));
+}
+
+// rare: is a member of the conflict list beaten by a smaller file position of the same bit?
+__device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list, const unsigned long long* mt, uint32_t n,
+                                                  uint32_t bit, uint32_t p) {
+    const unsigned long long lo = static_cast<unsigned long long>(bit) << 32, me = lo | p;
+    const unsigned long long best = mt[mt_slot(bit)];
+    if ((best >> 32) == bit) return best != me;
+    bool l = false;   // the hash slot belongs to a smaller bit: scan the list
+    for (uint32_t i = 0; i < n; i++) {
+        const unsigned long long o = list[i];
+        l |= (o >= lo) && (o < me);
+    }
+    return l;
 }
 
 __global__ void __launch_bounds__(BB_THREADS, 3)
@@ -242,6 +313,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, BloomRuns R) {
     extern __shared__ __align__(16) unsigned long long bb_smem[];
     unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(bb_smem + BB_LIST_CAP);       // BB_WORDS
+    __shared__ unsigned long long s_mt[2 * MT_SLOTS];
     __shared__ uint32_t s_mf[2 * MF_WORDS];
     __shared__ uint32_t s_n[2];
     const uint32_t s = blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
@@ -251,40 +323,123 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, BloomRuns R) {
     if (n_tiles == 0) return;
     const uint32_t cb = sp_cstart[s];
     for (uint32_t i = threadIdx.x; i < BB_WORDS; i += BB_THREADS) s_bits[i] = 0;
-    if (threadIdx.x < 2 * MF_WORDS) s_mf[threadIdx.x] = 0;
+    for (uint32_t i = threadIdx.x; i < 2 * MF_WORDS; i += BB_THREADS) s_mf[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 2 * MT_SLOTS; i += BB_THREADS) s_mt[i] = ~0ull;
     if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
     __syncthreads();
-    const StepShared S{s_list, s_mf, s_n};
+    const uint32_t a_bits = smem_addr(s_bits);
+    // this bucket's run lengths are contiguous; warp w owns run t0 + w of every step
+    const uint16_t* __restrict__ cnt = R.cnt + size_t(tg0) * BB_BUCKETS + size_t(beta) * n_tiles;
+    const uint32_t* __restrict__ ent = R.ent + (size_t(tg0) * BB_BUCKETS + beta) * R.cap + lane;
+    const size_t run_stride = size_t(BB_BUCKETS) * R.cap;
+    auto run_len = [&](uint32_t t) -> uint32_t { return t < n_tiles ? uint32_t(__ldg(cnt + t)) : 0u; };
+    auto lane_live = [&](uint32_t n) -> uint32_t {   // bit q set <=> lane + 32 q < n
+        return n > lane ? (2u << ((n - lane - 1u) >> 5)) - 1u : 0u;
+    };
+    // software pipeline: entries one step ahead, run lengths two steps ahead
+    uint32_t raw[RUN_Q];
+    uint32_t n_next = run_len(warp);
+    {
+        const uint32_t lv = lane_live(n_next);
+        const uint32_t* e = ent + size_t(warp) * run_stride;
+#pragma unroll
+        for (int q = 0; q < int(RUN_Q); q++)
+            if ((lv >> q) & 1u) raw[q] = __ldcs(e + 32 * q);
+    }
+    uint32_t n_next2 = run_len(BB_STEP_RUNS + warp);
     uint32_t par = 0;
     for (uint32_t t0 = 0; t0 < n_tiles; t0 += BB_STEP_RUNS, par ^= 1u) {
-        const uint32_t t = t0 + warp;   // this warp's run
-        uint32_t bit[RUN_Q], p[RUN_Q], live = 0;
+        const uint32_t t = t0 + warp;
+        const uint32_t n = n_next;
+        const uint32_t live = lane_live(n);
+        uint32_t cur[RUN_Q];
 #pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++) bit[q] = p[q] = 0;
-        if (t < n_tiles) {
-            const size_t run = size_t(tg0 + t) * BB_BUCKETS + beta;
-            const uint32_t n = R.cnt[run];
-            const uint32_t* __restrict__ e = R.ent + run * R.cap;
+        for (int q = 0; q < int(RUN_Q); q++) cur[q] = raw[q];
+        n_next = n_next2;
+        {
+            const uint32_t lv = lane_live(n_next);
+            const uint32_t* e = ent + size_t(t + BB_STEP_RUNS) * run_stride;
 #pragma unroll
-            for (int q = 0; q < int(RUN_Q); q++) {
-                const uint32_t i = lane + 32u * q;
-                if (i < n) {
-                    const uint32_t v = __ldcs(e + i);
-                    bit[q] = v >> BP_POS_BITS;
-                    p[q] = (warp << BP_POS_BITS) | (v & (BP_TILE - 1));
-                    live |= 1u << q;
+            for (int q = 0; q < int(RUN_Q); q++)
+                if ((lv >> q) & 1u) raw[q] = __ldcs(e + 32 * q);
+        }
+        n_next2 = run_len(t + 2 * BB_STEP_RUNS);
+        unsigned long long* mt = s_mt + par * MT_SLOTS;
+        uint32_t* mf = s_mf + par * MF_WORDS;
+        const uint32_t a_mf = smem_addr(mf);
+        // phase 1: bits set by earlier steps (= by smaller file positions)
+        uint32_t pre = 0;
+#pragma unroll
+        for (int q = 0; q < int(RUN_Q); q++) {
+            if (32u * q >= n) break;   // warp-uniform
+            if ((live >> q) & 1u) {
+                const uint32_t bit = cur[q] >> ENT_BIT_SHIFT;
+                pre |= ((lds_u32(a_bits + ((bit >> 5) << 2)) >> (bit & 31u)) & 1u) << q;
+            }
+        }
+        __syncthreads();
+        // the other parity's scratch was last read in the previous step
+        if (threadIdx.x < MF_WORDS) s_mf[(par ^ 1u) * MF_WORDS + threadIdx.x] = 0;
+        if (threadIdx.x < MT_SLOTS) s_mt[(par ^ 1u) * MT_SLOTS + threadIdx.x] = ~0ull;
+        if (threadIdx.x == 0) s_n[par ^ 1u] = 0;
+        // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
+        uint32_t won = 0, member = 0;
+        const uint32_t todo = live & ~pre;
+#pragma unroll
+        for (int q = 0; q < int(RUN_Q); q++) {
+            if (32u * q >= n) break;
+            if ((todo >> q) & 1u) {
+                const uint32_t bit = cur[q] >> ENT_BIT_SHIFT, m = 1u << (bit & 31u);
+                if (atoms_or_u32(a_bits + ((bit >> 5) << 2), m) & m) {
+                    member |= 1u << q;
+                    bucket_conflict_join(s_list, mt, mf, &s_n[par], bit, (warp << ENT_BIT_SHIFT) | (cur[q] & ((1u << ENT_BIT_SHIFT) - 1)), true);
+                } else {
+                    won |= 1u << q;
                 }
             }
         }
-        const uint32_t lost = bloom_step<int(RUN_Q), false>(s_bits, S, par, bit, p, live);
-        // lost probes: +1 on the 2-bit counter of their position
-        const uint32_t c_tile = tile_c0(cb, t);
+        __syncthreads();
+        uint32_t lost = pre;
+        if (s_n[par] != 0) {   // CTA-uniform: same-step conflicts exist
+            // phase 3a: the probes that set a marked bit join the list
 #pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++)
-            if ((lost >> q) & 1u) {
-                const uint32_t c = c_tile + (p[q] & (BP_TILE - 1));
-                atomicAdd(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK)));
+            for (int q = 0; q < int(RUN_Q); q++) {
+                if (32u * q >= n) break;
+                if ((won >> q) & 1u) {
+                    const uint32_t bit = cur[q] >> ENT_BIT_SHIFT;
+                    if ((lds_u32(a_mf + (((bit >> 5) & (MF_WORDS - 1)) << 2)) >> (bit & 31u)) & 1u) {
+                        member |= 1u << q;
+                        bucket_conflict_join(s_list, mt, mf, &s_n[par], bit, (warp << ENT_BIT_SHIFT) | (cur[q] & ((1u << ENT_BIT_SHIFT) - 1)), false);
+                    }
+                }
             }
+            __syncthreads();
+            // phase 3b: inside the list the smallest file position of a bit wins
+            const uint32_t nl = s_n[par];
+            if (nl > BB_LIST_CAP) {   // conflict list too small: bloom_slow_kernel redoes the species
+                if (threadIdx.x == 0) R.slow[s] = 1u;
+                return;
+            }
+            while (member) {
+                const int q = __ffs(member) - 1;
+                member &= member - 1;
+                uint32_t c = 0;
+#pragma unroll
+                for (int i = 0; i < int(RUN_Q); i++) c = i == q ? cur[i] : c;
+                if (bucket_conflict_lost(s_list, mt, nl, c >> ENT_BIT_SHIFT, (warp << ENT_BIT_SHIFT) | (c & ((1u << ENT_BIT_SHIFT) - 1))))
+                    lost |= 1u << q;
+            }
+        }
+        // lost probes -> lost map (atomicOr: idempotent)
+        if (lost) {
+            const uint32_t c_tile = tile_c0(cb, t);
+#pragma unroll
+            for (int q = 0; q < int(RUN_Q); q++)
+                if ((lost >> q) & 1u) {
+                    const uint32_t c = c_tile + ((cur[q] >> 1) & (BP_TILE - 1));
+                    atomicOr(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK) + (cur[q] & 1u)));
+                }
+        }
     }
 }
 
@@ -300,18 +455,20 @@ __global__ void __launch_bounds__(BS_THREADS, 1)
 bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, uint32_t n_sp, int k,
                   uint64_t k_mask, BloomRuns R, uint32_t* __restrict__ scratch_bits) {
     extern __shared__ __align__(16) unsigned long long bs_list[];   // BS_LIST_CAP
+    __shared__ unsigned long long s_mt[2 * MT_SLOTS];
     __shared__ uint32_t s_mf[2 * MF_WORDS];
     __shared__ uint32_t s_n[2];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t* bitset = scratch_bits + (size_t(blockIdx.x) << (BLOOM_BITS_LOG2 - 5));
-    const StepShared S{bs_list, s_mf, s_n};
+    const StepShared S{bs_list, BS_LIST_CAP, s_mf, s_mt, s_n};
     for (uint32_t s = blockIdx.x; s < n_sp; s += gridDim.x) {
         if (!R.slow[s]) continue;   // CTA-uniform
         const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
         const uint32_t n_tiles = R.sp_tile0[s + 1] - R.sp_tile0[s];
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < (1u << (BLOOM_BITS_LOG2 - 5)); i += BS_THREADS) bitset[i] = 0;
-        if (threadIdx.x < 2 * MF_WORDS) s_mf[threadIdx.x] = 0;
+        for (uint32_t i = threadIdx.x; i < 2 * MF_WORDS; i += BS_THREADS) s_mf[i] = 0;
+        for (uint32_t i = threadIdx.x; i < 2 * MT_SLOTS; i += BS_THREADS) s_mt[i] = ~0ull;
         if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
         __threadfence();
         __syncthreads();
@@ -331,16 +488,13 @@ bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
                 for (int j = 0; j < CHUNK; j++) {
                     if (!((todo >> j) & 1u)) continue;
                     bloom_indices(kmer[j], bit[2 * j], bit[2 * j + 1]);
-                    p[2 * j] = p[2 * j + 1] = warp * WARP_TILE + lane * CHUNK + j;
+                    p[2 * j] = p[2 * j + 1] = warp * WARP_TILE + lane * CHUNK + j;   // the two probes of a position never share a bit
                     live |= 3u << (2 * j);
                 }
             }
-            const uint32_t lost = bloom_step<int(BS_NE), true>(bitset, S, par, bit, p, live);
-            if (lost) {
-                // probes 2j and 2j+1 belong to position j: counter += number of lost probes
-                const uint32_t both = lost & (lost >> 1) & 0x55555555u, one = (lost ^ (lost >> 1)) & 0x55555555u;
-                atomicAdd(R.lost2 + c0 / CHUNK, (both << 1) | one);
-            }
+            uint32_t lost = 0;
+            bloom_step<int(BS_NE), true>(bitset, S, par, bit, p, live, int(BS_NE), lost);   // the list holds every probe: no overflow
+            if (lost) atomicOr(R.lost2 + c0 / CHUNK, lost);   // probe e = 2j + pr is bit 2j + pr of the chunk's word
             __threadfence();   // the bits live in global memory: order this step's atomics before the next step's loads
         }
     }
@@ -365,7 +519,8 @@ bloom_flags_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
         const uint32_t range = range_mask16(c0, cb, ce);
         const uint32_t valid = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer) & range;
         if (valid) {
-            uint32_t x = (__ldcs(R.lost2 + c0 / CHUNK) >> 1) & 0x55555555u;   // bit 2j: counter of position j is 2
+            const uint32_t lw = __ldcs(R.lost2 + c0 / CHUNK);
+            uint32_t x = lw & (lw >> 1) & 0x55555555u;                        // bit 2j: both probes of position j lost
             x = (x | (x >> 1)) & 0x33333333u;
             x = (x | (x >> 2)) & 0x0F0F0F0Fu;
             x = (x | (x >> 4)) & 0x00FF00FFu;
