@@ -80,7 +80,6 @@ struct Batch {
     DevBuf<uint8_t> raw, codes;
     DevBuf<uint64_t> rec_off, sp_rec_off;
     DevBuf<uint32_t> rec_cstart, sp_cstart;
-    DevBuf<uint16_t> flags;
     std::vector<uint32_t> h_sp_cstart;   // host copy (after framing)
     std::vector<uint64_t> h_sp_rec_off;
     // pass 2 results
@@ -122,9 +121,10 @@ struct kmn_ctx {
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
     DevBuf<uint16_t> bl_cnt;
+    std::vector<uint32_t> h_tile0, h_tile_sp, h_ct0, h_ct_sp;   // host sides of the tile tables
     uint32_t bloom_run_cap = RUN_CAP;     // test knob KMN_BLOOM_RUN_CAP: small slots force the slow exact path
     DevBuf<uint16_t> cms_ent;             // bucket lists of the CMS partition (scratch of count_staged)
-    DevBuf<uint32_t> cms_cursor, cms_spill, cms_state;
+    DevBuf<uint32_t> cms_cursor, cms_spill, cms_state, cms_tile_sp, cms_tile0;
     int cms_force = 0;                    // test knob: 1 = exact (u32) redo in every bucket, 2 = direct fallback
     uint32_t cms_cap_override = 0;        // test knob: bucket list capacity (forces the list-full fallback)
     uint32_t cms_slot_limit = PART_SLOT;  // test knob: staged entries per bucket and tile (forces spills)
@@ -193,7 +193,6 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     b->codes.ensure(b->codes_cap);
     b->rec_cstart.ensure(n_rec + 1);
     b->sp_cstart.ensure(size_t(n_sp) + 1);
-    b->flags.ensure(b->codes_cap / CHUNK + 2);   // +2: viewed as u32 words by bloom_flags_kernel
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
@@ -238,13 +237,15 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     frame_batch(c, b);
     KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    KMN_CUDA(cudaMemsetAsync(b.flags.p, 0, (b.codes_cap / CHUNK) * sizeof(uint16_t), c->stream));
     c->new_counts.ensure(size_t(b.n_sp) + 1);
     KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
     const int grid = grid_for(c, 8);
     if (b.n_codes > 0) {
         // source tiles: 8 Ki positions of one species each, on the warp-tile grid (count_kernels.cuh)
-        std::vector<uint32_t> h_tile0(size_t(b.n_sp) + 1, 0), h_tile_sp;
+        // (host staging vectors live in the context: the async copies below may still read them on return)
+        std::vector<uint32_t>&h_tile0 = c->h_tile0, &h_tile_sp = c->h_tile_sp;
+        h_tile0.assign(size_t(b.n_sp) + 1, 0);
+        h_tile_sp.clear();
         for (uint32_t s = 0; s < b.n_sp; s++) {
             const uint32_t cb = b.h_sp_cstart[s], ce = b.h_sp_cstart[s + 1];
             uint32_t nt = 0;
@@ -274,21 +275,36 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         if (n_tiles) {
             bloom_partition_kernel<<<n_tiles, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
             check_launch(c);
-            KMN_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors above back the async copies
             // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
             bloom_bucket_kernel<<<b.n_sp * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, R);
             check_launch(c);
             bloom_slow_kernel<<<std::min<uint32_t>(b.n_sp, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
                 b.codes.p, b.sp_cstart.p, b.n_sp, c->k, c->k_mask, R, c->bl_scratch.p);
             check_launch(c);
-            bloom_flags_kernel<<<n_tiles, BP_THREADS, 0, c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R,
-                                                                     reinterpret_cast<uint32_t*>(b.flags.p), c->new_counts.p);
-            check_launch(c);
         }
     }
     KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (b.n_codes > 0) {
         const uint32_t n_wtiles = (b.n_codes + WARP_TILE - 1) / WARP_TILE;
+        // partition tiles: 16 Ki positions of one species each, on the warp-tile grid
+        std::vector<uint32_t>&h_ct0 = c->h_ct0, &h_ct_sp = c->h_ct_sp;
+        h_ct0.assign(size_t(b.n_sp) + 1, 0);
+        h_ct_sp.clear();
+        for (uint32_t s = 0; s < b.n_sp; s++) {
+            const uint32_t cb = b.h_sp_cstart[s], ce = b.h_sp_cstart[s + 1];
+            uint32_t nt = 0;
+            if (ce > cb) nt = ((ce + WARP_TILE - 1) / WARP_TILE - cb / WARP_TILE + PART_WTILES - 1) / PART_WTILES;
+            h_ct0[s + 1] = h_ct0[s] + nt;
+            h_ct_sp.insert(h_ct_sp.end(), nt, s);
+        }
+        CmsTiles T;
+        T.n_tiles = h_ct0[b.n_sp];
+        c->cms_tile_sp.ensure(T.n_tiles);
+        c->cms_tile0.ensure(size_t(b.n_sp) + 1);
+        KMN_CUDA(cudaMemcpyAsync(c->cms_tile_sp.p, h_ct_sp.data(), size_t(T.n_tiles) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(c->cms_tile0.p, h_ct0.data(), h_ct0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        T.tile_sp = c->cms_tile_sp.p;
+        T.sp_tile0 = c->cms_tile0.p;
         CmsLists L;
         // expected list length <= n_codes / 1024 (every position new, uniform hashing); +25 % and a constant
         // cover the correlation between species that share k-mers.  A full list is not an error: the batch
@@ -304,20 +320,19 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         L.state = c->cms_state.p;
         KMN_CUDA(cudaMemsetAsync(L.cursor, 0, CMS_BUCKETS * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(L.state, 0, 2 * sizeof(uint32_t), c->stream));
+        // the partition also produces the per-species counts; when the direct path is forced its lists are unused
+        cms_partition_kernel<<<std::min<uint32_t>(T.n_tiles, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
+            b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
+        check_launch(c);
         if (c->cms_force == 2) {
-            const uint32_t one = 1;
+            static const uint32_t one = 1;
             KMN_CUDA(cudaMemcpyAsync(L.state, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
-        } else {
-            const uint32_t n_ptiles = (n_wtiles + PART_WTILES - 1) / PART_WTILES;
-            cms_partition_kernel<<<std::min<uint32_t>(n_ptiles, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
-                b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, L, c->cms_slot_limit);
-            check_launch(c);
-            cms_apply_kernel<<<CMS_BUCKETS, APPLY_THREADS, APPLY_SMEM, c->stream>>>(L, c->tab.p, c->cms_force == 1);
-            check_launch(c);
-            cms_spill_kernel<<<grid_for(c, 2), 256, 0, c->stream>>>(L, c->tab.p);
-            check_launch(c);
         }
-        cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, b.flags.p, n_wtiles, c->k, c->k_mask, c->tab.p, L.state);
+        cms_apply_kernel<<<CMS_BUCKETS, APPLY_THREADS, APPLY_SMEM, c->stream>>>(L, c->tab.p, c->cms_force == 1);
+        check_launch(c);
+        cms_spill_kernel<<<grid_for(c, 2), 256, 0, c->stream>>>(L, c->tab.p);
+        check_launch(c);
+        cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, c->bl_lost2.p, n_wtiles, c->k, c->k_mask, c->tab.p, L.state);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));

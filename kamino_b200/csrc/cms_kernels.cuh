@@ -5,12 +5,14 @@
 // runs at ~190 Gop/s chip-wide, into HBM at ~23-34 Gop/s, while shared-memory atomics run at
 // ~1000 Gop/s.  So the 4 x (new k-mers) increments never touch global memory as atomics:
 //
-//   cms_partition_kernel  each CTA hashes a tile of 16 Ki positions ONCE (k-mers stay in registers for
-//                         the four rows) and splits the cell indices of one row at a time over the
-//                         row's 1024 buckets of 2^16 cells: rank = shared atomicAdd on the bucket's
-//                         fill counter, the low 16 index bits go to a fixed 32-entry slot in shared
-//                         memory, and each bucket's slot is appended to its global list as one run
-//                         (one global atomicAdd per bucket and tile reserves the space).
+//   cms_partition_kernel  each CTA takes a tile of 16 Ki positions of one species, derives "passed the
+//                         Bloom filter" from the lost map (count_kernels.cuh), keeps the k-mers in
+//                         registers for the four rows and splits the cell indices of one row at a time
+//                         over the row's 1024 buckets of 2^16 cells: rank = shared atomicAdd on the
+//                         bucket's fill counter, the low 16 index bits go to a fixed 32-entry slot in
+//                         shared memory, and each bucket's slot is appended to its global list as one
+//                         run (one global atomicAdd per bucket and tile reserves the space).  Also
+//                         counts the passes per species.
 //   cms_apply_kernel      one CTA per bucket: a 128 KiB shared-memory histogram (two u16 counters per
 //                         word) of the bucket's list, then  cell = min(cell + count, 65535)  on the
 //                         u16 table by the bucket's only owner — no global atomics, no u32
@@ -25,7 +27,7 @@
 // (cms_spill_kernel, CAS loop on the u16 cell); a shared counter that would pass 65535 inside one
 // batch makes the CTA redo its bucket with u32 counters in two halves; a bucket list or spill list
 // that runs out of space raises a flag that disables apply/spill and enables cms_direct_kernel,
-// which rebuilds the batch's increments with global CAS loops straight from codes[] + flags.
+// which rebuilds the batch's increments with global CAS loops straight from codes[] + the lost map.
 #pragma once
 #include "kmn_device.cuh"
 
@@ -71,26 +73,41 @@ __device__ __forceinline__ void cms_cell_increment(uint16_t* __restrict__ tab, u
     }
 }
 
+// Source tiles of the partition: 16 Ki positions of ONE species on the warp-tile grid (so the per-species
+// counts of passing occurrences fall out of a block reduction).
+struct CmsTiles {
+    const uint32_t* tile_sp;    // [n_tiles] species of every tile
+    const uint32_t* sp_tile0;   // [n_sp + 1] first tile of every species
+    uint32_t n_tiles;
+};
+
 __global__ void __launch_bounds__(PART_THREADS, 1)
-cms_partition_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_wtiles,
-                     int k, uint64_t k_mask, CmsLists L, uint32_t slot_limit) {
+cms_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, CmsTiles T,
+                     const uint32_t* __restrict__ lost2, int k, uint64_t k_mask, CmsLists L, uint32_t slot_limit,
+                     unsigned long long* __restrict__ new_per_species) {
     extern __shared__ __align__(16) uint8_t part_smem[];
     uint16_t* stage = reinterpret_cast<uint16_t*>(part_smem);                                   // [1024][32]
-    uint32_t* fill = reinterpret_cast<uint32_t*>(part_smem + size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * 2);
+    uint32_t* fill = reinterpret_cast<uint32_t*>(part_smem + size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * 2);   // [1024]
+    __shared__ uint32_t s_new;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n_tiles = (n_wtiles + PART_WTILES - 1) / PART_WTILES;
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint32_t wt = t * PART_WTILES + warp;
+    if (threadIdx.x == 0) s_new = 0;
+    for (uint32_t tg = blockIdx.x; tg < T.n_tiles; tg += gridDim.x) {
+        const uint32_t s = T.tile_sp[tg];
+        const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+        const uint32_t wt = cb / WARP_TILE + (tg - T.sp_tile0[s]) * PART_WTILES + warp;
+        const uint32_t c0 = wt * WARP_TILE + lane * CHUNK;
         uint64_t kmer[CHUNK];
         uint32_t new_bits = 0;
-        if (wt < n_wtiles) {   // warp-uniform
-            load_chunk_kmers<true>(codes, wt * WARP_TILE, k, k_mask, kmer);   // a flag implies a valid k-mer
-            new_bits = __ldcs(flags + (size_t(wt) * WARP_TILE) / CHUNK + lane);
+        if (uint64_t(wt) * WARP_TILE < ce) {   // warp-uniform
+            const uint32_t valid = load_chunk_kmers<true>(codes, wt * WARP_TILE, k, k_mask, kmer) & range_mask16(c0, cb, ce);
+            if (valid) new_bits = valid & ~both_lost_mask16(__ldcs(lost2 + c0 / CHUNK));
         }
+        const uint32_t wn = __reduce_add_sync(0xffffffffu, uint32_t(__popc(new_bits)));
 #pragma unroll 1
         for (int r = 0; r < int(CMS_DEPTH); r++) {
             fill[threadIdx.x] = 0;
             __syncthreads();
+            if (r == 0 && lane == 0 && wn) atomicAdd(&s_new, wn);
             const uint64_t seed = cms_seed(r);
 #pragma unroll
             for (int j = 0; j < CHUNK; j++) {
@@ -101,12 +118,16 @@ cms_partition_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restri
                 if (rank < slot_limit) {
                     stage[b * PART_SLOT + rank] = uint16_t(idx);
                 } else {   // slot full: rare single-entry spill
-                    const uint32_t s = atomicAdd(L.state + 1, 1u);
-                    if (s < L.spill_cap) L.spill[s] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
+                    const uint32_t sp = atomicAdd(L.state + 1, 1u);
+                    if (sp < L.spill_cap) L.spill[sp] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
                     else L.state[0] = 1u;
                 }
             }
             __syncthreads();
+            if (r == 0 && threadIdx.x == 0 && s_new) {   // this tile's adds precede the barrier above, the next tile's follow later ones
+                atomicAdd(new_per_species + s, static_cast<unsigned long long>(s_new));
+                s_new = 0;
+            }
             // thread b reserves the run of bucket b; warp w then copies the slots of buckets 32w..32w+31
             uint32_t n = min(fill[threadIdx.x], slot_limit), base = 0;
             const uint32_t gb = uint32_t(r) * CMS_BUCKETS_PER_ROW + threadIdx.x;
@@ -114,14 +135,12 @@ cms_partition_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restri
                 base = atomicAdd(L.cursor + gb, n);
                 if (base + n > L.cap) { L.state[0] = 1u; n = 0; }   // list full: the batch falls back
             }
+            uint16_t* out = L.ent + size_t(uint32_t(r) * CMS_BUCKETS_PER_ROW + warp * 32u) * L.cap + lane;
 #pragma unroll 4
             for (int q = 0; q < 32; q++) {
                 const uint32_t nb = __shfl_sync(0xffffffffu, n, q);
                 const uint32_t bb = __shfl_sync(0xffffffffu, base, q);
-                if (lane < nb) {
-                    const uint32_t b = warp * 32u + uint32_t(q);
-                    L.ent[size_t(uint32_t(r) * CMS_BUCKETS_PER_ROW + b) * L.cap + bb + lane] = stage[b * PART_SLOT + lane];
-                }
+                if (lane < nb) out[size_t(q) * L.cap + bb] = stage[(warp * 32u + uint32_t(q)) * PART_SLOT + lane];
             }
             __syncthreads();
         }
@@ -206,10 +225,10 @@ cms_spill_kernel(CmsLists L, uint16_t* __restrict__ tab) {
         cms_cell_increment(tab, L.spill[i]);
 }
 
-// Exact slow path straight from codes[] + flags: runs only when the partition raised the fallback flag
-// (or when forced, for the parity tests).
+// Exact slow path straight from codes[] + the lost map: runs only when the partition raised the fallback
+// flag (or when forced, for the parity tests).  The per-species counts were already produced by the partition.
 __global__ void __launch_bounds__(256)
-cms_direct_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ flags, uint32_t n_wtiles,
+cms_direct_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ lost2, uint32_t n_wtiles,
                   int k, uint64_t k_mask, uint16_t* __restrict__ tab, const uint32_t* __restrict__ state) {
     if (!state[0]) return;
     const uint32_t warps_per_grid = gridDim.x * (blockDim.x / 32);
@@ -217,8 +236,8 @@ cms_direct_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict_
     const unsigned lane = threadIdx.x & 31u;
     for (uint32_t t = warp_id; t < n_wtiles; t += warps_per_grid) {
         uint64_t kmer[CHUNK];
-        load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
-        const uint32_t new_bits = flags[(size_t(t) * WARP_TILE) / CHUNK + lane];
+        const uint32_t valid = load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
+        const uint32_t new_bits = valid & ~both_lost_mask16(lost2[(size_t(t) * WARP_TILE) / CHUNK + lane]);
 #pragma unroll
         for (int j = 0; j < CHUNK; j++) {
             if (!((new_bits >> j) & 1u)) continue;

@@ -3,8 +3,8 @@
 // Replaces the filter half of the hot loop of count_species_kmers
 // (/root/reference/src/group_extraction.rs:385-391):
 //     if have == k && !bloom.test_and_set(roll) { cmsa.increment(roll) }
-// and produces one flag bit per codes[] position ("this occurrence passed the filter"), which
-// cms_kernels.cuh turns into count-min increments.
+// and produces the LOST MAP (two bits per codes[] position: probe 0 / probe 1 lost), from which
+// cms_kernels.cuh derives "this occurrence passed the filter" and the count-min increments.
 //
 // ---- exact semantics, order-free (proba_filter.rs:59-74) ---------------------------------------
 // test_and_set is sequential per species: an occurrence passes iff at least one of its two probe
@@ -37,8 +37,9 @@
 //   bloom_slow_kernel       same step logic on a 4 MiB global bitset, one CTA per species, straight from
 //                           codes[]: only for species whose probes overflow a run slot (massively
 //                           repeated k-mers) — exact for every input, fast for natural ones.
-//   bloom_flags_kernel      flag = valid k-mer and not both probes lost; per-species counts of passes.
-// The lost map is written with atomicOr only, so redoing a species on the slow path is idempotent.
+// An occurrence passes iff it is a valid k-mer and not both of its probes are in the lost map; the
+// count-min partition (cms_kernels.cuh) reads the map directly.  The map is written with atomicOr only,
+// so redoing a species on the slow path is idempotent.
 #pragma once
 #include "kmn_device.cuh"
 
@@ -77,14 +78,6 @@ struct BloomRuns {
     uint32_t* slow;             // [n_sp] != 0: a run slot / conflict list overflowed, bloom_slow_kernel owns the species
     uint32_t* lost2;            // lost map: bit 2j+pr of word c/16 <=> probe pr of position c+j lost
 };
-
-// bit j set <=> position c0+j lies inside [cb, ce)
-__device__ __forceinline__ uint32_t range_mask16(uint32_t c0, uint32_t cb, uint32_t ce) {
-    const uint32_t lo = c0 >= cb ? 0u : min(cb - c0, 16u);
-    const uint32_t hi = c0 + 16u <= ce ? 16u : (ce > c0 ? ce - c0 : 0u);
-    if (hi <= lo) return 0u;
-    return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-}
 
 // Positions whose k-mer equals the k-mer of the previous position (both valid): the earlier one set
 // both filter bits, so these can never pass (proba_filter.rs:59-74) and are not probed at all.
@@ -498,45 +491,6 @@ bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
             __threadfence();   // the bits live in global memory: order this step's atomics before the next step's loads
         }
     }
-}
-
-// flag = valid k-mer that did not lose both probes; per-species count of flags.
-__global__ void __launch_bounds__(BP_THREADS)
-bloom_flags_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k, uint64_t k_mask,
-                   BloomRuns R, uint32_t* __restrict__ flags32, unsigned long long* __restrict__ new_per_species) {
-    __shared__ uint32_t s_new;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tg = blockIdx.x;
-    const uint32_t s = R.tile_sp[tg];
-    const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
-    const uint32_t base = tile_c0(cb, tg - R.sp_tile0[s]);
-    if (threadIdx.x == 0) s_new = 0;
-    __syncthreads();
-    const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
-    uint32_t new_bits = 0;
-    if (base + warp * WARP_TILE < ce) {   // warp-uniform
-        uint64_t kmer[CHUNK];
-        const uint32_t range = range_mask16(c0, cb, ce);
-        const uint32_t valid = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer) & range;
-        if (valid) {
-            const uint32_t lw = __ldcs(R.lost2 + c0 / CHUNK);
-            uint32_t x = lw & (lw >> 1) & 0x55555555u;                        // bit 2j: both probes of position j lost
-            x = (x | (x >> 1)) & 0x33333333u;
-            x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-            x = (x | (x >> 4)) & 0x00FF00FFu;
-            x = (x | (x >> 8)) & 0x0000FFFFu;
-            new_bits = valid & ~x;
-        }
-        if (new_bits) {
-            // a chunk straddling a species boundary is shared by two CTAs: merge atomically
-            if (range == 0xFFFFu) reinterpret_cast<uint16_t*>(flags32)[c0 / CHUNK] = uint16_t(new_bits);
-            else atomicOr(flags32 + c0 / (2 * CHUNK), new_bits << (16u * ((c0 / CHUNK) & 1u)));
-        }
-    }
-    const uint32_t wn = __reduce_add_sync(0xffffffffu, uint32_t(__popc(new_bits)));
-    if (lane == 0 && wn) atomicAdd(&s_new, wn);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_new) atomicAdd(new_per_species + s, static_cast<unsigned long long>(s_new));
 }
 
 }  // namespace kmn

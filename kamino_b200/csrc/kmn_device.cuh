@@ -167,4 +167,23 @@ __device__ __forceinline__ uint32_t load_chunk_kmers(const uint8_t* __restrict__
     return valid;
 }
 
+// bit j set <=> position c0+j lies inside [cb, ce)
+__device__ __forceinline__ uint32_t range_mask16(uint32_t c0, uint32_t cb, uint32_t ce) {
+    const uint32_t lo = c0 >= cb ? 0u : min(cb - c0, 16u);
+    const uint32_t hi = c0 + 16u <= ce ? 16u : (ce > c0 ? ce - c0 : 0u);
+    if (hi <= lo) return 0u;
+    return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+
+// Lost map of the Bloom stage (count_kernels.cuh): bit 2j+pr of a chunk's word <=> probe pr of position j
+// lost.  Returns bit j set <=> BOTH probes of position j lost, i.e. the occurrence does not pass the filter.
+__device__ __forceinline__ uint32_t both_lost_mask16(uint32_t lw) {
+    uint32_t x = lw & (lw >> 1) & 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
 }  // namespace kmn
