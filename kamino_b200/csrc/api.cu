@@ -177,8 +177,7 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     b->n_raw = n_raw;
     b->n_rec = uint32_t(n_rec);
     b->n_sp = n_sp;
-    b->raw_pad = (size_t(n_raw) + FRAME_TILE - 1) / FRAME_TILE * FRAME_TILE;
-    if (b->raw_pad == 0) b->raw_pad = FRAME_TILE;
+    b->raw_pad = (size_t(n_raw) / FRAME_TILE + 1) * FRAME_TILE;   // at least one pad byte: offset n_raw has a chunk
     b->raw.ensure(b->raw_pad);
     b->rec_off.ensure(n_rec + 1);
     b->sp_rec_off.ensure(size_t(n_sp) + 1);
@@ -210,13 +209,8 @@ void frame_batch(kmn_ctx* c, Batch& b) {
         check_launch(c);
         exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_tiles);
         check_launch(c);
-        if (b.n_raw > 0) {
-            frame_scatter_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p,
-                                                                       b.rec_off.p, b.n_rec, b.codes.p);
-            check_launch(c);
-        }
-        frame_records_kernel<<<(b.n_rec + 1 + 255) / 256, 256, 0, c->stream>>>(
-            b.raw.p, c->lut, c->tile_base.p, c->warp_cnt.p, b.rec_off.p, b.n_rec, b.rec_cstart.p, b.codes.p);
+        frame_scatter_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p,
+                                                                   b.rec_off.p, b.n_rec, b.codes.p, b.rec_cstart.p);
         check_launch(c);
     } else {
         KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));

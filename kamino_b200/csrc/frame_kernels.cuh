@@ -106,27 +106,37 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_o
     return lo;
 }
 
-// Pass B: scatter recoded residues.  Output index of a kept raw byte i =
+// Pass B: scatter recoded residues and frame the records.  Output index of a kept raw byte i =
 //   (#kept bytes before i) + (index of the record containing i)      [one separator per earlier record]
+// The thread whose 16-byte chunk contains raw offset rec_off[b] also owns record boundary b (0..n_rec):
+//   rec_cstart[b] = (#kept bytes before rec_off[b]) + b, and record b-1's separator (0xFF) sits right before it.
+// raw is padded with at least one space, so the chunk that contains offset n_raw exists.
 __global__ void __launch_bounds__(FRAME_THREADS)
 frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut,
                      const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ rec_off,
-                     uint32_t n_rec, uint8_t* __restrict__ codes) {
+                     uint32_t n_rec, uint8_t* __restrict__ codes, uint32_t* __restrict__ rec_cstart) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
     __shared__ uint32_t s_rlo, s_rhi;
     load_lut(s_lut, lut);
     const uint64_t tile0 = uint64_t(blockIdx.x) * FRAME_TILE;
-    if (threadIdx.x == 0) s_rlo = record_of(rec_off, 0, n_rec - 1, tile0);
+    if (threadIdx.x == 0) s_rlo = record_of(rec_off, 0, n_rec, tile0);
     if (threadIdx.x == 32) {
         uint64_t last = tile0 + FRAME_TILE - 1;
-        if (last >= n_raw) last = n_raw - 1;
-        s_rhi = record_of(rec_off, 0, n_rec - 1, last);
+        if (last > n_raw) last = n_raw;
+        s_rhi = record_of(rec_off, 0, n_rec, last);
     }
     const uint64_t i0 = tile0 + uint64_t(threadIdx.x) * CHUNK;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + i0));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t n = count_kept(v, s_lut);
+    uint32_t kept = 0;   // bit j: byte j of the chunk is a residue (not whitespace, inside the data)
+    uint8_t c[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        c[j] = s_lut[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+        if (c[j] != CODE_SKIP && i0 + j < n_raw) kept |= 1u << j;
+    }
+    const uint32_t n = __popc(kept);
     // exclusive scan of n over the CTA
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t incl = n;
@@ -140,43 +150,35 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
     uint32_t woff = 0;
 #pragma unroll
     for (int i = 0; i < FRAME_WARPS; i++) woff += (i < int(warp)) ? s_w[i] : 0u;
-    uint32_t out = tile_base[blockIdx.x] + woff + incl - n;
-    if (i0 >= n_raw || n == 0) return;
+    uint32_t out = tile_base[blockIdx.x] + woff + incl - n;   // #kept bytes before i0
+    if (i0 > n_raw) return;
+    // r = last boundary at or before i0 (rec_off[0] == 0, so it exists)
     uint32_t r = record_of(rec_off, s_rlo, s_rhi, i0);
+    // record boundaries inside [i0, i0 + 16)
+    {
+        uint32_t b = r;
+        if (rec_off[b] < i0) b++;
+        else while (b > 0 && rec_off[b - 1] == i0) b--;   // empty records share the offset
+        for (; b <= n_rec; b++) {
+            const uint64_t x = rec_off[b];
+            if (x >= i0 + CHUNK) break;
+            const uint32_t cs = out + __popc(kept & ((1u << uint32_t(x - i0)) - 1u)) + b;
+            rec_cstart[b] = cs;
+            if (b > 0) codes[cs - 1] = CODE_INVALID;
+        }
+    }
+    if (n == 0) return;
+    if (r >= n_rec) r = n_rec - 1;
     uint64_t r_end = rec_off[r + 1];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const uint64_t i = i0 + j;
-        const uint8_t c = s_lut[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
-        if (i < n_raw && c != CODE_SKIP) {
+        if ((kept >> j) & 1u) {
+            const uint64_t i = i0 + j;
             while (i >= r_end) { r++; r_end = rec_off[r + 1]; }
-            codes[size_t(out) + r] = c;
+            codes[size_t(out) + r] = c[j];
             out++;
         }
     }
-}
-
-// Pass C: one thread per record boundary b in 0..n_rec: S(b) = #kept bytes before rec_off[b];
-// rec_cstart[b] = S(b) + b; and record b-1's separator (0xFF) is written at rec_cstart[b]-1.
-__global__ void __launch_bounds__(256)
-frame_records_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, const uint32_t* __restrict__ tile_base,
-                     const uint16_t* __restrict__ warp_cnt, const uint64_t* __restrict__ rec_off,
-                     uint32_t n_rec, uint32_t* __restrict__ rec_cstart, uint8_t* __restrict__ codes) {
-    __shared__ uint8_t s_lut[256];
-    load_lut(s_lut, lut);
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > n_rec) return;
-    const uint64_t x = rec_off[b];
-    const uint64_t tile = x / FRAME_TILE;
-    uint32_t s = tile_base[tile];
-    const uint32_t in_tile = uint32_t(x - tile * FRAME_TILE);
-    const uint32_t wfull = in_tile / WARP_TILE;
-    for (uint32_t wi = 0; wi < wfull; wi++) s += warp_cnt[tile * FRAME_WARPS + wi];
-    const uint64_t p0 = tile * FRAME_TILE + uint64_t(wfull) * WARP_TILE;
-    for (uint64_t p = p0; p < x; p++) s += s_lut[raw[p]] != CODE_SKIP;
-    const uint32_t cs = s + b;
-    rec_cstart[b] = cs;
-    if (b > 0) codes[cs - 1] = CODE_INVALID;
 }
 
 // species -> codes[] offsets: sp_cstart[s] = rec_cstart[sp_rec_off[s]]
