@@ -6,8 +6,8 @@
     python bench.py --impl reference            # CPU arm: C++ restatement of kamino 2.0.0
 
 A "step" is one pass of the hot path over one batch: 100 synthetic bacterial proteomes per GPU
-(BASELINE.json configs[1]) -> recode/frame, exact per-species Bloom, count-min build, snapshot
-clamp (+ at N>1 the table exchange: sum of the per-rank accumulators over NCCL).
+(BASELINE.json configs[1]) -> recode/frame, exact per-species Bloom, count-min build into the
+saturating u16 table (+ at N>1 the table exchange: fused NVLink peer kernel, or NCCL sum).
   value : residues/s, inputs already resident in HBM (kmn_count_staged + kmn_finalize_table)
   e2e   : residues/s through the C ABI from pinned HOST buffers (kmn_count_batch: H2D inside the
           timed region) + finalize + D2H of the per-species new-k-mer counts
@@ -252,7 +252,8 @@ def run_gpu(args):
 
     # ---- timed: resident inputs
     sampler = ClockSampler(local_rank)
-    stage_acc = {"frame": 0.0, "bloom": 0.0, "cms": 0.0, "finalize": 0.0}
+    stage_acc = {"frame": 0.0, "bloom": 0.0, "cms": 0.0, "finalize": 0.0, "cms_partition_kernel": 0.0,
+                 "bloom_bucket_kernel": 0.0}
     launches0 = ctx.launch_count()
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,30 +297,31 @@ def run_gpu(args):
     d2h = int(batch.n_sp * 8 + (batch.n_sp + 1) * 4)
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream)
-    # The CMS build is the dominant stage: `sweeps` launches of cms_sweep_kernel per step, each applying
-    # 1/sweeps of the table updates.  SURVEY.md 8d: B1 = 1 + 16u algorithmic bytes per residue for pass 1,
-    # so one launch carries (1 + 16u)/sweeps bytes per residue of the batch and lasts cms_ms/sweeps.
+    # cms_partition_kernel (one launch per step) is the longest kernel of pass 1: it hashes every k-mer that
+    # passed the Bloom filter into its 4 count-min cells and splits them over 4096 shared-memory-sized
+    # buckets.  SURVEY.md 8d: pass 1 moves B1 = 1 + 16u algorithmic bytes per residue (1 residue byte +
+    # 4 cells x (2 B read + 2 B write) per passing k-mer); the launch carries all of them for the batch.
     peak, peak_src = measured_peaks()
     stage_ms = {s: v / args.steps for s, v in stage_acc.items()}
-    sweeps = 4 * int(os.environ.get("KMN_CMS_SLICES_PER_ROW", "4"))
     alg_bytes = (1.0 + 16.0 * u) * batch.n_residues
-    dom_ms = stage_ms["cms"]
-    achieved = (alg_bytes / sweeps) / (dom_ms / sweeps * 1e-3) / 1e9
-    pass1_ms = sum(stage_ms.values())
+    dom_ms = stage_ms["cms_partition_kernel"]
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    pass1_ms = stage_ms["frame"] + stage_ms["bloom"] + stage_ms["cms"] + stage_ms["finalize"]
     traffic = None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text())["cms_sweep_kernel"]["dram_bytes_per_launch"]
+            traffic = json.loads(tp.read_text())["cms_partition_kernel"]["dram_bytes_per_launch"]
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "cms_sweep_kernel", "launches_per_step": sweeps, "achieved": achieved,
+        "bound": "hbm", "kernel": "cms_partition_kernel", "launches_per_step": 1, "achieved": achieved,
         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "algorithmic_bytes_per_launch": alg_bytes / sweeps,
-        "new_kmer_fraction_u": u, "kernel_ms_per_launch": dom_ms / sweeps, "stage_ms": stage_ms,
+        "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "algorithmic_bytes_per_launch": alg_bytes,
+        "new_kmer_fraction_u": u, "kernel_ms_per_launch": dom_ms, "stage_ms": stage_ms,
         "whole_pass1_frac": alg_bytes / (pass1_ms * 1e-3) / 1e9 / peak,
-        "note": "integer/atomic path: the binding resource is L2 atomic throughput, not HBM bytes (DESIGN.md 4)",
+        "note": "integer path: every pass-1 kernel is bound by instruction issue / shared-memory atomics, not by "
+                "HBM bytes (ncu: issue slots 65-77 % busy, DRAM < 10 %); see DESIGN.md 4",
     }
 
     cpu_baseline = None
@@ -339,7 +341,8 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{N_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa) per GPU, k={K}, {SCHEME_NAME}",
                        "residues_per_gpu": batch.n_residues, "species_per_gpu": batch.n_sp,
-                       "l2": "inputs (132 MB residues + 1 GiB accumulators) exceed the 126 MB L2; no explicit flush",
+                       "l2": "per step the kernels stream 122 MB of residues, ~2 GB of partition lists and the 512 MiB "
+                             "table: far beyond the 126 MB L2; no explicit flush",
                        "exchange": "none (1 GPU)" if world == 1 else (
                            "fused NVLink peer kernel: reduce-scatter + clamp + all-gather" if fused
                            else "NCCL all-reduce of the u32 accumulators")},

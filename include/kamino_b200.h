@@ -142,7 +142,8 @@ int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L,
 
 /* Device time (ms) of the last kmn_count_staged / kmn_scan_batch / kmn_pair_counts call on this
  * context, per stage, measured with CUDA events on the context's stream.
- * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts. */
+ * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts,
+ *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1). */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

@@ -115,8 +115,8 @@ struct kmn_ctx {
     bool peers_ready = false;
     std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
-    cudaEvent_t ev[8] = {};
-    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[12] = {};
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
@@ -270,8 +270,10 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
             bloom_partition_kernel<<<n_tiles, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
             check_launch(c);
             // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
+            KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
             bloom_bucket_kernel<<<b.n_sp * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, R);
             check_launch(c);
+            KMN_CUDA(cudaEventRecord(c->ev[9], c->stream));
             bloom_slow_kernel<<<std::min<uint32_t>(b.n_sp, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
                 b.codes.p, b.sp_cstart.p, b.n_sp, c->k, c->k_mask, R, c->bl_scratch.p);
             check_launch(c);
@@ -315,9 +317,11 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         KMN_CUDA(cudaMemsetAsync(L.cursor, 0, CMS_BUCKETS * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(L.state, 0, 2 * sizeof(uint32_t), c->stream));
         // the partition also produces the per-species counts; when the direct path is forced its lists are unused
+        KMN_CUDA(cudaEventRecord(c->ev[6], c->stream));
         cms_partition_kernel<<<std::min<uint32_t>(T.n_tiles, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
             b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
         check_launch(c);
+        KMN_CUDA(cudaEventRecord(c->ev[7], c->stream));
         if (c->cms_force == 2) {
             static const uint32_t one = 1;
             KMN_CUDA(cudaMemcpyAsync(L.state, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
@@ -340,6 +344,11 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[2], c->ev[2], c->ev[3]));
+    c->stage_ms[6] = c->stage_ms[7] = 0.f;
+    if (b.n_codes > 0) {
+        KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[6], c->ev[6], c->ev[7]));
+        if (c->h_tile0.back() > 0) KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[7], c->ev[8], c->ev[9]));
+    }
 }
 
 void finalize_table(kmn_ctx* c) {
@@ -755,7 +764,7 @@ int kmn_pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, u
 
 int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
     return guarded(c, [&] {
-        if (which < 0 || which > 5 || !ms) throw std::runtime_error("invalid stage index");
+        if (which < 0 || which > 7 || !ms) throw std::runtime_error("invalid stage index");
         *ms = c->stage_ms[which];
     });
 }

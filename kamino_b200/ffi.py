@@ -15,7 +15,8 @@ from . import build as _build
 DAYHOFF6, SR6, KGB6 = 0, 1, 2
 SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
 CMS_CELLS = 4 << 26
-STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5}
+STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5,
+          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7}
 
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
