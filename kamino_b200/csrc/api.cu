@@ -82,6 +82,7 @@ struct Batch {
     DevBuf<uint32_t> rec_cstart, sp_cstart;
     std::vector<uint32_t> h_sp_cstart;   // host copy (after framing)
     std::vector<uint64_t> h_sp_rec_off;
+    std::vector<uint64_t> h_sp_raw_off;  // raw byte offset of each species (plans the copy / compute ranges)
     // pass 2 results
     bool scanned = false;
     DevBuf<uint16_t> occ;
@@ -92,6 +93,8 @@ struct Batch {
 };
 
 }  // namespace
+
+constexpr uint32_t kMaxH2dChunks = 16;
 
 struct kmn_ctx {
     int device = 0;
@@ -109,19 +112,21 @@ struct kmn_ctx {
     bool finalized = false;
     DevBuf<unsigned long long> new_counts;
     DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
-    DevBuf<uint16_t> warp_cnt;
     std::vector<std::unique_ptr<Batch>> batches;
     PeerTables peers{};                   // mapped peer buffers of the fused exchange
     bool peers_ready = false;
     std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
+    cudaStream_t copy_stream = nullptr;   // host -> device copies of kmn_count_batch, overlapped with the kernels
     cudaEvent_t ev[12] = {};
+    cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
+    uint32_t h2d_chunks = 6;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
+    DevBuf<uint32_t> frame_carry, n_tiles_dev;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
     DevBuf<uint16_t> bl_cnt;
-    std::vector<uint32_t> h_tile0, h_tile_sp, h_ct0, h_ct_sp;   // host sides of the tile tables
     uint32_t bloom_run_cap = RUN_CAP;     // test knob KMN_BLOOM_RUN_CAP: small slots force the slow exact path
     DevBuf<uint16_t> cms_ent;             // bucket lists of the CMS partition (scratch of count_staged)
     DevBuf<uint32_t> cms_cursor, cms_spill, cms_state, cms_tile_sp, cms_tile0;
@@ -148,8 +153,9 @@ Batch& get_batch(kmn_ctx* c, uint32_t id) {
     return *c->batches[id];
 }
 
-void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
-                 const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+// Validates the offsets, takes a (recycled) Batch and sizes its buffers.  No device work.
+std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                                 const uint64_t* sp_rec_off, uint32_t n_sp) {
     if (!rec_off || !sp_rec_off) throw std::runtime_error("rec_off / sp_rec_off must not be NULL");
     if (n_rec >= (1ull << 31)) throw std::runtime_error("too many records in one batch");
     if (n_sp > 65535) throw std::runtime_error("too many species in one batch (maximum 65535)");  // group_extraction.rs:538
@@ -182,132 +188,146 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     b->rec_off.ensure(n_rec + 1);
     b->sp_rec_off.ensure(size_t(n_sp) + 1);
     b->h_sp_rec_off.assign(sp_rec_off, sp_rec_off + n_sp + 1);
-    if (n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, residues, n_raw, cudaMemcpyHostToDevice, c->stream));
-    if (b->raw_pad > n_raw)  // pad with spaces: skipped like any whitespace
-        KMN_CUDA(cudaMemsetAsync(b->raw.p + n_raw, 0x20, b->raw_pad - n_raw, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(b->rec_off.p, rec_off, (n_rec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    b->h_sp_raw_off.resize(size_t(n_sp) + 1);
+    for (uint32_t s = 0; s <= n_sp; s++) b->h_sp_raw_off[s] = rec_off[sp_rec_off[s]];
     // worst case: every raw byte is a residue, plus one separator per record
     b->codes_cap = (size_t(n_raw) + n_rec + WARP_TILE - 1) / WARP_TILE * WARP_TILE + WARP_TILE;
     b->codes.ensure(b->codes_cap);
     b->rec_cstart.ensure(n_rec + 1);
     b->sp_cstart.ensure(size_t(n_sp) + 1);
+    return b;
+}
+
+void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                 const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+    std::unique_ptr<Batch> b = new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp);
+    if (b->n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, residues, b->n_raw, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemsetAsync(b->raw.p + b->n_raw, 0x20, b->raw_pad - b->n_raw, c->stream));  // spaces: skipped like any whitespace
+    KMN_CUDA(cudaMemcpyAsync(b->rec_off.p, rec_off, (n_rec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
 }
 
-// K0 on a staged batch.
-void frame_batch(kmn_ctx* c, Batch& b) {
-    KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));
-    const uint32_t n_tiles = uint32_t(b.raw_pad / FRAME_TILE);
-    c->tile_cnt.ensure(n_tiles + 1);
-    c->tile_base.ensure(n_tiles + 2);
-    c->warp_cnt.ensure(size_t(n_tiles) * FRAME_WARPS);
-    if (b.n_rec > 0) {
-        frame_count_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, c->lut, c->tile_cnt.p, c->warp_cnt.p);
-        check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_tiles);
-        check_launch(c);
-        frame_scatter_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p,
-                                                                   b.rec_off.p, b.n_rec, b.codes.p, b.rec_cstart.p);
-        check_launch(c);
-    } else {
-        KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));
+// ---- pass 1 ---------------------------------------------------------------------------------------
+// One species range of a batch: its raw bytes arrive (or already sit) in HBM, then frame -> Bloom ->
+// count-min partition run on it.  Nothing here needs a host round trip: tile tables are built on the device
+// and grids are sized from host-side upper bounds, so with host residues the copy of range j+1 (copy stream)
+// overlaps the kernels of range j (compute stream).
+struct SpeciesRange {
+    uint32_t s0, s1;                // species [s0, s1)
+    uint64_t copy_begin, copy_end;  // raw bytes that must be resident before this range is framed
+    uint32_t tile_begin, tile_end;  // frame tiles (4096 raw bytes) processed with this range
+    uint64_t codes_bound;           // upper bound of the codes[] positions of the range
+};
+
+std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
+    std::vector<SpeciesRange> out;
+    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
+    if (b.n_sp == 0) {   // records without species cannot exist (sp_rec_off spans them); frame only
+        out.push_back({0, 0, 0, b.n_raw, 0, n_frame_tiles, 0});
+        return out;
     }
-    species_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_cstart.p, b.sp_rec_off.p, b.n_sp, b.sp_cstart.p);
-    check_launch(c);
-    b.h_sp_cstart.resize(size_t(b.n_sp) + 1);
-    KMN_CUDA(cudaMemcpyAsync(b.h_sp_cstart.data(), b.sp_cstart.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, c->stream));
-    KMN_CUDA(cudaStreamSynchronize(c->stream));
-    b.n_codes = b.h_sp_cstart[b.n_sp];
-    b.framed = true;
-    b.scanned = false;
+    want = std::max<uint32_t>(1, std::min<uint32_t>(want, b.n_sp));
+    const uint64_t per = b.n_raw / want + 1;
+    uint32_t s0 = 0;
+    uint64_t copied = 0;
+    uint32_t tiled = 0;
+    while (s0 < b.n_sp) {
+        uint32_t s1 = s0 + 1;
+        if (out.size() + 1 == want) s1 = b.n_sp;
+        else while (s1 < b.n_sp && b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0] < per) s1++;
+        SpeciesRange r;
+        r.s0 = s0;
+        r.s1 = s1;
+        // the frame tile that holds the range's closing record boundary must be complete
+        const uint64_t end_byte = b.h_sp_raw_off[s1];
+        const bool last = s1 == b.n_sp;
+        r.copy_begin = copied;
+        r.copy_end = last ? b.n_raw : std::min<uint64_t>(b.n_raw, (end_byte / FRAME_TILE + 1) * FRAME_TILE);
+        r.copy_end = std::max(r.copy_end, r.copy_begin);
+        r.tile_begin = tiled;
+        r.tile_end = last ? n_frame_tiles : std::max<uint32_t>(tiled, uint32_t(r.copy_end / FRAME_TILE));
+        if (r.copy_end == b.n_raw) r.tile_end = n_frame_tiles;   // the pad tile carries the boundaries at n_raw
+        const uint64_t recs = b.h_sp_rec_off[s1] - b.h_sp_rec_off[s0];
+        r.codes_bound = (b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0]) + recs;
+        copied = r.copy_end;
+        tiled = r.tile_end;
+        out.push_back(r);
+        s0 = s1;
+    }
+    return out;
 }
 
-void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
-    if (c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
-    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    frame_batch(c, b);
-    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    c->new_counts.ensure(size_t(b.n_sp) + 1);
-    KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
+// host_residues / host_rec_off / host_sp_rec_off != NULL: the batch's inputs still live on the host
+// (kmn_count_batch); NULL: staged before (kmn_count_staged).  frame_only: K0 alone (pass 2 on a loaded table).
+void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_t* host_rec_off,
+               const uint64_t* host_sp_rec_off, bool frame_only, uint64_t* new_kmers_per_species) {
+    if (!frame_only && c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
+    const bool from_host = host_rec_off != nullptr;
+    const uint32_t want = from_host ? std::max<uint32_t>(1, std::min<uint32_t>(c->h2d_chunks, uint32_t(b.n_raw >> 22))) : 1;
+    const std::vector<SpeciesRange> ranges = plan_ranges(b, want);
+    const bool timed = ranges.size() == 1;   // per-stage events only make sense without the pipeline
     const int grid = grid_for(c, 8);
-    if (b.n_codes > 0) {
-        // source tiles: 8 Ki positions of one species each, on the warp-tile grid (count_kernels.cuh)
-        // (host staging vectors live in the context: the async copies below may still read them on return)
-        std::vector<uint32_t>&h_tile0 = c->h_tile0, &h_tile_sp = c->h_tile_sp;
-        h_tile0.assign(size_t(b.n_sp) + 1, 0);
-        h_tile_sp.clear();
-        for (uint32_t s = 0; s < b.n_sp; s++) {
-            const uint32_t cb = b.h_sp_cstart[s], ce = b.h_sp_cstart[s + 1];
-            uint32_t nt = 0;
-            if (ce > cb) nt = ((ce + WARP_TILE - 1) / WARP_TILE - cb / WARP_TILE + BP_TILE_WT - 1) / BP_TILE_WT;
-            h_tile0[s + 1] = h_tile0[s] + nt;
-            h_tile_sp.insert(h_tile_sp.end(), nt, s);
+
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (from_host) {
+        KMN_CUDA(cudaMemcpyAsync(b.rec_off.p, host_rec_off, (size_t(b.n_rec) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(b.sp_rec_off.p, host_sp_rec_off, (size_t(b.n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        KMN_CUDA(cudaEventRecord(c->ev_copy[0], c->stream));
+        KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));   // the raw buffer's previous users are done
+    }
+    KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));
+    KMN_CUDA(cudaMemsetAsync(c->frame_carry.p, 0, sizeof(uint32_t), c->stream));
+    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
+    c->tile_cnt.ensure(n_frame_tiles + 1);
+    c->tile_base.ensure(n_frame_tiles + 2);
+    if (b.n_rec == 0) KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));
+
+    BloomRuns R{};
+    CmsTiles T{};
+    CmsLists L{};
+    if (!frame_only) {
+        c->new_counts.ensure(size_t(b.n_sp) + 1);
+        KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
+        uint64_t max_codes = 0;
+        uint32_t max_sp = 0;
+        for (const SpeciesRange& r : ranges) {
+            max_codes = std::max(max_codes, r.codes_bound);
+            max_sp = std::max(max_sp, r.s1 - r.s0);
         }
-        const uint32_t n_tiles = h_tile0[b.n_sp];
-        BloomRuns R;
+        // source tiles of a range: codes / tile size, plus two partial tiles per species
+        const uint32_t bl_tiles = uint32_t(max_codes / BP_TILE) + 2 * max_sp + 2;
+        const uint32_t cms_tiles = uint32_t(max_codes / PART_TILE) + 2 * max_sp + 2;
         R.cap = c->bloom_run_cap;
-        c->bl_tile_sp.ensure(n_tiles);
+        c->bl_tile_sp.ensure(bl_tiles);
         c->bl_tile0.ensure(size_t(b.n_sp) + 1);
-        c->bl_slow.ensure(b.n_sp);
-        c->bl_ent.ensure(size_t(n_tiles) * BB_BUCKETS * R.cap);
-        c->bl_cnt.ensure(size_t(n_tiles) * BB_BUCKETS);
+        c->bl_slow.ensure(size_t(b.n_sp) + 1);
+        c->bl_ent.ensure(size_t(bl_tiles) * BB_BUCKETS * R.cap);
+        c->bl_cnt.ensure(size_t(bl_tiles) * BB_BUCKETS);
         c->bl_lost2.ensure(b.codes_cap / CHUNK);
-        KMN_CUDA(cudaMemcpyAsync(c->bl_tile_sp.p, h_tile_sp.data(), size_t(n_tiles) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        KMN_CUDA(cudaMemcpyAsync(c->bl_tile0.p, h_tile0.data(), h_tile0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        KMN_CUDA(cudaMemsetAsync(c->bl_slow.p, 0, size_t(b.n_sp) * sizeof(uint32_t), c->stream));
+        c->cms_tile_sp.ensure(cms_tiles);
+        c->cms_tile0.ensure(size_t(b.n_sp) + 1);
+        KMN_CUDA(cudaMemsetAsync(c->bl_slow.p, 0, (size_t(b.n_sp) + 1) * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(c->bl_lost2.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
         R.ent = c->bl_ent.p;
         R.cnt = c->bl_cnt.p;
         R.tile_sp = c->bl_tile_sp.p;
         R.sp_tile0 = c->bl_tile0.p;
+        R.n_tiles = c->n_tiles_dev.p;
         R.slow = c->bl_slow.p;
         R.lost2 = c->bl_lost2.p;
-        if (n_tiles) {
-            bloom_partition_kernel<<<n_tiles, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
-            check_launch(c);
-            // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
-            KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
-            bloom_bucket_kernel<<<b.n_sp * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, R);
-            check_launch(c);
-            KMN_CUDA(cudaEventRecord(c->ev[9], c->stream));
-            bloom_slow_kernel<<<std::min<uint32_t>(b.n_sp, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
-                b.codes.p, b.sp_cstart.p, b.n_sp, c->k, c->k_mask, R, c->bl_scratch.p);
-            check_launch(c);
-        }
-    }
-    KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    if (b.n_codes > 0) {
-        const uint32_t n_wtiles = (b.n_codes + WARP_TILE - 1) / WARP_TILE;
-        // partition tiles: 16 Ki positions of one species each, on the warp-tile grid
-        std::vector<uint32_t>&h_ct0 = c->h_ct0, &h_ct_sp = c->h_ct_sp;
-        h_ct0.assign(size_t(b.n_sp) + 1, 0);
-        h_ct_sp.clear();
-        for (uint32_t s = 0; s < b.n_sp; s++) {
-            const uint32_t cb = b.h_sp_cstart[s], ce = b.h_sp_cstart[s + 1];
-            uint32_t nt = 0;
-            if (ce > cb) nt = ((ce + WARP_TILE - 1) / WARP_TILE - cb / WARP_TILE + PART_WTILES - 1) / PART_WTILES;
-            h_ct0[s + 1] = h_ct0[s] + nt;
-            h_ct_sp.insert(h_ct_sp.end(), nt, s);
-        }
-        CmsTiles T;
-        T.n_tiles = h_ct0[b.n_sp];
-        c->cms_tile_sp.ensure(T.n_tiles);
-        c->cms_tile0.ensure(size_t(b.n_sp) + 1);
-        KMN_CUDA(cudaMemcpyAsync(c->cms_tile_sp.p, h_ct_sp.data(), size_t(T.n_tiles) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        KMN_CUDA(cudaMemcpyAsync(c->cms_tile0.p, h_ct0.data(), h_ct0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         T.tile_sp = c->cms_tile_sp.p;
         T.sp_tile0 = c->cms_tile0.p;
-        CmsLists L;
-        // expected list length <= n_codes / 1024 (every position new, uniform hashing); +25 % and a constant
+        T.n_tiles = c->n_tiles_dev.p + 1;
+        // expected list length <= codes / 1024 (every position passes, uniform hashing); +25 % and a constant
         // cover the correlation between species that share k-mers.  A full list is not an error: the batch
         // then takes the exact direct path (cms_direct_kernel).
+        const uint64_t all_codes = b.n_raw + b.n_rec;
         L.cap = c->cms_cap_override ? c->cms_cap_override
-                                    : uint32_t((uint64_t(b.n_codes) / CMS_BUCKETS_PER_ROW * 5 / 4 + 4096 + 7) / 8 * 8);
-        L.spill_cap = b.n_codes / 64 + 65536;
+                                    : uint32_t((all_codes / CMS_BUCKETS_PER_ROW * 5 / 4 + 4096 + 7) / 8 * 8);
+        L.spill_cap = uint32_t(all_codes / 64 + 65536);
         c->cms_ent.ensure(size_t(CMS_BUCKETS) * L.cap);
         c->cms_spill.ensure(L.spill_cap);
         L.ent = c->cms_ent.p;
@@ -316,12 +336,73 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         L.state = c->cms_state.p;
         KMN_CUDA(cudaMemsetAsync(L.cursor, 0, CMS_BUCKETS * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(L.state, 0, 2 * sizeof(uint32_t), c->stream));
-        // the partition also produces the per-species counts; when the direct path is forced its lists are unused
-        KMN_CUDA(cudaEventRecord(c->ev[6], c->stream));
-        cms_partition_kernel<<<std::min<uint32_t>(T.n_tiles, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
+    }
+
+    if (from_host)   // pad with spaces: skipped like any whitespace (disjoint from the range copies)
+        KMN_CUDA(cudaMemsetAsync(b.raw.p + b.n_raw, 0x20, b.raw_pad - b.n_raw, c->copy_stream));
+    for (size_t j = 0; j < ranges.size(); j++) {
+        const SpeciesRange& r = ranges[j];
+        if (from_host) {   // copy stream: this range's raw bytes, then the compute stream may frame them
+            if (r.copy_end > r.copy_begin)
+                KMN_CUDA(cudaMemcpyAsync(b.raw.p + r.copy_begin, host_residues + r.copy_begin, r.copy_end - r.copy_begin,
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+            cudaEvent_t e = c->ev_copy[1 + j % (kMaxH2dChunks)];
+            KMN_CUDA(cudaEventRecord(e, c->copy_stream));
+            KMN_CUDA(cudaStreamWaitEvent(c->stream, e, 0));
+        }
+        // ---- K0 frame on the range's tiles (running total of kept bytes carried on the device)
+        const uint32_t nt = r.tile_end - r.tile_begin;
+        if (b.n_rec > 0 && nt > 0) {
+            frame_count_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, c->lut, r.tile_begin, c->tile_cnt.p);
+            check_launch(c);
+            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt,
+                                                           c->frame_carry.p);
+            check_launch(c);
+            frame_scatter_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
+                                                                   b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin);
+            check_launch(c);
+        }
+        {
+            const uint32_t s_begin = j == 0 ? 0 : r.s0 + 1, s_end = r.s1;   // boundary s0 was written by the previous range
+            if (s_end >= s_begin) {
+                species_offsets_kernel<<<(s_end - s_begin + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_cstart.p, b.sp_rec_off.p,
+                                                                                              s_begin, s_end, b.sp_cstart.p);
+                check_launch(c);
+            }
+        }
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+        if (frame_only || r.s1 == r.s0) continue;
+        // ---- K2 Bloom: probe partition, per-bucket shared-memory bitsets, slow exact path
+        const uint32_t n_sp_r = r.s1 - r.s0;
+        const uint32_t bl_bound = uint32_t(r.codes_bound / BP_TILE) + 2 * n_sp_r + 2;
+        species_tiles_kernel<<<1, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1, BP_TILE_WT, c->bl_tile0.p, c->bl_tile_sp.p,
+                                                      c->n_tiles_dev.p);
+        check_launch(c);
+        bloom_partition_kernel<<<bl_bound, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+        check_launch(c);
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
+        // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
+        bloom_bucket_kernel<<<n_sp_r * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, r.s0, R);
+        check_launch(c);
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[9], c->stream));
+        bloom_slow_kernel<<<std::min<uint32_t>(n_sp_r, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
+            b.codes.p, b.sp_cstart.p, r.s0, r.s1, c->k, c->k_mask, R, c->bl_scratch.p);
+        check_launch(c);
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        // ---- K3a count-min partition (also counts the passing occurrences per species)
+        species_tiles_kernel<<<1, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1, PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p,
+                                                      c->n_tiles_dev.p + 1);
+        check_launch(c);
+        const uint32_t cms_bound = uint32_t(r.codes_bound / PART_TILE) + 2 * n_sp_r + 2;
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[6], c->stream));
+        cms_partition_kernel<<<std::min<uint32_t>(cms_bound, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
             b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
         check_launch(c);
-        KMN_CUDA(cudaEventRecord(c->ev[7], c->stream));
+        if (timed) KMN_CUDA(cudaEventRecord(c->ev[7], c->stream));
+    }
+    const bool counted = !frame_only && b.n_sp > 0;
+    if (counted) {
+        // ---- K3b: per-bucket shared-memory histograms merged into the saturating table, once per batch
         if (c->cms_force == 2) {
             static const uint32_t one = 1;
             KMN_CUDA(cudaMemcpyAsync(L.state, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
@@ -330,24 +411,33 @@ void count_staged(kmn_ctx* c, Batch& b, uint64_t* new_kmers_per_species) {
         check_launch(c);
         cms_spill_kernel<<<grid_for(c, 2), 256, 0, c->stream>>>(L, c->tab.p);
         check_launch(c);
-        cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, c->bl_lost2.p, n_wtiles, c->k, c->k_mask, c->tab.p, L.state);
+        cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, c->bl_lost2.p, uint32_t(b.codes_cap / WARP_TILE) - 1, c->k, c->k_mask,
+                                                       c->tab.p, L.state);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    b.h_sp_cstart.resize(size_t(b.n_sp) + 1);
+    KMN_CUDA(cudaMemcpyAsync(b.h_sp_cstart.data(), b.sp_cstart.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, c->stream));
     std::vector<unsigned long long> h(b.n_sp);
-    if (new_kmers_per_species && b.n_sp)
+    if (counted && new_kmers_per_species)
         KMN_CUDA(cudaMemcpyAsync(h.data(), c->new_counts.p, size_t(b.n_sp) * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));
-    if (new_kmers_per_species)
-        for (uint32_t s = 0; s < b.n_sp; s++) new_kmers_per_species[s] = h[s];
-    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]));
-    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]));
-    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[2], c->ev[2], c->ev[3]));
-    c->stage_ms[6] = c->stage_ms[7] = 0.f;
-    if (b.n_codes > 0) {
-        KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[6], c->ev[6], c->ev[7]));
-        if (c->h_tile0.back() > 0) KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[7], c->ev[8], c->ev[9]));
+    b.n_codes = b.h_sp_cstart[b.n_sp];
+    b.framed = true;
+    b.scanned = false;
+    if (!frame_only && new_kmers_per_species)
+        for (uint32_t s = 0; s < b.n_sp; s++) new_kmers_per_species[s] = counted ? h[s] : 0;
+    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = c->stage_ms[6] = c->stage_ms[7] = 0.f;
+    if (timed && !frame_only) {
+        KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]));
+        if (counted) {
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]));
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[2], c->ev[2], c->ev[3]));
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[6], c->ev[6], c->ev[7]));
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[7], c->ev[8], c->ev[9]));
+        }
     }
 }
 
@@ -370,7 +460,7 @@ void finalize_table(kmn_ctx* c) {
 
 void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, uint64_t* n_ends) {
     if (!c->finalized) throw std::runtime_error("kmn_scan_batch needs a finalized table (kmn_finalize_table / kmn_table_load)");
-    if (!b.framed) frame_batch(c, b);
+    if (!b.framed) run_pass1(c, b, nullptr, nullptr, nullptr, true, nullptr);
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     const uint32_t n_tiles = uint32_t((size_t(b.n_codes) + WARP_TILE - 1) / WARP_TILE);
     b.occ.ensure(size_t(n_tiles + 1) * WARP_TILE);
@@ -387,7 +477,7 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     if (n_ctiles) {
         invalid_count_kernel<<<n_ctiles, 256, 0, c->stream>>>(b.codes.p, b.n_codes, c->tile_cnt.p);
         check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_ctiles);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_ctiles, nullptr);
         check_launch(c);
         KMN_CUDA(cudaMemcpyAsync(&n_inv, c->tile_base.p + n_ctiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
@@ -408,9 +498,9 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
             b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr,
             b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, nullptr, nullptr);
         check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_s_cnt.p, c->seg_s_off.p, n_inv);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_s_cnt.p, c->seg_s_off.p, n_inv, nullptr);
         check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_e_cnt.p, c->seg_e_off.p, n_inv);
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_e_cnt.p, c->seg_e_off.p, n_inv, nullptr);
         check_launch(c);
         KMN_CUDA(cudaMemcpyAsync(&tot_s, c->seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaMemcpyAsync(&tot_e, c->seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -530,7 +620,16 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         }
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        KMN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : c->ev_copy) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->frame_carry.alloc(1);
+        c->n_tiles_dev.alloc(2);
+        if (const char* e = std::getenv("KMN_H2D_CHUNKS")) {   // tuning knob
+            const long v = std::strtol(e, nullptr, 10);
+            if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
+            c->h2d_chunks = uint32_t(v);
+        }
         if (const char* e = std::getenv("KMN_BLOOM_RUN_CAP")) {   // test knob
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(RUN_CAP)) throw std::runtime_error("KMN_BLOOM_RUN_CAP must be in 1..208");
@@ -563,6 +662,8 @@ void kmn_destroy(kmn_ctx* c) {
     c->spare.clear();
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -573,17 +674,18 @@ int kmn_stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off
 }
 
 int kmn_count_staged(kmn_ctx* c, uint32_t batch_id, uint64_t* new_kmers_per_species) {
-    return guarded(c, [&] { count_staged(c, get_batch(c, batch_id), new_kmers_per_species); });
+    return guarded(c, [&] { run_pass1(c, get_batch(c, batch_id), nullptr, nullptr, nullptr, false, new_kmers_per_species); });
 }
 
 int kmn_count_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint64_t* new_kmers_per_species,
                     uint32_t* batch_id) {
     return guarded(c, [&] {
-        uint32_t id = 0;
-        stage_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, &id);
+        c->batches.push_back(new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp));
+        const uint32_t id = uint32_t(c->batches.size() - 1);
         if (batch_id) *batch_id = id;
-        count_staged(c, get_batch(c, id), new_kmers_per_species);
+        // host -> device copies of the species ranges overlap the kernels of the previous range
+        run_pass1(c, get_batch(c, id), residues, rec_off, sp_rec_off, false, new_kmers_per_species);
     });
 }
 

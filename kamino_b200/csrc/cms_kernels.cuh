@@ -77,8 +77,8 @@ __device__ __forceinline__ void cms_cell_increment(uint16_t* __restrict__ tab, u
 // counts of passing occurrences fall out of a block reduction).
 struct CmsTiles {
     const uint32_t* tile_sp;    // [n_tiles] species of every tile
-    const uint32_t* sp_tile0;   // [n_sp + 1] first tile of every species
-    uint32_t n_tiles;
+    const uint32_t* sp_tile0;   // [n_sp + 1] first tile of every species (species_tiles_kernel)
+    const uint32_t* n_tiles;    // device scalar
 };
 
 __global__ void __launch_bounds__(PART_THREADS, 1)
@@ -91,7 +91,8 @@ cms_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restri
     __shared__ uint32_t s_new;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_new = 0;
-    for (uint32_t tg = blockIdx.x; tg < T.n_tiles; tg += gridDim.x) {
+    const uint32_t n_tiles = *T.n_tiles;
+    for (uint32_t tg = blockIdx.x; tg < n_tiles; tg += gridDim.x) {
         const uint32_t s = T.tile_sp[tg];
         const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
         const uint32_t wt = cb / WARP_TILE + (tg - T.sp_tile0[s]) * PART_WTILES + warp;

@@ -74,7 +74,8 @@ struct BloomRuns {
     uint16_t* cnt;              // per species: [BB_BUCKETS][tiles of the species] (a bucket's counts are contiguous)
     uint32_t cap;               // RUN_CAP (smaller only under the test knob)
     const uint32_t* tile_sp;    // [n_tiles] species (index inside the batch) of every source tile
-    const uint32_t* sp_tile0;   // [n_sp + 1] first source tile of every species
+    const uint32_t* sp_tile0;   // [n_sp + 1] first source tile of every species (species_tiles_kernel)
+    const uint32_t* n_tiles;    // device scalar: source tiles of this launch (the grid is an upper bound)
     uint32_t* slow;             // [n_sp] != 0: a run slot / conflict list overflowed, bloom_slow_kernel owns the species
     uint32_t* lost2;            // lost map: bit 2j+pr of word c/16 <=> probe pr of position c+j lost
 };
@@ -117,6 +118,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
     uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * R.cap;   // [BB_BUCKETS]
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tg = blockIdx.x;
+    if (tg >= *R.n_tiles) return;
     const uint32_t s = R.tile_sp[tg];
     const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
     const uint32_t tg0 = R.sp_tile0[s], nt = R.sp_tile0[s + 1] - tg0;
@@ -302,14 +304,14 @@ __device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list
 }
 
 __global__ void __launch_bounds__(BB_THREADS, 3)
-bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, BloomRuns R) {
+bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRuns R) {
     extern __shared__ __align__(16) unsigned long long bb_smem[];
     unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(bb_smem + BB_LIST_CAP);       // BB_WORDS
     __shared__ unsigned long long s_mt[2 * MT_SLOTS];
     __shared__ uint32_t s_mf[2 * MF_WORDS];
     __shared__ uint32_t s_n[2];
-    const uint32_t s = blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
+    const uint32_t s = s0 + blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
     if (R.slow[s]) return;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tg0 = R.sp_tile0[s], n_tiles = R.sp_tile0[s + 1] - tg0;
@@ -445,8 +447,8 @@ constexpr size_t BS_SMEM = size_t(BS_LIST_CAP) * sizeof(unsigned long long);
 constexpr uint32_t BS_MAX_CTAS = 32;                        // 4 MiB of scratch bits each
 
 __global__ void __launch_bounds__(BS_THREADS, 1)
-bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, uint32_t n_sp, int k,
-                  uint64_t k_mask, BloomRuns R, uint32_t* __restrict__ scratch_bits) {
+bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t s1,
+                  int k, uint64_t k_mask, BloomRuns R, uint32_t* __restrict__ scratch_bits) {
     extern __shared__ __align__(16) unsigned long long bs_list[];   // BS_LIST_CAP
     __shared__ unsigned long long s_mt[2 * MT_SLOTS];
     __shared__ uint32_t s_mf[2 * MF_WORDS];
@@ -454,7 +456,7 @@ bloom_slow_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t* bitset = scratch_bits + (size_t(blockIdx.x) << (BLOOM_BITS_LOG2 - 5));
     const StepShared S{bs_list, BS_LIST_CAP, s_mf, s_mt, s_n};
-    for (uint32_t s = blockIdx.x; s < n_sp; s += gridDim.x) {
+    for (uint32_t s = s0 + blockIdx.x; s < s1; s += gridDim.x) {
         if (!R.slow[s]) continue;   // CTA-uniform
         const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
         const uint32_t n_tiles = R.sp_tile0[s + 1] - R.sp_tile0[s];

@@ -29,38 +29,37 @@ __device__ __forceinline__ uint32_t count_kept(const uint4& v, const uint8_t* s_
     return n;
 }
 
-// Pass A: kept-byte counts per CTA tile (4096 B) and per warp sub-tile (512 B).
+// Pass A: kept-byte counts per CTA tile (4096 B), for the tiles [tile_begin, tile_begin + gridDim.x).
 // raw is padded with spaces to a multiple of FRAME_TILE, so no tail guard is needed.
 __global__ void __launch_bounds__(FRAME_THREADS)
-frame_count_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, uint32_t* __restrict__ tile_cnt,
-                   uint16_t* __restrict__ warp_cnt) {
+frame_count_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, uint32_t tile_begin, uint32_t* __restrict__ tile_cnt) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
     load_lut(s_lut, lut);
-    const size_t base = size_t(blockIdx.x) * FRAME_TILE + size_t(threadIdx.x) * CHUNK;
+    const uint32_t tile = tile_begin + blockIdx.x;
+    const size_t base = size_t(tile) * FRAME_TILE + size_t(threadIdx.x) * CHUNK;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + base));
     uint32_t n = count_kept(v, s_lut);
     n = __reduce_add_sync(0xffffffffu, n);
     const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-        s_w[warp] = n;
-        warp_cnt[size_t(blockIdx.x) * FRAME_WARPS + warp] = uint16_t(n);
-    }
+    if ((threadIdx.x & 31) == 0) s_w[warp] = n;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t t = 0;
 #pragma unroll
         for (int i = 0; i < FRAME_WARPS; i++) t += s_w[i];
-        tile_cnt[blockIdx.x] = t;
+        tile_cnt[tile] = t;
     }
 }
 
-// Single-CTA exclusive scan of n u32 values (n <= a few 10^5 tiles); total -> out[n].
+// Single-CTA exclusive scan of n u32 values (n <= a few 10^5 tiles); total -> out[n].  With `carry` the scan
+// continues a running total kept in device memory (chunked framing: *carry in, *carry + sum out).
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __restrict__ in,
-                                                              uint32_t* __restrict__ out, uint32_t n) {
+                                                              uint32_t* __restrict__ out, uint32_t n,
+                                                              uint32_t* __restrict__ carry) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) s_carry = carry ? *carry : 0u;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t base = 0; base < n; base += 1024) {
@@ -91,7 +90,10 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __
         if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = s_carry;
+    if (threadIdx.x == 0) {
+        out[n] = s_carry;
+        if (carry) *carry = s_carry;
+    }
 }
 
 // index of the record that contains raw byte offset x: largest r with rec_off[r] <= x, skipping
@@ -114,12 +116,14 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_o
 __global__ void __launch_bounds__(FRAME_THREADS)
 frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut,
                      const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ rec_off,
-                     uint32_t n_rec, uint8_t* __restrict__ codes, uint32_t* __restrict__ rec_cstart) {
+                     uint32_t n_rec, uint8_t* __restrict__ codes, uint32_t* __restrict__ rec_cstart,
+                     uint32_t tile_begin) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
     __shared__ uint32_t s_rlo, s_rhi;
     load_lut(s_lut, lut);
-    const uint64_t tile0 = uint64_t(blockIdx.x) * FRAME_TILE;
+    const uint32_t tile = tile_begin + blockIdx.x;
+    const uint64_t tile0 = uint64_t(tile) * FRAME_TILE;
     if (threadIdx.x == 0) s_rlo = record_of(rec_off, 0, n_rec, tile0);
     if (threadIdx.x == 32) {
         uint64_t last = tile0 + FRAME_TILE - 1;
@@ -150,7 +154,7 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
     uint32_t woff = 0;
 #pragma unroll
     for (int i = 0; i < FRAME_WARPS; i++) woff += (i < int(warp)) ? s_w[i] : 0u;
-    uint32_t out = tile_base[blockIdx.x] + woff + incl - n;   // #kept bytes before i0
+    uint32_t out = tile_base[tile] + woff + incl - n;   // #kept bytes before i0
     if (i0 > n_raw) return;
     // r = last boundary at or before i0 (rec_off[0] == 0, so it exists)
     uint32_t r = record_of(rec_off, s_rlo, s_rhi, i0);
@@ -181,12 +185,63 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
     }
 }
 
-// species -> codes[] offsets: sp_cstart[s] = rec_cstart[sp_rec_off[s]]
+// species -> codes[] offsets for the species boundaries [s_begin, s_end]: sp_cstart[s] = rec_cstart[sp_rec_off[s]]
 __global__ void species_offsets_kernel(const uint32_t* __restrict__ rec_cstart,
-                                       const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp,
+                                       const uint64_t* __restrict__ sp_rec_off, uint32_t s_begin, uint32_t s_end,
                                        uint32_t* __restrict__ sp_cstart) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s <= n_sp) sp_cstart[s] = rec_cstart[sp_rec_off[s]];
+    const uint32_t s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= s_end) sp_cstart[s] = rec_cstart[sp_rec_off[s]];
+}
+
+// Per-species source tiles of `tile_wt` warp tiles for the species [s0, s1) (count_kernels.cuh,
+// cms_kernels.cuh): sp_tile0[s] = first tile of species s (indices local to this range, sp_tile0[s0] = 0),
+// tile_sp[t] = species of tile t, *n_tiles = total.  One CTA; no host round trip.
+__global__ void __launch_bounds__(1024)
+species_tiles_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t s1, uint32_t tile_wt,
+                     uint32_t* __restrict__ sp_tile0, uint32_t* __restrict__ tile_sp, uint32_t* __restrict__ n_tiles) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = s0; base < s1; base += 1024) {
+        const uint32_t s = base + threadIdx.x;
+        uint32_t x = 0;
+        if (s < s1) {
+            const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+            if (ce > cb) x = ((ce + WARP_TILE - 1) / WARP_TILE - cb / WARP_TILE + tile_wt - 1) / tile_wt;
+        }
+        uint32_t incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= unsigned(d)) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= unsigned(d)) wi += y;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t first = s_carry + s_warp[warp] + incl - x;
+        if (s < s1) {
+            sp_tile0[s] = first;
+            for (uint32_t t = 0; t < x; t++) tile_sp[first + t] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = first + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sp_tile0[s1] = s_carry;
+        *n_tiles = s_carry;
+    }
 }
 
 }  // namespace kmn
