@@ -355,8 +355,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         if (b.n_rec > 0 && nt > 0) {
             frame_count_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, c->lut, r.tile_begin, c->tile_cnt.p);
             check_launch(c);
-            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt,
-                                                           c->frame_carry.p);
+            const ScanJob job{c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt, c->frame_carry.p};
+            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
             check_launch(c);
             frame_scatter_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
                                                                    b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin);
@@ -465,9 +465,14 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     const uint32_t n_tiles = uint32_t((size_t(b.n_codes) + WARP_TILE - 1) / WARP_TILE);
     b.occ.ensure(size_t(n_tiles + 1) * WARP_TILE);
     const int grid = grid_for(c, 8);
-    if (n_tiles) {
-        occupancy_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(b.codes.p, n_tiles, c->k, c->k_mask, c->final_tab, b.occ.p);
-        check_launch(c);
+    if (n_tiles) {   // 8 L2-sized sweeps: (row, half-row)
+        for (uint32_t r = 0; r < CMS_DEPTH; r++)
+            for (uint32_t half = 0; half < 2; half++) {
+                occupancy_sweep_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(
+                    b.codes.p, n_tiles, c->k, c->k_mask, c->final_tab + (size_t(r) << CMS_WIDTH_LOG2), cms_seed(int(r)), half,
+                    r == 0 && half == 0, b.occ.p);
+                check_launch(c);
+            }
     }
     // reset positions -> segments
     const uint32_t n_ctiles = (b.n_codes + 4095) / 4096;
@@ -477,7 +482,8 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     if (n_ctiles) {
         invalid_count_kernel<<<n_ctiles, 256, 0, c->stream>>>(b.codes.p, b.n_codes, c->tile_cnt.p);
         check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tile_cnt.p, c->tile_base.p, n_ctiles, nullptr);
+        const ScanJob job{c->tile_cnt.p, c->tile_base.p, n_ctiles, nullptr};
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
         check_launch(c);
         KMN_CUDA(cudaMemcpyAsync(&n_inv, c->tile_base.p + n_ctiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
@@ -498,9 +504,8 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
             b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr,
             b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, nullptr, nullptr);
         check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_s_cnt.p, c->seg_s_off.p, n_inv, nullptr);
-        check_launch(c);
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(c->seg_e_cnt.p, c->seg_e_off.p, n_inv, nullptr);
+        exclusive_scan_kernel<<<2, 1024, 0, c->stream>>>(ScanJob{c->seg_s_cnt.p, c->seg_s_off.p, n_inv, nullptr},
+                                                       ScanJob{c->seg_e_cnt.p, c->seg_e_off.p, n_inv, nullptr});
         check_launch(c);
         KMN_CUDA(cudaMemcpyAsync(&tot_s, c->seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaMemcpyAsync(&tot_e, c->seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -56,7 +56,7 @@ struct CmsLists {
     uint32_t cap, spill_cap;
 };
 
-__device__ __forceinline__ uint64_t cms_seed(int r) {
+__host__ __device__ __forceinline__ uint64_t cms_seed(int r) {
     return r == 0 ? SEED_CMS_0 : r == 1 ? SEED_CMS_1 : r == 2 ? SEED_CMS_2 : SEED_CMS_3;
 }
 

@@ -52,20 +52,28 @@ frame_count_kernel(const uint8_t* __restrict__ raw, RecodeLut lut, uint32_t tile
     }
 }
 
-// Single-CTA exclusive scan of n u32 values (n <= a few 10^5 tiles); total -> out[n].  With `carry` the scan
-// continues a running total kept in device memory (chunked framing: *carry in, *carry + sum out).
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __restrict__ in,
-                                                              uint32_t* __restrict__ out, uint32_t n,
-                                                              uint32_t* __restrict__ carry) {
+// Single-CTA exclusive scan of n u32 values (up to a few 10^5 tiles / segments), 8 values per thread and
+// iteration; total -> out[n].  With `carry` the scan continues a running total kept in device memory
+// (chunked framing: *carry in, *carry + sum out).  blockIdx.x selects one of up to two independent scans.
+struct ScanJob { const uint32_t* in; uint32_t* out; uint32_t n; uint32_t* carry; };
+constexpr uint32_t SCAN_ITEMS = 8;
+
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(ScanJob j0, ScanJob j1) {
+    const ScanJob j = blockIdx.x == 0 ? j0 : j1;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = carry ? *carry : 0u;
+    if (threadIdx.x == 0) s_carry = j.carry ? *j.carry : 0u;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t x = i < n ? in[i] : 0u;
-        uint32_t incl = x;
+    for (uint32_t base = 0; base < j.n; base += 1024 * SCAN_ITEMS) {
+        const uint32_t i0 = base + threadIdx.x * SCAN_ITEMS;
+        uint32_t x[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < SCAN_ITEMS; q++) {
+            x[q] = i0 + q < j.n ? j.in[i0 + q] : 0u;
+            sum += x[q];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
@@ -85,14 +93,19 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __
         }
         __syncthreads();
         const uint32_t carry = s_carry;
-        if (i < n) out[i] = carry + s_warp[warp] + incl - x;
+        uint32_t run = carry + s_warp[warp] + incl - sum;
+#pragma unroll
+        for (uint32_t q = 0; q < SCAN_ITEMS; q++) {
+            if (i0 + q < j.n) j.out[i0 + q] = run;
+            run += x[q];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+        if (threadIdx.x == 1023) s_carry = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out[n] = s_carry;
-        if (carry) *carry = s_carry;
+        j.out[j.n] = s_carry;
+        if (j.carry) *j.carry = s_carry;
     }
 }
 

@@ -13,29 +13,50 @@ namespace kmn {
 constexpr int SCAN_THREADS = 256;
 
 // K5a: occ[c] = min over the 4 CMS rows for every valid k-mer END position c; 0 elsewhere.
+// 4.8e8 scattered 2-byte gathers per 100 proteomes into a 512 MiB table run at the HBM random-sector rate
+// (~60 Gop/s, 8 ms); against an L2-resident region the same loads run at 282 Gop/s
+// (tools/microbench/l2_atomics.cu).  So the table is swept in 8 L2-sized slices (half a row = 64 MiB):
+// sweep (row, half) streams the codes, hashes the row's index of every k-mer and folds the cells that
+// fall into its half into the running minimum kept in occ[] (streamed with evict-first hints so that it
+// does not displace the slice).
 __global__ void __launch_bounds__(SCAN_THREADS)
-occupancy_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int k, uint64_t k_mask,
-                 const uint16_t* __restrict__ cms, uint16_t* __restrict__ occ) {
+occupancy_sweep_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int k, uint64_t k_mask,
+                       const uint16_t* __restrict__ cms_row, uint64_t seed, uint32_t half, bool first,
+                       uint16_t* __restrict__ occ) {
     const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
     const unsigned lane = threadIdx.x & 31u;
     for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
         const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
-        uint32_t o[CHUNK / 2];
-#pragma unroll
-        for (int i = 0; i < CHUNK / 2; i++) o[i] = 0;
-        for_each_kmer_in_warp_tile(codes, t * WARP_TILE, k, k_mask, [&](uint32_t c, uint64_t kmer) {
-            const uint32_t a = __ldg(cms + (size_t(0) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_0));
-            const uint32_t b = __ldg(cms + (size_t(1) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_1));
-            const uint32_t d = __ldg(cms + (size_t(2) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_2));
-            const uint32_t e = __ldg(cms + (size_t(3) << CMS_WIDTH_LOG2) + cms_index(kmer, SEED_CMS_3));
-            const uint32_t m = min(min(a, b), min(d, e));
-            const uint32_t j = c - c0;
-            o[j >> 1] |= m << (16 * (j & 1));
-        });
+        uint64_t kmer[CHUNK];
+        const uint32_t valid = load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
         uint4* dst = reinterpret_cast<uint4*>(occ + c0);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        uint32_t o[CHUNK / 2];
+        if (first) {
+#pragma unroll
+            for (int i = 0; i < CHUNK / 2; i++)
+                o[i] = (((valid >> (2 * i)) & 1u) ? 0xFFFFu : 0u) | (((valid >> (2 * i + 1)) & 1u) ? 0xFFFF0000u : 0u);
+        } else {
+            const uint4 a = __ldcs(dst), b = __ldcs(dst + 1);
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+            o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+        }
+        uint32_t v[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {   // all gathers of the chunk in flight together
+            v[j] = 0xFFFFu;
+            if ((valid >> j) & 1u) {
+                const uint32_t idx = cms_index(kmer[j], seed);
+                if ((idx >> (CMS_WIDTH_LOG2 - 1)) == half) v[j] = __ldg(cms_row + idx);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; i++) {
+            const uint32_t lo = min(o[i] & 0xFFFFu, v[2 * i]), hi = min(o[i] >> 16, v[2 * i + 1]);
+            o[i] = lo | (hi << 16);
+        }
+        __stcs(dst, make_uint4(o[0], o[1], o[2], o[3]));
+        __stcs(dst + 1, make_uint4(o[4], o[5], o[6], o[7]));
     }
 }
 
