@@ -105,8 +105,10 @@ int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
  * kmn_exchange_setup maps the peers' buffers.  kmn_exchange_reduce then runs ONE kernel per rank that
  * loads this rank's 1/world cell range from every peer over NVLink, adds with saturation
  * (== snapshot of the summed sketch, proba_filter.rs:171-177) and stores the result into EVERY peer's
- * exchanged table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The caller
- * must barrier across ranks after counting (before the call) and after kmn_synchronize (after the call). */
+ * exchanged table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The ranks
+ * synchronise INSIDE the kernel through signal words in peer memory (cooperative launch): it starts moving
+ * data once every rank's counting kernels have finished and returns once every peer is done with this
+ * rank's buffers, so no host barrier is needed; every rank must call it the same number of times. */
 int kmn_exchange_export(kmn_ctx* ctx, uint8_t* acc_handle64, uint8_t* table_handle64);
 int kmn_exchange_setup(kmn_ctx* ctx, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles);
 int kmn_exchange_reduce(kmn_ctx* ctx);

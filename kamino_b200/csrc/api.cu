@@ -115,6 +115,9 @@ struct kmn_ctx {
     std::vector<std::unique_ptr<Batch>> batches;
     PeerTables peers{};                   // mapped peer buffers of the fused exchange
     bool peers_ready = false;
+    uint32_t exchange_epoch = 0;          // exchanges run so far (every rank counts alike)
+    DevBuf<uint32_t> xsync;               // [0] go word, [1] finished-CTA counter of exchange_reduce_kernel
+    int exchange_grid = 0;
     std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
     cudaStream_t copy_stream = nullptr;   // host -> device copies of kmn_count_batch, overlapped with the kernels
@@ -566,6 +569,16 @@ void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[1]));
 }
 
+// exchanged table + the signal words of the in-kernel rank synchronisation behind it (one IPC handle)
+constexpr size_t kXtabFlagsU16 = 2 * MAX_PEERS * sizeof(uint32_t) / sizeof(uint16_t);
+void alloc_exchange_buffers(kmn_ctx* c) {
+    if (c->xtab.p) return;
+    c->xtab.alloc(CMS_CELLS + kXtabFlagsU16);
+    KMN_CUDA(cudaMemset(c->xtab.p + CMS_CELLS, 0, kXtabFlagsU16 * sizeof(uint16_t)));
+    c->xsync.alloc(2);
+    KMN_CUDA(cudaMemset(c->xsync.p, 0, 2 * sizeof(uint32_t)));
+}
+
 template <typename F>
 int guarded(kmn_ctx* c, F&& f) {
     try {
@@ -761,7 +774,7 @@ int kmn_table_device_ptr(kmn_ctx* c, void** ptr) {
 int kmn_exchange_export(kmn_ctx* c, uint8_t* acc_handle64, uint8_t* table_handle64) {
     return guarded(c, [&] {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-        if (!c->xtab.p) c->xtab.alloc(CMS_CELLS);
+        alloc_exchange_buffers(c);
         cudaIpcMemHandle_t h;
         KMN_CUDA(cudaIpcGetMemHandle(&h, c->tab.p));
         std::memcpy(acc_handle64, &h, 64);
@@ -774,7 +787,7 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
     return guarded(c, [&] {
         if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) throw std::runtime_error("invalid world / rank");
         if (CMS_CELLS / 8 % uint64_t(world)) throw std::runtime_error("world size must divide the table");
-        if (!c->xtab.p) c->xtab.alloc(CMS_CELLS);
+        alloc_exchange_buffers(c);
         for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
         c->ipc_opened.clear();
         c->peers = PeerTables{};
@@ -784,6 +797,7 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
             if (p == rank) {
                 c->peers.part[p] = reinterpret_cast<const uint4*>(c->tab.p);
                 c->peers.full[p] = reinterpret_cast<uint4*>(c->xtab.p);
+                c->peers.flags[p] = reinterpret_cast<uint32_t*>(c->xtab.p + CMS_CELLS);
                 continue;
             }
             cudaIpcMemHandle_t h;
@@ -796,6 +810,7 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
             KMN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(ptr);
             c->peers.full[p] = reinterpret_cast<uint4*>(ptr);
+            c->peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(ptr) + CMS_CELLS);
         }
         c->peers_ready = true;
     });
@@ -806,7 +821,24 @@ int kmn_exchange_reduce(kmn_ctx* c) {
         if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
         const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(c->peers.world);   // uint4 = 8 cells
         KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        exchange_reduce_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(c->peers, per * c->peers.rank, per * (c->peers.rank + 1));
+        uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
+        uint32_t epoch = ++c->exchange_epoch;
+        uint32_t* xs = c->xsync.p;
+        void* args[] = {&c->peers, &v0, &v1, &epoch, &xs};
+        const void* fn;
+        switch (c->peers.world) {
+            case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
+            case 4: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<4, 2>); break;
+            case 8: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<8, 2>); break;
+            default: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<0, 1>); break;
+        }
+        if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
+            int per_sm = 0;
+            KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+            if (per_sm < 1) throw std::runtime_error("exchange_reduce_kernel does not fit on an SM");
+            c->exchange_grid = c->sm_count * std::min(per_sm, 8);
+        }
+        KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
         check_launch(c);
         KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));

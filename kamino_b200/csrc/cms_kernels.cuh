@@ -273,22 +273,93 @@ constexpr int MAX_PEERS = 16;
 struct PeerTables {
     const uint4* part[MAX_PEERS];   // every rank's own table (peer-mapped; part[rank] is local)
     uint4* full[MAX_PEERS];         // every rank's exchanged table
+    uint32_t* flags[MAX_PEERS];     // every rank's signal words: [0..16) "table of rank q complete", [16..32) "rank q done"
     int world, rank;
 };
 
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// WORLD > 0: compile-time rank count; U vectors per thread and iteration, so that WORLD x U 16-byte loads
+// (all peers) are in flight per thread: NVLink round trips are ~2-3 us and one load at a time leaves the
+// links idle.  WORLD == 0: generic loop for other rank counts.
+//
+// The ranks synchronise through signal words in peer memory instead of host barriers (cooperative launch:
+// every CTA is resident).  Prologue: CTA 0 publishes "my table is complete" (epoch) to every peer and waits
+// for theirs, then releases the other CTAs.  Epilogue: the last CTA to finish publishes "done" and waits
+// for every peer's "done": when the kernel ends, nobody still reads this rank's table and every peer has
+// written its slice into this rank's exchanged table.
+template <int WORLD, int U>
 __global__ void __launch_bounds__(256)
-exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end) {
-    for (uint64_t i = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_end;
-         i += uint64_t(gridDim.x) * blockDim.x) {
-        uint4 s = pt.part[pt.rank][i];
-#pragma unroll 1
-        for (int p = 1; p < pt.world; p++) {
-            const int peer = (pt.rank + p) % pt.world;   // stagger the peers across ranks
-            const uint4 a = pt.part[peer][i];
-            s.x = sat_add_u16x2(s.x, a.x); s.y = sat_add_u16x2(s.y, a.y);
-            s.z = sat_add_u16x2(s.z, a.z); s.w = sat_add_u16x2(s.w, a.w);
+exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end, uint32_t epoch, uint32_t* local_sync) {
+    constexpr int W = WORLD > 0 ? WORLD : 1;
+    const int world = pt.world;
+    if (blockIdx.x == 0) {
+        if (int(threadIdx.x) < world) {
+            const int q = (pt.rank + int(threadIdx.x)) % world;
+            st_release_sys(pt.flags[q] + pt.rank, epoch);
+            while (ld_acquire_sys(pt.flags[pt.rank] + q) < epoch) {}
         }
-        for (int p = 0; p < pt.world; p++) pt.full[(pt.rank + p) % pt.world][i] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
+    } else {
+        if (threadIdx.x == 0)
+            while (ld_acquire_sys(local_sync) < epoch) {}
+        __syncthreads();
+    }
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i0 = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < vec_end; i0 += stride * U) {
+        if (WORLD > 0) {
+            uint4 a[U][W];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int p = 0; p < W; p++)
+                    if (i0 + u * stride < vec_end) a[u][p] = __ldcs(pt.part[(pt.rank + p) % W] + i0 + u * stride);   // staggered across ranks
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (i0 + u * stride >= vec_end) break;
+                uint4 s = a[u][0];
+#pragma unroll
+                for (int p = 1; p < W; p++) {
+                    s.x = sat_add_u16x2(s.x, a[u][p].x); s.y = sat_add_u16x2(s.y, a[u][p].y);
+                    s.z = sat_add_u16x2(s.z, a[u][p].z); s.w = sat_add_u16x2(s.w, a[u][p].w);
+                }
+#pragma unroll
+                for (int p = 0; p < W; p++) pt.full[(pt.rank + p) % W][i0 + u * stride] = s;
+            }
+        } else {
+            for (int u = 0; u < U; u++) {
+                const uint64_t i = i0 + u * stride;
+                if (i >= vec_end) break;
+                uint4 s = pt.part[pt.rank][i];
+#pragma unroll 1
+                for (int p = 1; p < world; p++) {
+                    const uint4 a = pt.part[(pt.rank + p) % world][i];
+                    s.x = sat_add_u16x2(s.x, a.x); s.y = sat_add_u16x2(s.y, a.y);
+                    s.z = sat_add_u16x2(s.z, a.z); s.w = sat_add_u16x2(s.w, a.w);
+                }
+                for (int p = 0; p < world; p++) pt.full[(pt.rank + p) % world][i] = s;
+            }
+        }
+    }
+    __threadfence_system();   // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(local_sync + 1, 1u);
+        if (ticket == gridDim.x - 1) {   // last CTA of this rank
+            local_sync[1] = 0;
+            __threadfence_system();
+            for (int p = 0; p < world; p++) st_release_sys(pt.flags[(pt.rank + p) % world] + MAX_PEERS + pt.rank, epoch);
+            for (int p = 0; p < world; p++)
+                while (ld_acquire_sys(pt.flags[pt.rank] + MAX_PEERS + p) < epoch) {}
+        }
     }
 }
 

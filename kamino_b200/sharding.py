@@ -61,12 +61,10 @@ def setup_fused_exchange(ctx, group=None) -> bool:
 
 
 def fused_exchange(ctx, group=None):
-    """reduce-scatter + snapshot + all-gather in one kernel per rank over NVLink peer memory."""
-    import torch.distributed as dist
-    ctx.synchronize()
-    dist.barrier(group=group)      # every rank's accumulators are complete
-    ctx.exchange_reduce()          # synchronizes its own stream before returning
-    dist.barrier(group=group)      # every rank's table has been written by all peers
+    """reduce-scatter + snapshot + all-gather in one kernel per rank over NVLink peer memory.  The ranks
+    synchronise inside the kernel through signal words in peer memory (no host barrier): when the call
+    returns, every peer has written its slice into this rank's table and nobody still reads this rank's."""
+    ctx.exchange_reduce()          # stream-ordered after the counting kernels; synchronizes before returning
 
 
 def clamp_u16(acc: np.ndarray) -> np.ndarray:
