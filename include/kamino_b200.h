@@ -46,6 +46,17 @@ typedef struct kmn_hit {
     uint32_t occ;        /* CountMinSketch::estimate of the k-mer                                */
 } kmn_hit;
 
+/* One anchor pair of pass 2 ("bubble", group_extraction.rs:178-242): the amino-acid block is
+ * aa[seg_start + left_start .. seg_start + left_start + len) of the whitespace-stripped, upper-cased record. */
+typedef struct kmn_pair {
+    uint64_t left;       /* packed k-mer of the selected start anchor                                   */
+    uint64_t right;      /* packed k-mer of its best end anchor                                         */
+    uint32_t rec;        /* record (protein) index inside its species                                   */
+    uint32_t seg_start;  /* whitespace-stripped offset, inside the record, of the valid segment          */
+    uint32_t left_start; /* start of the left anchor inside that segment                                */
+    uint32_t len;        /* block length: right.start + k - left.start (both anchors included)          */
+} kmn_pair;
+
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
 uint32_t kmn_abi_version(void);   /* currently 2 */
@@ -129,6 +140,13 @@ int kmn_scan_batch(kmn_ctx* ctx, uint32_t batch_id, uint32_t min_needed, uint64_
  * (record, segment, position).  Two-call protocol: with starts == NULL only the counts are set. */
 int kmn_fetch_hits(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_hit* starts, uint64_t cap_starts,
                    uint64_t* n_starts, kmn_hit* ends, uint64_t cap_ends, uint64_t* n_ends);
+/* Anchor selection + bubble pairing on the device for every segment of a scanned batch: replaces
+ * select_best_starts_per_local_cluster (group_extraction.rs:151-175) and the anchor search of
+ * extract_bubble_pairs (group_extraction.rs:178-242); the caller only slices the amino-acid blocks.
+ * kmn_fetch_pairs: pairs of species `sp` in reference order (record, segment, left anchor); with
+ * out == NULL only *n is set. */
+int kmn_pair_batch(kmn_ctx* ctx, uint32_t batch_id, uint32_t length_middle, uint64_t* n_pairs);
+int kmn_fetch_pairs(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_pair* out, uint64_t cap, uint64_t* n);
 /* Occupancy per whitespace-stripped residue of species `sp` (records concatenated): estimate()
  * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues. */
 int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap,
@@ -145,7 +163,8 @@ int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L,
 /* Device time (ms) of the last kmn_count_staged / kmn_scan_batch / kmn_pair_counts call on this
  * context, per stage, measured with CUDA events on the context's stream.
  * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts,
- *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1). */
+ *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1),
+ *        8 pair_batch. */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

@@ -89,7 +89,12 @@ struct Batch {
     DevBuf<uint32_t> inv_pos;
     uint32_t n_inv = 0;
     DevBuf<kmn_hit> starts, ends;
+    DevBuf<uint32_t> seg_s_off, seg_e_off;   // per-segment offsets into starts / ends (n_inv + 1)
     std::vector<uint32_t> h_sp_starts_off, h_sp_ends_off;
+    // anchor pairs (kmn_pair_batch)
+    bool paired = false;
+    DevBuf<kmn_pair> pairs;
+    std::vector<uint32_t> h_sp_pairs_off;
 };
 
 }  // namespace
@@ -111,7 +116,7 @@ struct kmn_ctx {
     const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
     bool finalized = false;
     DevBuf<unsigned long long> new_counts;
-    DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, seg_s_off, seg_e_off, sp_s_off, sp_e_off;
+    DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, sp_s_off, sp_e_off;
     std::vector<std::unique_ptr<Batch>> batches;
     PeerTables peers{};                   // mapped peer buffers of the fused exchange
     bool peers_ready = false;
@@ -125,7 +130,7 @@ struct kmn_ctx {
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 6;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
     DevBuf<uint32_t> frame_carry, n_tiles_dev;
-    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float stage_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
@@ -178,7 +183,7 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     if (!c->spare.empty()) {
         b = std::move(c->spare.back());
         c->spare.pop_back();
-        b->framed = b->scanned = false;
+        b->framed = b->scanned = b->paired = false;
         b->n_codes = b->n_inv = 0;
     } else {
         b = std::make_unique<Batch>();
@@ -497,8 +502,8 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     b.n_inv = n_inv;
     c->seg_s_cnt.ensure(size_t(n_inv) + 1);
     c->seg_e_cnt.ensure(size_t(n_inv) + 1);
-    c->seg_s_off.ensure(size_t(n_inv) + 2);
-    c->seg_e_off.ensure(size_t(n_inv) + 2);
+    b.seg_s_off.ensure(size_t(n_inv) + 2);
+    b.seg_e_off.ensure(size_t(n_inv) + 2);
     c->sp_s_off.ensure(size_t(b.n_sp) + 1);
     c->sp_e_off.ensure(size_t(b.n_sp) + 1);
     uint32_t tot_s = 0, tot_e = 0;
@@ -507,20 +512,20 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
             b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr,
             b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, nullptr, nullptr);
         check_launch(c);
-        exclusive_scan_kernel<<<2, 1024, 0, c->stream>>>(ScanJob{c->seg_s_cnt.p, c->seg_s_off.p, n_inv, nullptr},
-                                                       ScanJob{c->seg_e_cnt.p, c->seg_e_off.p, n_inv, nullptr});
+        exclusive_scan_kernel<<<2, 1024, 0, c->stream>>>(ScanJob{c->seg_s_cnt.p, b.seg_s_off.p, n_inv, nullptr},
+                                                       ScanJob{c->seg_e_cnt.p, b.seg_e_off.p, n_inv, nullptr});
         check_launch(c);
-        KMN_CUDA(cudaMemcpyAsync(&tot_s, c->seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        KMN_CUDA(cudaMemcpyAsync(&tot_e, c->seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(&tot_s, b.seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaMemcpyAsync(&tot_e, b.seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         b.starts.ensure(tot_s);
         b.ends.ensure(tot_e);
         segment_boundary_kernel<true><<<grid, SCAN_THREADS, 0, c->stream>>>(
-            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, nullptr, nullptr, c->seg_s_off.p, c->seg_e_off.p,
+            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, nullptr, nullptr, b.seg_s_off.p, b.seg_e_off.p,
             b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, b.starts.p, b.ends.p);
         check_launch(c);
         species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
-            b.inv_pos.p, n_inv, b.sp_cstart.p, b.n_sp, c->seg_s_off.p, c->seg_e_off.p, c->sp_s_off.p, c->sp_e_off.p);
+            b.inv_pos.p, n_inv, b.sp_cstart.p, b.n_sp, b.seg_s_off.p, b.seg_e_off.p, c->sp_s_off.p, c->sp_e_off.p);
         check_launch(c);
         b.h_sp_starts_off.resize(size_t(b.n_sp) + 1);
         b.h_sp_ends_off.resize(size_t(b.n_sp) + 1);
@@ -534,8 +539,44 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     KMN_CUDA(cudaStreamSynchronize(c->stream));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[4], c->ev[0], c->ev[1]));
     b.scanned = true;
+    b.paired = false;
     if (n_starts) *n_starts = tot_s;
     if (n_ends) *n_ends = tot_e;
+}
+
+void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs) {
+    if (!b.scanned) throw std::runtime_error("batch has not been scanned (kmn_scan_batch)");
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const uint32_t n_seg = b.n_inv;
+    uint32_t total = 0;
+    b.h_sp_pairs_off.assign(size_t(b.n_sp) + 1, 0);
+    if (n_seg) {
+        c->seg_s_cnt.ensure(size_t(n_seg) + 1);   // scratch: pairs per segment, then their offsets in seg_e_cnt
+        c->seg_e_cnt.ensure(size_t(n_seg) + 2);
+        const uint32_t blocks = (n_seg + 255) / 256;
+        pair_segments_kernel<false><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
+                                                                 uint32_t(c->k), length_middle, c->seg_s_cnt.p, nullptr, nullptr);
+        check_launch(c);
+        const ScanJob job{c->seg_s_cnt.p, c->seg_e_cnt.p, n_seg, nullptr};
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(&total, c->seg_e_cnt.p + n_seg, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        b.pairs.ensure(total);
+        pair_segments_kernel<true><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
+                                                                uint32_t(c->k), length_middle, nullptr, c->seg_e_cnt.p, b.pairs.p);
+        check_launch(c);
+        species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
+            b.inv_pos.p, n_seg, b.sp_cstart.p, b.n_sp, c->seg_e_cnt.p, c->seg_e_cnt.p, c->sp_s_off.p, c->sp_e_off.p);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(b.h_sp_pairs_off.data(), c->sp_s_off.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    }
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[8], c->ev[0], c->ev[1]));
+    b.paired = true;
+    if (n_pairs) *n_pairs = total;
 }
 
 void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
@@ -875,6 +916,24 @@ int kmn_fetch_hits(kmn_ctx* c, uint32_t batch_id, uint32_t sp, kmn_hit* starts, 
     });
 }
 
+int kmn_pair_batch(kmn_ctx* c, uint32_t batch_id, uint32_t length_middle, uint64_t* n_pairs) {
+    return guarded(c, [&] { pair_batch(c, get_batch(c, batch_id), length_middle, n_pairs); });
+}
+
+int kmn_fetch_pairs(kmn_ctx* c, uint32_t batch_id, uint32_t sp, kmn_pair* out, uint64_t cap, uint64_t* n) {
+    return guarded(c, [&] {
+        Batch& b = get_batch(c, batch_id);
+        if (!b.paired) throw std::runtime_error("batch has not been paired (kmn_pair_batch)");
+        if (sp >= b.n_sp) throw std::runtime_error("species index out of range");
+        const uint64_t p0 = b.h_sp_pairs_off[sp], p1 = b.h_sp_pairs_off[sp + 1];
+        if (n) *n = p1 - p0;
+        if (!out || p1 == p0) return;
+        if (cap < p1 - p0) throw std::runtime_error("pair buffer too small");
+        KMN_CUDA(cudaMemcpyAsync(out, b.pairs.p + p0, (p1 - p0) * sizeof(kmn_pair), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
 int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap, uint64_t* n) {
     return guarded(c, [&] {
         Batch& b = get_batch(c, batch_id);
@@ -903,7 +962,7 @@ int kmn_pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, u
 
 int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
     return guarded(c, [&] {
-        if (which < 0 || which > 7 || !ms) throw std::runtime_error("invalid stage index");
+        if (which < 0 || which > 8 || !ms) throw std::runtime_error("invalid stage index");
         *ms = c->stage_ms[which];
     });
 }

@@ -225,6 +225,65 @@ __global__ void species_hit_offsets_kernel(const uint32_t* __restrict__ inv_pos,
     sp_ends_off[s] = seg_ends_off[lo];
 }
 
+// K5d ("next" row 1 of SURVEY 8f): anchor selection + bubble pairing on the device, one thread per segment.
+// Restates select_best_starts_per_local_cluster (group_extraction.rs:151-175: a cluster spans
+// [first.start, first.start + 10); better = higher occupancy, then smaller start) and extract_bubble_pairs
+// (group_extraction.rs:178-242: best end anchor with left.end < right.start, right.start - left.end <=
+// length_middle; better = higher occupancy, then smaller start) on the segment's start / end hit lists.
+// EMIT == false: pairs per segment; EMIT == true: write them in (segment, left anchor) order.
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+pair_segments_kernel(const kmn_hit* __restrict__ starts, const kmn_hit* __restrict__ ends,
+                     const uint32_t* __restrict__ seg_s_off, const uint32_t* __restrict__ seg_e_off, uint32_t n_seg,
+                     uint32_t k, uint32_t length_middle, uint32_t* __restrict__ seg_p_cnt,
+                     const uint32_t* __restrict__ seg_p_off, kmn_pair* __restrict__ pairs) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_seg) return;
+    const uint32_t s0 = seg_s_off[j], s1 = seg_s_off[j + 1], e0 = seg_e_off[j], e1 = seg_e_off[j + 1];
+    uint32_t n = 0;
+    if (s1 > s0 && e1 > e0) {
+        const uint32_t out = EMIT ? seg_p_off[j] : 0u;
+        auto pos_occ = [](const kmn_hit* h) { return *reinterpret_cast<const uint2*>(&h->start); };   // (start, occ)
+        uint32_t first_end = e0;
+        auto handle = [&](uint32_t li, uint32_t lstart) {
+            const uint32_t left_end = lstart + k;
+            while (first_end < e1 && pos_occ(ends + first_end).x <= left_end) first_end++;
+            uint32_t bj = 0xFFFFFFFFu, bo = 0, bs = 0;
+            for (uint32_t q = first_end; q < e1; q++) {
+                const uint2 r = pos_occ(ends + q);
+                if (r.x <= left_end) continue;
+                if (r.x - left_end > length_middle) break;
+                if (bj == 0xFFFFFFFFu || r.y > bo || (r.y == bo && r.x < bs)) { bj = q; bo = r.y; bs = r.x; }
+            }
+            if (bj == 0xFFFFFFFFu) return;
+            if (EMIT) {
+                kmn_pair p;
+                p.left = starts[li].kmer;
+                p.right = ends[bj].kmer;
+                p.rec = starts[li].rec;
+                p.seg_start = starts[li].seg_start;
+                p.left_start = lstart;
+                p.len = bs + k - lstart;
+                pairs[out + n] = p;
+            }
+            n++;
+        };
+        uint2 f = pos_occ(starts + s0);
+        uint32_t cluster_at = f.x, best_i = s0, best_start = f.x, best_occ = f.y;
+        for (uint32_t i = s0 + 1; i < s1; i++) {
+            const uint2 c = pos_occ(starts + i);
+            if (c.x < cluster_at + 10u) {
+                if (c.y > best_occ || (c.y == best_occ && c.x < best_start)) { best_i = i; best_start = c.x; best_occ = c.y; }
+            } else {
+                handle(best_i, best_start);
+                cluster_at = c.x; best_i = i; best_start = c.x; best_occ = c.y;
+            }
+        }
+        handle(best_i, best_start);
+    }
+    if (!EMIT) seg_p_cnt[j] = n;
+}
+
 // Parity helper: occupancy per stripped residue of one species (separators removed).
 __global__ void occupancy_gather_kernel(const uint16_t* __restrict__ occ, const uint32_t* __restrict__ rec_cstart,
                                         uint32_t r0, uint32_t r1, uint16_t* __restrict__ out) {

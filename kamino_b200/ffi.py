@@ -16,10 +16,14 @@ DAYHOFF6, SR6, KGB6 = 0, 1, 2
 SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
 CMS_CELLS = 4 << 26
 STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5,
-          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7}
+          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8}
 
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
+)
+
+PAIR_DTYPE = np.dtype(
+    [("left", "<u8"), ("right", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("left_start", "<u4"), ("len", "<u4")]
 )
 
 # every symbol declared in include/kamino_b200.h
@@ -28,7 +32,7 @@ ABI_SYMBOLS = [
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
-    "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
+    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
 
@@ -80,6 +84,8 @@ def load_library() -> C.CDLL:
     lib.kmn_scan_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
     lib.kmn_fetch_hits.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p, vp, C.c_uint64, u64p]
     lib.kmn_fetch_occupancy.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.kmn_pair_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p]
+    lib.kmn_fetch_pairs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
     lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
     lib.kmn_last_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.kmn_launch_count.argtypes = [vp]
@@ -221,6 +227,19 @@ class Context:
         self._check(self.lib.kmn_fetch_hits(self._h, batch_id, sp, _ptr(starts), ns.value, C.byref(ns),
                                             _ptr(ends), ne.value, C.byref(ne)))
         return starts, ends
+
+    def pair_batch(self, batch_id: int, length_middle: int) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.kmn_pair_batch(self._h, batch_id, length_middle, C.byref(n)))
+        return n.value
+
+    def fetch_pairs(self, batch_id: int, sp: int) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self.lib.kmn_fetch_pairs(self._h, batch_id, sp, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=PAIR_DTYPE)
+        if n.value:
+            self._check(self.lib.kmn_fetch_pairs(self._h, batch_id, sp, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def fetch_occupancy(self, batch_id: int, sp: int) -> np.ndarray:
         n = C.c_uint64()

@@ -187,6 +187,58 @@ int orc_scan_species(void* cms_, const uint8_t* residues, const uint64_t* rec_of
     } catch (const std::exception& e) { return fail(e); }
 }
 
+// Anchor pairs of one species (group_extraction.rs:245-322 without the arena): for every valid segment
+// scan_valid_segment -> select_best_starts_per_local_cluster -> pair_anchors, in reference order.
+struct orc_pair { uint64_t left, right; uint32_t rec, seg_start, left_start, len; };   // == kmn_pair
+int orc_pair_species(void* cms_, const uint8_t* residues, const uint64_t* rec_off, uint64_t rec_begin,
+                     uint64_t rec_end, int k_, int scheme, uint32_t min_needed, uint64_t length_middle,
+                     orc_pair* out, uint64_t cap, uint64_t* n_out) {
+    try {
+        auto* cms = static_cast<CountMinSketch*>(cms_);
+        size_t k = size_t(k_);
+        uint64_t mask = k_mask_for(k);
+        uint64_t n = 0;
+        std::vector<uint8_t> recoded;
+        std::vector<KmerHit> sc, ea;
+        for (uint64_t r = rec_begin; r < rec_end; r++) {
+            uint32_t rec = uint32_t(r - rec_begin);
+            recoded.clear();
+            uint32_t off_in_rec = 0, seg_start = 0;
+            auto flush = [&]() {
+                if (recoded.size() >= 2 * k + 1 && k > 0) {
+                    sc.clear(); ea.clear();
+                    scan_valid_segment(recoded.data(), recoded.size(), k, mask, *cms, min_needed, sc, ea, nullptr);
+                    std::vector<KmerHit> sel = select_best_starts_per_local_cluster(sc);
+                    for (const auto& pr : pair_anchors(sel, ea, size_t(length_middle))) {
+                        const KmerHit& left = sel[pr.first];
+                        const KmerHit& right = ea[pr.second];
+                        if (n < cap) out[n] = orc_pair{left.kmer, right.kmer, rec, seg_start, uint32_t(left.start),
+                                                       uint32_t(right.end - left.start)};
+                        n++;
+                    }
+                }
+            };
+            for (uint64_t i = rec_off[r]; i < rec_off[r + 1]; i++) {
+                uint8_t b = residues[i];
+                if (b == 0x20 || b == 0x09 || b == 0x0A || b == 0x0C || b == 0x0D) continue;
+                uint8_t up = (b >= 'a' && b <= 'z') ? uint8_t(b - 32) : b;
+                uint8_t rv = recode_byte(up, RecodeScheme(scheme));
+                if (rv == 255) {
+                    flush();
+                    recoded.clear();
+                    seg_start = off_in_rec + 1;
+                } else {
+                    recoded.push_back(rv);
+                }
+                off_in_rec++;
+            }
+            flush();
+        }
+        *n_out = n;
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 // --nj integer counts (phylo.rs:84-95) for all pairs i<j; valid/mismatch are n*n row-major,
 // only the strict upper triangle is written.
 int orc_pair_counts(const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch, int threads) {

@@ -53,15 +53,18 @@ std::vector<KmerHit> select_best_starts_per_local_cluster(const std::vector<Kmer
     return selected;
 }
 
-void extract_bubble_pairs(const uint8_t* aa, const std::vector<KmerHit>& start_anchors,
-                          const std::vector<KmerHit>& end_anchors, size_t length_middle,
-                          uint16_t sid, uint32_t protein_id, RawDirectGroups& groups,
-                          BlockArena& arena) {  // :178-242
+// The anchor search of extract_bubble_pairs (group_extraction.rs:188-231): for every selected start anchor,
+// in order, its best end anchor (index into end_anchors) or none.
+std::vector<std::pair<size_t, size_t>> pair_anchors(const std::vector<KmerHit>& start_anchors,
+                                                    const std::vector<KmerHit>& end_anchors, size_t length_middle) {
+    std::vector<std::pair<size_t, size_t>> out;
     size_t first_end = 0;
-    for (const KmerHit& left : start_anchors) {
+    for (size_t li = 0; li < start_anchors.size(); li++) {
+        const KmerHit& left = start_anchors[li];
         while (first_end < end_anchors.size() && end_anchors[first_end].start <= left.end) first_end++;
         size_t j = first_end;
         bool have_best = false;
+        size_t best_j = 0;
         KmerHit best{};
         while (j < end_anchors.size()) {
             const KmerHit& right = end_anchors[j];
@@ -70,10 +73,21 @@ void extract_bubble_pairs(const uint8_t* aa, const std::vector<KmerHit>& start_a
             if (middle_len > length_middle) break;
             bool replace = !have_best || right.occupancy > best.occupancy ||
                            (right.occupancy == best.occupancy && right.start < best.start);
-            if (replace) { best = right; have_best = true; }
+            if (replace) { best = right; best_j = j; have_best = true; }
             j++;
         }
-        if (!have_best) continue;
+        if (have_best) out.emplace_back(li, best_j);
+    }
+    return out;
+}
+
+void extract_bubble_pairs(const uint8_t* aa, const std::vector<KmerHit>& start_anchors,
+                          const std::vector<KmerHit>& end_anchors, size_t length_middle,
+                          uint16_t sid, uint32_t protein_id, RawDirectGroups& groups,
+                          BlockArena& arena) {  // :178-242
+    for (const auto& pr : pair_anchors(start_anchors, end_anchors, length_middle)) {
+        const KmerHit& left = start_anchors[pr.first];
+        const KmerHit& best = end_anchors[pr.second];
         BlockAa blk = arena.push(aa + left.start, best.end - left.start);
         groups[AnchorPair{left.kmer, best.kmer}].push_back(BlockObs{sid, protein_id, blk});
     }

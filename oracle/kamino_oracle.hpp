@@ -111,6 +111,8 @@ using RawDirectGroups = std::unordered_map<AnchorPair, std::vector<BlockObs>, An
 struct KmerHit { uint64_t kmer; size_t start, end; uint32_t occupancy; bool shared; }; // :131-139
 
 std::vector<KmerHit> select_best_starts_per_local_cluster(const std::vector<KmerHit>& starts); // :151-175
+std::vector<std::pair<size_t, size_t>> pair_anchors(const std::vector<KmerHit>& start_anchors,
+                                                    const std::vector<KmerHit>& end_anchors, size_t length_middle);
 void extract_bubble_pairs(const uint8_t* aa, const std::vector<KmerHit>& starts,
                           const std::vector<KmerHit>& ends, size_t length_middle, uint16_t sid,
                           uint32_t protein_id, RawDirectGroups& groups, BlockArena& arena);   // :178-242

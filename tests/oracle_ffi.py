@@ -19,6 +19,9 @@ CMS_CELLS = 4 << 26
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
 )
+PAIR_DTYPE = np.dtype(
+    [("left", "<u8"), ("right", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("left_start", "<u4"), ("len", "<u4")]
+)
 
 
 def build(force: bool = False) -> Path:
@@ -73,6 +76,8 @@ class Oracle:
         lib.orc_count_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int, C.c_int, C.c_int, vp]
         lib.orc_scan_species.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,
                                          vp, C.c_uint64, vp, vp, C.c_uint64, vp, vp]
+        lib.orc_pair_species.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint64,
+                                         vp, C.c_uint64, vp]
         lib.orc_pair_counts.argtypes = [vp, C.c_uint32, C.c_uint64, vp, vp, C.c_int]
         lib.orc_aa_index.argtypes = [C.c_uint8]
         lib.orc_aa_index.restype = C.c_uint8
@@ -159,6 +164,16 @@ class Oracle:
                                               min_needed, _p(starts), cap, C.byref(ns), _p(ends), cap,
                                               C.byref(ne), _p(occ)))
         return starts[:ns.value], ends[:ne.value], occ
+
+    def pair_species(self, cms, residues, rec_off, rec_begin, rec_end, k, scheme, min_needed, length_middle):
+        residues = np.ascontiguousarray(residues, np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, np.uint64)
+        cap = max(int(rec_off[rec_end] - rec_off[rec_begin]), 1)
+        out = np.zeros(cap, dtype=PAIR_DTYPE)
+        n = C.c_uint64()
+        self._check(self.lib.orc_pair_species(cms, _p(residues), _p(rec_off), rec_begin, rec_end, k, scheme,
+                                              min_needed, length_middle, _p(out), cap, C.byref(n)))
+        return out[:n.value]
 
     # --nj
     def pair_counts(self, mapped: np.ndarray, threads=8):

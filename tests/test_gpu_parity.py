@@ -52,6 +52,13 @@ def _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, min_ne
                     assert np.array_equal(gocc, wocc[:len(gocc)]), f"occupancy differs (species {s})"
                     assert np.array_equal(gs, ws), f"start candidates differ (species {s})"
                     assert np.array_equal(ge, we), f"end anchors differ (species {s})"
+                # anchor selection + bubble pairing on the device (group_extraction.rs:151-242)
+                for lm in (35, 3):
+                    ctx.pair_batch(bid, lm)
+                    for s in (range(n_sp) if scan_species is None else scan_species):
+                        wp = oracle.pair_species(cms, residues, rec_off, int(sp[s]), int(sp[s + 1]), k, scheme,
+                                                 min_needed, lm)
+                        assert np.array_equal(ctx.fetch_pairs(bid, s), wp), f"anchor pairs differ (species {s}, l={lm})"
             finally:
                 oracle.cms_free(cms)
         return want_new, got_table   # owned copy, verified equal to the oracle's (freed below)
