@@ -73,25 +73,6 @@ std::string protein_name_of(const std::string& head) {
     return name;
 }
 
-// Best start candidate of every local cluster: a cluster spans [first.start, first.start + 10);
-// better = higher occupancy, then smaller start (group_extraction.rs:21, :146-175).
-void pick_cluster_starts(const kmn_hit* s, size_t n, std::vector<kmn_hit>& out) {
-    out.clear();
-    if (n == 0) return;
-    uint32_t cluster_at = s[0].start;
-    kmn_hit best = s[0];
-    for (size_t i = 1; i < n; i++) {
-        if (s[i].start < cluster_at + 10) {
-            if (s[i].occ > best.occ || (s[i].occ == best.occ && s[i].start < best.start)) best = s[i];
-        } else {
-            out.push_back(best);
-            cluster_at = s[i].start;
-            best = s[i];
-        }
-    }
-    out.push_back(best);
-}
-
 }  // namespace
 
 Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
@@ -159,97 +140,117 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     t_p1.reset();
     auto t_p2 = std::make_unique<StageTimer>("pass 2 (scan + pairing)");
 
-    // ---- pass 2: boundary hits from the device, pairing on the host, merged in sid order (:611-636)
+    // ---- pass 2: occupancy scan, boundary rule, anchor selection and bubble pairing on the device
+    // (kmn_scan_batch + kmn_pair_batch); the host slices the amino-acid blocks per species on its threads
+    // and merges them in sid order (:611-636)
     if (!opt.quiet) std::fprintf(stderr, " . pass 2: extract sequences\n");
     Extraction ex;
     ex.k = k;
     ex.min_needed = min_needed;
     ex.n_species = n;
     for (auto& in : inputs) ex.species_names.push_back(in.name);
-    std::vector<kmn_hit> starts, ends, picked;
-    std::vector<uint8_t> aa;     // whitespace-stripped, upper-cased residues of the current record
-    uint64_t order = 0;
+    struct SpeciesOut {
+        std::vector<kmn_pair> pairs;
+        std::vector<Observation> obs;   // protein = record index, aa_off local to `arena`
+        std::vector<uint8_t> arena;
+        std::vector<std::string> names;  // protein names of the species' records
+        std::string err;
+    };
+    std::vector<SpeciesOut> outs(n);
     for (const BatchRef& b : batches) {
-        uint64_t ts = 0, te = 0;
+        uint64_t ts = 0, te = 0, np = 0;
         gpu.ok(kmn_scan_batch(gpu.p, b.id, min_needed, &ts, &te));
-        for (size_t sid = b.sp0; sid < b.sp1; sid++) {
-            const Proteome& pr = prot[sid];
-            const size_t n_rec = pr.rec_off.size() - 1;
-            for (const std::string& h : pr.heads) {   // id()/desc() are validated for every record (:429-430)
-                const size_t sp = h.find(' ');
-                if (!valid_utf8(sp == std::string::npos ? h : h.substr(0, sp)) ||
-                    (sp != std::string::npos && !valid_utf8(h.substr(sp + 1))))
-                    throw std::runtime_error("invalid UTF-8 in FASTA header of species " + inputs[sid].name);
-            }
-            const size_t protein_base = ex.protein_names.size();
-            if (protein_base + n_rec > 0xFFFFFFFFull)   // :342-344
-                throw std::runtime_error("too many protein records across all species to index with u32");
-            for (const std::string& h : pr.heads) ex.protein_names.push_back(protein_name_of(h));
-            uint64_t ns = 0, ne = 0;
-            gpu.ok(kmn_fetch_hits(gpu.p, b.id, uint32_t(sid - b.sp0), nullptr, 0, &ns, nullptr, 0, &ne));
-            starts.resize(ns);
-            ends.resize(ne);
-            if (ns == 0 || ne == 0) continue;
-            gpu.ok(kmn_fetch_hits(gpu.p, b.id, uint32_t(sid - b.sp0), starts.data(), ns, &ns, ends.data(), ne, &ne));
-            size_t ei = 0;
-            uint32_t aa_rec = 0xFFFFFFFFu;
-            for (size_t si = 0; si < ns;) {
-                const uint32_t rec = starts[si].rec, seg = starts[si].seg_start;
-                size_t sj = si;
-                while (sj < ns && starts[sj].rec == rec && starts[sj].seg_start == seg) sj++;
-                while (ei < ne && (ends[ei].rec < rec || (ends[ei].rec == rec && ends[ei].seg_start < seg))) ei++;
-                size_t ej = ei;
-                while (ej < ne && ends[ej].rec == rec && ends[ej].seg_start == seg) ej++;
-                pick_cluster_starts(starts.data() + si, sj - si, picked);
-                // right anchor of every selected start (group_extraction.rs:178-242)
-                size_t first_end = ei;
-                for (const kmn_hit& left : picked) {
-                    const uint32_t left_end = left.start + uint32_t(k);
-                    while (first_end < ej && ends[first_end].start <= left_end) first_end++;
-                    const kmn_hit* best = nullptr;
-                    for (size_t j = first_end; j < ej; j++) {
-                        const kmn_hit& right = ends[j];
-                        if (right.start <= left_end) continue;
-                        if (right.start - left_end > length_middle) break;
-                        if (!best || right.occ > best->occ || (right.occ == best->occ && right.start < best->start)) best = &right;
+        gpu.ok(kmn_pair_batch(gpu.p, b.id, uint32_t(std::min<size_t>(length_middle, 0xFFFFFFFFu)), &np));
+        for (size_t sid = b.sp0; sid < b.sp1; sid++) {   // calls on one context are serialised
+            uint64_t cnt = 0;
+            gpu.ok(kmn_fetch_pairs(gpu.p, b.id, uint32_t(sid - b.sp0), nullptr, 0, &cnt));
+            outs[sid].pairs.resize(cnt);
+            if (cnt) gpu.ok(kmn_fetch_pairs(gpu.p, b.id, uint32_t(sid - b.sp0), outs[sid].pairs.data(), cnt, &cnt));
+        }
+    }
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            std::vector<uint8_t> aa;     // whitespace-stripped, upper-cased residues of the current record
+            for (size_t sid; (sid = next.fetch_add(1)) < n;) {
+                const Proteome& pr = prot[sid];
+                SpeciesOut& o = outs[sid];
+                for (const std::string& h : pr.heads) {   // id()/desc() are validated for every record (:429-430)
+                    const size_t sp = h.find(' ');
+                    if (!valid_utf8(sp == std::string::npos ? h : h.substr(0, sp)) ||
+                        (sp != std::string::npos && !valid_utf8(h.substr(sp + 1)))) {
+                        o.err = "invalid UTF-8 in FASTA header of species " + inputs[sid].name;
+                        break;
                     }
-                    if (!best) continue;
-                    if (aa_rec != rec) {   // strip + upper-case the record once (group_extraction.rs:455-482)
+                }
+                if (!o.err.empty()) continue;
+                o.names.reserve(pr.heads.size());
+                for (const std::string& h : pr.heads) o.names.push_back(protein_name_of(h));
+                uint32_t aa_rec = 0xFFFFFFFFu;
+                o.obs.reserve(o.pairs.size());
+                for (const kmn_pair& p : o.pairs) {
+                    if (p.len > 0xFFFF) {   // :92-94
+                        o.err = "amino-acid block length " + std::to_string(p.len) + " exceeds u16::MAX";
+                        break;
+                    }
+                    if (aa_rec != p.rec) {   // strip + upper-case the record once (group_extraction.rs:455-482)
                         aa.clear();
-                        for (uint64_t i = pr.rec_off[rec]; i < pr.rec_off[rec + 1]; i++) {
+                        for (uint64_t i = pr.rec_off[p.rec]; i < pr.rec_off[p.rec + 1]; i++) {
                             const uint8_t c = pr.seq[i];
                             if (c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0C || c == 0x0D) continue;
                             aa.push_back((c >= 'a' && c <= 'z') ? uint8_t(c - 32) : c);
                         }
-                        aa_rec = rec;
+                        aa_rec = p.rec;
                     }
-                    const size_t lo = size_t(seg) + left.start, hi = size_t(seg) + best->start + k;
-                    if (hi - lo > 0xFFFF)   // :92-94
-                        throw std::runtime_error("amino-acid block length " + std::to_string(hi - lo) + " exceeds u16::MAX");
-                    Observation o;
-                    o.left = left.kmer;
-                    o.right = best->kmer;
-                    o.sid = uint32_t(sid);
-                    o.protein = uint32_t(protein_base + rec);
-                    o.aa_off = ex.arena.size();
-                    o.len = uint32_t(hi - lo);
-                    o.order = order++;
-                    ex.arena.insert(ex.arena.end(), aa.begin() + lo, aa.begin() + hi);
-                    ex.obs.push_back(o);
+                    const size_t lo = size_t(p.seg_start) + p.left_start;
+                    Observation ob;
+                    ob.left = p.left;
+                    ob.right = p.right;
+                    ob.sid = uint32_t(sid);
+                    ob.protein = p.rec;
+                    ob.aa_off = o.arena.size();
+                    ob.len = p.len;
+                    ob.order = 0;
+                    o.arena.insert(o.arena.end(), aa.begin() + lo, aa.begin() + lo + p.len);
+                    o.obs.push_back(ob);
                 }
-                si = sj;
-                ei = ej;
+                std::vector<kmn_pair>().swap(o.pairs);
             }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, n)); t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    uint64_t order = 0;
+    for (size_t sid = 0; sid < n; sid++) {   // ordered merge (:611-636): first error in species order
+        SpeciesOut& o = outs[sid];
+        if (!o.err.empty()) throw std::runtime_error(o.err);
+        const Proteome& pr = prot[sid];
+        const size_t n_rec = pr.rec_off.size() - 1;
+        const size_t protein_base = ex.protein_names.size();
+        if (protein_base + n_rec > 0xFFFFFFFFull)   // :342-344
+            throw std::runtime_error("too many protein records across all species to index with u32");
+        for (std::string& nm : o.names) ex.protein_names.push_back(std::move(nm));
+        std::vector<std::string>().swap(o.names);
+        const uint64_t arena_base = ex.arena.size();
+        ex.arena.insert(ex.arena.end(), o.arena.begin(), o.arena.end());
+        for (Observation ob : o.obs) {
+            ob.protein = uint32_t(protein_base + ob.protein);
+            ob.aa_off += arena_base;
+            ob.order = order++;
+            ex.obs.push_back(ob);
         }
+        SpeciesOut().obs.swap(o.obs);
+        std::vector<uint8_t>().swap(o.arena);
     }
     t_p2.reset();
     StageTimer t_sort("group observations");
     // group by anchor pair; inside a group keep emission order == the reference's Vec order (sid, then file order)
-    std::sort(ex.obs.begin(), ex.obs.end(), [](const Observation& a, const Observation& b) {
+    parallel_sort(ex.obs, [](const Observation& a, const Observation& b) {
         if (a.left != b.left) return a.left < b.left;
         if (a.right != b.right) return a.right < b.right;
         return a.order < b.order;
-    });
+    }, opt.threads);
     for (size_t i = 0; i < ex.obs.size(); i++)
         if (i == 0 || ex.obs[i].left != ex.obs[i - 1].left || ex.obs[i].right != ex.obs[i - 1].right) ex.n_groups++;
     return ex;

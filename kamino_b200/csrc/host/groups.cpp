@@ -54,6 +54,42 @@ bool roll_block(const uint8_t* aa, size_t len, size_t k, Scheme scheme, F&& f) {
     return false;
 }
 
+// Open-addressing set of u64 keys (linear probing, power-of-two capacity): the greedy non-overlap filter
+// inserts tens of millions of recoded k-mers, where std::unordered_set's node allocations dominate.
+class KmerSet {
+    std::vector<uint64_t> slot_;
+    std::vector<uint8_t> full_;
+    size_t n_ = 0, mask_ = 0;
+    static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; return x; }
+    void grow() {
+        std::vector<uint64_t> old;
+        std::vector<uint8_t> of;
+        old.swap(slot_);
+        of.swap(full_);
+        const size_t cap = old.empty() ? (size_t(1) << 16) : old.size() * 2;
+        slot_.assign(cap, 0);
+        full_.assign(cap, 0);
+        mask_ = cap - 1;
+        n_ = 0;
+        for (size_t i = 0; i < old.size(); i++) if (of[i]) insert(old[i]);
+    }
+public:
+    bool contains(uint64_t k) const {
+        if (slot_.empty()) return false;
+        for (size_t i = mix(k) & mask_;; i = (i + 1) & mask_) {
+            if (!full_[i]) return false;
+            if (slot_[i] == k) return true;
+        }
+    }
+    void insert(uint64_t k) {
+        if ((n_ + 1) * 2 > slot_.size()) grow();
+        for (size_t i = mix(k) & mask_;; i = (i + 1) & mask_) {
+            if (!full_[i]) { full_[i] = 1; slot_[i] = k; n_++; return; }
+            if (slot_[i] == k) return;
+        }
+    }
+};
+
 }  // namespace
 
 std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme scheme) {   // group_sorting.rs:329-380
@@ -101,13 +137,13 @@ std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme 
     });
     // greedy non-overlap on recoded overlap_k-mers (group_sorting.rs:12-22, :246-286)
     const size_t overlap_k = ex.k < 10 ? 2 * ex.k + 1 : 21;
-    std::unordered_set<uint64_t> used;
+    KmerSet used;
     std::vector<Candidate> kept;
     for (Candidate& c : cands) {
         bool clash = false;
         for (uint32_t r : c.rows) {
             const Observation& o = obs[r];
-            if (roll_block(ex.arena.data() + o.aa_off, o.len, overlap_k, scheme, [&](uint64_t v) { return used.count(v) != 0; })) {
+            if (roll_block(ex.arena.data() + o.aa_off, o.len, overlap_k, scheme, [&](uint64_t v) { return used.contains(v); })) {
                 clash = true;
                 break;
             }

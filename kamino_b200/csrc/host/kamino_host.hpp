@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace kh {
@@ -92,6 +94,32 @@ void run(const Options& opt);
 int cli(int argc, char** argv);
 
 uint8_t recode(uint8_t b, Scheme s);
+
+// std::sort on `threads` host threads: sorted chunks, then pairwise in-place merges (same result as one
+// std::sort for a strict weak order whose ties are broken by a unique key).
+template <typename T, typename Cmp>
+void parallel_sort(std::vector<T>& v, Cmp cmp, size_t threads) {
+    const size_t n = v.size();
+    size_t parts = 1;
+    while (parts * 2 <= threads && n / (parts * 2) >= (size_t(1) << 15)) parts *= 2;
+    if (parts == 1) { std::sort(v.begin(), v.end(), cmp); return; }
+    std::vector<size_t> cut(parts + 1);
+    for (size_t i = 0; i <= parts; i++) cut[i] = n * i / parts;
+    {
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < parts; i++)
+            pool.emplace_back([&, i] { std::sort(v.begin() + cut[i], v.begin() + cut[i + 1], cmp); });
+        for (auto& t : pool) t.join();
+    }
+    for (size_t width = 1; width < parts; width *= 2) {
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i + width < parts; i += 2 * width)
+            pool.emplace_back([&, i] {
+                std::inplace_merge(v.begin() + cut[i], v.begin() + cut[i + width], v.begin() + cut[std::min(parts, i + 2 * width)], cmp);
+            });
+        for (auto& t : pool) t.join();
+    }
+}
 
 // Wall-clock stage timer: prints "[time] <what>: <s>" to stderr when KAMINO_TIMING is set.
 struct StageTimer {
