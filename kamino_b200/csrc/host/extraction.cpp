@@ -157,6 +157,7 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         std::string err;
     };
     std::vector<SpeciesOut> outs(n);
+    auto t_dev = std::make_unique<StageTimer>("  pass 2: device scan + pairing + fetch");
     for (const BatchRef& b : batches) {
         uint64_t ts = 0, te = 0, np = 0;
         gpu.ok(kmn_scan_batch(gpu.p, b.id, min_needed, &ts, &te));
@@ -168,7 +169,9 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
             if (cnt) gpu.ok(kmn_fetch_pairs(gpu.p, b.id, uint32_t(sid - b.sp0), outs[sid].pairs.data(), cnt, &cnt));
         }
     }
+    t_dev.reset();
     {
+        StageTimer t_par("  pass 2: host block slicing (threads)");
         std::atomic<size_t> next{0};
         auto work = [&] {
             std::vector<uint8_t> aa;     // whitespace-stripped, upper-cased residues of the current record
@@ -221,27 +224,43 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, n)); t++) pool.emplace_back(work);
         for (auto& t : pool) t.join();
     }
-    uint64_t order = 0;
-    for (size_t sid = 0; sid < n; sid++) {   // ordered merge (:611-636): first error in species order
-        SpeciesOut& o = outs[sid];
-        if (!o.err.empty()) throw std::runtime_error(o.err);
-        const Proteome& pr = prot[sid];
-        const size_t n_rec = pr.rec_off.size() - 1;
-        const size_t protein_base = ex.protein_names.size();
-        if (protein_base + n_rec > 0xFFFFFFFFull)   // :342-344
-            throw std::runtime_error("too many protein records across all species to index with u32");
-        for (std::string& nm : o.names) ex.protein_names.push_back(std::move(nm));
-        std::vector<std::string>().swap(o.names);
-        const uint64_t arena_base = ex.arena.size();
-        ex.arena.insert(ex.arena.end(), o.arena.begin(), o.arena.end());
-        for (Observation ob : o.obs) {
-            ob.protein = uint32_t(protein_base + ob.protein);
-            ob.aa_off += arena_base;
-            ob.order = order++;
-            ex.obs.push_back(ob);
+    // ordered merge (:611-636): offsets by prefix sums in species order, copies on the host threads
+    for (size_t sid = 0; sid < n; sid++)
+        if (!outs[sid].err.empty()) throw std::runtime_error(outs[sid].err);   // first error in species order
+    {
+        StageTimer t_merge("  pass 2: ordered merge");
+        std::vector<uint64_t> obs0(n + 1, 0), arena0(n + 1, 0), prot0(n + 1, 0);
+        for (size_t sid = 0; sid < n; sid++) {
+            obs0[sid + 1] = obs0[sid] + outs[sid].obs.size();
+            arena0[sid + 1] = arena0[sid] + outs[sid].arena.size();
+            prot0[sid + 1] = prot0[sid] + (prot[sid].rec_off.size() - 1);
+            if (prot0[sid + 1] > 0xFFFFFFFFull)   // :342-344
+                throw std::runtime_error("too many protein records across all species to index with u32");
         }
-        SpeciesOut().obs.swap(o.obs);
-        std::vector<uint8_t>().swap(o.arena);
+        ex.obs.resize(obs0[n]);
+        ex.arena.resize(arena0[n]);
+        ex.protein_names.resize(prot0[n]);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t sid; (sid = next.fetch_add(1)) < n;) {
+                SpeciesOut& o = outs[sid];
+                if (!o.arena.empty()) std::memcpy(ex.arena.data() + arena0[sid], o.arena.data(), o.arena.size());
+                for (size_t i = 0; i < o.obs.size(); i++) {
+                    Observation ob = o.obs[i];
+                    ob.protein = uint32_t(prot0[sid] + ob.protein);
+                    ob.aa_off += arena0[sid];
+                    ob.order = obs0[sid] + i;   // emission order == the reference's Vec order
+                    ex.obs[obs0[sid] + i] = ob;
+                }
+                for (size_t r = 0; r < o.names.size(); r++) ex.protein_names[prot0[sid] + r] = std::move(o.names[r]);
+                SpeciesOut().obs.swap(o.obs);
+                std::vector<uint8_t>().swap(o.arena);
+                std::vector<std::string>().swap(o.names);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, n)); t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
     }
     t_p2.reset();
     StageTimer t_sort("group observations");

@@ -44,6 +44,11 @@ def main():
             ctx.scan_batch(bid, min_needed)
             ms.append(ctx.stage_ms("scan"))
         scan_ms = float(np.median(ms))
+        pm = []
+        for _ in range(args.reps):
+            n_pairs = ctx.pair_batch(bid, 35)
+            pm.append(ctx.stage_ms("pair_batch"))
+        pair_ms = float(np.median(pm))
         # CPU: oracle scan of a few species (single thread per species, run sequentially)
         cms = orc.cms_from_table(table)
         n_cpu = min(4, b.n_sp)
@@ -55,10 +60,14 @@ def main():
             res_cpu += int(species[s].lens.sum())
             gs, ge = ctx.fetch_hits(bid, s)
             assert np.array_equal(gs, ws) and np.array_equal(ge, we)
+            wp = orc.pair_species(cms, b.residues, b.rec_off, int(b.sp_rec_off[s]), int(b.sp_rec_off[s + 1]), 13, 1,
+                                  min_needed, 35)
+            assert np.array_equal(ctx.fetch_pairs(bid, s), wp)
         cpu_dt = time.perf_counter() - t0
         orc.cms_free(cms)
         print(json.dumps({"what": "pass2_scan", "species": b.n_sp, "residues": b.n_residues, "ms": scan_ms,
                           "residues_per_s": b.n_residues / (scan_ms * 1e-3), "starts": ns, "ends": ne,
+                          "pair_batch_ms": pair_ms, "anchor_pairs": n_pairs,
                           "cpu_single_thread_residues_per_s": res_cpu / cpu_dt, "parity_species_checked": n_cpu}))
 
     # ---- --nj pair counts
