@@ -139,10 +139,11 @@ def run_reference(args):
         return 0
     batch = make_batch(0)
     threads = host_threads()
-    # bounded sample: as many whole species as ~4 s of CPU work per step
-    n_res, dt, _, n_sp = cpu_pass1(batch, threads, n_species=8)
+    # the step is the same workload as the GPU arm (100 proteomes) unless that would take more than ~10 s of
+    # CPU time per step; then a bounded sample of whole species
+    n_res, dt, _, n_sp = cpu_pass1(batch, threads, n_species=2 * threads)
     per_species = dt / n_sp
-    n_sample = int(max(4, min(N_SPECIES, 4.0 / max(per_species, 1e-6))))
+    n_sample = N_SPECIES if per_species * N_SPECIES <= 10.0 else int(max(threads, min(N_SPECIES, 10.0 / max(per_species, 1e-6))))
     for _ in range(args.warmup):
         cpu_pass1(batch, threads, n_species=n_sample)
     tot_res, tot_dt = 0, 0.0
