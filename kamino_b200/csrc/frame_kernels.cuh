@@ -126,6 +126,12 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_o
 // The thread whose 16-byte chunk contains raw offset rec_off[b] also owns record boundary b (0..n_rec):
 //   rec_cstart[b] = (#kept bytes before rec_off[b]) + b, and record b-1's separator (0xFF) sits right before it.
 // raw is padded with at least one space, so the chunk that contains offset n_raw exists.
+// The codes of a tile (residues + separators) form one contiguous range of codes[]: they are staged in
+// shared memory at the same 16-byte alignment and written out as 16-byte vectors (bytes only at the two
+// ragged ends); a tile with thousands of empty records falls back to direct byte stores.
+constexpr uint32_t FRAME_MAX_BOUNDS = 2048;                                  // record boundaries staged per tile
+constexpr uint32_t FRAME_STAGE = FRAME_TILE + FRAME_MAX_BOUNDS + 32;
+
 __global__ void __launch_bounds__(FRAME_THREADS)
 frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut,
                      const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ rec_off,
@@ -133,11 +139,20 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
                      uint32_t tile_begin) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
-    __shared__ uint32_t s_rlo, s_rhi;
+    __shared__ uint32_t s_rlo, s_rhi, s_blo, s_first, s_last;
+    __shared__ __align__(16) uint8_t s_stage[FRAME_STAGE];
     load_lut(s_lut, lut);
     const uint32_t tile = tile_begin + blockIdx.x;
     const uint64_t tile0 = uint64_t(tile) * FRAME_TILE;
-    if (threadIdx.x == 0) s_rlo = record_of(rec_off, 0, n_rec, tile0);
+    if (threadIdx.x == 0) {
+        const uint32_t rlo = record_of(rec_off, 0, n_rec, tile0);
+        uint32_t blo = rlo;   // empty records that end exactly at tile0: their boundaries belong to this tile too
+        while (blo > 0 && rec_off[blo - 1] == tile0) blo--;
+        s_rlo = rlo;
+        s_blo = blo;
+        s_first = 0xFFFFFFFFu;
+        s_last = 0;
+    }
     if (threadIdx.x == 32) {
         uint64_t last = tile0 + FRAME_TILE - 1;
         if (last > n_raw) last = n_raw;
@@ -167,34 +182,71 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
     uint32_t woff = 0;
 #pragma unroll
     for (int i = 0; i < FRAME_WARPS; i++) woff += (i < int(warp)) ? s_w[i] : 0u;
-    uint32_t out = tile_base[tile] + woff + incl - n;   // #kept bytes before i0
-    if (i0 > n_raw) return;
-    // r = last boundary at or before i0 (rec_off[0] == 0, so it exists)
-    uint32_t r = record_of(rec_off, s_rlo, s_rhi, i0);
-    // record boundaries inside [i0, i0 + 16)
-    {
-        uint32_t b = r;
-        if (rec_off[b] < i0) b++;
-        else while (b > 0 && rec_off[b - 1] == i0) b--;   // empty records share the offset
-        for (; b <= n_rec; b++) {
-            const uint64_t x = rec_off[b];
-            if (x >= i0 + CHUNK) break;
-            const uint32_t cs = out + __popc(kept & ((1u << uint32_t(x - i0)) - 1u)) + b;
-            rec_cstart[b] = cs;
-            if (b > 0) codes[cs - 1] = CODE_INVALID;
+    const uint32_t tb = tile_base[tile];
+    uint32_t out = tb + woff + incl - n;   // #kept bytes before i0
+    // staging origin: no code of this tile lies before q0; smem index = position - g0, g0 16-byte aligned
+    const bool staged = s_rhi - s_blo < FRAME_MAX_BOUNDS;   // CTA-uniform
+    const uint32_t q0 = tb + max(s_blo, 1u) - 1u;
+    const uint32_t g0 = q0 & ~15u;
+    uint32_t my_first = 0xFFFFFFFFu, my_last = 0;
+    auto put = [&](uint32_t pos, uint8_t val) {
+        if (staged) {
+            s_stage[pos - g0] = val;
+            my_first = min(my_first, pos);
+            my_last = max(my_last, pos + 1);
+        } else {
+            codes[pos] = val;
+        }
+    };
+    if (i0 <= n_raw) {
+        // r = last boundary at or before i0 (rec_off[0] == 0, so it exists)
+        uint32_t r = record_of(rec_off, s_rlo, s_rhi, i0);
+        // record boundaries inside [i0, i0 + 16)
+        {
+            uint32_t b = r;
+            if (rec_off[b] < i0) b++;
+            else while (b > 0 && rec_off[b - 1] == i0) b--;   // empty records share the offset
+            for (; b <= n_rec; b++) {
+                const uint64_t x = rec_off[b];
+                if (x >= i0 + CHUNK) break;
+                const uint32_t cs = out + __popc(kept & ((1u << uint32_t(x - i0)) - 1u)) + b;
+                rec_cstart[b] = cs;
+                if (b > 0) put(cs - 1, CODE_INVALID);
+            }
+        }
+        if (n) {
+            if (r >= n_rec) r = n_rec - 1;
+            uint64_t r_end = rec_off[r + 1];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((kept >> j) & 1u) {
+                    const uint64_t i = i0 + j;
+                    while (i >= r_end) { r++; r_end = rec_off[r + 1]; }
+                    put(out + r, c[j]);
+                    out++;
+                }
+            }
         }
     }
-    if (n == 0) return;
-    if (r >= n_rec) r = n_rec - 1;
-    uint64_t r_end = rec_off[r + 1];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        if ((kept >> j) & 1u) {
-            const uint64_t i = i0 + j;
-            while (i >= r_end) { r++; r_end = rec_off[r + 1]; }
-            codes[size_t(out) + r] = c[j];
-            out++;
-        }
+    if (!staged) return;
+    // the tile's codes are one contiguous range [first, last): copy it out, vectors where whole
+    my_first = __reduce_min_sync(0xffffffffu, my_first);
+    my_last = __reduce_max_sync(0xffffffffu, my_last);
+    if (lane == 0 && my_last) {
+        atomicMin(&s_first, my_first);
+        atomicMax(&s_last, my_last);
+    }
+    __syncthreads();
+    const uint32_t first = s_first, last = s_last;
+    if (last <= first) return;
+    const uint32_t v_lo = (first - g0 + 15u) & ~15u, v_hi = (last - g0) & ~15u;   // whole vectors in smem coordinates
+    if (v_hi > v_lo) {
+        for (uint32_t x = v_lo + threadIdx.x * 16u; x < v_hi; x += FRAME_THREADS * 16u)
+            *reinterpret_cast<uint4*>(codes + g0 + x) = *reinterpret_cast<const uint4*>(s_stage + x);
+        for (uint32_t x = first - g0 + threadIdx.x; x < v_lo; x += FRAME_THREADS) codes[g0 + x] = s_stage[x];
+        for (uint32_t x = v_hi + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[g0 + x] = s_stage[x];
+    } else {
+        for (uint32_t x = first - g0 + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[g0 + x] = s_stage[x];
     }
 }
 

@@ -315,3 +315,21 @@ def test_bloom_natural_overflow_takes_slow_path(ffi, oracle):
     residues, rec_off, sp = _batch_from_records([normal, rep, normal[:100]])
     new, _ = _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, SR6, 2)
     assert new[1] > 0
+
+
+def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
+    """Record boundaries exactly on the 4096-byte frame tiles, empty records on both sides of them, and
+    thousands of empty records inside one tile (the staged write-out of frame_scatter_kernel falls back
+    to direct stores there)."""
+    rng = np.random.default_rng(41)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+
+    def prot(n):
+        return aa[rng.integers(0, 20, n)].tobytes()
+
+    sp0 = [prot(4096), b"", b"", prot(4096 - 7), b"", prot(7), b"", prot(8192), b"\n" * 4096, prot(100)]
+    sp1 = [b""] * 3000 + [prot(500)] + [b""] * 2500 + [prot(4096 * 2 - 500)] + [b""]
+    sp2 = [prot(30) + b"\n" + prot(30) + b" \t" + prot(4036 - 63)] + [b"", prot(4096)]
+    residues, rec_off, sp = _batch_from_records([sp0, sp1, [], sp2])
+    for k in (13, 5):
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
