@@ -333,3 +333,49 @@ def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
     residues, rec_off, sp = _batch_from_records([sp0, sp1, [], sp2])
     for k in (13, 5):
         _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
+
+
+def test_full_size_properties_100_proteomes(ffi):
+    """BASELINE.json configs[1] at full size (100 synthetic bacterial proteomes, 1.2e8 residues), checked
+    through size-independent properties of the path instead of the (slow) oracle: the table is invariant
+    under the order of the species and under the split into batches, per-species counts travel with their
+    species, counting a batch twice doubles every unsaturated cell, and pass 2 on it is deterministic."""
+    species = synth.bacterial(100)
+    b = synth.stage(species)
+    order = np.arange(99, -1, -1)
+    rev = synth.stage([species[i] for i in order])
+    half_a, half_b = synth.stage(species[:37]), synth.stage(species[37:])
+    with ffi.Context(13, SR6) as ctx:
+        bid, new = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+        ctx.finalize_table()
+        t_all = ctx.table_snapshot()
+        hits = ctx.scan_batch(bid, 85)
+        pairs = ctx.pair_batch(bid, 35)
+        p7 = ctx.fetch_pairs(bid, 7).copy()
+        ctx.release_batches()
+        assert int(new.sum()) > 0.9 * b.n_residues * 0.95 and hits[0] > 0 and pairs > 0
+
+        ctx.reset_table()
+        bid, new_rev = ctx.count_batch(rev.residues, rev.rec_off, rev.sp_rec_off)
+        ctx.finalize_table()
+        assert np.array_equal(ctx.table_snapshot(), t_all), "table depends on the species order"
+        assert np.array_equal(new_rev, new[order]), "per-species counts do not follow their species"
+        assert ctx.scan_batch(bid, 85) == hits
+        assert ctx.pair_batch(bid, 35) == pairs
+        assert np.array_equal(ctx.fetch_pairs(bid, 99 - 7), p7), "pass 2 of a species depends on its neighbours"
+        ctx.release_batches()
+
+        ctx.reset_table()
+        _, na = ctx.count_batch(half_a.residues, half_a.rec_off, half_a.sp_rec_off)
+        _, nb = ctx.count_batch(half_b.residues, half_b.rec_off, half_b.sp_rec_off)
+        ctx.finalize_table()
+        assert np.array_equal(ctx.table_snapshot(), t_all), "table depends on the batch split"
+        assert np.array_equal(np.concatenate([na, nb]), new)
+        ctx.release_batches()
+
+        ctx.reset_table()
+        bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+        ctx.count_staged(bid)
+        ctx.count_staged(bid)
+        ctx.finalize_table()
+        assert np.array_equal(ctx.table_snapshot(), np.minimum(t_all.astype(np.uint32) * 2, 65535).astype(np.uint16))
