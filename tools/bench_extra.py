@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--nj-n", type=int, default=2000)
     ap.add_argument("--nj-l", type=int, default=100_000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--euk", type=int, default=0, help="also run pass 1 on N synthetic eukaryotic proteomes "
+                    "(BASELINE.json configs[3] shape, ~10 M residues each) and compare the table with the oracle")
     args = ap.parse_args()
     import oracle_ffi
     from kamino_b200 import ffi, synth
@@ -69,6 +71,29 @@ def main():
                           "residues_per_s": b.n_residues / (scan_ms * 1e-3), "starts": ns, "ends": ne,
                           "pair_batch_ms": pair_ms, "anchor_pairs": n_pairs,
                           "cpu_single_thread_residues_per_s": res_cpu / cpu_dt, "parity_species_checked": n_cpu}))
+
+    # ---- pass 1 on the eukaryotic shape (long proteomes: ~1200 Bloom tiles per species, visible Bloom FP rate)
+    if args.euk:
+        species = synth.eukaryotic(args.euk)
+        b = synth.stage(species)
+        with ffi.Context(13, "sr6") as ctx:
+            bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+            for _ in range(2):
+                ctx.reset_table()
+                new = ctx.count_staged(bid, b.n_sp)
+            ms = sum(ctx.stage_ms(s) for s in ("frame", "bloom", "cms"))
+            ctx.finalize_table()
+            table = ctx.table_snapshot()
+        h = orc.cmsa_new()
+        t0 = time.perf_counter()
+        want_new = orc.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, 13, 1, threads=threads)
+        cpu_dt = time.perf_counter() - t0
+        same = bool(np.array_equal(table, orc.cmsa_table(h))) and new.tolist() == want_new.tolist()
+        orc.cmsa_free(h)
+        print(json.dumps({"what": "pass1_eukaryotic", "species": b.n_sp, "residues": b.n_residues, "ms": ms,
+                          "residues_per_s": b.n_residues / (ms * 1e-3), "passing_fraction": float(new.sum()) / b.n_residues,
+                          "cpu_residues_per_s": b.n_residues / cpu_dt, "cpu_threads": threads, "table_equals_oracle": same}))
+        assert same
 
     # ---- --nj pair counts
     rng = np.random.default_rng(1)
