@@ -57,6 +57,19 @@ typedef struct kmn_pair {
     uint32_t len;        /* block length: right.start + k - left.start (both anchors included)          */
 } kmn_pair;
 
+/* One run of observations sharing an anchor pair after kmn_group_observations. */
+typedef struct kmn_group {
+    uint32_t first;      /* position of the run in the sorted order (index into perm)                   */
+    uint32_t count;      /* observations in the run                                                     */
+    uint32_t best_len;   /* block length with the largest support (distinct species)                    */
+    uint32_t coverage;   /* that support                                                                */
+    uint32_t flags;      /* KMN_GROUP_VALID: unique best length, coverage >= min_needed, length >= 2k+1;
+                            KMN_GROUP_HOST: not decided on the device (more than 12 distinct lengths or
+                            observations not species-major): the caller applies group_sorting.rs:90-143 */
+} kmn_group;
+#define KMN_GROUP_VALID 1u
+#define KMN_GROUP_HOST  2u
+
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
 uint32_t kmn_abi_version(void);   /* currently 2 */
@@ -147,6 +160,15 @@ int kmn_fetch_hits(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_hit* starts
  * out == NULL only *n is set. */
 int kmn_pair_batch(kmn_ctx* ctx, uint32_t batch_id, uint32_t length_middle, uint64_t* n_pairs);
 int kmn_fetch_pairs(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_pair* out, uint64_t cap, uint64_t* n);
+/* Grouping of block observations by anchor pair + per-group length selection on the device: replaces the
+ * HashMap merge of merge_species_extraction (group_extraction.rs:335-357) by a stable radix sort of the
+ * observation indices by (left, right) and select_unique_best_supported_length (group_sorting.rs:90-143)
+ * by a segmented reduction.  Inputs are host arrays over the n observations of ALL species in emission
+ * order (species-major): anchor k-mers, species index, block length.  perm[n] receives the sorted order
+ * (ties keep emission order), groups[] one entry per distinct anchor pair in ascending (left, right). */
+int kmn_group_observations(kmn_ctx* ctx, uint64_t n, const uint64_t* left, const uint64_t* right,
+                           const uint32_t* sid, const uint32_t* len, uint32_t min_needed, uint32_t* perm,
+                           kmn_group* groups, uint64_t cap_groups, uint64_t* n_groups);
 /* Occupancy per whitespace-stripped residue of species `sp` (records concatenated): estimate()
  * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues. */
 int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap,
@@ -164,7 +186,7 @@ int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L,
  * context, per stage, measured with CUDA events on the context's stream.
  * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts,
  *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1),
- *        8 pair_batch. */
+ *        8 pair_batch, 9 group_observations (kernels only). */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

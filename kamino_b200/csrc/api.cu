@@ -6,6 +6,7 @@
 #include "cms_kernels.cuh"
 #include "count_kernels.cuh"
 #include "frame_kernels.cuh"
+#include "group_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "scan_kernels.cuh"
 
@@ -130,7 +131,7 @@ struct kmn_ctx {
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 6;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
     DevBuf<uint32_t> frame_carry, n_tiles_dev;
-    float stage_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
@@ -579,6 +580,70 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
     if (n_pairs) *n_pairs = total;
 }
 
+void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const uint64_t* right, const uint32_t* sid,
+                        const uint32_t* len, uint32_t min_needed, uint32_t* perm, kmn_group* groups, uint64_t cap_groups,
+                        uint64_t* n_groups) {
+    if (n64 >= (1ull << 31)) throw std::runtime_error("too many observations for one grouping call");
+    const uint32_t n = uint32_t(n64);
+    if (n_groups) *n_groups = 0;
+    if (n == 0) return;
+    if (!left || !right || !sid || !len || !perm || !groups) throw std::runtime_error("NULL argument");
+    DevBuf<uint64_t> d_left, d_right;
+    DevBuf<uint32_t> d_sid, d_len, d_perm[2], d_hist, d_base, d_head, d_scan, d_first;
+    DevBuf<kmn_group> d_groups;
+    const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    d_left.alloc(n); d_right.alloc(n); d_sid.alloc(n); d_len.alloc(n);
+    d_perm[0].alloc(n); d_perm[1].alloc(n);
+    d_hist.alloc(size_t(RS_BINS) * n_blocks + 1); d_base.alloc(size_t(RS_BINS) * n_blocks + 2);
+    d_head.alloc(n); d_scan.alloc(size_t(n) + 1); d_first.alloc(size_t(n) + 1);
+    KMN_CUDA(cudaMemcpyAsync(d_left.p, left, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(d_right.p, right, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(d_sid.p, sid, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(d_len.p, len, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const uint32_t eb = (n + 255) / 256;
+    iota_kernel<<<eb, 256, 0, c->stream>>>(d_perm[0].p, n);
+    check_launch(c);
+    // stable LSD radix sort by (left, right): the digits of right first, then those of left
+    const uint32_t bits = uint32_t(3 * c->k);   // packed k-mers use 3k bits (group_extraction.rs:545-549)
+    int cur = 0;
+    for (int word = 0; word < 2; word++) {
+        const uint64_t* key = word == 0 ? d_right.p : d_left.p;
+        for (uint32_t shift = 0; shift < bits; shift += 4) {
+            radix_hist_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(key, d_perm[cur].p, n, shift, d_hist.p);
+            check_launch(c);
+            const ScanJob job{d_hist.p, d_base.p, RS_BINS * n_blocks, nullptr};
+            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
+            check_launch(c);
+            radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(key, d_perm[cur].p, n, shift, d_base.p, d_perm[cur ^ 1].p);
+            check_launch(c);
+            cur ^= 1;
+        }
+    }
+    // runs of equal keys -> groups
+    group_heads_kernel<<<eb, 256, 0, c->stream>>>(d_left.p, d_right.p, d_perm[cur].p, n, d_head.p);
+    check_launch(c);
+    const ScanJob hjob{d_head.p, d_scan.p, n, nullptr};
+    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(hjob, hjob);
+    check_launch(c);
+    uint32_t ng = 0;
+    KMN_CUDA(cudaMemcpyAsync(&ng, d_scan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    if (ng > cap_groups) throw std::runtime_error("group buffer too small");
+    group_firsts_kernel<<<eb, 256, 0, c->stream>>>(d_head.p, d_scan.p, n, d_first.p);
+    check_launch(c);
+    d_groups.alloc(ng);
+    group_select_kernel<<<(ng + 127) / 128, 128, 0, c->stream>>>(d_perm[cur].p, d_sid.p, d_len.p, d_first.p, ng, n, min_needed,
+                                                             uint32_t(2 * c->k + 1), d_groups.p);
+    check_launch(c);
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    KMN_CUDA(cudaMemcpyAsync(perm, d_perm[cur].p, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(groups, d_groups.p, size_t(ng) * sizeof(kmn_group), cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[9], c->ev[0], c->ev[1]));
+    if (n_groups) *n_groups = ng;
+}
+
 void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
     if (n < 2) return;
     if (L >= (1ull << 32)) throw std::runtime_error("alignment too long for u32 counts");
@@ -934,6 +999,12 @@ int kmn_fetch_pairs(kmn_ctx* c, uint32_t batch_id, uint32_t sp, kmn_pair* out, u
     });
 }
 
+int kmn_group_observations(kmn_ctx* c, uint64_t n, const uint64_t* left, const uint64_t* right, const uint32_t* sid,
+                           const uint32_t* len, uint32_t min_needed, uint32_t* perm, kmn_group* groups,
+                           uint64_t cap_groups, uint64_t* n_groups) {
+    return guarded(c, [&] { group_observations(c, n, left, right, sid, len, min_needed, perm, groups, cap_groups, n_groups); });
+}
+
 int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap, uint64_t* n) {
     return guarded(c, [&] {
         Batch& b = get_batch(c, batch_id);
@@ -962,7 +1033,7 @@ int kmn_pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, u
 
 int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
     return guarded(c, [&] {
-        if (which < 0 || which > 8 || !ms) throw std::runtime_error("invalid stage index");
+        if (which < 0 || which > 9 || !ms) throw std::runtime_error("invalid stage index");
         *ms = c->stage_ms[which];
     });
 }

@@ -264,14 +264,36 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     }
     t_p2.reset();
     StageTimer t_sort("group observations");
-    // group by anchor pair; inside a group keep emission order == the reference's Vec order (sid, then file order)
-    parallel_sort(ex.obs, [](const Observation& a, const Observation& b) {
-        if (a.left != b.left) return a.left < b.left;
-        if (a.right != b.right) return a.right < b.right;
-        return a.order < b.order;
-    }, opt.threads);
-    for (size_t i = 0; i < ex.obs.size(); i++)
-        if (i == 0 || ex.obs[i].left != ex.obs[i - 1].left || ex.obs[i].right != ex.obs[i - 1].right) ex.n_groups++;
+    // group by anchor pair on the device (stable radix sort of the observation indices by (left, right): inside
+    // a group the emission order == the reference's Vec order survives) + per-group length selection
+    const size_t n_obs = ex.obs.size();
+    if (n_obs) {
+        std::vector<uint64_t> left(n_obs), right(n_obs);
+        std::vector<uint32_t> sid(n_obs), len(n_obs), perm(n_obs);
+        for (size_t i = 0; i < n_obs; i++) {
+            left[i] = ex.obs[i].left;
+            right[i] = ex.obs[i].right;
+            sid[i] = ex.obs[i].sid;
+            len[i] = ex.obs[i].len;
+        }
+        ex.groups.resize(n_obs);
+        uint64_t ng = 0;
+        gpu.ok(kmn_group_observations(gpu.p, n_obs, left.data(), right.data(), sid.data(), len.data(), min_needed,
+                                      perm.data(), ex.groups.data(), ex.groups.size(), &ng));
+        ex.groups.resize(ng);
+        ex.n_groups = ng;
+        std::vector<Observation> sorted(n_obs);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            const size_t step = size_t(1) << 16;
+            for (size_t i0; (i0 = next.fetch_add(step)) < n_obs;)
+                for (size_t i = i0; i < std::min(n_obs, i0 + step); i++) sorted[i] = ex.obs[perm[i]];
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < std::max<size_t>(1, opt.threads); t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+        ex.obs.swap(sorted);
+    }
     return ex;
 }
 

@@ -95,13 +95,10 @@ public:
 std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme scheme) {   // group_sorting.rs:329-380
     std::vector<Candidate> cands;
     const auto& obs = ex.obs;
-    std::vector<std::pair<uint32_t, uint32_t>> len_sid;
-    for (size_t g0 = 0; g0 < obs.size();) {
-        size_t g1 = g0;
-        while (g1 < obs.size() && obs[g1].left == obs[g0].left && obs[g1].right == obs[g0].right) g1++;
-        // support of every block length = number of DISTINCT species (group_sorting.rs:90-143);
-        // buckets are visited in first-appearance order, ties reject the group
-        len_sid.clear();
+    // support of every block length = number of DISTINCT species (group_sorting.rs:90-143); buckets are visited
+    // in first-appearance order, ties reject the group.  Only for the runs the device left undecided.
+    auto select_on_host = [&](size_t g0, size_t g1, size_t& best_len, size_t& best_c) -> bool {
+        std::vector<std::pair<uint32_t, uint32_t>> len_sid;
         std::vector<uint32_t> lens_in_order;
         for (size_t i = g0; i < g1; i++) {
             len_sid.emplace_back(obs[i].len, obs[i].sid);
@@ -110,23 +107,29 @@ std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme 
         }
         std::sort(len_sid.begin(), len_sid.end());
         len_sid.erase(std::unique(len_sid.begin(), len_sid.end()), len_sid.end());
-        size_t best_len = 0, best_c = 0;
+        best_len = 0;
+        best_c = 0;
         bool tie = false;
         for (uint32_t len : lens_in_order) {
             const size_t c = size_t(std::count_if(len_sid.begin(), len_sid.end(), [len](const auto& p) { return p.first == len; }));
             if (c > best_c) { best_len = len; best_c = c; tie = false; }
             else if (c == best_c) tie = true;
         }
-        if (!tie && best_c >= ex.min_needed && best_len >= 2 * ex.k + 1) {
-            Candidate c;
-            c.left = obs[g0].left;
-            c.right = obs[g0].right;
-            c.coverage = best_c;
-            c.raw_len = best_len;
-            for (size_t i = g0; i < g1; i++) if (obs[i].len == best_len) c.rows.push_back(uint32_t(i));
-            cands.push_back(std::move(c));
-        }
-        g0 = g1;
+        return !tie && best_c >= ex.min_needed && best_len >= 2 * ex.k + 1;
+    };
+    for (const kmn_group& g : ex.groups) {   // runs of equal (left, right) with the device's length selection
+        const size_t g0 = g.first, g1 = size_t(g.first) + g.count;
+        size_t best_len = g.best_len, best_c = g.coverage;
+        bool ok = (g.flags & KMN_GROUP_VALID) != 0;
+        if (g.flags & KMN_GROUP_HOST) ok = select_on_host(g0, g1, best_len, best_c);
+        if (!ok) continue;
+        Candidate c;
+        c.left = obs[g0].left;
+        c.right = obs[g0].right;
+        c.coverage = best_c;
+        c.raw_len = best_len;
+        for (size_t i = g0; i < g1; i++) if (obs[i].len == best_len) c.rows.push_back(uint32_t(i));
+        cands.push_back(std::move(c));
     }
     // strongest first: coverage desc, length desc, key asc (group_sorting.rs:252-258)
     std::sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) {

@@ -8,6 +8,8 @@
 // (paths under /root/reference).  Data structures are deliberately flat (sorted observation tables
 // instead of hash maps) so the grouping can later move to the device.
 #pragma once
+#include "kamino_b200.h"
+
 #include <cstddef>
 #include <cstdint>
 #include <stdexcept>
@@ -62,6 +64,7 @@ struct Extraction {                    // RawExtractedGroups, group_extraction.r
     std::vector<std::string> species_names, protein_names;
     std::vector<uint8_t> arena;
     std::vector<Observation> obs;      // sorted by (left, right, order) once extraction is finished
+    std::vector<kmn_group> groups;     // one run of obs per anchor pair, length selection done on the device
     size_t k = 0, min_needed = 0, n_species = 0, n_groups = 0;
 };
 

@@ -16,7 +16,7 @@ DAYHOFF6, SR6, KGB6 = 0, 1, 2
 SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
 CMS_CELLS = 4 << 26
 STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5,
-          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8}
+          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8, "group_observations": 9}
 
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
@@ -26,13 +26,18 @@ PAIR_DTYPE = np.dtype(
     [("left", "<u8"), ("right", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("left_start", "<u4"), ("len", "<u4")]
 )
 
+GROUP_DTYPE = np.dtype(
+    [("first", "<u4"), ("count", "<u4"), ("best_len", "<u4"), ("coverage", "<u4"), ("flags", "<u4")]
+)
+GROUP_VALID, GROUP_HOST = 1, 2
+
 # every symbol declared in include/kamino_b200.h
 ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
-    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
+    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
 
@@ -85,6 +90,7 @@ def load_library() -> C.CDLL:
     lib.kmn_fetch_hits.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p, vp, C.c_uint64, u64p]
     lib.kmn_fetch_occupancy.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
     lib.kmn_pair_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p]
+    lib.kmn_group_observations.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.kmn_fetch_pairs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
     lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
     lib.kmn_last_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
@@ -240,6 +246,17 @@ class Context:
         if n.value:
             self._check(self.lib.kmn_fetch_pairs(self._h, batch_id, sp, _ptr(out), n.value, C.byref(n)))
         return out
+
+    def group_observations(self, left, right, sid, length, min_needed: int) -> tuple[np.ndarray, np.ndarray]:
+        left, right = _as(left, np.uint64), _as(right, np.uint64)
+        sid, length = _as(sid, np.uint32), _as(length, np.uint32)
+        n = left.size
+        perm = np.zeros(n, dtype=np.uint32)
+        groups = np.zeros(max(n, 1), dtype=GROUP_DTYPE)
+        ng = C.c_uint64()
+        self._check(self.lib.kmn_group_observations(self._h, n, _ptr(left), _ptr(right), _ptr(sid), _ptr(length),
+                                                    min_needed, _ptr(perm), _ptr(groups), groups.size, C.byref(ng)))
+        return perm, groups[:ng.value]
 
     def fetch_occupancy(self, batch_id: int, sp: int) -> np.ndarray:
         n = C.c_uint64()

@@ -379,3 +379,70 @@ def test_full_size_properties_100_proteomes(ffi):
         ctx.count_staged(bid)
         ctx.finalize_table()
         assert np.array_equal(ctx.table_snapshot(), np.minimum(t_all.astype(np.uint32) * 2, 65535).astype(np.uint16))
+
+
+def _group_reference(left, right, sid, length, min_needed, k):
+    """merge_species_extraction (group_extraction.rs:335-357) + select_unique_best_supported_length
+    (group_sorting.rs:90-143) restated with numpy / python containers."""
+    order = np.lexsort((np.arange(left.size), right, left))        # stable: ties keep emission order
+    keys = np.stack([left[order], right[order]], axis=1)
+    heads = np.ones(left.size, bool)
+    heads[1:] = np.any(keys[1:] != keys[:-1], axis=1)
+    firsts = np.flatnonzero(heads)
+    out = []
+    for g, i0 in enumerate(firsts):
+        i1 = firsts[g + 1] if g + 1 < firsts.size else left.size
+        by_len = {}
+        for o in order[i0:i1]:
+            by_len.setdefault(int(length[o]), set()).add(int(sid[o]))
+        best_len, best_c, tie = 0, 0, False
+        for l, sp in by_len.items():          # first-appearance order
+            if len(sp) > best_c:
+                best_len, best_c, tie = l, len(sp), False
+            elif len(sp) == best_c:
+                tie = True
+        ok = (not tie) and best_c >= min_needed and best_len >= 2 * k + 1
+        out.append((int(i0), int(i1 - i0), best_len, best_c, 1 if ok else 0))
+    return order.astype(np.uint32), out
+
+
+@pytest.mark.parametrize("n,n_keys,seed", [(1, 1, 0), (5000, 40, 1), (200_000, 3000, 2), (70_000, 70_000, 3)])
+def test_group_observations(ffi, n, n_keys, seed):
+    rng = np.random.default_rng(seed)
+    k = 13
+    pool_l = rng.integers(0, 1 << 39, n_keys, dtype=np.uint64)
+    pool_r = rng.integers(0, 1 << 39, n_keys, dtype=np.uint64)
+    pool_r[::7] = pool_r[0]                       # many pairs share one anchor
+    pick = rng.integers(0, n_keys, n)
+    sid = np.sort(rng.integers(0, 60, n)).astype(np.uint32)        # emission order is species-major
+    length = (27 + rng.choice([0, 0, 0, 1, 5, 30], n)).astype(np.uint32)
+    length[rng.random(n) < 0.02] = 20                               # shorter than 2k+1
+    left, right = pool_l[pick], pool_r[pick]
+    with ffi.Context(k, SR6) as ctx:
+        perm, groups = ctx.group_observations(left, right, sid, length, 3)
+    want_perm, want = _group_reference(left, right, sid, length, 3, k)
+    assert np.array_equal(perm, want_perm)
+    assert len(groups) == len(want)
+    for g, w in zip(groups, want):
+        assert not (int(g["flags"]) & ffi.GROUP_HOST)
+        assert (int(g["first"]), int(g["count"])) == w[:2]
+        assert (int(g["flags"]) & ffi.GROUP_VALID) == w[4]
+        if w[4]:
+            assert (int(g["best_len"]), int(g["coverage"])) == w[2:4]
+
+
+def test_group_observations_host_fallback_flags(ffi):
+    """More distinct block lengths than the device tracks, and a run that is not species-major."""
+    n = 40
+    left = np.full(n, 5, np.uint64)
+    right = np.full(n, 9, np.uint64)
+    sid = np.arange(n, dtype=np.uint32)
+    length = (30 + np.arange(n)).astype(np.uint32)
+    left[30:] = 6
+    length[30:] = 31
+    sid[30:] = np.array([3, 4, 5, 2, 6, 7, 8, 9, 10, 11], np.uint32)     # 2 after 5: not species-major
+    with ffi.Context(13, SR6) as ctx:
+        perm, groups = ctx.group_observations(left, right, sid, length, 1)
+    assert np.array_equal(perm, np.arange(n))
+    assert [int(g["count"]) for g in groups] == [30, 10]
+    assert all(int(g["flags"]) & ffi.GROUP_HOST for g in groups)

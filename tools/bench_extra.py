@@ -51,6 +51,16 @@ def main():
             n_pairs = ctx.pair_batch(bid, 35)
             pm.append(ctx.stage_ms("pair_batch"))
         pair_ms = float(np.median(pm))
+        # grouping of all anchor pairs by (left, right) + per-group length selection on the device
+        allp = [ctx.fetch_pairs(bid, s) for s in range(b.n_sp)]
+        sid_all = np.concatenate([np.full(len(p), s, np.uint32) for s, p in enumerate(allp)])
+        allp = np.concatenate(allp)
+        gm = []
+        for _ in range(args.reps):
+            perm, groups = ctx.group_observations(allp["left"], allp["right"], sid_all, allp["len"], min_needed)
+            gm.append(ctx.stage_ms("group_observations"))
+        group_ms = float(np.median(gm))
+        n_valid = int(np.count_nonzero(groups["flags"] & 1))
         # CPU: oracle scan of a few species (single thread per species, run sequentially)
         cms = orc.cms_from_table(table)
         n_cpu = min(4, b.n_sp)
@@ -70,6 +80,7 @@ def main():
         print(json.dumps({"what": "pass2_scan", "species": b.n_sp, "residues": b.n_residues, "ms": scan_ms,
                           "residues_per_s": b.n_residues / (scan_ms * 1e-3), "starts": ns, "ends": ne,
                           "pair_batch_ms": pair_ms, "anchor_pairs": n_pairs,
+                          "group_kernels_ms": group_ms, "groups": int(len(groups)), "groups_passing_length_selection": n_valid,
                           "cpu_single_thread_residues_per_s": res_cpu / cpu_dt, "parity_species_checked": n_cpu}))
 
     # ---- pass 1 on the eukaryotic shape (long proteomes: ~1200 Bloom tiles per species, visible Bloom FP rate)
