@@ -129,7 +129,7 @@ struct kmn_ctx {
     cudaStream_t copy_stream = nullptr;   // host -> device copies of kmn_count_batch, overlapped with the kernels
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
-    uint32_t h2d_chunks = 6;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
+    uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
     DevBuf<uint32_t> frame_carry, n_tiles_dev;
     float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
@@ -239,14 +239,19 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
         return out;
     }
     want = std::max<uint32_t>(1, std::min<uint32_t>(want, b.n_sp));
-    const uint64_t per = b.n_raw / want + 1;
+    // only the first range's copy is exposed (the kernels are slower than the link afterwards): keep it small
+    const uint64_t first_bytes = want > 2 ? b.n_raw / (3 * uint64_t(want)) + 1 : b.n_raw / want + 1;
+    const uint64_t rest_bytes = want > 2 ? (b.n_raw - first_bytes) / (want - 1) + 1 : b.n_raw / want + 1;
     uint32_t s0 = 0;
     uint64_t copied = 0;
     uint32_t tiled = 0;
     while (s0 < b.n_sp) {
         uint32_t s1 = s0 + 1;
         if (out.size() + 1 == want) s1 = b.n_sp;
-        else while (s1 < b.n_sp && b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0] < per) s1++;
+        else {
+            const uint64_t per = out.empty() ? first_bytes : rest_bytes;
+            while (s1 < b.n_sp && b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0] < per) s1++;
+        }
         SpeciesRange r;
         r.s0 = s0;
         r.s1 = s1;
