@@ -80,6 +80,12 @@ uint32_t kmn_abi_version(void);   /* currently 2 */
 int  kmn_create(kmn_ctx** out, int device, int k, int scheme);
 void kmn_destroy(kmn_ctx* ctx);
 
+/* Page-locked host memory for the batch buffers handed to kmn_count_batch / kmn_stage_batch (io.rs side of
+ * the pipeline: FASTA bytes are gunzipped straight into it).  Optional — any host pointer works — but only
+ * pinned buffers let the host-to-device copies of kmn_count_batch overlap its kernels at full link speed. */
+int  kmn_host_alloc(void** ptr, uint64_t bytes);
+void kmn_host_free(void* ptr);
+
 /* ---- pass 1: table build ------------------------------------------------------------------
  * Replaces count_species_kmers (group_extraction.rs:359-395) driven by extract_groups stage 2
  * (group_extraction.rs:557-567) for a batch of WHOLE species.

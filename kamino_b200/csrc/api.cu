@@ -131,6 +131,10 @@ struct kmn_ctx {
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
     DevBuf<uint32_t> frame_carry, n_tiles_dev;
+    // scratch of kmn_group_observations
+    DevBuf<uint64_t> g_left, g_right;
+    DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first;
+    DevBuf<kmn_group> g_groups;
     float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
@@ -593,14 +597,17 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     if (n_groups) *n_groups = 0;
     if (n == 0) return;
     if (!left || !right || !sid || !len || !perm || !groups) throw std::runtime_error("NULL argument");
-    DevBuf<uint64_t> d_left, d_right;
-    DevBuf<uint32_t> d_sid, d_len, d_perm[2], d_hist, d_base, d_head, d_scan, d_first;
-    DevBuf<kmn_group> d_groups;
+    // scratch lives in the context (cudaMalloc / cudaFree per call would dominate the few ms of kernels)
+    DevBuf<uint64_t>&d_left = c->g_left, &d_right = c->g_right;
+    DevBuf<uint32_t>&d_sid = c->g_sid, &d_len = c->g_len, &d_hist = c->g_hist, &d_base = c->g_base, &d_head = c->g_head,
+                    &d_scan = c->g_scan, &d_first = c->g_first;
+    DevBuf<uint32_t>* d_perm = c->g_perm;
+    DevBuf<kmn_group>& d_groups = c->g_groups;
     const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
-    d_left.alloc(n); d_right.alloc(n); d_sid.alloc(n); d_len.alloc(n);
-    d_perm[0].alloc(n); d_perm[1].alloc(n);
-    d_hist.alloc(size_t(RS_BINS) * n_blocks + 1); d_base.alloc(size_t(RS_BINS) * n_blocks + 2);
-    d_head.alloc(n); d_scan.alloc(size_t(n) + 1); d_first.alloc(size_t(n) + 1);
+    d_left.ensure(n); d_right.ensure(n); d_sid.ensure(n); d_len.ensure(n);
+    d_perm[0].ensure(n); d_perm[1].ensure(n);
+    d_hist.ensure(size_t(RS_BINS) * n_blocks + 1); d_base.ensure(size_t(RS_BINS) * n_blocks + 2);
+    d_head.ensure(n); d_scan.ensure(size_t(n) + 1); d_first.ensure(size_t(n) + 1);
     KMN_CUDA(cudaMemcpyAsync(d_left.p, left, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaMemcpyAsync(d_right.p, right, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaMemcpyAsync(d_sid.p, sid, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -637,7 +644,7 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     if (ng > cap_groups) throw std::runtime_error("group buffer too small");
     group_firsts_kernel<<<eb, 256, 0, c->stream>>>(d_head.p, d_scan.p, n, d_first.p);
     check_launch(c);
-    d_groups.alloc(ng);
+    d_groups.ensure(ng);
     group_select_kernel<<<(ng + 127) / 128, 128, 0, c->stream>>>(d_perm[cur].p, d_sid.p, d_len.p, d_first.p, ng, n, min_needed,
                                                              uint32_t(2 * c->k + 1), d_groups.p);
     check_launch(c);
@@ -796,6 +803,19 @@ void kmn_destroy(kmn_ctx* c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
+
+int kmn_host_alloc(void** ptr, uint64_t bytes) {
+    try {
+        if (!ptr) throw std::runtime_error("ptr must not be NULL");
+        *ptr = nullptr;
+        KMN_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+void kmn_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int kmn_stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {

@@ -110,7 +110,22 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     auto t_p1 = std::make_unique<StageTimer>("pass 1 (stage + count + finalize)");
     struct BatchRef { uint32_t id; size_t sp0, sp1; };
     std::vector<BatchRef> batches;
-    std::vector<uint8_t> buf;
+    // the batch buffer is page-locked (kmn_host_alloc): its copies then overlap the kernels of kmn_count_batch
+    struct Pinned {
+        uint8_t* p = nullptr;
+        size_t cap = 0;
+        ~Pinned() { kmn_host_free(p); }
+        void ensure(size_t n, const Ctx& gpu) {
+            if (n <= cap) return;
+            kmn_host_free(p);
+            p = nullptr;
+            cap = 0;
+            void* q = nullptr;
+            gpu.ok(kmn_host_alloc(&q, n));
+            p = static_cast<uint8_t*>(q);
+            cap = n;
+        }
+    } buf;
     std::vector<uint64_t> rec_off, sp_rec_off;
     for (size_t s0 = 0; s0 < n;) {
         size_t s1 = s0, bytes = 0, recs = 0;
@@ -120,18 +135,29 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
             s1++;
         }
         if (bytes + recs >= (uint64_t(1) << 31)) throw std::runtime_error("species " + inputs[s0].name + " is too large for one GPU batch");
-        buf.resize(bytes);
+        buf.ensure(bytes, gpu);
         rec_off.assign(1, 0);
         sp_rec_off.assign(1, 0);
         size_t at = 0;
+        std::vector<size_t> sp_at(s1 - s0);
         for (size_t s = s0; s < s1; s++) {
-            std::memcpy(buf.data() + at, prot[s].seq.data(), prot[s].seq.size());
+            sp_at[s - s0] = at;
             for (size_t r = 1; r < prot[s].rec_off.size(); r++) rec_off.push_back(at + prot[s].rec_off[r]);
             at += prot[s].seq.size();
             sp_rec_off.push_back(rec_off.size() - 1);
         }
+        {   // gather the species into the pinned buffer on the host threads
+            std::atomic<size_t> next{s0};
+            auto work = [&] {
+                for (size_t s; (s = next.fetch_add(1)) < s1;)
+                    if (!prot[s].seq.empty()) std::memcpy(buf.p + sp_at[s - s0], prot[s].seq.data(), prot[s].seq.size());
+            };
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, s1 - s0)); t++) pool.emplace_back(work);
+            for (auto& t : pool) t.join();
+        }
         uint32_t id = 0;
-        gpu.ok(kmn_count_batch(gpu.p, buf.data(), rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
+        gpu.ok(kmn_count_batch(gpu.p, buf.p, rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
                                uint32_t(s1 - s0), nullptr, &id));
         batches.push_back({id, s0, s1});
         s0 = s1;

@@ -33,7 +33,7 @@ GROUP_VALID, GROUP_HOST = 1, 2
 
 # every symbol declared in include/kamino_b200.h
 ABI_SYMBOLS = [
-    "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_count_batch",
+    "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_host_alloc", "kmn_host_free", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
@@ -70,6 +70,9 @@ def load_library() -> C.CDLL:
     lib.kmn_create.argtypes = [vpp, C.c_int, C.c_int, C.c_int]
     lib.kmn_destroy.argtypes = [vp]
     lib.kmn_destroy.restype = None
+    lib.kmn_host_alloc.argtypes = [vpp, C.c_uint64]
+    lib.kmn_host_free.argtypes = [vp]
+    lib.kmn_host_free.restype = None
     lib.kmn_count_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, vp, u32p]
     lib.kmn_stage_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, u32p]
     lib.kmn_count_staged.argtypes = [vp, C.c_uint32, vp]
