@@ -303,7 +303,7 @@ __device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list
     return l;
 }
 
-__global__ void __launch_bounds__(BB_THREADS, 3)
+__global__ void __launch_bounds__(BB_THREADS, 2)
 bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRuns R) {
     extern __shared__ __align__(16) unsigned long long bb_smem[];
     unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
