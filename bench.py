@@ -32,7 +32,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "residues/sec k-mer table build"
 UNIT = "residues/s"
 K, SCHEME_NAME, SCHEME = 13, "sr6", 1
-N_SPECIES = 100   # per GPU (weak scaling)
+N_SPECIES = int(os.environ.get("KMN_BENCH_SPECIES", "100"))   # proteomes per GPU (weak scaling); 100 = BASELINE configs[1]
 
 
 def log(*a):
