@@ -72,7 +72,7 @@ typedef struct kmn_group {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);   /* currently 2 */
+uint32_t kmn_abi_version(void);   /* currently 3 */
 
 /* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
  * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.

@@ -718,7 +718,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 2; }
+uint32_t kmn_abi_version(void) { return 3; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
