@@ -120,6 +120,8 @@ struct kmn_ctx {
     DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, sp_s_off, sp_e_off;
     std::vector<std::unique_ptr<Batch>> batches;
     PeerTables peers{};                   // mapped peer buffers of the fused exchange
+    PeerPlanes planes{};                  // the same peers, byte-plane views (default exchange)
+    bool exchange_planes = true;          // KMN_EXCHANGE_PLANES=0: exchange whole u16 cells instead
     bool peers_ready = false;
     uint32_t exchange_epoch = 0;          // exchanges run so far (every rank counts alike)
     DevBuf<uint32_t> xsync;               // [0] go word, [1] finished-CTA counter of exchange_reduce_kernel
@@ -687,14 +689,32 @@ void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[1]));
 }
 
-// exchanged table + the signal words of the in-kernel rank synchronisation behind it (one IPC handle)
-constexpr size_t kXtabFlagsU16 = 2 * MAX_PEERS * sizeof(uint32_t) / sizeof(uint16_t);
+// One IPC-exported allocation per rank: the exchanged u16 table, the signal words of the in-kernel rank
+// synchronisation, and the byte planes of the plane exchange (partial table: P_*, exchanged table: F_*).
+constexpr size_t kXOffFlags = CMS_CELLS * sizeof(uint16_t);
+constexpr size_t kXOffPLo = kXOffFlags + 256;
+constexpr size_t kXOffPHi = kXOffPLo + CMS_CELLS;
+constexpr size_t kXOffPBm = kXOffPHi + CMS_CELLS;
+constexpr size_t kXOffFLo = kXOffPBm + PLANE_BM_WORDS * sizeof(uint32_t);
+constexpr size_t kXOffFHi = kXOffFLo + CMS_CELLS;
+constexpr size_t kXOffFBm = kXOffFHi + CMS_CELLS;
+constexpr size_t kXBytes = kXOffFBm + PLANE_BM_WORDS * sizeof(uint32_t);
 void alloc_exchange_buffers(kmn_ctx* c) {
     if (c->xtab.p) return;
-    c->xtab.alloc(CMS_CELLS + kXtabFlagsU16);
-    KMN_CUDA(cudaMemset(c->xtab.p + CMS_CELLS, 0, kXtabFlagsU16 * sizeof(uint16_t)));
+    c->xtab.alloc(kXBytes / sizeof(uint16_t));
+    KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
     c->xsync.alloc(2);
     KMN_CUDA(cudaMemset(c->xsync.p, 0, 2 * sizeof(uint32_t)));
+}
+void set_peer_planes(PeerPlanes& pp, int p, void* xbuf) {
+    uint8_t* b = static_cast<uint8_t*>(xbuf);
+    pp.p_lo[p] = reinterpret_cast<const uint4*>(b + kXOffPLo);
+    pp.p_hi[p] = reinterpret_cast<const uint4*>(b + kXOffPHi);
+    pp.p_bm[p] = reinterpret_cast<const uint32_t*>(b + kXOffPBm);
+    pp.f_lo[p] = reinterpret_cast<uint4*>(b + kXOffFLo);
+    pp.f_hi[p] = reinterpret_cast<uint4*>(b + kXOffFHi);
+    pp.f_bm[p] = reinterpret_cast<uint32_t*>(b + kXOffFBm);
+    pp.flags[p] = reinterpret_cast<uint32_t*>(b + kXOffFlags);
 }
 
 template <typename F>
@@ -761,6 +781,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         for (auto& ev : c->ev_copy) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         c->frame_carry.alloc(1);
         c->n_tiles_dev.alloc(2);
+        if (const char* e = std::getenv("KMN_EXCHANGE_PLANES")) c->exchange_planes = std::strtol(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("KMN_H2D_CHUNKS")) {   // tuning knob
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
@@ -924,11 +945,15 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
         c->peers = PeerTables{};
         c->peers.world = world;
         c->peers.rank = rank;
+        c->planes = PeerPlanes{};
+        c->planes.world = world;
+        c->planes.rank = rank;
         for (int p = 0; p < world; p++) {
             if (p == rank) {
                 c->peers.part[p] = reinterpret_cast<const uint4*>(c->tab.p);
                 c->peers.full[p] = reinterpret_cast<uint4*>(c->xtab.p);
                 c->peers.flags[p] = reinterpret_cast<uint32_t*>(c->xtab.p + CMS_CELLS);
+                set_peer_planes(c->planes, p, c->xtab.p);
                 continue;
             }
             cudaIpcMemHandle_t h;
@@ -942,6 +967,7 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
             c->ipc_opened.push_back(ptr);
             c->peers.full[p] = reinterpret_cast<uint4*>(ptr);
             c->peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(ptr) + CMS_CELLS);
+            set_peer_planes(c->planes, p, ptr);
         }
         c->peers_ready = true;
     });
@@ -950,26 +976,55 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
 int kmn_exchange_reduce(kmn_ctx* c) {
     return guarded(c, [&] {
         if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
-        const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(c->peers.world);   // uint4 = 8 cells
-        KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
+        const int world = c->peers.world;
+        const bool planes = c->exchange_planes && (world == 2 || world == 4 || world == 8);
         uint32_t epoch = ++c->exchange_epoch;
         uint32_t* xs = c->xsync.p;
-        void* args[] = {&c->peers, &v0, &v1, &epoch, &xs};
-        const void* fn;
-        switch (c->peers.world) {
-            case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
-            case 4: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<4, 2>); break;
-            case 8: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<8, 2>); break;
-            default: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<0, 1>); break;
+        KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if (planes) {
+            // byte planes: split this rank's table, reduce + scatter planes over NVLink, rebuild the u16 table
+            uint8_t* xb = reinterpret_cast<uint8_t*>(c->xtab.p);
+            planes_split_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->tab.p),
+                                                                     reinterpret_cast<uint4*>(xb + kXOffPLo),
+                                                                     reinterpret_cast<uint4*>(xb + kXOffPHi),
+                                                                     reinterpret_cast<uint32_t*>(xb + kXOffPBm));
+            check_launch(c);
+            uint64_t per = PLANE_BLOCKS / uint64_t(world), b0 = per * c->peers.rank, b1 = per * (c->peers.rank + 1);
+            void* args[] = {&c->planes, &b0, &b1, &epoch, &xs};
+            const void* fn = world == 2 ? reinterpret_cast<const void*>(exchange_planes_kernel<2>)
+                           : world == 4 ? reinterpret_cast<const void*>(exchange_planes_kernel<4>)
+                                        : reinterpret_cast<const void*>(exchange_planes_kernel<8>);
+            if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
+                int per_sm = 0;
+                KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+                if (per_sm < 1) throw std::runtime_error("exchange_planes_kernel does not fit on an SM");
+                c->exchange_grid = c->sm_count * std::min(per_sm, 8);
+            }
+            KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
+            check_launch(c);
+            planes_join_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(xb + kXOffFLo),
+                                                                    reinterpret_cast<const uint4*>(xb + kXOffFHi),
+                                                                    reinterpret_cast<const uint32_t*>(xb + kXOffFBm),
+                                                                    reinterpret_cast<uint4*>(c->xtab.p));
+        } else {
+            const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(world);   // uint4 = 8 cells
+            uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
+            void* args[] = {&c->peers, &v0, &v1, &epoch, &xs};
+            const void* fn;
+            switch (world) {
+                case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
+                case 4: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<4, 2>); break;
+                case 8: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<8, 2>); break;
+                default: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<0, 1>); break;
+            }
+            if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
+                int per_sm = 0;
+                KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+                if (per_sm < 1) throw std::runtime_error("exchange_reduce_kernel does not fit on an SM");
+                c->exchange_grid = c->sm_count * std::min(per_sm, 8);
+            }
+            KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
         }
-        if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
-            int per_sm = 0;
-            KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
-            if (per_sm < 1) throw std::runtime_error("exchange_reduce_kernel does not fit on an SM");
-            c->exchange_grid = c->sm_count * std::min(per_sm, 8);
-        }
-        KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
         check_launch(c);
         KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));

@@ -363,4 +363,130 @@ exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end, uint
     }
 }
 
+// ---- byte-plane exchange ---------------------------------------------------------------------------
+// The exchange is NVLink-bound (0.94 GB per link direction and GPU at 8 ranks with u16 cells), and almost
+// every cell of a partial table — and most cells of the final one — fits a byte.  So the ranks exchange
+// byte planes: lo = cell & 0xFF (always), hi = cell >> 8 only for the 16-cell blocks whose bit is set in a
+// bitmap (1 bit per block).  planes_split_kernel builds the planes of this rank's table,
+// exchange_planes_kernel reduces this rank's slice from every peer's planes and scatters the planes of the
+// result to every peer, planes_join_kernel rebuilds the u16 table.  Exact: nothing is approximated, a block
+// with a large cell simply also moves its hi bytes.
+constexpr uint32_t PLANE_BLOCK = 16;                                  // cells per bitmap bit
+constexpr uint64_t PLANE_BLOCKS = CMS_CELLS / PLANE_BLOCK;            // 2^24
+constexpr uint64_t PLANE_BM_WORDS = PLANE_BLOCKS / 32;
+
+struct PeerPlanes {
+    const uint4* p_lo[MAX_PEERS];      // partial-table planes of every rank (peer-mapped)
+    const uint4* p_hi[MAX_PEERS];
+    const uint32_t* p_bm[MAX_PEERS];
+    uint4* f_lo[MAX_PEERS];            // planes of the exchanged table in every rank
+    uint4* f_hi[MAX_PEERS];
+    uint32_t* f_bm[MAX_PEERS];
+    uint32_t* flags[MAX_PEERS];
+    int world, rank;
+};
+
+// 16 u16 cells (two uint4) -> 16 lo bytes, 16 hi bytes
+__device__ __forceinline__ void split_block(const uint4& a, const uint4& b, uint4& lo, uint4& hi) {
+    lo = make_uint4(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420), __byte_perm(b.x, b.y, 0x6420), __byte_perm(b.z, b.w, 0x6420));
+    hi = make_uint4(__byte_perm(a.x, a.y, 0x7531), __byte_perm(a.z, a.w, 0x7531), __byte_perm(b.x, b.y, 0x7531), __byte_perm(b.z, b.w, 0x7531));
+}
+__device__ __forceinline__ void join_block(const uint4& lo, const uint4& hi, uint4& a, uint4& b) {
+    a = make_uint4(__byte_perm(lo.x, hi.x, 0x5140), __byte_perm(lo.x, hi.x, 0x7362), __byte_perm(lo.y, hi.y, 0x5140), __byte_perm(lo.y, hi.y, 0x7362));
+    b = make_uint4(__byte_perm(lo.z, hi.z, 0x5140), __byte_perm(lo.z, hi.z, 0x7362), __byte_perm(lo.w, hi.w, 0x5140), __byte_perm(lo.w, hi.w, 0x7362));
+}
+
+__global__ void __launch_bounds__(256)
+planes_split_kernel(const uint4* __restrict__ tab, uint4* __restrict__ lo, uint4* __restrict__ hi, uint32_t* __restrict__ bm) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < PLANE_BLOCKS; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 a = __ldcs(tab + 2 * i), b = __ldcs(tab + 2 * i + 1);
+        uint4 l, h;
+        split_block(a, b, l, h);
+        const bool any_hi = (h.x | h.y | h.z | h.w) != 0;
+        lo[i] = l;
+        if (any_hi) hi[i] = h;
+        const unsigned m = __ballot_sync(0xffffffffu, any_hi);   // i is warp-aligned: 32 consecutive blocks per warp
+        if (lane == 0) bm[i >> 5] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+planes_join_kernel(const uint4* __restrict__ lo, const uint4* __restrict__ hi, const uint32_t* __restrict__ bm, uint4* __restrict__ tab) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < PLANE_BLOCKS; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 l = __ldcs(lo + i);
+        uint4 h = make_uint4(0, 0, 0, 0);
+        if ((bm[i >> 5] >> (i & 31u)) & 1u) h = __ldcs(hi + i);
+        uint4 a, b;
+        join_block(l, h, a, b);
+        tab[2 * i] = a;
+        tab[2 * i + 1] = b;
+    }
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(256)
+exchange_planes_kernel(PeerPlanes pt, uint64_t blk_begin, uint64_t blk_end, uint32_t epoch, uint32_t* local_sync) {
+    constexpr int W = WORLD;
+    if (blockIdx.x == 0) {   // every rank's planes are complete before anybody loads them
+        if (int(threadIdx.x) < W) {
+            const int q = (pt.rank + int(threadIdx.x)) % W;
+            st_release_sys(pt.flags[q] + pt.rank, epoch);
+            while (ld_acquire_sys(pt.flags[pt.rank] + q) < epoch) {}
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
+    } else {
+        if (threadIdx.x == 0)
+            while (ld_acquire_sys(local_sync) < epoch) {}
+        __syncthreads();
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    // blk_begin, blk_end and stride are multiples of 32: a warp always owns 32 consecutive blocks (one bitmap word)
+    for (uint64_t i = blk_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < blk_end; i += stride) {
+        uint4 l[W];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            const int q = (pt.rank + p) % W;   // staggered across ranks
+            l[p] = __ldcs(pt.p_lo[q] + i);
+            bits |= ((__ldcs(pt.p_bm[q] + (i >> 5)) >> lane) & 1u) << p;
+        }
+        uint4 sa = make_uint4(0, 0, 0, 0), sb = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            uint4 h = make_uint4(0, 0, 0, 0);
+            if ((bits >> p) & 1u) h = __ldcs(pt.p_hi[(pt.rank + p) % W] + i);   // rare for partial tables
+            uint4 a, b;
+            join_block(l[p], h, a, b);
+            sa.x = sat_add_u16x2(sa.x, a.x); sa.y = sat_add_u16x2(sa.y, a.y); sa.z = sat_add_u16x2(sa.z, a.z); sa.w = sat_add_u16x2(sa.w, a.w);
+            sb.x = sat_add_u16x2(sb.x, b.x); sb.y = sat_add_u16x2(sb.y, b.y); sb.z = sat_add_u16x2(sb.z, b.z); sb.w = sat_add_u16x2(sb.w, b.w);
+        }
+        uint4 ol, oh;
+        split_block(sa, sb, ol, oh);
+        const bool any_hi = (oh.x | oh.y | oh.z | oh.w) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, any_hi);
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            const int q = (pt.rank + p) % W;
+            pt.f_lo[q][i] = ol;
+            if (any_hi) pt.f_hi[q][i] = oh;
+            if (lane == 0) pt.f_bm[q][i >> 5] = m;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(local_sync + 1, 1u);
+        if (ticket == gridDim.x - 1) {   // last CTA of this rank
+            local_sync[1] = 0;
+            __threadfence_system();
+            for (int p = 0; p < W; p++) st_release_sys(pt.flags[(pt.rank + p) % W] + MAX_PEERS + pt.rank, epoch);
+            for (int p = 0; p < W; p++)
+                while (ld_acquire_sys(pt.flags[pt.rank] + MAX_PEERS + p) < epoch) {}
+        }
+    }
+}
+
 }  // namespace kmn

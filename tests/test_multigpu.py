@@ -26,7 +26,7 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, planes):
     import torch
     import torch.distributed as dist
     import oracle_ffi
@@ -34,6 +34,7 @@ def _worker(rank, world, port, out_dir):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["KMN_EXCHANGE_PLANES"] = planes   # "1": byte-plane exchange (default), "0": whole u16 cells
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -57,12 +58,33 @@ def _worker(rank, world, port, out_dir):
                 results[mode] = ctx.table_snapshot()
                 ctx.release_batches()
                 dist.barrier()
+            # large cells: every rank holds 35 000 species made of one and the same 13-mer, so its four cells
+            # are 35 000 per rank (hi bytes in play) and 70 000 -> 65 535 after the exchange (saturation)
+            big_ok = True
+            if fused_ok:
+                one = np.frombuffer(b"ACDEFGHIKLMNP", np.uint8)
+                n_big = 35_000
+                ctx.reset_table()
+                ctx.count_batch(np.tile(one, n_big), np.arange(n_big + 1, dtype=np.uint64) * 13,
+                                np.arange(n_big + 1, dtype=np.uint64), want_counts=False)
+                ctx.count_batch(res, rec, sp)
+                sharding.fused_exchange(ctx)
+                t = ctx.table_snapshot()
+                orc0 = oracle_ffi.load()
+                idx = orc0.cms_indices(int(orc0.roll_kmers(one.tobytes(), 13, 1)[0]))
+                cells = [r * (1 << 26) + int(idx[r]) for r in range(4)]
+                base = results["fused"].astype(np.int64)
+                want_big = base.copy()
+                want_big[cells] = np.minimum(base[cells] + world * n_big, 65535)
+                big_ok = bool(np.array_equal(t.astype(np.int64), want_big))
+                ctx.release_batches()
+                dist.barrier()
         orc = oracle_ffi.load()
         h = orc.cmsa_new()
         try:
             orc.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, 13, 1, threads=4)
             want = orc.cmsa_table(h)
-            ok = all(np.array_equal(t, want) for t in results.values())
+            ok = all(np.array_equal(t, want) for t in results.values()) and big_ok
         finally:
             orc.cmsa_free(h)
         Path(out_dir, f"rank{rank}.txt").write_text(("ok " if ok else "mismatch ") + ",".join(results))
@@ -71,12 +93,13 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_gpu_exchange_matches_oracle(tmp_path):
+@pytest.mark.parametrize("planes", ["1", "0"])
+def test_two_gpu_exchange_matches_oracle(tmp_path, planes):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), planes), nprocs=2, join=True)
     for r in range(2):
         txt = (tmp_path / f"rank{r}.txt").read_text()
         assert txt.startswith("ok"), txt
