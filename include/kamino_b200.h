@@ -133,7 +133,8 @@ int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
 /* Fused NVLink exchange (one process per GPU): every rank exports CUDA IPC handles of its own table
  * and of its exchanged table (64 bytes each); after an all-gather of the handles by the caller,
  * kmn_exchange_setup maps the peers' buffers.  kmn_exchange_reduce then runs ONE kernel per rank that
- * loads this rank's 1/world cell range from every peer over NVLink, adds with saturation
+ * loads this rank's 1/world cell range from every peer over NVLink (as byte planes: low bytes always, high
+ * bytes only for the 16-cell blocks that have any), adds with saturation
  * (== snapshot of the summed sketch, proba_filter.rs:171-177) and stores the result into EVERY peer's
  * exchanged table: reduce-scatter + snapshot + all-gather without NCCL on the data path.  The ranks
  * synchronise INSIDE the kernel through signal words in peer memory (cooperative launch): it starts moving
