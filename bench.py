@@ -345,7 +345,9 @@ def run_gpu(args):
                        "l2": "per step the kernels stream 122 MB of residues, ~2 GB of partition lists and the 512 MiB "
                              "table: far beyond the 126 MB L2; no explicit flush",
                        "exchange": "none (1 GPU)" if world == 1 else (
-                           "fused NVLink peer kernel: reduce-scatter + clamp + all-gather" if fused
+                           ("fused NVLink peer kernel on byte planes: reduce-scatter + saturate + all-gather, in-kernel rank sync"
+                            if os.environ.get("KMN_EXCHANGE_PLANES", "1") != "0" else
+                            "fused NVLink peer kernel on u16 cells: reduce-scatter + saturate + all-gather, in-kernel rank sync") if fused
                            else "NCCL all-reduce of the u32 accumulators")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_elapsed / args.steps},
