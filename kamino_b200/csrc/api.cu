@@ -89,7 +89,10 @@ struct Batch {
     DevBuf<uint16_t> occ;
     DevBuf<uint32_t> inv_pos;
     uint32_t n_inv = 0;
-    DevBuf<kmn_hit> starts, ends;
+    DevBuf<uint2> starts, ends;              // compact hits: (start inside the segment, occupancy)
+    DevBuf<kmn_hit> full_starts, full_ends;  // kmn_hit form, expanded on the first kmn_fetch_hits
+    bool hits_expanded = false;
+    uint32_t tot_starts = 0, tot_ends = 0;
     DevBuf<uint32_t> seg_s_off, seg_e_off;   // per-segment offsets into starts / ends (n_inv + 1)
     std::vector<uint32_t> h_sp_starts_off, h_sp_ends_off;
     // anchor pairs (kmn_pair_batch)
@@ -190,7 +193,7 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     if (!c->spare.empty()) {
         b = std::move(c->spare.back());
         c->spare.pop_back();
-        b->framed = b->scanned = b->paired = false;
+        b->framed = b->scanned = b->paired = b->hits_expanded = false;
         b->n_codes = b->n_inv = 0;
     } else {
         b = std::make_unique<Batch>();
@@ -521,8 +524,7 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     uint32_t tot_s = 0, tot_e = 0;
     if (n_inv) {
         segment_boundary_kernel<false><<<grid, SCAN_THREADS, 0, c->stream>>>(
-            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr,
-            b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, nullptr, nullptr);
+            b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr, nullptr, nullptr);
         check_launch(c);
         exclusive_scan_kernel<<<2, 1024, 0, c->stream>>>(ScanJob{c->seg_s_cnt.p, b.seg_s_off.p, n_inv, nullptr},
                                                        ScanJob{c->seg_e_cnt.p, b.seg_e_off.p, n_inv, nullptr});
@@ -533,8 +535,7 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
         b.starts.ensure(tot_s);
         b.ends.ensure(tot_e);
         segment_boundary_kernel<true><<<grid, SCAN_THREADS, 0, c->stream>>>(
-            b.codes.p, b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, nullptr, nullptr, b.seg_s_off.p, b.seg_e_off.p,
-            b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp, b.starts.p, b.ends.p);
+            b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, nullptr, nullptr, b.seg_s_off.p, b.seg_e_off.p, b.starts.p, b.ends.p);
         check_launch(c);
         species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
             b.inv_pos.p, n_inv, b.sp_cstart.p, b.n_sp, b.seg_s_off.p, b.seg_e_off.p, c->sp_s_off.p, c->sp_e_off.p);
@@ -552,6 +553,9 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[4], c->ev[0], c->ev[1]));
     b.scanned = true;
     b.paired = false;
+    b.hits_expanded = false;
+    b.tot_starts = tot_s;
+    b.tot_ends = tot_e;
     if (n_starts) *n_starts = tot_s;
     if (n_ends) *n_ends = tot_e;
 }
@@ -567,7 +571,9 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
         c->seg_e_cnt.ensure(size_t(n_seg) + 2);
         const uint32_t blocks = (n_seg + 255) / 256;
         pair_segments_kernel<false><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
-                                                                 uint32_t(c->k), length_middle, c->seg_s_cnt.p, nullptr, nullptr);
+                                                                 uint32_t(c->k), length_middle, c->seg_s_cnt.p, nullptr, nullptr,
+                                                                 b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec, b.sp_cstart.p,
+                                                                 b.sp_rec_off.p, b.n_sp);
         check_launch(c);
         const ScanJob job{c->seg_s_cnt.p, c->seg_e_cnt.p, n_seg, nullptr};
         exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
@@ -576,7 +582,9 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         b.pairs.ensure(total);
         pair_segments_kernel<true><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
-                                                                uint32_t(c->k), length_middle, nullptr, c->seg_e_cnt.p, b.pairs.p);
+                                                                uint32_t(c->k), length_middle, nullptr, c->seg_e_cnt.p, b.pairs.p,
+                                                                b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec, b.sp_cstart.p,
+                                                                b.sp_rec_off.p, b.n_sp);
         check_launch(c);
         species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
             b.inv_pos.p, n_seg, b.sp_cstart.p, b.n_sp, c->seg_e_cnt.p, c->seg_e_cnt.p, c->sp_s_off.p, c->sp_e_off.p);
@@ -1053,10 +1061,26 @@ int kmn_fetch_hits(kmn_ctx* c, uint32_t batch_id, uint32_t sp, kmn_hit* starts, 
         if (n_ends) *n_ends = e1 - e0;
         if (!starts && !ends) return;
         if ((starts && cap_starts < s1 - s0) || (ends && cap_ends < e1 - e0)) throw std::runtime_error("hit buffers too small");
+        if (!b.hits_expanded) {   // the scan keeps compact hits; the full form is built once, when somebody asks for it
+            b.full_starts.ensure(b.tot_starts);
+            b.full_ends.ensure(b.tot_ends);
+            if (b.n_inv) {
+                const int g = grid_for(c, 8);
+                expand_hits_kernel<<<g, SCAN_THREADS, 0, c->stream>>>(b.codes.p, b.inv_pos.p, b.n_inv, c->k, b.starts.p, b.seg_s_off.p,
+                                                                     b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp,
+                                                                     b.full_starts.p);
+                check_launch(c);
+                expand_hits_kernel<<<g, SCAN_THREADS, 0, c->stream>>>(b.codes.p, b.inv_pos.p, b.n_inv, c->k, b.ends.p, b.seg_e_off.p,
+                                                                     b.rec_cstart.p, b.n_rec, b.sp_cstart.p, b.sp_rec_off.p, b.n_sp,
+                                                                     b.full_ends.p);
+                check_launch(c);
+            }
+            b.hits_expanded = true;
+        }
         if (starts && s1 > s0)
-            KMN_CUDA(cudaMemcpyAsync(starts, b.starts.p + s0, (s1 - s0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
+            KMN_CUDA(cudaMemcpyAsync(starts, b.full_starts.p + s0, (s1 - s0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
         if (ends && e1 > e0)
-            KMN_CUDA(cudaMemcpyAsync(ends, b.ends.p + e0, (e1 - e0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
+            KMN_CUDA(cudaMemcpyAsync(ends, b.full_ends.p + e0, (e1 - e0) * sizeof(kmn_hit), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
     });
 }

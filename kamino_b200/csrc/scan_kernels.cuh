@@ -135,16 +135,16 @@ __device__ __forceinline__ uint64_t kmer_ending_at(const uint8_t* __restrict__ c
 
 // K5b/K5c: one warp per valid segment (the codes strictly between two consecutive resets).
 // EMIT == false: count start candidates / end anchors per segment.
-// EMIT == true : write them, in position order, at the scanned offsets.
+// EMIT == true : write them, in position order, at the scanned offsets, as COMPACT hits (start inside the
+//                segment, occupancy).  k-mer, record and segment offset of a hit are only materialised for
+//                what is actually consumed: the anchor pairs (pair_segments_kernel) or kmn_fetch_hits
+//                (expand_hits_kernel).
 template <bool EMIT>
 __global__ void __launch_bounds__(SCAN_THREADS)
-segment_boundary_kernel(const uint8_t* __restrict__ codes, const uint16_t* __restrict__ occ,
-                        const uint32_t* __restrict__ inv_pos, uint32_t n_inv, int k, uint32_t min_needed,
-                        uint32_t* __restrict__ seg_starts_cnt, uint32_t* __restrict__ seg_ends_cnt,
+segment_boundary_kernel(const uint16_t* __restrict__ occ, const uint32_t* __restrict__ inv_pos, uint32_t n_inv, int k,
+                        uint32_t min_needed, uint32_t* __restrict__ seg_starts_cnt, uint32_t* __restrict__ seg_ends_cnt,
                         const uint32_t* __restrict__ seg_starts_off, const uint32_t* __restrict__ seg_ends_off,
-                        const uint32_t* __restrict__ rec_cstart, uint32_t n_rec,
-                        const uint32_t* __restrict__ sp_cstart, const uint64_t* __restrict__ sp_rec_off,
-                        uint32_t n_sp, kmn_hit* __restrict__ starts, kmn_hit* __restrict__ ends) {
+                        uint2* __restrict__ starts, uint2* __restrict__ ends) {
     const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
     const unsigned lane = threadIdx.x & 31u;
@@ -154,13 +154,9 @@ segment_boundary_kernel(const uint8_t* __restrict__ codes, const uint16_t* __res
         const uint32_t seg_hi = inv_pos[j];                        // one past its last code
         const uint32_t len = seg_hi - seg_lo;
         uint32_t ns = 0, ne = 0;
-        uint32_t rec = 0, seg_start = 0, os = 0, oe = 0;
+        uint32_t os = 0, oe = 0;
         if (len >= uint32_t(2 * k + 1)) {   // group_extraction.rs:424,462,484
             if (EMIT) {
-                const uint32_t r = upper_index_le(rec_cstart, n_rec, seg_lo);
-                const uint32_t s = upper_index_le(sp_cstart, n_sp, seg_lo);
-                rec = r - uint32_t(sp_rec_off[s]);
-                seg_start = seg_lo - rec_cstart[r];
                 os = seg_starts_off[j];
                 oe = seg_ends_off[j];
             }
@@ -177,24 +173,8 @@ segment_boundary_kernel(const uint8_t* __restrict__ codes, const uint16_t* __res
                 }
                 const unsigned bs = __ballot_sync(0xffffffffu, is_s), be = __ballot_sync(0xffffffffu, is_e);
                 if (EMIT) {
-                    if (is_s) {
-                        kmn_hit h;
-                        h.kmer = kmer_ending_at(codes, c - 1, k);
-                        h.rec = rec;
-                        h.seg_start = seg_start;
-                        h.start = (c - 1) - (k - 1) - seg_lo;
-                        h.occ = prev;
-                        starts[os + ns + __popc(bs & lt_mask)] = h;
-                    }
-                    if (is_e) {
-                        kmn_hit h;
-                        h.kmer = kmer_ending_at(codes, c, k);
-                        h.rec = rec;
-                        h.seg_start = seg_start;
-                        h.start = c - (k - 1) - seg_lo;
-                        h.occ = cur;
-                        ends[oe + ne + __popc(be & lt_mask)] = h;
-                    }
+                    if (is_s) starts[os + ns + __popc(bs & lt_mask)] = make_uint2((c - 1) - (k - 1) - seg_lo, prev);
+                    if (is_e) ends[oe + ne + __popc(be & lt_mask)] = make_uint2(c - (k - 1) - seg_lo, cur);
                 }
                 ns += __popc(bs);
                 ne += __popc(be);
@@ -203,6 +183,43 @@ segment_boundary_kernel(const uint8_t* __restrict__ codes, const uint16_t* __res
         if (!EMIT && lane == 0) {
             seg_starts_cnt[j] = ns;
             seg_ends_cnt[j] = ne;
+        }
+    }
+}
+
+// record / segment coordinates of segment j (the segment starts at codes index seg_lo)
+struct SegCoords { uint32_t rec, seg_start; };
+__device__ __forceinline__ SegCoords segment_coords(uint32_t seg_lo, const uint32_t* __restrict__ rec_cstart, uint32_t n_rec,
+                                                   const uint32_t* __restrict__ sp_cstart,
+                                                   const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp) {
+    const uint32_t r = upper_index_le(rec_cstart, n_rec, seg_lo);
+    const uint32_t s = upper_index_le(sp_cstart, n_sp, seg_lo);
+    return SegCoords{r - uint32_t(sp_rec_off[s]), seg_lo - rec_cstart[r]};
+}
+
+// compact hits -> kmn_hit (kmn_fetch_hits only): one warp per segment
+__global__ void __launch_bounds__(SCAN_THREADS)
+expand_hits_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ inv_pos, uint32_t n_inv, int k,
+                   const uint2* __restrict__ compact, const uint32_t* __restrict__ seg_off,
+                   const uint32_t* __restrict__ rec_cstart, uint32_t n_rec, const uint32_t* __restrict__ sp_cstart,
+                   const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp, kmn_hit* __restrict__ out) {
+    const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
+    const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t j = warp_id; j < n_inv; j += warps_per_grid) {
+        const uint32_t h0 = seg_off[j], h1 = seg_off[j + 1];
+        if (h1 == h0) continue;
+        const uint32_t seg_lo = j == 0 ? 0u : inv_pos[j - 1] + 1;
+        const SegCoords sc = segment_coords(seg_lo, rec_cstart, n_rec, sp_cstart, sp_rec_off, n_sp);
+        for (uint32_t i = h0 + lane; i < h1; i += 32) {
+            const uint2 c = compact[i];
+            kmn_hit h;
+            h.kmer = kmer_ending_at(codes, seg_lo + c.x + k - 1, k);
+            h.rec = sc.rec;
+            h.seg_start = sc.seg_start;
+            h.start = c.x;
+            h.occ = c.y;
+            out[i] = h;
         }
     }
 }
@@ -233,53 +250,59 @@ __global__ void species_hit_offsets_kernel(const uint32_t* __restrict__ inv_pos,
 // EMIT == false: pairs per segment; EMIT == true: write them in (segment, left anchor) order.
 template <bool EMIT>
 __global__ void __launch_bounds__(256)
-pair_segments_kernel(const kmn_hit* __restrict__ starts, const kmn_hit* __restrict__ ends,
+pair_segments_kernel(const uint2* __restrict__ starts, const uint2* __restrict__ ends,
                      const uint32_t* __restrict__ seg_s_off, const uint32_t* __restrict__ seg_e_off, uint32_t n_seg,
                      uint32_t k, uint32_t length_middle, uint32_t* __restrict__ seg_p_cnt,
-                     const uint32_t* __restrict__ seg_p_off, kmn_pair* __restrict__ pairs) {
+                     const uint32_t* __restrict__ seg_p_off, kmn_pair* __restrict__ pairs,
+                     const uint8_t* __restrict__ codes, const uint32_t* __restrict__ inv_pos,
+                     const uint32_t* __restrict__ rec_cstart, uint32_t n_rec, const uint32_t* __restrict__ sp_cstart,
+                     const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_seg) return;
     const uint32_t s0 = seg_s_off[j], s1 = seg_s_off[j + 1], e0 = seg_e_off[j], e1 = seg_e_off[j + 1];
     uint32_t n = 0;
     if (s1 > s0 && e1 > e0) {
         const uint32_t out = EMIT ? seg_p_off[j] : 0u;
-        auto pos_occ = [](const kmn_hit* h) { return *reinterpret_cast<const uint2*>(&h->start); };   // (start, occ)
+        const uint32_t seg_lo = j == 0 ? 0u : inv_pos[j - 1] + 1;
+        SegCoords sc{0, 0};
+        if (EMIT && seg_p_off[j + 1] > out) sc = segment_coords(seg_lo, rec_cstart, n_rec, sp_cstart, sp_rec_off, n_sp);
         uint32_t first_end = e0;
-        auto handle = [&](uint32_t li, uint32_t lstart) {
+        auto handle = [&](uint32_t lstart) {
             const uint32_t left_end = lstart + k;
-            while (first_end < e1 && pos_occ(ends + first_end).x <= left_end) first_end++;
-            uint32_t bj = 0xFFFFFFFFu, bo = 0, bs = 0;
+            while (first_end < e1 && ends[first_end].x <= left_end) first_end++;
+            uint32_t bo = 0, bs = 0;
+            bool have = false;
             for (uint32_t q = first_end; q < e1; q++) {
-                const uint2 r = pos_occ(ends + q);
+                const uint2 r = ends[q];
                 if (r.x <= left_end) continue;
                 if (r.x - left_end > length_middle) break;
-                if (bj == 0xFFFFFFFFu || r.y > bo || (r.y == bo && r.x < bs)) { bj = q; bo = r.y; bs = r.x; }
+                if (!have || r.y > bo || (r.y == bo && r.x < bs)) { have = true; bo = r.y; bs = r.x; }
             }
-            if (bj == 0xFFFFFFFFu) return;
+            if (!have) return;
             if (EMIT) {
                 kmn_pair p;
-                p.left = starts[li].kmer;
-                p.right = ends[bj].kmer;
-                p.rec = starts[li].rec;
-                p.seg_start = starts[li].seg_start;
+                p.left = kmer_ending_at(codes, seg_lo + lstart + k - 1, int(k));
+                p.right = kmer_ending_at(codes, seg_lo + bs + k - 1, int(k));
+                p.rec = sc.rec;
+                p.seg_start = sc.seg_start;
                 p.left_start = lstart;
                 p.len = bs + k - lstart;
                 pairs[out + n] = p;
             }
             n++;
         };
-        uint2 f = pos_occ(starts + s0);
-        uint32_t cluster_at = f.x, best_i = s0, best_start = f.x, best_occ = f.y;
+        const uint2 f = starts[s0];
+        uint32_t cluster_at = f.x, best_start = f.x, best_occ = f.y;
         for (uint32_t i = s0 + 1; i < s1; i++) {
-            const uint2 c = pos_occ(starts + i);
+            const uint2 c = starts[i];
             if (c.x < cluster_at + 10u) {
-                if (c.y > best_occ || (c.y == best_occ && c.x < best_start)) { best_i = i; best_start = c.x; best_occ = c.y; }
+                if (c.y > best_occ || (c.y == best_occ && c.x < best_start)) { best_start = c.x; best_occ = c.y; }
             } else {
-                handle(best_i, best_start);
-                cluster_at = c.x; best_i = i; best_start = c.x; best_occ = c.y;
+                handle(best_start);
+                cluster_at = c.x; best_start = c.x; best_occ = c.y;
             }
         }
-        handle(best_i, best_start);
+        handle(best_start);
     }
     if (!EMIT) seg_p_cnt[j] = n;
 }
