@@ -135,7 +135,7 @@ struct kmn_ctx {
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
-    DevBuf<uint32_t> frame_carry, n_tiles_dev;
+    DevBuf<uint32_t> frame_carry, n_tiles_dev, scan_sums, scan_offs;
     // scratch of kmn_group_observations
     DevBuf<uint64_t> g_left, g_right;
     DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first;
@@ -165,6 +165,27 @@ void check_launch(kmn_ctx* c) {
 }
 
 int grid_for(kmn_ctx* c, int ctas_per_sm) { return c->sm_count * ctas_per_sm; }
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total) on the context's stream: one CTA for short arrays,
+// per-tile sums + their scan + per-tile scans for long ones.
+void device_exclusive_scan(kmn_ctx* c, const uint32_t* in, uint32_t* out, uint32_t n) {
+    if (n <= 4 * SCAN_TILE) {
+        const ScanJob job{in, out, n, nullptr};
+        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
+        check_launch(c);
+        return;
+    }
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    c->scan_sums.ensure(tiles);
+    c->scan_offs.ensure(size_t(tiles) + 1);
+    scan_tile_sums_kernel<<<tiles, 1024, 0, c->stream>>>(in, n, c->scan_sums.p);
+    check_launch(c);
+    const ScanJob job{c->scan_sums.p, c->scan_offs.p, tiles, nullptr};
+    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
+    check_launch(c);
+    scan_tiles_kernel<<<tiles, 1024, 0, c->stream>>>(in, n, c->scan_offs.p, out);
+    check_launch(c);
+}
 
 Batch& get_batch(kmn_ctx* c, uint32_t id) {
     if (id >= c->batches.size() || !c->batches[id]) throw std::runtime_error("unknown batch id");
@@ -526,9 +547,8 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
         segment_boundary_kernel<false><<<grid, SCAN_THREADS, 0, c->stream>>>(
             b.occ.p, b.inv_pos.p, n_inv, c->k, min_needed, c->seg_s_cnt.p, c->seg_e_cnt.p, nullptr, nullptr, nullptr, nullptr);
         check_launch(c);
-        exclusive_scan_kernel<<<2, 1024, 0, c->stream>>>(ScanJob{c->seg_s_cnt.p, b.seg_s_off.p, n_inv, nullptr},
-                                                       ScanJob{c->seg_e_cnt.p, b.seg_e_off.p, n_inv, nullptr});
-        check_launch(c);
+        device_exclusive_scan(c, c->seg_s_cnt.p, b.seg_s_off.p, n_inv);
+        device_exclusive_scan(c, c->seg_e_cnt.p, b.seg_e_off.p, n_inv);
         KMN_CUDA(cudaMemcpyAsync(&tot_s, b.seg_s_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaMemcpyAsync(&tot_e, b.seg_e_off.p + n_inv, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
@@ -575,9 +595,7 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
                                                                  b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec, b.sp_cstart.p,
                                                                  b.sp_rec_off.p, b.n_sp);
         check_launch(c);
-        const ScanJob job{c->seg_s_cnt.p, c->seg_e_cnt.p, n_seg, nullptr};
-        exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
-        check_launch(c);
+        device_exclusive_scan(c, c->seg_s_cnt.p, c->seg_e_cnt.p, n_seg);
         KMN_CUDA(cudaMemcpyAsync(&total, c->seg_e_cnt.p + n_seg, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         b.pairs.ensure(total);
@@ -645,9 +663,7 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     // runs of equal keys -> groups
     group_heads_kernel<<<eb, 256, 0, c->stream>>>(d_left.p, d_right.p, d_perm[cur].p, n, d_head.p);
     check_launch(c);
-    const ScanJob hjob{d_head.p, d_scan.p, n, nullptr};
-    exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(hjob, hjob);
-    check_launch(c);
+    device_exclusive_scan(c, d_head.p, d_scan.p, n);
     uint32_t ng = 0;
     KMN_CUDA(cudaMemcpyAsync(&ng, d_scan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));

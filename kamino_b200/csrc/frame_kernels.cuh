@@ -109,6 +109,64 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(ScanJob j0, ScanJo
     }
 }
 
+// Two-level scan for long arrays (segments, hits, observations: 10^5 .. 10^7 values): per-CTA sums of
+// SCAN_TILE values, a single-CTA scan of those sums (exclusive_scan_kernel), then per-CTA scans offset by them.
+constexpr uint32_t SCAN_TILE = 1024 * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < SCAN_ITEMS; q++) sum += i0 + q < n ? in[i0 + q] : 0u;
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t t = __reduce_add_sync(0xffffffffu, s_warp[threadIdx.x]);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+
+// out[i] = tile_off[tile] + exclusive prefix inside the tile; the last CTA also writes out[n] = total
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const uint32_t* __restrict__ in, uint32_t n,
+                                                          const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < SCAN_ITEMS; q++) {
+        x[q] = i0 + q < n ? in[i0 + q] : 0u;
+        sum += x[q];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= unsigned(d)) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= unsigned(d)) wi += y;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = tile_off[blockIdx.x] + s_warp[warp] + incl - sum;
+#pragma unroll
+    for (uint32_t q = 0; q < SCAN_ITEMS; q++) {
+        if (i0 + q < n) out[i0 + q] = run;
+        run += x[q];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) out[n] = run;   // padding items are zero
+}
+
 // index of the record that contains raw byte offset x: largest r with rec_off[r] <= x, skipping
 // empty records (rec_off[r] == rec_off[r+1]); search window [lo, hi].
 __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_off, uint32_t lo,
