@@ -703,7 +703,7 @@ void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint
         pair_pack_kernel<<<uint32_t((items + 255) / 256), 256, 0, c->stream>>>(d_mapped.p, n, L, n_pad, W, d_planes.p);
         check_launch(c);
         const uint32_t n_blocks = n_tiles * (n_tiles + 1) / 2;
-        pair_count_kernel<<<n_blocks, PAIR_THREADS, 0, c->stream>>>(d_planes.p, n, W, n_tiles, d_valid.p, d_mism.p);
+        pair_count_kernel<<<n_blocks, PAIR_THREADS, PAIR_COUNT_SMEM, c->stream>>>(d_planes.p, n, W, n_tiles, d_valid.p, d_mism.p);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -817,6 +817,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
             c->bloom_run_cap = uint32_t(v);
         }
         c->bl_scratch.alloc(size_t(BS_MAX_CTAS) << (BLOOM_BITS_LOG2 - 5));
+        KMN_CUDA(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PAIR_COUNT_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
         KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BB_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BS_SMEM)));

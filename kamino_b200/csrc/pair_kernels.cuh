@@ -7,6 +7,8 @@
 // Codes 0..20 are sliced into 5 bit planes + a validity plane per 32-column word, so one pair-word
 // costs 7 LOP3 + 2 POPC.  Integer only — no tensor cores (not a floating-point contraction).
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "kmn_device.cuh"
 
 namespace kmn {
@@ -16,6 +18,7 @@ constexpr int PAIR_TILE = 64;      // pairs tile is 64 x 64 rows
 constexpr int PAIR_WB = 8;         // 32-column words per smem stage
 constexpr int PAIR_ROW_STRIDE = PAIR_WB * PAIR_PLANES + 4;  // u32; +4 keeps LDS.128 conflict-free
 constexpr int PAIR_THREADS = 256;
+constexpr size_t PAIR_COUNT_SMEM = size_t(4) * PAIR_TILE * PAIR_ROW_STRIDE * sizeof(uint32_t);   // two stages x two operands
 
 // planes[(i * W + w) * 8 + p]; columns >= L and rows >= n are "invalid" (valid plane 0).
 __global__ void __launch_bounds__(256)
@@ -46,12 +49,31 @@ pair_pack_kernel(const uint8_t* __restrict__ mapped, uint32_t n, uint64_t L, uin
     dst[1] = make_uint4(p[4], p[5], 0u, 0u);
 }
 
-// One CTA per 64x64 tile (ti <= tj) of the pair matrix; each thread owns a 4x4 micro-tile.
-__global__ void __launch_bounds__(PAIR_THREADS)
+// One CTA per 64x64 tile (ti <= tj) of the pair matrix; each thread owns a 4x4 micro-tile.  The operand
+// stages (64 rows x 8 words x 8 planes each) are double-buffered with cp.async so that the next stage's
+// global loads fly while the current one is being counted.
+__device__ __forceinline__ void pair_stage_load(uint32_t* sA, uint32_t* sB, const uint32_t* __restrict__ planes, uint32_t ti,
+                                                uint32_t tj, uint32_t W, uint32_t w0) {
+    for (uint32_t e = threadIdx.x; e < PAIR_TILE * PAIR_WB * 2; e += PAIR_THREADS) {
+        const uint32_t row = e / (PAIR_WB * 2), q = e % (PAIR_WB * 2);  // q: (word, half)
+        const uint32_t w = w0 + (q >> 1);
+        uint32_t* da = &sA[row * PAIR_ROW_STRIDE + q * 4];
+        uint32_t* db = &sB[row * PAIR_ROW_STRIDE + q * 4];
+        if (w < W) {
+            __pipeline_memcpy_async(da, reinterpret_cast<const uint4*>(planes + (uint64_t(ti * PAIR_TILE + row) * W + w) * PAIR_PLANES) + (q & 1), 16);
+            __pipeline_memcpy_async(db, reinterpret_cast<const uint4*>(planes + (uint64_t(tj * PAIR_TILE + row) * W + w) * PAIR_PLANES) + (q & 1), 16);
+        } else {
+            *reinterpret_cast<uint4*>(da) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(db) = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PAIR_THREADS, 3)
 pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, uint32_t n_tiles,
                   uint32_t* __restrict__ valid, uint32_t* __restrict__ mismatch) {
-    __shared__ __align__(16) uint32_t sA[PAIR_TILE * PAIR_ROW_STRIDE];
-    __shared__ __align__(16) uint32_t sB[PAIR_TILE * PAIR_ROW_STRIDE];
+    extern __shared__ __align__(16) uint32_t pair_smem[];   // [2 buffers][A, B][PAIR_TILE * PAIR_ROW_STRIDE]
+    constexpr uint32_t OPER = PAIR_TILE * PAIR_ROW_STRIDE;
     // linear block index -> (ti, tj), ti <= tj
     uint32_t rem = blockIdx.x, ti = 0;
     while (rem >= n_tiles - ti) { rem -= n_tiles - ti; ti++; }
@@ -63,18 +85,19 @@ pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, u
 #pragma unroll
         for (int b = 0; b < 4; b++) { cv[a][b] = 0; cm[a][b] = 0; }
 
-    for (uint32_t w0 = 0; w0 < W; w0 += PAIR_WB) {
-        // stage 64 rows x 8 words x 8 planes for both operands: 64*8*2 uint4 per operand
-        for (uint32_t e = threadIdx.x; e < PAIR_TILE * PAIR_WB * 2; e += PAIR_THREADS) {
-            const uint32_t row = e / (PAIR_WB * 2), q = e % (PAIR_WB * 2);  // q: (word, half)
-            const uint32_t w = w0 + (q >> 1);
-            uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
-            if (w < W) {
-                va = __ldg(reinterpret_cast<const uint4*>(planes + (uint64_t(ti * PAIR_TILE + row) * W + w) * PAIR_PLANES) + (q & 1));
-                vb = __ldg(reinterpret_cast<const uint4*>(planes + (uint64_t(tj * PAIR_TILE + row) * W + w) * PAIR_PLANES) + (q & 1));
-            }
-            *reinterpret_cast<uint4*>(&sA[row * PAIR_ROW_STRIDE + q * 4]) = va;
-            *reinterpret_cast<uint4*>(&sB[row * PAIR_ROW_STRIDE + q * 4]) = vb;
+    pair_stage_load(pair_smem, pair_smem + OPER, planes, ti, tj, W, 0);
+    __pipeline_commit();
+    uint32_t buf = 0;
+    for (uint32_t w0 = 0; w0 < W; w0 += PAIR_WB, buf ^= 1u) {
+        const uint32_t* sA = pair_smem + buf * 2 * OPER;
+        const uint32_t* sB = sA + OPER;
+        if (w0 + PAIR_WB < W) {   // CTA-uniform
+            uint32_t* nA = pair_smem + (buf ^ 1u) * 2 * OPER;
+            pair_stage_load(nA, nA + OPER, planes, ti, tj, W, w0 + PAIR_WB);
+            __pipeline_commit();
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
         }
         __syncthreads();
 #pragma unroll 2
@@ -104,7 +127,7 @@ pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, u
                     cm[a][b] += __popc(d & v);
                 }
         }
-        __syncthreads();
+        __syncthreads();   // everybody is done with this buffer before the stage after next overwrites it
     }
 #pragma unroll
     for (int a = 0; a < 4; a++)
