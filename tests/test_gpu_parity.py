@@ -335,7 +335,7 @@ def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
         _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
 
 
-def test_full_size_properties_100_proteomes(ffi):
+def test_full_size_properties_100_proteomes(ffi, monkeypatch):
     """BASELINE.json configs[1] at full size (100 synthetic bacterial proteomes, 1.2e8 residues), checked
     through size-independent properties of the path instead of the (slow) oracle: the table is invariant
     under the order of the species and under the split into batches, per-species counts travel with their
@@ -379,6 +379,13 @@ def test_full_size_properties_100_proteomes(ffi):
         ctx.count_staged(bid)
         ctx.finalize_table()
         assert np.array_equal(ctx.table_snapshot(), np.minimum(t_all.astype(np.uint32) * 2, 65535).astype(np.uint16))
+    # the copy / compute pipeline of kmn_count_batch: 1 and 16 species ranges give the same table as the default 5
+    for chunks in ("1", "16"):
+        monkeypatch.setenv("KMN_H2D_CHUNKS", chunks)
+        with ffi.Context(13, SR6) as ctx:
+            _, n2 = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+            ctx.finalize_table()
+            assert np.array_equal(ctx.table_snapshot(), t_all) and np.array_equal(n2, new), f"KMN_H2D_CHUNKS={chunks}"
 
 
 def _group_reference(left, right, sid, length, min_needed, k):
