@@ -202,8 +202,11 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     const uint64_t n_raw = rec_off[n_rec];
     if (n_raw + n_rec >= (1ull << 31)) throw std::runtime_error("batch too large: residues + records must stay below 2^31");
     if (n_raw && !residues) throw std::runtime_error("residues must not be NULL");
-    for (uint64_t r = 0; r < n_rec; r++)
-        if (rec_off[r + 1] < rec_off[r]) throw std::runtime_error("rec_off must be non-decreasing");
+    {   // branch-free so that it vectorises: this loop runs before any device work of kmn_count_batch is queued
+        uint64_t bad = 0;
+        for (uint64_t r = 0; r < n_rec; r++) bad |= uint64_t(rec_off[r + 1] < rec_off[r]);
+        if (bad) throw std::runtime_error("rec_off must be non-decreasing");
+    }
     if (sp_rec_off[0] != 0 || sp_rec_off[n_sp] != n_rec) throw std::runtime_error("sp_rec_off must span [0, n_rec]");
     for (uint32_t s = 0; s < n_sp; s++)
         if (sp_rec_off[s + 1] < sp_rec_off[s]) throw std::runtime_error("sp_rec_off must be non-decreasing");
