@@ -72,7 +72,7 @@ typedef struct kmn_group {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);   /* currently 3 */
+uint32_t kmn_abi_version(void);   /* currently 4 */
 
 /* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
  * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.
@@ -188,6 +188,18 @@ int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* 
  * triangle is written.  The f64 correction (phylo.rs:96-105) stays on the host (glibc log). */
 int kmn_pair_counts(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid,
                     uint32_t* mismatch);
+/* Rows [row_begin, row_end) of the same matrix: the row block one rank computes when the rayon loop
+ * over rows i of compute_distance_matrix (phylo.rs:124-138) is sharded over GPUs.  Every rank passes
+ * the whole `mapped`; row_begin must be a multiple of 64 and row_end a multiple of 64 or n.
+ * valid / mismatch are (row_end - row_begin) x n row-major; entry (i - row_begin, j) is written for
+ * j > i, the rest is 0.  kmn_pair_counts == rows [0, n).  valid / mismatch may be NULL: the counts
+ * then stay on the device only (kmn_pair_counts_device), e.g. to be gathered by a collective. */
+int kmn_pair_counts_rows(kmn_ctx* ctx, const uint8_t* mapped, uint32_t n, uint64_t L,
+                         uint32_t row_begin, uint32_t row_end, uint32_t* valid, uint32_t* mismatch);
+/* Device copies of the counts of the last kmn_pair_counts / kmn_pair_counts_rows call: *rows x *n
+ * row-major u32 each, owned by the context, valid until the next such call or kmn_destroy. */
+int kmn_pair_counts_device(kmn_ctx* ctx, const uint32_t** valid, const uint32_t** mismatch,
+                           uint32_t* rows, uint32_t* n);
 
 /* Device time (ms) of the last kmn_count_staged / kmn_scan_batch / kmn_pair_counts call on this
  * context, per stage, measured with CUDA events on the context's stream.

@@ -140,6 +140,8 @@ struct kmn_ctx {
     DevBuf<uint64_t> g_left, g_right;
     DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first;
     DevBuf<kmn_group> g_groups;
+    DevBuf<uint32_t> nj_valid, nj_mism;   // counts of the last pair_counts call (kmn_pair_counts_device)
+    uint32_t nj_rows = 0, nj_n = 0;
     float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
@@ -685,33 +687,46 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     if (n_groups) *n_groups = ng;
 }
 
-void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
-    if (n < 2) return;
+// rows [row0, row1) of the pair matrix (row0 a multiple of the 64-row tile; row1 a multiple or n): the
+// row block one rank computes when the matrix is sharded; the whole matrix is rows [0, n).
+void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t row0, uint32_t row1, uint32_t* valid,
+                 uint32_t* mismatch) {
+    if (row0 > row1 || row1 > n) throw std::runtime_error("pair_counts: invalid row range");
+    if (row0 % PAIR_TILE != 0 || (row1 % PAIR_TILE != 0 && row1 != n))
+        throw std::runtime_error("pair_counts: row range must be aligned to 64-row tiles");
+    c->nj_rows = row1 - row0;
+    c->nj_n = n;
+    if (row0 == row1) return;
     if (L >= (1ull << 32)) throw std::runtime_error("alignment too long for u32 counts");
     const uint32_t n_tiles = (n + PAIR_TILE - 1) / PAIR_TILE;
     const uint32_t n_pad = n_tiles * PAIR_TILE;
     const uint32_t W = uint32_t((L + 31) / 32);
+    const uint32_t t0 = row0 / PAIR_TILE, t1 = (row1 + PAIR_TILE - 1) / PAIR_TILE;
+    const size_t out_cells = size_t(row1 - row0) * n;
     DevBuf<uint8_t> d_mapped;
-    DevBuf<uint32_t> d_planes, d_valid, d_mism;
-    d_mapped.alloc(size_t(n) * L);
+    DevBuf<uint32_t> d_planes;
+    DevBuf<uint32_t>&d_valid = c->nj_valid, &d_mism = c->nj_mism;
+    d_mapped.alloc(std::max<size_t>(size_t(n) * L, 1));
     d_planes.alloc(size_t(n_pad) * std::max<uint32_t>(W, 1) * PAIR_PLANES);
-    d_valid.alloc(size_t(n) * n);
-    d_mism.alloc(size_t(n) * n);
+    d_valid.ensure(out_cells);
+    d_mism.ensure(out_cells);
     if (L) KMN_CUDA(cudaMemcpyAsync(d_mapped.p, mapped, size_t(n) * L, cudaMemcpyHostToDevice, c->stream));
-    KMN_CUDA(cudaMemsetAsync(d_valid.p, 0, size_t(n) * n * sizeof(uint32_t), c->stream));
-    KMN_CUDA(cudaMemsetAsync(d_mism.p, 0, size_t(n) * n * sizeof(uint32_t), c->stream));
+    KMN_CUDA(cudaMemsetAsync(d_valid.p, 0, out_cells * sizeof(uint32_t), c->stream));
+    KMN_CUDA(cudaMemsetAsync(d_mism.p, 0, out_cells * sizeof(uint32_t), c->stream));
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (W) {
         const uint64_t items = uint64_t(n_pad) * W;
         pair_pack_kernel<<<uint32_t((items + 255) / 256), 256, 0, c->stream>>>(d_mapped.p, n, L, n_pad, W, d_planes.p);
         check_launch(c);
-        const uint32_t n_blocks = n_tiles * (n_tiles + 1) / 2;
-        pair_count_kernel<<<n_blocks, PAIR_THREADS, PAIR_COUNT_SMEM, c->stream>>>(d_planes.p, n, W, n_tiles, d_valid.p, d_mism.p);
+        // tile rows t0..t1-1 of the upper triangle: sum of (n_tiles - t)
+        const uint64_t n_blocks = uint64_t(t1 - t0) * n_tiles - (uint64_t(t1) * (t1 - 1) / 2 - uint64_t(t0) * (t0 > 0 ? t0 - 1 : 0) / 2);
+        pair_count_kernel<<<uint32_t(n_blocks), PAIR_THREADS, PAIR_COUNT_SMEM, c->stream>>>(d_planes.p, n, W, n_tiles, t0, d_valid.p,
+                                                                                          d_mism.p);
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    KMN_CUDA(cudaMemcpyAsync(valid, d_valid.p, size_t(n) * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(mismatch, d_mism.p, size_t(n) * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (valid) KMN_CUDA(cudaMemcpyAsync(valid, d_valid.p, out_cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (mismatch) KMN_CUDA(cudaMemcpyAsync(mismatch, d_mism.p, out_cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[1]));
 }
@@ -765,7 +780,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 3; }
+uint32_t kmn_abi_version(void) { return 4; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
@@ -1151,7 +1166,26 @@ int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* oc
 int kmn_pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t* valid, uint32_t* mismatch) {
     return guarded(c, [&] {
         if (!mapped || !valid || !mismatch) throw std::runtime_error("NULL argument");
-        pair_counts(c, mapped, n, L, valid, mismatch);
+        if (n < 2) return;
+        pair_counts(c, mapped, n, L, 0, n, valid, mismatch);
+    });
+}
+
+int kmn_pair_counts_rows(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t row_begin, uint32_t row_end,
+                         uint32_t* valid, uint32_t* mismatch) {
+    return guarded(c, [&] {
+        if (!mapped) throw std::runtime_error("NULL argument");
+        pair_counts(c, mapped, n, L, row_begin, row_end, valid, mismatch);
+    });
+}
+
+int kmn_pair_counts_device(kmn_ctx* c, const uint32_t** valid, const uint32_t** mismatch, uint32_t* rows, uint32_t* n) {
+    return guarded(c, [&] {
+        if (!valid || !mismatch || !rows || !n) throw std::runtime_error("NULL argument");
+        *valid = c->nj_valid.p;
+        *mismatch = c->nj_mism.p;
+        *rows = c->nj_rows;
+        *n = c->nj_n;
     });
 }
 

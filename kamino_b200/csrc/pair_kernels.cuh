@@ -70,12 +70,13 @@ __device__ __forceinline__ void pair_stage_load(uint32_t* sA, uint32_t* sB, cons
 }
 
 __global__ void __launch_bounds__(PAIR_THREADS, 3)
-pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, uint32_t n_tiles,
+pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, uint32_t n_tiles, uint32_t tile_row0,
                   uint32_t* __restrict__ valid, uint32_t* __restrict__ mismatch) {
     extern __shared__ __align__(16) uint32_t pair_smem[];   // [2 buffers][A, B][PAIR_TILE * PAIR_ROW_STRIDE]
     constexpr uint32_t OPER = PAIR_TILE * PAIR_ROW_STRIDE;
-    // linear block index -> (ti, tj), ti <= tj
-    uint32_t rem = blockIdx.x, ti = 0;
+    // linear block index -> (ti, tj), ti <= tj; the launch covers tile rows tile_row0.. (a rank's row block
+    // when the matrix is sharded), and the outputs hold rows tile_row0 * PAIR_TILE.. only
+    uint32_t rem = blockIdx.x, ti = tile_row0;
     while (rem >= n_tiles - ti) { rem -= n_tiles - ti; ti++; }
     const uint32_t tj = ti + rem;
     const uint32_t tx = threadIdx.x & 15u, ty = threadIdx.x >> 4;
@@ -136,8 +137,9 @@ pair_count_kernel(const uint32_t* __restrict__ planes, uint32_t n, uint32_t W, u
             const uint32_t i = ti * PAIR_TILE + ty * 4 + a;
             const uint32_t j = tj * PAIR_TILE + b * 16 + tx;
             if (i < n && j < n && i < j) {
-                valid[uint64_t(i) * n + j] = cv[a][b];
-                mismatch[uint64_t(i) * n + j] = cm[a][b];
+                const uint64_t o = uint64_t(i - tile_row0 * PAIR_TILE) * n + j;
+                valid[o] = cv[a][b];
+                mismatch[o] = cm[a][b];
             }
         }
 }

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
-    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_last_stage_ms", "kmn_launch_count",
+    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library() -> C.CDLL:
     lib.kmn_group_observations.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.kmn_fetch_pairs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
     lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
+    lib.kmn_pair_counts_rows.argtypes = [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
+    lib.kmn_pair_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.kmn_last_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.kmn_launch_count.argtypes = [vp]
     lib.kmn_launch_count.restype = C.c_uint64
@@ -276,6 +278,26 @@ class Context:
         mism = np.zeros((n, n), dtype=np.uint32)
         self._check(self.lib.kmn_pair_counts(self._h, _ptr(mapped), n, L, _ptr(valid), _ptr(mism)))
         return valid, mism
+
+    def pair_counts_rows(self, mapped: np.ndarray, row_begin: int, row_end: int, fetch: bool = True):
+        """Rows [row_begin, row_end) of the pair matrix (one rank's block of the sharded --nj counts).
+        fetch=False leaves the counts on the device (pair_counts_device) and returns None."""
+        mapped = _as(mapped, np.uint8)
+        n, L = mapped.shape
+        rows = max(row_end - row_begin, 0)
+        if not fetch:
+            self._check(self.lib.kmn_pair_counts_rows(self._h, _ptr(mapped), n, L, row_begin, row_end, None, None))
+            return None
+        valid = np.zeros((rows, n), dtype=np.uint32)
+        mism = np.zeros((rows, n), dtype=np.uint32)
+        self._check(self.lib.kmn_pair_counts_rows(self._h, _ptr(mapped), n, L, row_begin, row_end, _ptr(valid), _ptr(mism)))
+        return valid, mism
+
+    def pair_counts_device(self) -> tuple[int, int, int, int]:
+        """(valid device pointer, mismatch device pointer, rows, n) of the last pair-count call."""
+        v, m, rows, n = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.kmn_pair_counts_device(self._h, C.byref(v), C.byref(m), C.byref(rows), C.byref(n)))
+        return int(v.value or 0), int(m.value or 0), rows.value, n.value
 
     # ---- instrumentation
     def stage_ms(self, name: str) -> float:

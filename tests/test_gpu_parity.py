@@ -239,6 +239,35 @@ def test_pair_counts(ffi, oracle, n, L):
     assert np.array_equal(gv[iu], wv[iu]) and np.array_equal(gm[iu], wm[iu])
 
 
+def test_pair_counts_row_blocks(ffi, oracle):
+    """kmn_pair_counts_rows: every row block equals the same rows of the whole matrix (SURVEY 8e, K6 sharding)."""
+    from kamino_b200 import sharding
+    rng = np.random.default_rng(99)
+    n, L = 333, 517
+    m = rng.integers(0, 21, size=(n, L), dtype=np.uint8)
+    wv, wm = oracle.pair_counts(m, threads=4)
+    up = np.triu(np.ones((n, n), bool), 1)
+    with ffi.Context(13, SR6) as ctx:
+        for world in (1, 2, 5):
+            for b0, b1 in sharding.pair_row_blocks(n, world):
+                gv, gm = ctx.pair_counts_rows(m, b0, b1)
+                assert gv.shape == (b1 - b0, n)
+                assert np.array_equal(gv, np.where(up, wv, 0)[b0:b1]) and np.array_equal(gm, np.where(up, wm, 0)[b0:b1])
+        # counts left on the device for a collective: same numbers behind kmn_pair_counts_device
+        import torch
+        from kamino_b200.sharding import _DevArray
+        assert ctx.pair_counts_rows(m, 64, 192, fetch=False) is None
+        pv, pm, rows, cols = ctx.pair_counts_device()
+        assert (rows, cols) == (128, n)
+        dv = torch.as_tensor(_DevArray(pv, (rows, cols), "<i4"), device="cuda").cpu().numpy().view(np.uint32)
+        dm = torch.as_tensor(_DevArray(pm, (rows, cols), "<i4"), device="cuda").cpu().numpy().view(np.uint32)
+        assert np.array_equal(dv, np.where(up, wv, 0)[64:192]) and np.array_equal(dm, np.where(up, wm, 0)[64:192])
+        with pytest.raises(ffi.KaminoError):
+            ctx.pair_counts_rows(m, 10, 64)        # not tile-aligned
+        with pytest.raises(ffi.KaminoError):
+            ctx.pair_counts_rows(m, 64, 400)       # past the matrix
+
+
 @pytest.mark.parametrize("knobs", [
     {"KMN_CMS_FORCE": "1"},                      # every bucket redone with u32 counters
     {"KMN_CMS_FORCE": "2"},                      # direct CAS path only

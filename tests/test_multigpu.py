@@ -104,3 +104,39 @@ def test_two_gpu_exchange_matches_oracle(tmp_path, planes):
         txt = (tmp_path / f"rank{r}.txt").read_text()
         assert txt.startswith("ok"), txt
         print("rank", r, txt)
+
+
+def _pair_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import oracle_ffi
+    from kamino_b200 import ffi, sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(17)
+        n, L = 300, 1999
+        m = rng.integers(0, 21, size=(n, L), dtype=np.uint8)
+        with ffi.Context(13, "sr6", device=rank) as ctx:
+            got = sharding.pair_counts_sharded(ctx, m)
+        if rank == 0:
+            wv, wm = oracle_ffi.load().pair_counts(m, threads=4)
+            iu = np.triu_indices(n, 1)
+            ok = np.array_equal(got[0][iu], wv[iu]) and np.array_equal(got[1][iu], wm[iu])
+            Path(out_dir, "pair.txt").write_text("ok" if ok else "mismatch")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_pair_counts_row_blocks(tmp_path):
+    """--nj counts with the pair matrix sharded by row blocks over two GPUs, gathered on rank 0."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_pair_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "pair.txt").read_text() == "ok"

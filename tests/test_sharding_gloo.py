@@ -99,3 +99,58 @@ def test_clamp_is_exact_under_saturation():
     rng = np.random.default_rng(0)
     parts = rng.integers(0, 50000, size=(4, 1000))
     assert np.array_equal(np.minimum(np.minimum(parts, 65535).sum(0), 65535), np.minimum(parts.sum(0), 65535))
+
+
+def test_pair_row_blocks_cover_the_matrix():
+    from kamino_b200 import sharding
+    for n, w in [(0, 2), (1, 3), (64, 2), (100, 4), (130, 3), (5000, 1), (5000, 2), (5000, 8), (777, 5)]:
+        blocks = sharding.pair_row_blocks(n, w)
+        assert len(blocks) == w and blocks[0][0] == 0 and blocks[-1][1] == n
+        for (b0, b1), (c0, _) in zip(blocks, blocks[1:]):
+            assert b1 == c0                                            # contiguous, disjoint
+        for b0, b1 in blocks:
+            assert b0 <= b1 and b0 % 64 == 0 and (b1 % 64 == 0 or b1 == n)
+    # balanced by upper-triangle tiles, not by rows
+    nt = (5000 + 63) // 64
+    work = [sum(nt - t for t in range(b0 // 64, (b1 + 63) // 64)) for b0, b1 in sharding.pair_row_blocks(5000, 8)]
+    assert max(work) <= 1.12 * (sum(work) / 8)
+
+
+def _pair_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import oracle_ffi
+    from kamino_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = oracle_ffi.load()
+        rng = np.random.default_rng(5)
+        n, L = 150, 333
+        m = rng.integers(0, 21, size=(n, L), dtype=np.uint8)
+        want_v, want_m = orc.pair_counts(m, threads=2)
+        iu = np.triu_indices(n, 1)
+
+        def count_rows(mapped, b0, b1):   # the oracle stands in for Context.pair_counts_rows on CPU
+            v = np.zeros((b1 - b0, n), np.uint32)
+            mm = np.zeros((b1 - b0, n), np.uint32)
+            for i in range(b0, b1):
+                v[i - b0, i + 1:] = want_v[i, i + 1:]
+                mm[i - b0, i + 1:] = want_m[i, i + 1:]
+            return v, mm
+
+        got = sharding.pair_counts_sharded(count_rows, m)
+        if rank == 0:
+            ok = np.array_equal(got[0][iu], want_v[iu]) and np.array_equal(got[1][iu], want_m[iu])
+            Path(out_dir, "pair.txt").write_text("ok" if ok else "mismatch")
+        else:
+            assert got is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_pair_counts_gather(tmp_path):
+    mp.spawn(_pair_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "pair.txt").read_text() == "ok"
