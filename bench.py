@@ -35,6 +35,28 @@ K, SCHEME_NAME, SCHEME = 13, "sr6", 1
 N_SPECIES = int(os.environ.get("KMN_BENCH_SPECIES", "100"))   # proteomes per GPU (weak scaling); 100 = BASELINE configs[1]
 
 
+# stdout carries the ONE JSON line and nothing else: libraries that chat on fd 1 (NCCL prints its version
+# banner there) are pointed at stderr for the whole run, and emit() writes to the saved descriptor.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -153,7 +175,7 @@ def run_reference(args):
         tot_dt += dt
     value = tot_res / tot_dt
     sample = f"{n_sample} of {N_SPECIES} species per step ({tot_res // args.steps} residues), pass 1 + snapshot"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -162,7 +184,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
     return 0
 
 
@@ -336,7 +358,7 @@ def run_gpu(args):
                                   "C++ restatement of kamino 2.0.0"}
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -355,7 +377,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-        }))
+        })
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -371,6 +393,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
