@@ -72,7 +72,7 @@ typedef struct kmn_group {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);   /* currently 4 */
+uint32_t kmn_abi_version(void);   /* currently 5 */
 
 /* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
  * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.
@@ -106,6 +106,30 @@ int kmn_count_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_o
 int kmn_stage_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
 int kmn_count_staged(kmn_ctx* ctx, uint32_t batch_id, uint64_t* new_kmers_per_species);
+
+/* ---- FASTA framing on the device ("next" row 3 of SURVEY 8f) --------------------------------
+ * kmn_count_fasta = the record splitting of seq_io::fasta::Reader as count_species_kmers drives
+ * it (group_extraction.rs:368-375) + kmn_count_batch: the caller hands over whole (decompressed)
+ * FASTA files and the device finds the records.
+ *   bytes     n_files files back to back, file f = bytes[file_off[f] .. file_off[f+1]),
+ *             file_off[0] = 0; one file = one species, in species order.  Every non-empty file
+ *             must end with '\n' (append one to a file that lacks it: that only adds whitespace to
+ *             its last sequence).  Pinned memory (kmn_host_alloc) makes the copy faster.
+ * A record starts at every line whose first byte is '>' (lines end with '\n'); its sequence is
+ * everything up to the next such line; only empty lines ("\n", "\r\n") may precede the first
+ * record of a file, otherwise the call fails with "FASTA parse error in file <f>: expected '>' at
+ * record start" and counts nothing.  Record indices (kmn_hit.rec, kmn_pair.rec) count the '>'
+ * lines of a file in order, like the reference's protein ids.
+ *   n_records (optional out): records found in the whole batch. */
+int kmn_count_fasta(kmn_ctx* ctx, const uint8_t* bytes, const uint64_t* file_off, uint32_t n_files,
+                    uint64_t* new_kmers_per_species, uint32_t* batch_id, uint64_t* n_records);
+/* Record table of a kmn_count_fasta batch: hdr_off[r] = offset in `bytes` of the '>' of record r
+ * (the header runs to the next '\n', the sequence from there to hdr_off[r+1] or to the end of the
+ * file), sp_rec_off[f] (optional, n_files + 1 values) = first record of file f.  *n = records;
+ * hdr_off may be NULL to query the count. */
+int kmn_fetch_records(kmn_ctx* ctx, uint32_t batch_id, uint64_t* hdr_off, uint64_t cap, uint64_t* n,
+                      uint64_t* sp_rec_off);
+
 /* Zero the table (a fresh AtomicCountMinSketch). */
 int kmn_reset_table(kmn_ctx* ctx);
 /* Drop every staged batch (frees their HBM). */

@@ -5,6 +5,7 @@
 #include "../../include/kamino_b200.h"
 #include "cms_kernels.cuh"
 #include "count_kernels.cuh"
+#include "fasta_kernels.cuh"
 #include "frame_kernels.cuh"
 #include "group_kernels.cuh"
 #include "pair_kernels.cuh"
@@ -80,6 +81,8 @@ struct Batch {
     bool framed = false;
     DevBuf<uint8_t> raw, codes;
     DevBuf<uint64_t> rec_off, sp_rec_off;
+    DevBuf<uint64_t> hdr_off;    // kmn_count_fasta: offset of each record's '>' in the caller's bytes
+    bool from_fasta = false;
     DevBuf<uint32_t> rec_cstart, sp_cstart;
     std::vector<uint32_t> h_sp_cstart;   // host copy (after framing)
     std::vector<uint64_t> h_sp_rec_off;
@@ -140,6 +143,9 @@ struct kmn_ctx {
     DevBuf<uint64_t> g_left, g_right;
     DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first;
     DevBuf<kmn_group> g_groups;
+    DevBuf<uint64_t> fa_file_off;          // scratch of kmn_count_fasta
+    DevBuf<uint8_t> fa_tile_sum, fa_tile_in;
+    DevBuf<uint32_t> fa_tile_hdr, fa_tile_base, fa_err;
     DevBuf<uint32_t> nj_valid, nj_mism;   // counts of the last pair_counts call (kmn_pair_counts_device)
     uint32_t nj_rows = 0, nj_n = 0;
     float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -195,6 +201,19 @@ Batch& get_batch(kmn_ctx* c, uint32_t id) {
 }
 
 // Validates the offsets, takes a (recycled) Batch and sizes its buffers.  No device work.
+std::unique_ptr<Batch> take_batch(kmn_ctx* c) {
+    std::unique_ptr<Batch> b;
+    if (!c->spare.empty()) {
+        b = std::move(c->spare.back());
+        c->spare.pop_back();
+        b->framed = b->scanned = b->paired = b->hits_expanded = b->from_fasta = false;
+        b->n_codes = b->n_inv = 0;
+    } else {
+        b = std::make_unique<Batch>();
+    }
+    return b;
+}
+
 std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                                  const uint64_t* sp_rec_off, uint32_t n_sp) {
     if (!rec_off || !sp_rec_off) throw std::runtime_error("rec_off / sp_rec_off must not be NULL");
@@ -215,15 +234,7 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
 
     // staged batches recycle the device buffers of released ones (cudaMalloc/cudaFree of ~1 GB per
     // batch would otherwise dominate the host-to-table path)
-    std::unique_ptr<Batch> b;
-    if (!c->spare.empty()) {
-        b = std::move(c->spare.back());
-        c->spare.pop_back();
-        b->framed = b->scanned = b->paired = b->hits_expanded = false;
-        b->n_codes = b->n_inv = 0;
-    } else {
-        b = std::make_unique<Batch>();
-    }
+    std::unique_ptr<Batch> b = take_batch(c);
     b->n_raw = n_raw;
     b->n_rec = uint32_t(n_rec);
     b->n_sp = n_sp;
@@ -252,6 +263,81 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
+}
+
+// kmn_count_fasta, front half: whole FASTA files -> (header-blanked raw bytes, rec_off, sp_rec_off) on the
+// device (fasta_kernels.cuh).  Two small host round trips: the record count sizes the record tables, the
+// per-file record ranges plan pass 1.
+std::unique_ptr<Batch> frame_fasta(kmn_ctx* c, const uint8_t* bytes, const uint64_t* file_off, uint32_t n_files) {
+    if (!file_off) throw std::runtime_error("file_off must not be NULL");
+    if (n_files > 65535) throw std::runtime_error("too many species in one batch (maximum 65535)");  // group_extraction.rs:538
+    if (file_off[0] != 0) throw std::runtime_error("file_off[0] must be 0");
+    for (uint32_t f = 0; f < n_files; f++)
+        if (file_off[f + 1] < file_off[f]) throw std::runtime_error("file_off must be non-decreasing");
+    const uint64_t n_raw = file_off[n_files];
+    if (n_raw >= (1ull << 31)) throw std::runtime_error("batch too large: bytes + records must stay below 2^31");
+    if (n_raw && !bytes) throw std::runtime_error("bytes must not be NULL");
+
+    std::unique_ptr<Batch> b = take_batch(c);
+    b->from_fasta = true;
+    b->n_raw = n_raw;
+    b->n_sp = n_files;
+    b->raw_pad = (size_t(n_raw) / FRAME_TILE + 1) * FRAME_TILE;
+    b->raw.ensure(b->raw_pad);
+    const uint32_t n_tiles = uint32_t(b->raw_pad / FRAME_TILE);
+    c->fa_file_off.ensure(size_t(n_files) + 1);
+    c->fa_tile_sum.ensure(n_tiles);
+    c->fa_tile_in.ensure(n_tiles);
+    c->fa_tile_hdr.ensure(n_tiles);
+    c->fa_tile_base.ensure(size_t(n_tiles) + 1);
+    c->fa_err.ensure(1);
+    if (n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, bytes, n_raw, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemsetAsync(b->raw.p + n_raw, 0x20, b->raw_pad - n_raw, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(c->fa_file_off.p, file_off, (size_t(n_files) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemsetAsync(c->fa_err.p, 0xFF, sizeof(uint32_t), c->stream));
+    if (n_files) {
+        fasta_check_kernel<<<(n_files + 127) / 128, 128, 0, c->stream>>>(b->raw.p, c->fa_file_off.p, n_files, c->fa_err.p);
+        check_launch(c);
+    }
+    fasta_summary_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b->raw.p, c->fa_tile_sum.p, c->fa_tile_hdr.p);
+    check_launch(c);
+    device_exclusive_scan(c, c->fa_tile_hdr.p, c->fa_tile_base.p, n_tiles);
+    fasta_tile_state_kernel<<<1, 1024, 0, c->stream>>>(c->fa_tile_sum.p, n_tiles, c->fa_tile_in.p);
+    check_launch(c);
+    uint32_t n_rec = 0, err = 0;
+    KMN_CUDA(cudaMemcpyAsync(&n_rec, c->fa_tile_base.p + n_tiles, sizeof n_rec, cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(&err, c->fa_err.p, sizeof err, cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    if (err != 0xFFFFFFFFu) {
+        c->spare.push_back(std::move(b));
+        const uint32_t f = (err & 0x7FFFFFFFu) - 1;
+        if (err & 0x80000000u)
+            throw std::runtime_error("file " + std::to_string(f) + " does not end with a line feed (append one before kmn_count_fasta)");
+        throw std::runtime_error("FASTA parse error in file " + std::to_string(f) + ": expected '>' at record start");
+    }
+    if (n_raw + n_rec >= (1ull << 31)) {
+        c->spare.push_back(std::move(b));
+        throw std::runtime_error("batch too large: bytes + records must stay below 2^31");
+    }
+    b->n_rec = n_rec;
+    b->rec_off.ensure(size_t(n_rec) + 1);
+    b->hdr_off.ensure(size_t(n_rec) + 1);
+    b->sp_rec_off.ensure(size_t(n_files) + 1);
+    fasta_blank_kernel<<<n_tiles, FRAME_THREADS, 0, c->stream>>>(b->raw.p, c->fa_tile_in.p, c->fa_tile_base.p, b->hdr_off.p, b->rec_off.p);
+    check_launch(c);
+    fasta_species_kernel<<<(n_files + 1 + 127) / 128, 128, 0, c->stream>>>(b->hdr_off.p, n_rec, c->fa_file_off.p, n_files, n_raw,
+                                                                         b->sp_rec_off.p, b->rec_off.p);
+    check_launch(c);
+    b->h_sp_rec_off.resize(size_t(n_files) + 1);
+    KMN_CUDA(cudaMemcpyAsync(b->h_sp_rec_off.data(), b->sp_rec_off.p, (size_t(n_files) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                             c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    b->h_sp_raw_off.assign(file_off, file_off + n_files + 1);
+    b->codes_cap = (size_t(n_raw) + n_rec + WARP_TILE - 1) / WARP_TILE * WARP_TILE + WARP_TILE;
+    b->codes.ensure(b->codes_cap);
+    b->rec_cstart.ensure(size_t(n_rec) + 1);
+    b->sp_cstart.ensure(size_t(n_files) + 1);
+    return b;
 }
 
 // ---- pass 1 ---------------------------------------------------------------------------------------
@@ -780,7 +866,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 4; }
+uint32_t kmn_abi_version(void) { return 5; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
@@ -899,6 +985,32 @@ int kmn_count_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off
         if (batch_id) *batch_id = id;
         // host -> device copies of the species ranges overlap the kernels of the previous range
         run_pass1(c, get_batch(c, id), residues, rec_off, sp_rec_off, false, new_kmers_per_species);
+    });
+}
+
+int kmn_count_fasta(kmn_ctx* c, const uint8_t* bytes, const uint64_t* file_off, uint32_t n_files,
+                    uint64_t* new_kmers_per_species, uint32_t* batch_id, uint64_t* n_records) {
+    return guarded(c, [&] {
+        if (c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
+        c->batches.push_back(frame_fasta(c, bytes, file_off, n_files));
+        const uint32_t id = uint32_t(c->batches.size() - 1);
+        if (batch_id) *batch_id = id;
+        if (n_records) *n_records = get_batch(c, id).n_rec;
+        run_pass1(c, get_batch(c, id), nullptr, nullptr, nullptr, false, new_kmers_per_species);
+    });
+}
+
+int kmn_fetch_records(kmn_ctx* c, uint32_t batch_id, uint64_t* hdr_off, uint64_t cap, uint64_t* n, uint64_t* sp_rec_off) {
+    return guarded(c, [&] {
+        Batch& b = get_batch(c, batch_id);
+        if (!b.from_fasta) throw std::runtime_error("batch was not built by kmn_count_fasta");
+        if (!n) throw std::runtime_error("n must not be NULL");
+        *n = b.n_rec;
+        if (sp_rec_off) std::copy(b.h_sp_rec_off.begin(), b.h_sp_rec_off.end(), sp_rec_off);
+        if (!hdr_off) return;
+        if (cap < b.n_rec) throw std::runtime_error("hdr_off capacity too small");
+        if (b.n_rec) KMN_CUDA(cudaMemcpyAsync(hdr_off, b.hdr_off.p, size_t(b.n_rec) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
     });
 }
 

@@ -34,7 +34,7 @@ GROUP_VALID, GROUP_HOST = 1, 2
 # every symbol declared in include/kamino_b200.h
 ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_host_alloc", "kmn_host_free", "kmn_count_batch",
-    "kmn_stage_batch", "kmn_count_staged", "kmn_reset_table", "kmn_release_batches",
+    "kmn_stage_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
@@ -96,6 +96,8 @@ def load_library() -> C.CDLL:
     lib.kmn_group_observations.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.kmn_fetch_pairs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
     lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
+    lib.kmn_count_fasta.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(C.c_uint32), u64p]
+    lib.kmn_fetch_records.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p, vp]
     lib.kmn_pair_counts_rows.argtypes = [vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
     lib.kmn_pair_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.kmn_last_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
@@ -169,6 +171,26 @@ class Context:
         self._check(self.lib.kmn_count_batch(self._h, _ptr(residues), _ptr(rec_off), len(rec_off) - 1,
                                              _ptr(sp_rec_off), n_sp, _ptr(out), C.byref(bid)))
         return bid.value, out
+
+    def count_fasta(self, data, file_off, want_counts: bool = True):
+        """Whole FASTA files back to back (every non-empty file ends with a line feed): record detection on
+        the device, then pass 1.  Returns (batch id, new k-mers per species or None, number of records)."""
+        data = _as(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data, np.uint8)
+        file_off = _as(file_off, np.uint64)
+        n_files = len(file_off) - 1
+        new = np.zeros(n_files, dtype=np.uint64) if want_counts else None
+        bid, n_rec = C.c_uint32(), C.c_uint64()
+        self._check(self.lib.kmn_count_fasta(self._h, _ptr(data), _ptr(file_off), n_files, _ptr(new), C.byref(bid), C.byref(n_rec)))
+        return bid.value, new, int(n_rec.value)
+
+    def fetch_records(self, batch_id: int, n_files: int) -> tuple[np.ndarray, np.ndarray]:
+        """(offset of each record's '>' in the bytes given to count_fasta, first record of each file)."""
+        n = C.c_uint64()
+        sp = np.zeros(n_files + 1, dtype=np.uint64)
+        self._check(self.lib.kmn_fetch_records(self._h, batch_id, None, 0, C.byref(n), _ptr(sp)))
+        hdr = np.zeros(int(n.value), dtype=np.uint64)
+        self._check(self.lib.kmn_fetch_records(self._h, batch_id, _ptr(hdr), n.value, C.byref(n), None))
+        return hdr, sp
 
     def reset_table(self):
         self._check(self.lib.kmn_reset_table(self._h))

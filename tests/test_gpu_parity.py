@@ -29,14 +29,14 @@ def _batch_from_records(species_records):
 
 
 def _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, min_needed, scan_species=None,
-                           threads=8):
+                           threads=8, count=None):
     n_sp = len(sp) - 1
     h = oracle.cmsa_new()
     try:
         want_new = oracle.count_batch(h, residues, rec_off, sp, k, scheme, threads=threads)
         want_table = oracle.cmsa_table(h)
         with ffi.Context(k, scheme) as ctx:
-            bid, got_new = ctx.count_batch(residues, rec_off, sp)
+            bid, got_new = count(ctx) if count else ctx.count_batch(residues, rec_off, sp)
             assert got_new.tolist() == want_new.tolist()
             ctx.finalize_table()
             got_table = ctx.table_snapshot()
@@ -482,3 +482,130 @@ def test_group_observations_host_fallback_flags(ffi):
     assert np.array_equal(perm, np.arange(n))
     assert [int(g["count"]) for g in groups] == [30, 10]
     assert all(int(g["flags"]) & ffi.GROUP_HOST for g in groups)
+
+
+# ---- FASTA framing on the device (kmn_count_fasta): the oracle parses the same files on the CPU ----------
+
+def _fasta_inputs(oracle, tmp_path, files):
+    """files: raw bytes of each FASTA file.  Returns the oracle's (residues, rec_off, sp_rec_off), the bytes
+    handed to kmn_count_fasta (a line feed appended to files that lack one) and their file offsets."""
+    recs, parts, file_off = [], [], [0]
+    for i, data in enumerate(files):
+        p = tmp_path / f"f{i}.faa"
+        p.write_bytes(data)
+        r, o = oracle.read_fasta(p)
+        recs.append([r[int(o[j]):int(o[j + 1])].tobytes() for j in range(len(o) - 1)])
+        if data and not data.endswith(b"\n"):
+            data += b"\n"
+        parts.append(data)
+        file_off.append(file_off[-1] + len(data))
+    residues, rec_off, sp = _batch_from_records(recs)
+    return residues, rec_off, sp, b"".join(parts), np.asarray(file_off, np.uint64), recs
+
+
+def _fasta_text(sp, width=60, eol=b"\n", header=lambda pid: f">p{pid} some protein {pid} [Synth sp]".encode()):
+    out, pos = [], 0
+    for pid, ln in enumerate(sp.lens):
+        out.append(header(pid) + eol)
+        s = sp.seq[pos:pos + ln].tobytes()
+        pos += int(ln)
+        if width:
+            out += [s[i:i + width] + eol for i in range(0, len(s), width)]
+        else:
+            out.append(s + eol)
+    return b"".join(out)
+
+
+def _adversarial_fasta_files():
+    sps = synth.bacterial(5, seed=41, n_prot=90, mean_len=170.0)
+    big = synth.bacterial(1, seed=42, n_prot=3, mean_len=9000.0)[0]
+    files = [
+        _fasta_text(sps[0]),                                                        # plain 60-column FASTA
+        b"\n\r\n\n" + _fasta_text(sps[1], eol=b"\r\n"),                            # CRLF, leading empty lines
+        _fasta_text(sps[2], width=0)[:-1],                                          # one line per sequence, no final line feed
+        _fasta_text(sps[3], width=37, header=lambda pid: b">" + b"h>" * (pid % 7) + b"x" * (13 * pid % 5000)),   # '>' inside long headers
+        b"\n\n\n",                                                                 # empty lines only: no record
+        b"",                                                                        # empty file
+        b">a\n>b\n\n>c desc\nACDEFGHIKLMNPQRSTVWY>ACDEFGHIKLMNPQRSTVWYACDEFGHIK\n  \t\n>d\nacdefghiklmnpqrstvwyACDEFGHIKLMNP\n>e",  # empty records, '>' inside a sequence, blanks, lower case, header at EOF
+        _fasta_text(big, width=0),                                                  # lines far longer than a 4096-byte tile
+        _fasta_text(sps[4]).lower(),
+    ]
+    return files
+
+
+def test_count_fasta_matches_host_parsed_batch(ffi, oracle, tmp_path):
+    files = _adversarial_fasta_files()
+    residues, rec_off, sp, data, file_off, recs = _fasta_inputs(oracle, tmp_path, files)
+    n_files = len(files)
+    seen = {}
+
+    def count(ctx):
+        bid, new, n_rec = ctx.count_fasta(data, file_off)
+        hdr, sp_rec = ctx.fetch_records(bid, n_files)
+        seen.update(n_rec=n_rec, hdr=hdr, sp_rec=sp_rec)
+        return bid, new
+
+    _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, SR6, oracle.min_needed(0.6, n_files), count=count)
+    assert seen["n_rec"] == len(rec_off) - 1 and seen["sp_rec"].tolist() == sp.tolist()
+    # every record's '>' is where a host parser finds it
+    want_hdr = []
+    for f in range(n_files):
+        chunk = data[int(file_off[f]):int(file_off[f + 1])]
+        pos = 0
+        for line in chunk.split(b"\n"):
+            if line.startswith(b">"):
+                want_hdr.append(int(file_off[f]) + pos)
+            pos += len(line) + 1
+    assert seen["hdr"].tolist() == want_hdr
+
+
+@pytest.mark.parametrize("scheme", [DAYHOFF6, SR6])
+def test_count_fasta_3diff_golden_files(ffi, oracle, golden_dir, tmp_path, scheme):
+    import gzip
+    names = ["A.fas.gz", "B.fas", "C.fas", "D1.fas", "D2.fas", "E1.fas", "E2.fas", "E3.fas"]
+    files = []
+    for n in names:
+        raw = (golden_dir / "test_3diff" / "input" / n).read_bytes()
+        files.append(gzip.decompress(raw) if n.endswith(".gz") else raw)
+    residues, rec_off, sp, data, file_off, _ = _fasta_inputs(oracle, tmp_path, files)
+    new, _ = _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, 13, scheme, 7,
+                                    count=lambda ctx: ctx.count_fasta(data, file_off)[:2])
+    assert new.tolist() == [84] * 8
+
+
+def test_count_fasta_rejects_bad_input(ffi):
+    with ffi.Context(13, SR6) as ctx:
+        good = b">a\nACDEFGHIKLMNPQRSTVWY\n"
+        for bad, what in [(b"ACDE\n>a\nACDE\n", "expected '>'"), (b"\r>a\nACDE\n", "expected '>'"),
+                          (b" \n>a\nACDE\n", "expected '>'"), (b">a\nACDE", "line feed")]:
+            data = good + bad
+            with pytest.raises(ffi.KaminoError, match=what):
+                ctx.count_fasta(data, np.array([0, len(good), len(data)], np.uint64))
+        # the context stays usable and nothing was counted
+        bid, new, n_rec = ctx.count_fasta(good, np.array([0, len(good)], np.uint64))
+        assert n_rec == 1 and new.tolist() == [8]
+        ctx.finalize_table()
+        assert int(ctx.table_snapshot().astype(np.int64).sum()) == 4 * 8
+
+
+def test_count_fasta_full_size(ffi, oracle):
+    """100 proteomes as FASTA text: same table and counts as the host-parsed batch (property at full size)."""
+    species = synth.bacterial(100)
+    b = synth.stage(species)
+    parts, file_off = [], [0]
+    for sp_ in species:
+        t = _fasta_text(sp_)
+        parts.append(t)
+        file_off.append(file_off[-1] + len(t))
+    data = np.frombuffer(b"".join(parts), np.uint8)
+    with ffi.Context(13, SR6) as ctx:
+        _, new_a = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+        ctx.finalize_table()
+        table_a = ctx.table_snapshot()
+        ctx.reset_table()
+        ctx.release_batches()
+        bid, new_b, n_rec = ctx.count_fasta(data, np.asarray(file_off, np.uint64))
+        ctx.finalize_table()
+        assert n_rec == len(b.rec_off) - 1
+        assert new_a.tolist() == new_b.tolist()
+        assert np.array_equal(ctx.table_snapshot(), table_a)
