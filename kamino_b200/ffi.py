@@ -115,6 +115,23 @@ def _as(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+class PinnedBuffer:
+    """Page-locked host bytes (kmn_host_alloc) as a numpy array: .array, released by .free()."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load_library()
+        self._p = C.c_void_p()
+        if self.lib.kmn_host_alloc(C.byref(self._p), max(int(nbytes), 1)) != 0:
+            raise KaminoError(self.lib.kmn_last_error().decode())
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(int(nbytes),))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self.lib.kmn_host_free(self._p)
+            self._p = None
+
+
 class Context:
     """One kmn_ctx: one GPU, one table (mirrors AtomicCountMinSketch + CountMinSketch ownership)."""
 

@@ -20,6 +20,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--species", type=int, default=100)
+    ap.add_argument("--fasta", action="store_true", help="also time kmn_count_fasta on the FASTA text of the species")
     ap.add_argument("--nj-n", type=int, default=2000)
     ap.add_argument("--nj-l", type=int, default=100_000)
     ap.add_argument("--reps", type=int, default=3)
@@ -82,6 +83,55 @@ def main():
                           "pair_batch_ms": pair_ms, "anchor_pairs": n_pairs,
                           "group_kernels_ms": group_ms, "groups": int(len(groups)), "groups_passing_length_selection": n_valid,
                           "cpu_single_thread_residues_per_s": res_cpu / cpu_dt, "parity_species_checked": n_cpu}))
+
+    # ---- FASTA text in, table out: record detection on the device (kmn_count_fasta) next to the host-parsed batch
+    if args.fasta:
+        import tempfile
+        parts, file_off = [], [0]
+        for sid, sp_ in enumerate(species):
+            chunks, pos = [], 0
+            for pid, ln in enumerate(sp_.lens):
+                chunks.append(f">sp{sid}_p{pid} hypothetical protein {pid} [Synth sp]\n".encode())
+                seq = sp_.seq[pos:pos + ln].tobytes()
+                pos += int(ln)
+                chunks += [seq[i:i + 60] + b"\n" for i in range(0, len(seq), 60)]
+            parts.append(b"".join(chunks))
+            file_off.append(file_off[-1] + len(parts[-1]))
+        file_off = np.asarray(file_off, np.uint64)
+        text = ffi.PinnedBuffer(int(file_off[-1]))
+        text.array[:] = np.frombuffer(b"".join(parts), np.uint8)
+        pin = ffi.PinnedBuffer(b.residues.size)
+        pin.array[:] = b.residues
+        with tempfile.NamedTemporaryFile(suffix=".faa") as f:   # the CPU parser on one proteome
+            f.write(parts[0])
+            f.flush()
+            t0 = time.perf_counter()
+            orc.read_fasta(f.name)
+            parse_dt = time.perf_counter() - t0
+        with ffi.Context(13, "sr6") as ctx:
+            t_fa, t_batch = [], []
+            for rep in range(args.reps + 1):
+                ctx.reset_table(); ctx.synchronize()
+                t0 = time.perf_counter()
+                _, new_fa, n_rec = ctx.count_fasta(text.array, file_off)
+                t_fa.append((time.perf_counter() - t0) * 1e3)
+                ctx.finalize_table()
+                tab_fa = ctx.table_snapshot() if rep == 0 else None
+                ctx.release_batches()
+                ctx.reset_table(); ctx.synchronize()
+                t0 = time.perf_counter()
+                _, new_b = ctx.count_batch(pin.array, b.rec_off, b.sp_rec_off)
+                t_batch.append((time.perf_counter() - t0) * 1e3)
+                ctx.finalize_table()
+                if rep == 0:
+                    assert np.array_equal(ctx.table_snapshot(), tab_fa) and new_fa.tolist() == new_b.tolist()
+                ctx.release_batches()
+        fa_ms, batch_ms = float(np.median(t_fa[1:])), float(np.median(t_batch[1:]))
+        print(json.dumps({"what": "count_fasta", "species": b.n_sp, "fasta_bytes": int(file_off[-1]), "records": n_rec,
+                          "residues": b.n_residues, "count_fasta_ms": fa_ms, "residues_per_s": b.n_residues / (fa_ms * 1e-3),
+                          "count_batch_ms_host_parsed_input": batch_ms,
+                          "cpu_parse_one_proteome_ms_single_thread": parse_dt * 1e3, "table_equal": True}))
+        text.free(); pin.free()
 
     # ---- pass 1 on the eukaryotic shape (long proteomes: ~1200 Bloom tiles per species, visible Bloom FP rate)
     if args.euk:
