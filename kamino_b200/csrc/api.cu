@@ -123,7 +123,7 @@ struct kmn_ctx {
     const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
     bool finalized = false;
     DevBuf<unsigned long long> new_counts;
-    DevBuf<uint32_t> tile_cnt, tile_base, seg_s_cnt, seg_e_cnt, sp_s_off, sp_e_off;
+    DevBuf<uint32_t> tile_cnt, tile_base, tile_rec, seg_s_cnt, seg_e_cnt, sp_s_off, sp_e_off;
     std::vector<std::unique_ptr<Batch>> batches;
     PeerTables peers{};                   // mapped peer buffers of the fused exchange
     PeerPlanes planes{};                  // the same peers, byte-plane views (default exchange)
@@ -418,6 +418,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
     c->tile_cnt.ensure(n_frame_tiles + 1);
     c->tile_base.ensure(n_frame_tiles + 2);
+    c->tile_rec.ensure(n_frame_tiles + 2);
     if (b.n_rec == 0) KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));
 
     BloomRuns R{};
@@ -493,8 +494,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             const ScanJob job{c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt, c->frame_carry.p};
             exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
             check_launch(c);
+            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p);
+            check_launch(c);
             frame_scatter_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
-                                                                   b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin);
+                                                                   b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin, c->tile_rec.p);
             check_launch(c);
         }
         {

@@ -187,6 +187,17 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_o
 // The codes of a tile (residues + separators) form one contiguous range of codes[]: they are staged in
 // shared memory at the same 16-byte alignment and written out as 16-byte vectors (bytes only at the two
 // ragged ends); a tile with thousands of empty records falls back to direct byte stores.
+// tile_rec[t] = record_of(rec_off, 0, n_rec, t * FRAME_TILE) for the tiles [tile_begin, tile_begin + n]: one
+// thread per tile, so the ~19 dependent loads of each search overlap across all tiles instead of heading
+// every CTA of frame_scatter_kernel.
+__global__ void frame_tile_records_kernel(const uint64_t* __restrict__ rec_off, uint32_t n_rec, uint32_t tile_begin, uint32_t n,
+                                          uint32_t* __restrict__ tile_rec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = tile_begin + i;
+    tile_rec[t] = record_of(rec_off, 0, n_rec, uint64_t(t) * FRAME_TILE);
+}
+
 constexpr uint32_t FRAME_MAX_BOUNDS = 2048;                                  // record boundaries staged per tile
 constexpr uint32_t FRAME_STAGE = FRAME_TILE + FRAME_MAX_BOUNDS + 32;
 
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(FRAME_THREADS)
 frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut,
                      const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ rec_off,
                      uint32_t n_rec, uint8_t* __restrict__ codes, uint32_t* __restrict__ rec_cstart,
-                     uint32_t tile_begin) {
+                     uint32_t tile_begin, const uint32_t* __restrict__ tile_rec) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
     __shared__ uint32_t s_rlo, s_rhi, s_blo, s_first, s_last;
@@ -203,7 +214,7 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
     const uint32_t tile = tile_begin + blockIdx.x;
     const uint64_t tile0 = uint64_t(tile) * FRAME_TILE;
     if (threadIdx.x == 0) {
-        const uint32_t rlo = record_of(rec_off, 0, n_rec, tile0);
+        const uint32_t rlo = tile_rec[tile];
         uint32_t blo = rlo;   // empty records that end exactly at tile0: their boundaries belong to this tile too
         while (blo > 0 && rec_off[blo - 1] == tile0) blo--;
         s_rlo = rlo;
@@ -211,11 +222,7 @@ frame_scatter_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut 
         s_first = 0xFFFFFFFFu;
         s_last = 0;
     }
-    if (threadIdx.x == 32) {
-        uint64_t last = tile0 + FRAME_TILE - 1;
-        if (last > n_raw) last = n_raw;
-        s_rhi = record_of(rec_off, 0, n_rec, last);
-    }
+    if (threadIdx.x == 32) s_rhi = tile_rec[tile + 1];   // record of the next tile's first byte: bounds every search below
     const uint64_t i0 = tile0 + uint64_t(threadIdx.x) * CHUNK;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + i0));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};

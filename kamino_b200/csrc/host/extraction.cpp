@@ -83,9 +83,15 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     const float nf = float(n < 1 ? size_t(1) : n);
     volatile float prod = min_freq * nf;                       // f32 arithmetic, group_extraction.rs:544
     const uint32_t min_needed = uint32_t(std::ceil(float(prod)));
+    // the CUDA context and the 512 MiB table come up on a side thread while the host threads load the proteomes
     std::unique_ptr<Ctx> gpu_holder;
-    { StageTimer t("kmn_create"); gpu_holder = std::make_unique<Ctx>(opt.device, int(k), int(scheme)); }
-    Ctx& gpu = *gpu_holder;
+    std::string gpu_err;
+    std::thread gpu_init([&] {
+        StageTimer t("kmn_create (overlaps the load)");
+        try { gpu_holder = std::make_unique<Ctx>(opt.device, int(k), int(scheme)); }
+        catch (const std::exception& e) { gpu_err = *e.what() ? e.what() : "GPU front end: error"; }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } gpu_joiner{gpu_init};
 
     // ---- load every proteome (host threads; gunzip + framing only)
     if (!opt.quiet) std::fprintf(stderr, " . pass 1: estimate k-mer occupancies\n");
@@ -104,7 +110,10 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, n)); t++) pool.emplace_back(work);
         for (auto& t : pool) t.join();
     }
+    gpu_init.join();
+    if (!gpu_err.empty()) throw std::runtime_error(gpu_err);
     for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);   // first error in species order (:569-571)
+    Ctx& gpu = *gpu_holder;
 
     // ---- pass 1: batches of whole species through kmn_count_batch
     auto t_p1 = std::make_unique<StageTimer>("pass 1 (stage + count + finalize)");
