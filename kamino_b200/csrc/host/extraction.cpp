@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -93,7 +94,9 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } gpu_joiner{gpu_init};
 
-    // ---- load every proteome (host threads; gunzip + framing only)
+    // ---- load every proteome (host threads; gunzip, and FASTA framing only with KAMINO_HOST_FASTA=1: by
+    // default the file bytes go to the GPU as they are and kmn_count_fasta finds the records)
+    const bool device_fasta = std::getenv("KAMINO_HOST_FASTA") == nullptr;
     if (!opt.quiet) std::fprintf(stderr, " . pass 1: estimate k-mer occupancies\n");
     std::vector<Proteome> prot(n);
     std::vector<std::string> errs(n);
@@ -102,7 +105,10 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         std::atomic<size_t> next{0};
         auto work = [&] {
             for (size_t i; (i = next.fetch_add(1)) < n;) {
-                try { prot[i] = load_proteome(inputs[i].path); }
+                try {
+                    if (device_fasta) prot[i].seq = load_fasta_bytes(inputs[i].path);   // records are found on the device
+                    else prot[i] = load_proteome(inputs[i].path);
+                }
                 catch (const std::exception& e) { errs[i] = *e.what() ? e.what() : "error"; }
             }
         };
@@ -135,12 +141,12 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
             cap = n;
         }
     } buf;
-    std::vector<uint64_t> rec_off, sp_rec_off;
+    std::vector<uint64_t> rec_off, sp_rec_off, hdr_off;
     for (size_t s0 = 0; s0 < n;) {
         size_t s1 = s0, bytes = 0, recs = 0;
         while (s1 < n && (s1 == s0 || bytes + prot[s1].seq.size() <= opt.batch_bytes)) {
             bytes += prot[s1].seq.size();
-            recs += prot[s1].rec_off.size() - 1;
+            recs += prot[s1].n_rec();
             s1++;
         }
         if (bytes + recs >= (uint64_t(1) << 31)) throw std::runtime_error("species " + inputs[s0].name + " is too large for one GPU batch");
@@ -148,26 +154,50 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         rec_off.assign(1, 0);
         sp_rec_off.assign(1, 0);
         size_t at = 0;
-        std::vector<size_t> sp_at(s1 - s0);
+        std::vector<uint64_t> sp_at(s1 - s0 + 1);
         for (size_t s = s0; s < s1; s++) {
             sp_at[s - s0] = at;
-            for (size_t r = 1; r < prot[s].rec_off.size(); r++) rec_off.push_back(at + prot[s].rec_off[r]);
+            for (size_t r = 0; r < prot[s].n_rec(); r++) rec_off.push_back(at + prot[s].rec_end[r]);
             at += prot[s].seq.size();
             sp_rec_off.push_back(rec_off.size() - 1);
         }
-        {   // gather the species into the pinned buffer on the host threads
+        sp_at[s1 - s0] = at;
+        auto on_threads = [&](auto&& per_species) {
             std::atomic<size_t> next{s0};
-            auto work = [&] {
-                for (size_t s; (s = next.fetch_add(1)) < s1;)
-                    if (!prot[s].seq.empty()) std::memcpy(buf.p + sp_at[s - s0], prot[s].seq.data(), prot[s].seq.size());
-            };
+            auto work = [&] { for (size_t s; (s = next.fetch_add(1)) < s1;) per_species(s); };
             std::vector<std::thread> pool;
             for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, s1 - s0)); t++) pool.emplace_back(work);
             for (auto& t : pool) t.join();
-        }
+        };
+        // gather the species into the pinned buffer on the host threads
+        on_threads([&](size_t s) {
+            if (!prot[s].seq.empty()) std::memcpy(buf.p + sp_at[s - s0], prot[s].seq.data(), prot[s].seq.size());
+        });
         uint32_t id = 0;
-        gpu.ok(kmn_count_batch(gpu.p, buf.p, rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
-                               uint32_t(s1 - s0), nullptr, &id));
+        if (device_fasta) {
+            uint64_t n_rec = 0;
+            if (kmn_count_fasta(gpu.p, buf.p, sp_at.data(), uint32_t(s1 - s0), nullptr, &id, &n_rec) != 0) {
+                const std::string gpu_msg = kmn_last_error();
+                // a format error: the host reader words it like the reference does, first bad file in species order
+                for (size_t s = s0; s < s1; s++) parse_proteome(prot[s].seq, inputs[s].path);
+                throw std::runtime_error("GPU front end: " + gpu_msg);
+            }
+            hdr_off.resize(n_rec);
+            sp_rec_off.assign(s1 - s0 + 1, 0);
+            uint64_t got = 0;
+            gpu.ok(kmn_fetch_records(gpu.p, id, hdr_off.data(), n_rec, &got, sp_rec_off.data()));
+            std::vector<std::string> idx_err(s1 - s0);
+            on_threads([&](size_t s) {   // headers and sequence ranges of the records the device found
+                try {
+                    index_records(prot[s], hdr_off.data() + sp_rec_off[s - s0], size_t(sp_rec_off[s - s0 + 1] - sp_rec_off[s - s0]),
+                                  sp_at[s - s0]);
+                } catch (const std::exception& e) { idx_err[s - s0] = e.what(); }
+            });
+            for (auto& e : idx_err) if (!e.empty()) throw std::runtime_error(e);
+        } else {
+            gpu.ok(kmn_count_batch(gpu.p, buf.p, rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
+                                   uint32_t(s1 - s0), nullptr, &id));
+        }
         batches.push_back({id, s0, s1});
         s0 = s1;
     }
@@ -233,7 +263,7 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
                     }
                     if (aa_rec != p.rec) {   // strip + upper-case the record once (group_extraction.rs:455-482)
                         aa.clear();
-                        for (uint64_t i = pr.rec_off[p.rec]; i < pr.rec_off[p.rec + 1]; i++) {
+                        for (uint64_t i = pr.rec_begin[p.rec]; i < pr.rec_end[p.rec]; i++) {
                             const uint8_t c = pr.seq[i];
                             if (c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0C || c == 0x0D) continue;
                             aa.push_back((c >= 'a' && c <= 'z') ? uint8_t(c - 32) : c);
@@ -268,7 +298,7 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         for (size_t sid = 0; sid < n; sid++) {
             obs0[sid + 1] = obs0[sid] + outs[sid].obs.size();
             arena0[sid + 1] = arena0[sid] + outs[sid].arena.size();
-            prot0[sid + 1] = prot0[sid] + (prot[sid].rec_off.size() - 1);
+            prot0[sid + 1] = prot0[sid] + prot[sid].n_rec();
             if (prot0[sid + 1] > 0xFFFFFFFFull)   // :342-344
                 throw std::runtime_error("too many protein records across all species to index with u32");
         }

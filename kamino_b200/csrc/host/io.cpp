@@ -155,13 +155,11 @@ static std::vector<uint8_t> slurp(const std::string& path) {   // io.rs:185-200
 // Record = a line starting with '>' up to the next such line; seq() keeps its line terminators
 // (the device skips them).  Blank lines before the first record are ignored; any other leading byte
 // is a format error (seq_io fasta::Reader).
-Proteome load_proteome(const std::string& path) {
-    const std::vector<uint8_t> b = slurp(path);
+Proteome parse_proteome(const std::vector<uint8_t>& b, const std::string& path) {
     Proteome p;
     const size_t n = b.size();
     size_t pos = 0;
     while (pos < n && (b[pos] == '\n' || (b[pos] == '\r' && pos + 1 < n && b[pos + 1] == '\n'))) pos += b[pos] == '\n' ? 1 : 2;
-    p.rec_off.push_back(0);
     if (pos >= n) return p;
     if (b[pos] != '>') throw std::runtime_error("FASTA parse error in \"" + path + "\": expected '>' at record start");
     p.seq.reserve(n);
@@ -183,11 +181,40 @@ Proteome load_proteome(const std::string& path) {
                 if (b[q] == '>') { next = q; break; }
             }
         }
+        p.rec_begin.push_back(p.seq.size());
         p.seq.insert(p.seq.end(), b.begin() + seq_begin, b.begin() + next);
-        p.rec_off.push_back(p.seq.size());
+        p.rec_end.push_back(p.seq.size());
         pos = next;
     }
     return p;
+}
+
+Proteome load_proteome(const std::string& path) { return parse_proteome(slurp(path), path); }
+
+std::vector<uint8_t> load_fasta_bytes(const std::string& path) {
+    std::vector<uint8_t> b = slurp(path);
+    if (!b.empty() && b.back() != '\n') b.push_back('\n');
+    return b;
+}
+
+void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base) {
+    const std::vector<uint8_t>& b = p.seq;
+    const size_t n = b.size();
+    p.heads.clear();
+    p.rec_begin.assign(n_rec, 0);
+    p.rec_end.assign(n_rec, 0);
+    p.heads.reserve(n_rec);
+    for (size_t r = 0; r < n_rec; r++) {
+        const size_t pos = size_t(hdr[r] - base);
+        if (pos >= n || b[pos] != '>') throw std::runtime_error("record table of the device does not match the file bytes");
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(b.data() + pos, '\n', n - pos));
+        const size_t head_end = nl ? size_t(nl - b.data()) : n;
+        size_t he = head_end;
+        if (he > pos + 1 && b[he - 1] == '\r') he--;
+        p.heads.emplace_back(reinterpret_cast<const char*>(b.data() + pos + 1), he - pos - 1);
+        p.rec_begin[r] = nl ? head_end + 1 : n;
+        p.rec_end[r] = r + 1 < n_rec ? size_t(hdr[r + 1] - base) : n;
+    }
 }
 
 }  // namespace kh

@@ -41,14 +41,22 @@ std::vector<SpeciesFile> inputs_from_directory(const std::string& dir);   // io.
 std::vector<SpeciesFile> inputs_from_table(const std::string& tsv);       // io.rs:82-162
 std::string species_name_of(const std::string& path);                      // io.rs:164-183
 
-// One proteome as the front end wants it: all rec.seq() bytes back to back + record offsets,
-// plus the raw header lines (needed only when a record contributes a block).
+// One proteome as the front end wants it.  Host-parsed (load_proteome): `seq` = all rec.seq() bytes back to
+// back.  Device-framed (load_fasta_bytes + index_records): `seq` = the file's bytes as read, the records
+// located by kmn_count_fasta.  Either way record r's sequence is seq[rec_begin[r] .. rec_end[r]).
 struct Proteome {
-    std::vector<uint8_t> seq;          // concatenated seq() bytes (line terminators included)
-    std::vector<uint64_t> rec_off;     // [n_rec + 1]
+    std::vector<uint8_t> seq;
+    std::vector<uint64_t> rec_begin, rec_end;
     std::vector<std::string> heads;    // header line without '>' / CR
+    size_t n_rec() const { return rec_begin.size(); }
 };
 Proteome load_proteome(const std::string& path);      // io.rs:185-200 + seq_io::fasta::Reader
+// The file's (gunzipped) bytes, a line feed appended if the last line lacks one (kmn_count_fasta's contract).
+std::vector<uint8_t> load_fasta_bytes(const std::string& path);
+// seq_io's parse of bytes already in memory; throws the reader's format error for `path`.
+Proteome parse_proteome(const std::vector<uint8_t>& bytes, const std::string& path);
+// Record table of a device-framed proteome: hdr[r] = offset of record r's '>' in p.seq (kmn_fetch_records).
+void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base);
 
 // One observed block between an anchor pair (group_extraction.rs:118-127), flat form.
 struct Observation {

@@ -18,8 +18,14 @@ def product_cli():
     return build.build_host()
 
 
-def _run(cli, args):
-    r = subprocess.run([str(cli), *map(str, args)], capture_output=True, text=True)
+def _run(cli, args, host_fasta=False):
+    """host_fasta: KAMINO_HOST_FASTA=1 — FASTA records split by the host threads instead of kmn_count_fasta."""
+    import os
+    env = dict(os.environ)
+    env.pop("KAMINO_HOST_FASTA", None)
+    if host_fasta:
+        env["KAMINO_HOST_FASTA"] = "1"
+    r = subprocess.run([str(cli), *map(str, args)], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     return r
 
@@ -54,11 +60,50 @@ def test_synthetic_matches_oracle_cli(product_cli, oracle, synthetic_dir, tmp_pa
                 if a != "--batch-bytes" and (i == 0 or common[i - 1] != "--batch-bytes")]
     r = oracle.run_cli([*ref_args, "-o", want / "kamino"])
     assert r.returncode == 0, r.stderr
-    _run(product_cli, [*common, "-o", got / "kamino"])
-    for f in FILES:
-        assert (got / f).read_bytes() == (want / f).read_bytes(), (f, extra)
+    for host_fasta in (False, True):   # records found on the device (default) / by the host threads
+        for f in FILES:
+            (got / f).unlink(missing_ok=True)
+        _run(product_cli, [*common, "-o", got / "kamino"], host_fasta=host_fasta)
+        for f in FILES:
+            assert (got / f).read_bytes() == (want / f).read_bytes(), (f, extra, host_fasta)
     aln = (got / "kamino_alignment.fas").read_text().splitlines()
     assert len(aln) >= 48 and len(aln[1]) > 0, "expected a non-empty alignment on related proteomes"
+
+
+def test_awkward_fasta_files_match_oracle_cli(product_cli, oracle, synthetic_dir, tmp_path):
+    """CRLF files, leading empty lines, a missing final line feed, '>' inside headers and a file whose first
+    line is not a header: same outputs / same error text as the oracle CLI, with the records found on the device."""
+    src = sorted((synthetic_dir / "in").glob("*.faa"))[:10]
+    d = tmp_path / "in"
+    d.mkdir()
+    for i, f in enumerate(src):
+        data = f.read_bytes()
+        if i == 1:
+            data = data.replace(b"\n", b"\r\n")
+        elif i == 2:
+            data = b"\n\r\n" + data
+        elif i == 3:
+            data = data.rstrip(b"\n")
+        elif i == 4:
+            data = data.replace(b" hypothetical", b" >hypo>thetical")
+        elif i == 5:
+            data = data.replace(b"\n", b"\n\n", 50)
+        (d / f.name).write_bytes(data)
+    want, got = tmp_path / "want", tmp_path / "got"
+    want.mkdir(); got.mkdir()
+    common = ["-i", d, "--nj", "-t", 4, "-f", 0.7]
+    r = oracle.run_cli([*common, "-o", want / "kamino"])
+    assert r.returncode == 0, r.stderr
+    _run(product_cli, [*common, "-o", got / "kamino"])
+    for f in FILES:
+        assert (got / f).read_bytes() == (want / f).read_bytes(), f
+    # a file that does not start with '>': both stop with the reader's message
+    (d / src[6].name).write_bytes(b"MKV\n" + src[6].read_bytes())
+    r_ref = oracle.run_cli([*common, "-o", want / "bad"])
+    r_got = subprocess.run([str(product_cli), *map(str, [*common, "-o", got / "bad"])], capture_output=True, text=True)
+    assert r_ref.returncode != 0 and r_got.returncode != 0
+    assert "expected '>' at record start" in r_ref.stderr and "expected '>' at record start" in r_got.stderr
+    assert src[6].name in r_got.stderr
 
 
 def test_cli_errors(product_cli, golden_dir, tmp_path):
