@@ -169,6 +169,7 @@ fasta_blank_kernel(uint8_t* __restrict__ raw, const uint8_t* __restrict__ tile_i
     }
     const uint32_t before = m_has & ((1u << lane) - 1u);
     if (before) in = (m_val >> (31 - __clz(before))) & 1u;
+    if (!in && !s.hdr_starts) return;   // a chunk of sequence lines (the common case): nothing to blank or record
     // walk the chunk: state flips only at line starts
     uint32_t w4[4] = {v.x, v.y, v.z, v.w};
     bool hdr = in != 0, changed = false;
