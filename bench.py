@@ -79,8 +79,10 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
+        self.windows, self._open = [], None
 
     def start(self):
+        """Started BEFORE the warm-up: nvidia-smi needs ~0.1 s to come up, the timed region can be shorter."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
@@ -92,7 +94,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.monotonic(), line.strip()))
+
+    def wait_first(self, timeout: float = 3.0):
+        t_end = time.monotonic() + timeout
+        while self.proc and not self.samples and time.monotonic() < t_end:
+            time.sleep(0.005)
+
+    def begin(self):
+        self._open = time.monotonic()
+
+    def end(self):
+        if self._open is not None:
+            self.windows.append((self._open, time.monotonic()))
+            self._open = None
 
     def stop(self):
         if not self.proc:
@@ -102,21 +117,34 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+
+        def digest(lines):
+            sm, mx, reasons = [], [], set()
+            for s in lines:
+                f = [x.strip() for x in s.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+
+        timed = [l for t, l in self.samples if any(a <= t <= b for a, b in self.windows)]
+        sm, mx, reasons = digest(timed)
+        window = "timed regions"
+        if len(sm) < 2 and self.windows:   # regions shorter than the sampling period: everything from the first timed step on
+            sm, mx, reasons = digest([l for t, l in self.samples if t >= self.windows[0][0]])
+            window = "from the first timed step to the end of the run"
+        if not sm:
+            sm, mx, reasons = digest([l for _, l in self.samples])
+            window = "whole run under load (warm-up + timed)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_batch(rank: int):
@@ -269,19 +297,21 @@ def run_gpu(args):
         exchange_and_finalize()
         return new                                       # D2H: per-species counts
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # comes up during the warm-up; only samples inside the timed regions count
     for _ in range(args.warmup):
         new = step_resident()
     u = float(new.sum()) / batch.n_residues
+    sampler.wait_first()
 
     # ---- timed: resident inputs
-    sampler = ClockSampler(local_rank)
     stage_acc = {"frame": 0.0, "bloom": 0.0, "cms": 0.0, "finalize": 0.0, "cms_partition_kernel": 0.0,
                  "bloom_bucket_kernel": 0.0}
     launches0 = ctx.launch_count()
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    sampler.begin()
     ev0.record(lib_stream)
     for _ in range(args.steps):
         step_resident()
@@ -289,8 +319,8 @@ def run_gpu(args):
             stage_acc[s] += ctx.stage_ms(s)
     ev1.record(lib_stream)
     barrier()
+    sampler.end()
     elapsed = ev0.elapsed_time(ev1) * 1e-3     # device clock, CUDA events on the launching stream
-    clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
@@ -304,12 +334,15 @@ def run_gpu(args):
     if e2e_steps:
         step_e2e(); ctx.release_batches()
     barrier()
+    sampler.begin()
     ev0.record(lib_stream)
     for _ in range(e2e_steps):
         step_e2e()
         ctx.release_batches()
     ev1.record(lib_stream)
     barrier()
+    sampler.end()
+    clocks = sampler.stop()
     e2e_elapsed = max(ev0.elapsed_time(ev1) * 1e-3, 1e-9)
     if world > 1:
         t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
