@@ -360,9 +360,11 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
         return out;
     }
     want = std::max<uint32_t>(1, std::min<uint32_t>(want, b.n_sp));
-    // only the first range's copy is exposed (the kernels are slower than the link afterwards): keep it small
-    const uint64_t first_bytes = want > 2 ? b.n_raw / (3 * uint64_t(want)) + 1 : b.n_raw / want + 1;
-    const uint64_t rest_bytes = want > 2 ? (b.n_raw - first_bytes) / (want - 1) + 1 : b.n_raw / want + 1;
+    // Only the first range's copy is exposed, and the link moves bytes about twice as fast as the kernels
+    // consume them: every range may be twice as large as the one before it (weights 1, 2, 4, ...), which keeps
+    // the first copy tiny without multiplying the number of ranges.
+    const uint64_t weight_sum = (uint64_t(1) << want) - 1;
+    auto range_bytes = [&](size_t j) { return b.n_raw / weight_sum * (uint64_t(1) << j) + 1; };
     uint32_t s0 = 0;
     uint64_t copied = 0;
     uint32_t tiled = 0;
@@ -370,7 +372,7 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
         uint32_t s1 = s0 + 1;
         if (out.size() + 1 == want) s1 = b.n_sp;
         else {
-            const uint64_t per = out.empty() ? first_bytes : rest_bytes;
+            const uint64_t per = range_bytes(out.size());
             while (s1 < b.n_sp && b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0] < per) s1++;
         }
         SpeciesRange r;
