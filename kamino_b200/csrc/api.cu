@@ -121,6 +121,7 @@ struct kmn_ctx {
     DevBuf<uint32_t> wide;                // u32 widening of the table for the NCCL variant (allocated on demand)
     bool widened = false;
     const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
+    bool tab_zero = false;                // kmn_reset_table: tab is LOGICALLY zero, its memory is stale (materialize_table)
     bool finalized = false;
     DevBuf<unsigned long long> new_counts;
     DevBuf<uint32_t> tile_cnt, tile_base, tile_rec, seg_s_cnt, seg_e_cnt, sp_s_off, sp_e_off;
@@ -547,8 +548,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             static const uint32_t one = 1;
             KMN_CUDA(cudaMemcpyAsync(L.state, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
         }
-        cms_apply_kernel<<<CMS_BUCKETS, APPLY_THREADS, APPLY_SMEM, c->stream>>>(L, c->tab.p, c->cms_force == 1);
+        // the first batch after kmn_reset_table writes every cell instead of adding to it
+        cms_apply_kernel<<<CMS_BUCKETS, APPLY_THREADS, APPLY_SMEM, c->stream>>>(L, c->tab.p, c->cms_force == 1, c->tab_zero);
         check_launch(c);
+        c->tab_zero = false;
         cms_spill_kernel<<<grid_for(c, 2), 256, 0, c->stream>>>(L, c->tab.p);
         check_launch(c);
         cms_direct_kernel<<<grid, 256, 0, c->stream>>>(b.codes.p, c->bl_lost2.p, uint32_t(b.codes_cap / WARP_TILE) - 1, c->k, c->k_mask,
@@ -581,10 +584,18 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     }
 }
 
+// A reset table that no batch has been counted into yet is zeroed here, on first use.
+void materialize_table(kmn_ctx* c) {
+    if (!c->tab_zero) return;
+    KMN_CUDA(cudaMemsetAsync(c->tab.p, 0, CMS_CELLS * sizeof(uint16_t), c->stream));
+    c->tab_zero = false;
+}
+
 void finalize_table(kmn_ctx* c) {
     // The table is the saturating u16 snapshot at all times (cms_kernels.cuh); only the NCCL variant,
     // which summed a widened copy across ranks, has something to clamp back.
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (!c->widened) materialize_table(c);
     if (c->widened) {
         cms_narrow_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->wide.p),
                                                                reinterpret_cast<uint2*>(c->tab.p), CMS_CELLS / 4);
@@ -1021,7 +1032,7 @@ int kmn_fetch_records(kmn_ctx* c, uint32_t batch_id, uint64_t* hdr_off, uint64_t
 
 int kmn_reset_table(kmn_ctx* c) {
     return guarded(c, [&] {
-        KMN_CUDA(cudaMemsetAsync(c->tab.p, 0, CMS_CELLS * sizeof(uint16_t), c->stream));
+        c->tab_zero = true;   // zeroed lazily: by the first batch's apply pass, or by materialize_table
         c->finalized = false;
         c->widened = false;
         c->final_tab = nullptr;
@@ -1053,6 +1064,7 @@ int kmn_table_load(kmn_ctx* c, const uint16_t* table) {
         if (!table) throw std::runtime_error("table must not be NULL");
         KMN_CUDA(cudaMemcpyAsync(c->tab.p, table, CMS_CELLS * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->tab_zero = false;
         c->widened = false;
         c->final_tab = c->tab.p;
         c->finalized = true;
@@ -1070,6 +1082,7 @@ int kmn_table_widen(kmn_ctx* c) {
     return guarded(c, [&] {
         if (c->finalized) throw std::runtime_error("table is finalized");
         if (!c->wide.p) c->wide.alloc(CMS_CELLS);
+        materialize_table(c);
         cms_widen_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint2*>(c->tab.p),
                                                               reinterpret_cast<uint4*>(c->wide.p), CMS_CELLS / 4);
         check_launch(c);
@@ -1080,6 +1093,7 @@ int kmn_table_widen(kmn_ctx* c) {
 int kmn_table_device_ptr(kmn_ctx* c, void** ptr) {
     return guarded(c, [&] {
         if (!ptr) throw std::runtime_error("ptr must not be NULL");
+        materialize_table(c);
         *ptr = const_cast<uint16_t*>(c->finalized ? c->final_tab : c->tab.p);
     });
 }
@@ -1140,6 +1154,7 @@ int kmn_exchange_reduce(kmn_ctx* c) {
         const bool planes = c->exchange_planes && (world == 2 || world == 4 || world == 8);
         uint32_t epoch = ++c->exchange_epoch;
         uint32_t* xs = c->xsync.p;
+        materialize_table(c);
         KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if (planes) {
             // byte planes: split this rank's table, reduce + scatter planes over NVLink, rebuild the u16 table

@@ -155,12 +155,20 @@ __device__ __forceinline__ uint32_t sat_add_u16x2(uint32_t g, uint32_t d) {
 }
 
 __global__ void __launch_bounds__(APPLY_THREADS, 1)
-cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact) {
+cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact, int fresh) {
+    // fresh: the table is logically zero (kmn_reset_table does not touch the 512 MiB; the first batch after it
+    // overwrites every cell here instead of read-modify-writing it)
     extern __shared__ __align__(16) uint32_t s_cnt[];   // APPLY_WORDS words
-    if (L.state[0]) return;                             // fallback: cms_direct_kernel owns this batch
     const uint32_t B = blockIdx.x;
-    const uint32_t n = min(L.cursor[B], L.cap);
-    if (n == 0) return;
+    const bool fallback = L.state[0] != 0;              // cms_direct_kernel owns this batch
+    const uint32_t n = fallback ? 0u : min(L.cursor[B], L.cap);
+    if (n == 0) {
+        if (fresh) {
+            uint4* z4 = reinterpret_cast<uint4*>(tab + (size_t(B) << CMS_BUCKET_LOG2));
+            for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) z4[i] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
     uint4* s4 = reinterpret_cast<uint4*>(s_cnt);
     for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -183,6 +191,10 @@ cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact) {
     uint16_t* __restrict__ cells = tab + (size_t(B) << CMS_BUCKET_LOG2);   // B = row * 1024 + bucket
     if (!__syncthreads_or(ovf)) {
         uint4* g4 = reinterpret_cast<uint4*>(cells);
+        if (fresh) {   // counters never passed 65535 (ovf is false): they are the cells
+            for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) g4[i] = s4[i];
+            return;
+        }
         for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) {
             const uint4 d = s4[i];
             if (!(d.x | d.y | d.z | d.w)) continue;
@@ -208,8 +220,8 @@ cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact) {
         uint32_t* g32 = reinterpret_cast<uint32_t*>(cells + half * APPLY_WORDS);
         for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 2; i += APPLY_THREADS) {
             const uint32_t d0 = s_cnt[2 * i], d1 = s_cnt[2 * i + 1];
-            if (!(d0 | d1)) continue;
-            const uint32_t g = g32[i];
+            if (!(d0 | d1) && !fresh) continue;
+            const uint32_t g = fresh ? 0u : g32[i];
             const uint32_t lo = min((g & 0xFFFFu) + min(d0, 0xFFFFu), 0xFFFFu);
             const uint32_t hi = min((g >> 16) + min(d1, 0xFFFFu), 0xFFFFu);
             g32[i] = lo | (hi << 16);

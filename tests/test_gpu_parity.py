@@ -281,8 +281,19 @@ def test_cms_rare_paths(ffi, oracle, knobs, monkeypatch):
         monkeypatch.setenv(key, v)
     species = synth.bacterial(6, seed=21, n_prot=400, mean_len=220.0)
     b = synth.stage(species)
-    _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, oracle.min_needed(0.85, 6),
-                           scan_species=[0])
+    _, once = _check_pass1_and_pass2(ffi, oracle, b.residues, b.rec_off, b.sp_rec_off, 13, SR6, oracle.min_needed(0.85, 6),
+                                     scan_species=[0])
+    # kmn_reset_table zeroes lazily: stale cells must neither survive a reset + count nor a bare reset
+    with ffi.Context(13, SR6) as ctx:
+        ctx.table_load(np.full(4 << 26, 12345, np.uint16))
+        ctx.reset_table()
+        bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+        ctx.count_staged(bid)
+        ctx.finalize_table()
+        assert np.array_equal(ctx.table_snapshot(), once)
+        ctx.reset_table()
+        ctx.finalize_table()
+        assert not ctx.table_snapshot().any()
     # twice into the same table: merge on top of non-zero cells
     h = oracle.cmsa_new()
     try:
