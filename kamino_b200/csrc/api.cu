@@ -516,8 +516,9 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         // ---- K2 Bloom: probe partition, per-bucket shared-memory bitsets, slow exact path
         const uint32_t n_sp_r = r.s1 - r.s0;
         const uint32_t bl_bound = uint32_t(r.codes_bound / BP_TILE) + 2 * n_sp_r + 2;
-        species_tiles_kernel<<<1, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1, BP_TILE_WT, c->bl_tile0.p, c->bl_tile_sp.p,
-                                                      c->n_tiles_dev.p);
+        species_tiles_kernel<<<2, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1,
+                                                      TilesJob{BP_TILE_WT, c->bl_tile0.p, c->bl_tile_sp.p, c->n_tiles_dev.p},
+                                                      TilesJob{PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p, c->n_tiles_dev.p + 1});
         check_launch(c);
         bloom_partition_kernel<<<bl_bound, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
         check_launch(c);
@@ -531,9 +532,6 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[2], c->stream));
         // ---- K3a count-min partition (also counts the passing occurrences per species)
-        species_tiles_kernel<<<1, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1, PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p,
-                                                      c->n_tiles_dev.p + 1);
-        check_launch(c);
         const uint32_t cms_bound = uint32_t(r.codes_bound / PART_TILE) + 2 * n_sp_r + 2;
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[6], c->stream));
         cms_partition_kernel<<<std::min<uint32_t>(cms_bound, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(

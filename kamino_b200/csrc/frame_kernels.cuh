@@ -326,9 +326,16 @@ __global__ void species_offsets_kernel(const uint32_t* __restrict__ rec_cstart,
 // Per-species source tiles of `tile_wt` warp tiles for the species [s0, s1) (count_kernels.cuh,
 // cms_kernels.cuh): sp_tile0[s] = first tile of species s (indices local to this range, sp_tile0[s0] = 0),
 // tile_sp[t] = species of tile t, *n_tiles = total.  One CTA; no host round trip.
+struct TilesJob { uint32_t tile_wt; uint32_t* sp_tile0; uint32_t* tile_sp; uint32_t* n_tiles; };
+
 __global__ void __launch_bounds__(1024)
-species_tiles_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t s1, uint32_t tile_wt,
-                     uint32_t* __restrict__ sp_tile0, uint32_t* __restrict__ tile_sp, uint32_t* __restrict__ n_tiles) {
+species_tiles_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t s1, TilesJob j0, TilesJob j1) {
+    // blockIdx.x selects one of two independent tile tables (Bloom partition / count-min partition): one launch
+    const TilesJob job = blockIdx.x == 0 ? j0 : j1;
+    const uint32_t tile_wt = job.tile_wt;
+    uint32_t* __restrict__ sp_tile0 = job.sp_tile0;
+    uint32_t* __restrict__ tile_sp = job.tile_sp;
+    uint32_t* __restrict__ n_tiles = job.n_tiles;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
