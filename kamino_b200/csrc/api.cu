@@ -107,6 +107,7 @@ struct Batch {
 }  // namespace
 
 constexpr uint32_t kMaxH2dChunks = 16;
+constexpr float kSlowLinkGBs = 40.f;   // below this measured host-to-device rate the copies, not the kernels, pace pass 1
 
 struct kmn_ctx {
     int device = 0;
@@ -139,6 +140,9 @@ struct kmn_ctx {
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
+    cudaEvent_t ev_h2d[2] = {};           // first / last host-to-device range copy of the last kmn_count_batch
+    float h2d_gbs = 0.f;                  // measured link rate of that call (0: not measured yet)
+    int h2d_mode = 0;                     // KMN_H2D_MODE: 0 adaptive, 1 doubling ranges, 2 equal ranges
     DevBuf<uint32_t> frame_carry, n_tiles_dev, scan_sums, scan_offs;
     // scratch of kmn_group_observations
     DevBuf<uint64_t> g_left, g_right;
@@ -353,7 +357,7 @@ struct SpeciesRange {
     uint64_t codes_bound;           // upper bound of the codes[] positions of the range
 };
 
-std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
+std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, bool equal) {
     std::vector<SpeciesRange> out;
     const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
     if (b.n_sp == 0) {   // records without species cannot exist (sp_rec_off spans them); frame only
@@ -364,8 +368,10 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want) {
     // Only the first range's copy is exposed, and the link moves bytes about twice as fast as the kernels
     // consume them: every range may be twice as large as the one before it (weights 1, 2, 4, ...), which keeps
     // the first copy tiny without multiplying the number of ranges.
+    // On a slow link (several ranks sharing the host's PCIe / memory path) the copies are the critical path and
+    // the kernels of the LAST range are what is left after them: equal, more numerous ranges keep that tail short.
     const uint64_t weight_sum = (uint64_t(1) << want) - 1;
-    auto range_bytes = [&](size_t j) { return b.n_raw / weight_sum * (uint64_t(1) << j) + 1; };
+    auto range_bytes = [&](size_t j) { return equal ? b.n_raw / want + 1 : b.n_raw / weight_sum * (uint64_t(1) << j) + 1; };
     uint32_t s0 = 0;
     uint64_t copied = 0;
     uint32_t tiled = 0;
@@ -404,8 +410,12 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                const uint64_t* host_sp_rec_off, bool frame_only, uint64_t* new_kmers_per_species) {
     if (!frame_only && c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
     const bool from_host = host_rec_off != nullptr;
-    const uint32_t want = from_host ? std::max<uint32_t>(1, std::min<uint32_t>(c->h2d_chunks, uint32_t(b.n_raw >> 22))) : 1;
-    const std::vector<SpeciesRange> ranges = plan_ranges(b, want);
+    // range schedule: doubling sizes while the link outruns the kernels (~27 GB/s of raw bytes), equal sizes and
+    // more of them when the previous call measured a slower link
+    const bool equal = from_host && (c->h2d_mode == 2 || (c->h2d_mode == 0 && c->h2d_gbs > 0.f && c->h2d_gbs < kSlowLinkGBs));
+    const uint32_t chunks = equal && c->h2d_mode == 0 ? std::max<uint32_t>(c->h2d_chunks, 8) : c->h2d_chunks;
+    const uint32_t want = from_host ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, uint32_t(b.n_raw >> 22))) : 1;
+    const std::vector<SpeciesRange> ranges = plan_ranges(b, want, equal);
     const bool timed = ranges.size() == 1;   // per-stage events only make sense without the pipeline
     const int grid = grid_for(c, 8);
 
@@ -482,9 +492,11 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     for (size_t j = 0; j < ranges.size(); j++) {
         const SpeciesRange& r = ranges[j];
         if (from_host) {   // copy stream: this range's raw bytes, then the compute stream may frame them
+            if (j == 0) KMN_CUDA(cudaEventRecord(c->ev_h2d[0], c->copy_stream));
             if (r.copy_end > r.copy_begin)
                 KMN_CUDA(cudaMemcpyAsync(b.raw.p + r.copy_begin, host_residues + r.copy_begin, r.copy_end - r.copy_begin,
                                          cudaMemcpyHostToDevice, c->copy_stream));
+            if (j + 1 == ranges.size()) KMN_CUDA(cudaEventRecord(c->ev_h2d[1], c->copy_stream));
             cudaEvent_t e = c->ev_copy[1 + j % (kMaxH2dChunks)];
             KMN_CUDA(cudaEventRecord(e, c->copy_stream));
             KMN_CUDA(cudaStreamWaitEvent(c->stream, e, 0));
@@ -565,6 +577,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         KMN_CUDA(cudaMemcpyAsync(h.data(), c->new_counts.p, size_t(b.n_sp) * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));
+    if (from_host && b.n_raw >= (uint64_t(8) << 20)) {   // link rate of this call: steers the next call's range schedule
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_h2d[0], c->ev_h2d[1]) == cudaSuccess && ms > 0.f) c->h2d_gbs = float(b.n_raw) / (ms * 1e6f);
+    }
     b.n_codes = b.h_sp_cstart[b.n_sp];
     b.framed = true;
     b.scanned = false;
@@ -921,6 +937,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         KMN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
         for (auto& ev : c->ev_copy) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : c->ev_h2d) KMN_CUDA(cudaEventCreate(&ev));
         c->frame_carry.alloc(1);
         c->n_tiles_dev.alloc(2);
         if (const char* e = std::getenv("KMN_EXCHANGE_PLANES")) c->exchange_planes = std::strtol(e, nullptr, 10) != 0;
@@ -928,6 +945,13 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
             c->h2d_chunks = uint32_t(v);
+        }
+        if (const char* e = std::getenv("KMN_H2D_MODE")) {     // tuning knob: adaptive / doubling / equal
+            const std::string m = e;
+            if (m == "adaptive") c->h2d_mode = 0;
+            else if (m == "doubling") c->h2d_mode = 1;
+            else if (m == "equal") c->h2d_mode = 2;
+            else throw std::runtime_error("KMN_H2D_MODE must be adaptive, doubling or equal");
         }
         if (const char* e = std::getenv("KMN_BLOOM_RUN_CAP")) {   // test knob
             const long v = std::strtol(e, nullptr, 10);
