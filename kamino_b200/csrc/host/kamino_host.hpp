@@ -32,6 +32,7 @@ struct Options {                     // src/lib.rs:119-175
     int device = 0;                  // new, non-breaking: CUDA ordinal (env KAMINO_DEVICE)
     size_t batch_bytes = size_t(1) << 30;   // residues per kmn_count_batch call
     bool quiet = false;
+    std::string predict_only;        // new, hidden: with --genomes, write the predicted proteomes here and stop (no GPU)
 };
 
 struct SpeciesFile { std::string name, path; };      // src/io.rs:51-58
@@ -57,6 +58,11 @@ std::vector<uint8_t> load_fasta_bytes(const std::string& path);
 Proteome parse_proteome(const std::vector<uint8_t>& bytes, const std::string& path);
 // Record table of a device-framed proteome: hdr[r] = offset of record r's '>' in p.seq (kmn_fetch_records).
 void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base);
+
+// protein_prediction.rs:265-294: `--genomes` — one predicted `<name>.faa` per nucleotide FASTA, written to tmp_dir.
+std::vector<SpeciesFile> predict_proteomes(const std::vector<SpeciesFile>& genomes, const std::string& tmp_dir, size_t threads);
+
+std::string prediction_self_test();   // the reference's unit tests of protein_prediction.rs; empty = all passed
 
 // One observed block between an anchor pair (group_extraction.rs:118-127), flat form.
 struct Observation {

@@ -222,7 +222,33 @@ void run(const Options& o) {   // lib.rs:206-298
     if (o.has_file) { auto v = inputs_from_table(o.input_file); inputs.insert(inputs.end(), v.begin(), v.end()); }
     if (o.has_dir) { auto v = inputs_from_directory(o.input_dir); inputs.insert(inputs.end(), v.begin(), v.end()); }
     if (!o.quiet) std::fprintf(stderr, "# process input files\n");
-    if (o.genomes) throw std::runtime_error("--genomes (protein prediction) is not part of the GPU front end");
+    // Genome mode (lib.rs:235-248): predicted proteomes go to a temporary directory next to the output prefix,
+    // removed when the run ends (TempDir's drop, lib.rs:296)
+    struct TempDir {
+        std::string path;
+        ~TempDir() {
+            if (path.empty()) return;
+            std::error_code ec;
+            std::filesystem::remove_all(path, ec);
+        }
+    } tmp;
+    if (o.genomes) {
+        if (!o.quiet) std::fprintf(stderr, " . predict proteins from bacterial genomes\n");
+        std::string dir;
+        if (!o.predict_only.empty()) {
+            std::filesystem::create_directories(o.predict_only);
+            dir = o.predict_only;
+        } else {
+            std::string parent = std::filesystem::path(o.output).parent_path().string();
+            if (parent.empty()) parent = ".";
+            std::string tmpl = parent + "/tmp_kamino_XXXXXX";
+            if (!mkdtemp(tmpl.data())) throw std::runtime_error("create temporary directory in " + parent);
+            tmp.path = tmpl;
+            dir = tmpl;
+        }
+        inputs = predict_proteomes(inputs, dir, o.threads);
+        if (!o.predict_only.empty()) return;
+    }
     if (inputs.empty()) throw std::runtime_error("At least one input source with files must be provided.");
     StageTimer t_all("total");
     Extraction ex = extract_groups(inputs, k, o.min_freq, o.length_middle, o.recode, o);
@@ -274,6 +300,13 @@ int cli(int argc, char** argv) {   // main.rs:5-9 + clap surface of lib.rs:119-1
             else if (a == "--nj" || a == "--NJ") o.nj = true;           // README spells it --NJ, clap accepts --nj
             else if (a == "--device") o.device = std::stoi(need());
             else if (a == "--batch-bytes") o.batch_bytes = std::stoull(need());
+            else if (a == "--predict-only") o.predict_only = need();
+            else if (a == "--self-test") {   // hidden: host-logic unit tests that need no GPU
+                const std::string r = prediction_self_test();
+                if (!r.empty()) throw std::runtime_error("protein prediction self-test " + r);
+                std::printf("self-test ok\n");
+                return 0;
+            }
             else if (a == "-v" || a == "-V" || a == "--version") { std::printf("kamino 2.0.0 (b200)\n"); return 0; }
             else throw std::runtime_error("unexpected argument '" + a + "'");
         }

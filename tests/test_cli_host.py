@@ -28,8 +28,9 @@ def test_flag_validation(cli, tmp_path):
     assert r.returncode != 0
     r = _run(cli, "-i", str(GOLDEN / "input"), "-k", "5", "-c", "6", "-o", str(tmp_path / "x"))   # lib.rs:219
     assert r.returncode != 0
-    r = _run(cli, "-i", str(GOLDEN / "input"), "--genomes", "-o", str(tmp_path / "x"))
-    assert r.returncode != 0 and "genomes" in r.stderr
+    r = _run(cli, "-i", str(GOLDEN / "input"), "--genomes", "-o", str(tmp_path / "x"))   # proteins are not genomes
+    assert r.returncode != 0 and "does not appear to contain DNA sequences" in r.stderr      # protein_prediction.rs:301-306
+    assert not list(tmp_path.glob("tmp_kamino_*")), "the temporary proteome directory must not outlive the run"
     r = _run(cli, "-i", str(tmp_path / "does_not_exist"), "-o", str(tmp_path / "x"))
     assert r.returncode != 0
 
@@ -43,3 +44,77 @@ def test_no_gpu_means_error_not_fallback(cli, tmp_path):
     assert r.returncode != 0
     assert "CUDA" in r.stderr or "GPU" in r.stderr
     assert not list(tmp_path.glob("kamino_*"))
+
+
+# ---- --genomes: the ORF predictor in front of the pipeline (protein_prediction.rs) is host logic, testable here
+
+GENOMES = ROOT / "tests" / "golden" / "test_genomes"
+
+
+def test_prediction_unit_tests_of_the_reference(cli):
+    """protein_prediction.rs:1152-1286 restated on the host functions (kamino-b200 --self-test)."""
+    r = _run(cli, "--self-test")
+    assert r.returncode == 0 and "self-test ok" in r.stdout, r.stderr
+
+
+def test_golden_genomes_predictor_then_oracle(cli, tmp_path):
+    """tests/golden.rs:126-139 (golden_genomes): the product's predictor writes the proteomes, the oracle runs
+    the rest of the pipeline on them on the CPU, and the three outputs equal the reference's expected files."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_ffi
+    pred = tmp_path / "pred"
+    r = _run(cli, "-i", str(GENOMES / "input"), "--genomes", "--predict-only", str(pred), "-t", "2")
+    assert r.returncode == 0, r.stderr
+    assert sorted(p.name for p in pred.iterdir()) == ["genome_A.faa", "genome_B.faa"]
+    a = (pred / "genome_A.faa").read_text().splitlines()
+    assert a[0] == ">protein_1" and all(len(line) <= 60 for line in a[1:])
+    prot = "".join(a[1:])
+    assert prot.startswith("M") and len(prot) >= 90 and "*" not in prot
+    out = tmp_path / "out"
+    out.mkdir()
+    ro = oracle_ffi.load().run_cli(["-i", pred, "--length-middle", 50, "--recode", "sr6", "-t", 2, "-o", out / "kamino"])
+    assert ro.returncode == 0, ro.stderr
+    for f in ("kamino_alignment.fas", "kamino_missing.tsv", "kamino_partitions.tsv"):
+        assert (out / f).read_bytes() == (GENOMES / "expected" / f).read_bytes(), f
+
+
+def test_predictor_on_a_synthetic_genome(cli, tmp_path):
+    """A 300 kb random genome with planted genes on both strands (enough long ORFs to train the adaptive codon
+    model): planted genes are recovered, every protein obeys the emission rules, and the output does not
+    depend on the thread count or on line wrapping / case of the input."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    codons = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT" if a + b + c not in ("TAA", "TAG", "TGA")]
+    comp = str.maketrans("ACGT", "TGCA")
+    parts, genes = [], []
+    for g in range(160):
+        parts.append("".join(rng.choice(list("ACGT"), int(rng.integers(60, 400)))))
+        body = "".join(rng.choice(codons, int(rng.integers(130, 400))))
+        gene = "ATG" + body + "TAA"
+        genes.append(gene)
+        parts.append(gene if g % 2 == 0 else gene.translate(comp)[::-1])
+    genome = "".join(parts)
+    d1, d2 = tmp_path / "in1", tmp_path / "in2"
+    d1.mkdir(); d2.mkdir()
+    (d1 / "g.fna").write_text(">contig1 test\n" + "\n".join(genome[i:i + 70] for i in range(0, len(genome), 70)) + "\n")
+    (d2 / "g.fna").write_text(">contig1\n" + genome.lower() + "\n")
+    outs = []
+    for d, t in ((d1, "1"), (d1, "4"), (d2, "2")):
+        o = tmp_path / f"pred_{d.name}_{t}"
+        r = _run(cli, "-i", str(d), "--genomes", "--predict-only", str(o), "-t", t)
+        assert r.returncode == 0, r.stderr
+        outs.append((o / "g.faa").read_text())
+    assert outs[0] == outs[1] == outs[2]
+    recs = outs[0].split(">")[1:]
+    prots = ["".join(r.splitlines()[1:]) for r in recs]
+    assert [r.splitlines()[0] for r in recs] == [f"protein_{i + 1}" for i in range(len(recs))]
+    assert len(prots) >= 150
+    assert all(p.startswith("M") and len(p) >= 90 and "*" not in p for p in prots)
+    table = dict(zip([a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"],
+                     "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"))
+    found = 0
+    for gene in genes:
+        want = "".join(table[gene[i:i + 3]] for i in range(0, len(gene) - 3, 3))
+        found += any(p.endswith(want[-80:]) for p in prots)     # the start may be an upstream alternative
+    assert found >= 150, found

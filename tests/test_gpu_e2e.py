@@ -40,6 +40,17 @@ def test_golden_3diff_through_gpu(product_cli, golden_dir, tmp_path, mode, schem
         assert (tmp_path / f).read_text() == (src / "expected" / f).read_text(), f
 
 
+def test_golden_genomes_through_gpu(product_cli, golden_dir, tmp_path):
+    """tests/golden.rs:126-139: --genomes (host ORF prediction into a temporary directory) in front of the GPU
+    pipeline; the temporary proteomes are gone afterwards (lib.rs:296)."""
+    src = golden_dir / "test_genomes"
+    _run(product_cli, ["-i", src / "input", "--genomes", "--length-middle", 50, "--recode", "sr6", "-t", 2,
+                       "-o", tmp_path / "kamino"])
+    for f in FILES[:3]:
+        assert (tmp_path / f).read_text() == (src / "expected" / f).read_text(), f
+    assert not list(tmp_path.glob("tmp_kamino_*"))
+
+
 @pytest.fixture(scope="module")
 def synthetic_dir(tmp_path_factory):
     d = tmp_path_factory.mktemp("synth")
