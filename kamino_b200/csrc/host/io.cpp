@@ -217,4 +217,45 @@ void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base
     }
 }
 
+// Host-only check of the device-framed path's bookkeeping: for awkward FASTA texts, index_records() fed with
+// the header offsets a line scan finds (what kmn_fetch_records returns) must describe the same records —
+// headers and whitespace-stripped sequences — as the seq_io-style parser.
+std::string fasta_index_self_test() {
+    const std::vector<std::string> texts = {
+        ">a desc\nACDE\nFGH\n>b\nKLMN\n",
+        "\n\r\n>a\r\nAC\r\nDE\r\n>b x y\r\n\r\nFG\r\n",
+        ">a\n>b\n\n>c d\nAC>DE\n \t\n>e",
+        ">only header",
+        "",
+        "\n\n",
+        ">x>y>z\nMKV\n>w\nLLL",
+    };
+    auto strip = [](const std::vector<uint8_t>& v, uint64_t b, uint64_t e) {
+        std::string out;
+        for (uint64_t i = b; i < e; i++) {
+            const uint8_t c = v[i];
+            if (c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0C || c == 0x0D) continue;
+            out.push_back(char(c));
+        }
+        return out;
+    };
+    for (size_t t = 0; t < texts.size(); t++) {
+        const std::vector<uint8_t> raw(texts[t].begin(), texts[t].end());
+        const Proteome want = parse_proteome(raw, "self-test");
+        Proteome got;
+        got.seq = raw;
+        if (!got.seq.empty() && got.seq.back() != '\n') got.seq.push_back('\n');
+        std::vector<uint64_t> hdr;
+        const uint64_t base = 1000 + t;   // offsets are relative to the batch buffer
+        for (size_t i = 0; i < got.seq.size(); i++)
+            if (got.seq[i] == '>' && (i == 0 || got.seq[i - 1] == '\n')) hdr.push_back(base + i);
+        index_records(got, hdr.data(), hdr.size(), base);
+        if (got.n_rec() != want.n_rec() || got.heads != want.heads) return "failed: record table of text " + std::to_string(t);
+        for (size_t r = 0; r < want.n_rec(); r++)
+            if (strip(got.seq, got.rec_begin[r], got.rec_end[r]) != strip(want.seq, want.rec_begin[r], want.rec_end[r]))
+                return "failed: sequence " + std::to_string(r) + " of text " + std::to_string(t);
+    }
+    return std::string();
+}
+
 }  // namespace kh

@@ -62,6 +62,7 @@ void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base
 // protein_prediction.rs:265-294: `--genomes` — one predicted `<name>.faa` per nucleotide FASTA, written to tmp_dir.
 std::vector<SpeciesFile> predict_proteomes(const std::vector<SpeciesFile>& genomes, const std::string& tmp_dir, size_t threads);
 
+std::string fasta_index_self_test();  // index_records vs parse_proteome on awkward FASTA texts; empty = passed
 std::string prediction_self_test();   // the reference's unit tests of protein_prediction.rs; empty = all passed
 
 // One observed block between an anchor pair (group_extraction.rs:118-127), flat form.

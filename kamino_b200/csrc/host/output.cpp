@@ -304,6 +304,8 @@ int cli(int argc, char** argv) {   // main.rs:5-9 + clap surface of lib.rs:119-1
             else if (a == "--self-test") {   // hidden: host-logic unit tests that need no GPU
                 const std::string r = prediction_self_test();
                 if (!r.empty()) throw std::runtime_error("protein prediction self-test " + r);
+                const std::string f = fasta_index_self_test();
+                if (!f.empty()) throw std::runtime_error("FASTA record table self-test " + f);
                 std::printf("self-test ok\n");
                 return 0;
             }

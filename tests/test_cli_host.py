@@ -52,7 +52,8 @@ GENOMES = ROOT / "tests" / "golden" / "test_genomes"
 
 
 def test_prediction_unit_tests_of_the_reference(cli):
-    """protein_prediction.rs:1152-1286 restated on the host functions (kamino-b200 --self-test)."""
+    """protein_prediction.rs:1152-1286 restated on the host functions (kamino-b200 --self-test); the same flag
+    checks the record bookkeeping of the device-framed FASTA path against the seq_io-style host parser."""
     r = _run(cli, "--self-test")
     assert r.returncode == 0 and "self-test ok" in r.stdout, r.stderr
 
