@@ -119,3 +119,59 @@ def test_predictor_on_a_synthetic_genome(cli, tmp_path):
         want = "".join(table[gene[i:i + 3]] for i in range(0, len(gene) - 3, 3))
         found += any(p.endswith(want[-80:]) for p in prots)     # the start may be an upstream alternative
     assert found >= 150, found
+
+
+def _synthetic_genome(seed, n_genes, with_n=False):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    codons = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT" if a + b + c not in ("TAA", "TAG", "TGA")]
+    comp = str.maketrans("ACGT", "TGCA")
+    parts = []
+    for g in range(n_genes):
+        parts.append("".join(rng.choice(list("ACGT"), int(rng.integers(20, 400)))))
+        if g % 9 == 3:
+            parts.append("AAGGAGG" + "".join(rng.choice(list("ACGT"), int(rng.integers(3, 12)))))   # Shine-Dalgarno-like
+        start = ["ATG", "GTG", "TTG"][int(rng.integers(0, 3))]
+        gene = start + "".join(rng.choice(codons, int(rng.integers(60, 420)))) + ["TAA", "TAG", "TGA"][g % 3]
+        if with_n and g % 11 == 5:
+            gene = gene[:150] + "N" * int(rng.integers(1, 5)) + gene[150:]
+        parts.append(gene if g % 2 == 0 else gene.translate(comp)[::-1])
+    return "".join(parts)
+
+
+def test_predictor_matches_the_python_restatement(cli, tmp_path):
+    """Differential test: the C++ host predictor against oracle/protein_prediction.py (written independently from
+    the Rust source) on synthetic genomes — several contigs, N runs, lower case, CRLF, a contig shorter than a
+    codon, enough long ORFs on one contig to train the adaptive codon model, and the golden genomes."""
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from oracle import protein_prediction as orc
+    d = tmp_path / "in"
+    d.mkdir()
+    big = _synthetic_genome(11, 140)                     # adaptive model kicks in
+    small = _synthetic_genome(12, 25, with_n=True)
+    (d / "big.fna").write_text(">c1\n" + "\n".join(big[i:i + 80] for i in range(0, len(big), 80)) + "\n")
+    (d / "multi.fa").write_text(">c1 first\r\n" + small.lower() + "\r\n>c2\r\nAC\r\n>c3\r\n" + _synthetic_genome(13, 12) + "\r\n")
+    import gzip
+    with gzip.open(d / "zipped.fas.GZ", "wb") as f:      # the predictor gunzips "gz" in any case (:361-365)
+        f.write((">x\n" + _synthetic_genome(14, 30, with_n=True) + "\n").encode())
+    for f in (GENOMES / "input").iterdir():
+        (d / f.name).write_bytes(f.read_bytes())
+    out = tmp_path / "pred"
+    r = _run(cli, "-i", str(d), "--genomes", "--predict-only", str(out), "-t", "3")
+    assert r.returncode == 0, r.stderr
+    n_checked = 0
+    for f in sorted(d.iterdir()):
+        name = {"zipped.fas.GZ": "zipped.fas.GZ"}.get(f.name, f.name.split(".")[0])   # io.rs:164-183 strips only a lower-case ".gz"
+        got = (out / f"{name}.faa").read_text()
+        want = orc.predict_one_genome(f)
+        assert got == want, f.name
+        n_checked += got.count(">")
+    assert n_checked > 150
+    # the big contig does reach the adaptive codon model (otherwise that path would be compared vacuously)
+    rc = "".join(orc.COMPLEMENT.get(ch, "N") for ch in reversed(big))
+    gm = orc.gc_model(orc.f32(sum(ch in "GC" for ch in big) / len(big)))
+    orfs = []
+    orc.find_orfs_on_strand(big, 1, 270, gm, orfs)
+    orc.find_orfs_on_strand(rc, -1, 270, gm, orfs)
+    assert orc.train_adaptive(orfs, big, rc) is not None

@@ -185,3 +185,27 @@ def test_pair_counts_small(oracle):
         for j in range(i + 1, 7):
             ok = (m[i] < 20) & (m[j] < 20)
             assert v[i, j] == ok.sum() and mm[i, j] == (ok & (m[i] != m[j])).sum()
+
+
+def test_golden_genomes_with_the_python_predictor(oracle, golden_dir, tmp_path):
+    """tests/golden.rs:126-139 inside the oracle alone: oracle/protein_prediction.py writes the proteomes, the
+    oracle CLI runs the pipeline, outputs equal the reference's expected files (pins the Python restatement)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import protein_prediction as pp
+    src = golden_dir / "test_genomes"
+    pred = tmp_path / "pred"
+    pred.mkdir()
+    for f in sorted((src / "input").iterdir()):
+        name = f.name[:-3] if f.name.endswith(".gz") else f.name
+        name = name.rsplit(".", 1)[0]
+        (pred / f"{name}.faa").write_text(pp.predict_one_genome(f))
+    r = oracle.run_cli(["-i", pred, "--length-middle", 50, "--recode", "sr6", "-t", 2, "-o", tmp_path / "kamino"])
+    assert r.returncode == 0, r.stderr
+    for f in ("kamino_alignment.fas", "kamino_missing.tsv", "kamino_partitions.tsv"):
+        assert (tmp_path / f).read_bytes() == (src / "expected" / f).read_bytes(), f
+    # known answers of the scoring arithmetic (hand-computed from the reference's formulas)
+    assert pp.gc_model(pp.f32(0.5)) == (576, 400, 549)
+    assert pp.length_score(270) == 31 and pp.calibrated_start_term(13, 600) == 6
+    assert pp.translate_table11("GTGAAATAGNNN", True) == "MK*X"
