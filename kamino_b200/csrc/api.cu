@@ -579,7 +579,11 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     KMN_CUDA(cudaStreamSynchronize(c->stream));
     if (from_host && b.n_raw >= (uint64_t(8) << 20)) {   // link rate of this call: steers the next call's range schedule
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev_h2d[0], c->ev_h2d[1]) == cudaSuccess && ms > 0.f) c->h2d_gbs = float(b.n_raw) / (ms * 1e6f);
+        if (cudaEventElapsedTime(&ms, c->ev_h2d[0], c->ev_h2d[1]) == cudaSuccess) {
+            if (ms > 0.f) c->h2d_gbs = float(b.n_raw) / (ms * 1e6f);
+        } else {
+            (void)cudaGetLastError();   // a failed measurement must not surface as the next launch's error
+        }
     }
     b.n_codes = b.h_sp_cstart[b.n_sp];
     b.framed = true;
