@@ -76,6 +76,20 @@ std::string protein_name_of(const std::string& head) {
 
 }  // namespace
 
+// group_extraction.rs:666-677 (truncate_protein_name_keeps_record_id_and_removes_organism_suffix) on protein_name_of,
+// plus the UTF-8 gate of the header fields (:429-430)
+std::string extraction_self_test() {
+    if (protein_name_of("WP_012345.1 hypothetical protein [Escherichia coli]") != "WP_012345.1 hypothetical protein")
+        return "failed: group_extraction::truncate_protein_name (organism suffix)";
+    if (protein_name_of("WP_012345.1 hypothetical protein") != "WP_012345.1 hypothetical protein")
+        return "failed: group_extraction::truncate_protein_name (no suffix)";
+    if (protein_name_of("id_only") != "id_only" || protein_name_of("id   spaced  desc [x] [y]") != "id spaced  desc")
+        return "failed: group_extraction::protein names (id only / inner spaces)";
+    if (!valid_utf8("caf\xc3\xa9") || valid_utf8("bad\xff") || valid_utf8("\xc3") || valid_utf8("\xed\xa0\x80"))
+        return "failed: group_extraction::header UTF-8 validation";
+    return std::string();
+}
+
 Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
                           Scheme scheme, const Options& opt) {
     const size_t n = inputs.size();

@@ -327,4 +327,153 @@ Alignment filter_groups(const Extraction& ex, const std::vector<Candidate>& cand
     return al;
 }
 
+// ---- the reference's unit tests of this logic, restated on the functions above (kamino-b200 --self-test) -------
+// group_filtering.rs:484-693 (every filter_groups case) and group_sorting.rs:486-638 (the sort / non-overlap /
+// length-selection cases).  Observations are built by hand; groups carry KMN_GROUP_HOST so that the length
+// selection runs here and not on the device.
+
+namespace {
+
+struct TestGroup { uint64_t left, right; std::vector<std::string> rows; std::vector<uint32_t> sids; };
+
+Extraction test_extraction(const std::vector<TestGroup>& groups, size_t k, size_t min_needed, size_t n_species) {
+    Extraction ex;
+    ex.k = k;
+    ex.min_needed = min_needed;
+    ex.n_species = n_species;
+    for (size_t s = 0; s < n_species; s++) ex.species_names.push_back("species_" + std::to_string(s));
+    ex.protein_names.assign(n_species, "protein");
+    std::vector<TestGroup> sorted = groups;   // obs are kept sorted by (left, right, order)
+    std::stable_sort(sorted.begin(), sorted.end(), [](const TestGroup& a, const TestGroup& b) {
+        return a.left != b.left ? a.left < b.left : a.right < b.right;
+    });
+    for (const TestGroup& g : sorted) {
+        kmn_group kg{};
+        kg.first = uint32_t(ex.obs.size());
+        kg.count = uint32_t(g.rows.size());
+        kg.flags = KMN_GROUP_HOST;
+        for (size_t i = 0; i < g.rows.size(); i++) {
+            Observation o{};
+            o.left = g.left;
+            o.right = g.right;
+            o.sid = g.sids.empty() ? uint32_t(i) : g.sids[i];
+            o.protein = o.sid;
+            o.aa_off = ex.arena.size();
+            o.len = uint32_t(g.rows[i].size());
+            o.order = ex.obs.size();
+            ex.arena.insert(ex.arena.end(), g.rows[i].begin(), g.rows[i].end());
+            ex.obs.push_back(o);
+        }
+        ex.groups.push_back(kg);
+    }
+    ex.n_groups = ex.groups.size();
+    return ex;
+}
+
+struct FilterCase {
+    const char* name;
+    std::vector<std::string> rows;
+    size_t k;
+    float min_freq;
+    size_t constant, mask;
+    std::vector<std::string> want;   // empty: the group is discarded
+};
+
+}  // namespace
+
+std::string host_logic_self_test() {
+    const std::vector<FilterCase> cases = {
+        {"retained_middle_starts_at_first_retained_polymorphic_column", {"ACCEF", "ACCHF", "ACCEF", "ACCHF"}, 1, 1.0f, 0, 0, {"E", "H", "E", "H"}},
+        {"retained_middle_trims_past_raw_only_polymorphism", {"AAPCF", "APDCF", "AAPCF", "APDCF"}, 1, 1.0f, 0, 0, {"P", "D", "P", "D"}},
+        {"ambiguous_x_does_not_create_early_polymorphism", {"ACCEF", "ACCHF", "AXCEF", "ACXHF"}, 1, 0.75f, 0, 0, {"E", "H", "E", "H"}},
+        {"discards_when_only_retained_middle_columns_are_conserved", {"ACCEF", "ACCDF", "ACC-F", "ACC-F"}, 1, 0.75f, 0, 0, {}},
+        {"right_anchor_tail_is_appended_after_polymorphic_middle", {"ACEFT", "ACHFT", "ACEFT", "ACHFT"}, 1, 1.0f, 1, 0, {"ET", "HT", "ET", "HT"}},
+        {"polymorphic_right_anchor_tail_cannot_rescue_conserved_middle", {"ACCD", "ACCE", "ACCD", "ACCE"}, 1, 1.0f, 1, 0, {}},
+        {"discards_when_only_raw_polymorphic_middle_column_fails_missingness", {"ACGT", "ADGT", "A-GT", "A-GT"}, 1, 0.75f, 0, 0, {}},
+        {"retains_group_with_retained_polymorphic_middle_column", {"ACGT", "ADGT", "ACGT", "ADGT"}, 1, 0.75f, 1, 0, {"CT", "DT", "CT", "DT"}},
+        {"constant_tail_cannot_rescue_without_retained_polymorphic_middle", {"AC-T", "AD-T", "A--T", "A--T"}, 1, 0.75f, 1, 0, {}},
+        {"middle_is_trimmed_on_both_sides_before_appending_constants", {"AAAQFCPQRRR", "AAAQDCDQRRR"}, 3, 1.0f, 3, 0, {"FCPRRR", "DCDRRR"}},
+        {"missingness_filtering_happens_before_polymorphic_trimming", {"AFCPR", "ADCDR", "A-CPR", "A-CDR"}, 1, 0.75f, 0, 0, {"P", "D", "P", "D"}},
+        {"raw_amino_acid_differences_in_same_recoded_state_do_not_count_as_polymorphism", {"AACA", "APCA"}, 1, 1.0f, 0, 0, {}},
+        {"gaps_and_x_are_ignored_when_detecting_polymorphism", {"ACPR", "AXPR", "A-DR", "ACDR"}, 1, 0.5f, 0, 0, {"P", "P", "D", "D"}},
+        {"constant_zero_emits_only_trimmed_polymorphic_middle_region", {"AAAQFCPQRRR", "AAAQDCDQRRR"}, 3, 1.0f, 0, 0, {"FCP", "DCD"}},
+        {"one_polymorphic_middle_column_with_constant_three_has_length_four", {"AAACRRR", "AAADRRR"}, 3, 1.0f, 3, 0, {"CRRR", "DRRR"}},
+        {"divergent_row_masking_happens_before_polymorphic_middle_filtering", {"ACDEFGK", "ACDEFGK", "APPPPPK"}, 1, 1.0f, 0, 5, {}},
+        {"mask_zero_disables_divergent_row_masking", {"ACDEFGK", "ACDEFGK", "APPPPPK"}, 1, 1.0f, 0, 0, {"CDEFG", "CDEFG", "PPPPP"}},
+        {"constant_tail_columns_failing_missingness_are_not_appended", {"ACT", "AD-", "AC-", "AD-"}, 1, 0.75f, 1, 0, {"C", "D", "C", "D"}},
+    };
+    for (const FilterCase& fc : cases) {
+        const size_t n = fc.rows.size();
+        const Extraction ex = test_extraction({{1, 2, fc.rows, {}}}, fc.k, 1, n);
+        Candidate c;
+        c.left = 1;
+        c.right = 2;
+        c.coverage = n;
+        c.raw_len = fc.rows[0].size();
+        for (uint32_t i = 0; i < n; i++) c.rows.push_back(i);
+        const Alignment al = filter_groups(ex, {c}, fc.min_freq, fc.constant, fc.mask, SR6, 1);
+        const std::string where = std::string("failed: group_filtering::") + fc.name;
+        if (fc.want.empty()) {
+            if (!al.partitions.empty()) return where;
+            for (const auto& row : al.concat) if (!row.empty()) return where;
+            continue;
+        }
+        const size_t len = fc.want[0].size();
+        if (al.partitions.size() != 1 || al.partitions[0].start != 0 || al.partitions[0].end != len - 1 || al.partitions[0].len != len) return where;
+        for (size_t s = 0; s < n; s++)
+            if (std::string(al.concat[s].begin(), al.concat[s].end()) != fc.want[s]) return where;
+    }
+    auto keys_of = [](const std::vector<Candidate>& v) {
+        std::vector<std::pair<uint64_t, uint64_t>> k;
+        for (const Candidate& c : v) k.emplace_back(c.left, c.right);
+        return k;
+    };
+    using Keys = std::vector<std::pair<uint64_t, uint64_t>>;
+    {   // sort_nonoverlap_uses_shorter_overlap_k_when_k_less_than_11 (group_sorting.rs:486-521)
+        const std::string b = "ACDEFGHIKLMNPQRSTVW";
+        const Extraction ex = test_extraction({{10, 20, {b, b}, {}}, {30, 40, {b, b}, {}}}, 9, 2, 2);
+        if (keys_of(sort_and_deduplicate_groups(ex, SR6)) != Keys{{10, 20}}) return "failed: group_sorting::sort_nonoverlap_uses_shorter_overlap_k_when_k_less_than_11";
+    }
+    {   // nonoverlap_filter_drops_weaker_shared_kmer_and_retains_empty_kmer_candidates (:540-558): coverage 2 beats 1
+        const std::string shared = "ACDEFGHIKLMNPQRSTVWYA", xs(21, 'X');
+        const Extraction ex = test_extraction({{20, 21, {shared}, {}}, {30, 31, {xs}, {}}, {10, 11, {shared, shared}, {}}}, 10, 1, 2);
+        if (keys_of(sort_and_deduplicate_groups(ex, SR6)) != Keys{{10, 11}, {30, 31}}) return "failed: group_sorting::nonoverlap_filter_drops_weaker_shared_kmer";
+    }
+    {   // streaming_nonoverlap_preserves_full_path_overlap_semantics (:561-576), overlap k = 5 <=> k = 2
+        const Extraction ex = test_extraction({{20, 21, {"ZZACDEFZZ", "ZZACDEFZZ", "ZZACDEFZZ"}, {}}, {40, 41, {"GGGGG"}, {}},
+                                               {30, 31, {"XXXXX"}, {}}, {10, 11, {"ACDEF", "ACDEF", "ACDEF", "ACDEF"}, {}}}, 2, 1, 4);
+        if (keys_of(sort_and_deduplicate_groups(ex, SR6)) != Keys{{10, 11}, {30, 31}, {40, 41}}) return "failed: group_sorting::streaming_nonoverlap_preserves_full_path_overlap_semantics";
+    }
+    {   // length_filter_rejects_ties_low_support_and_short_blocks (:579-603)
+        const Extraction tie = test_extraction({{1, 2, {"ACDEF", "ACDEF", "ACDEFG", "ACDEFG"}, {}}}, 2, 2, 4);
+        const Extraction low = test_extraction({{1, 2, {"ACDEF"}, {}}}, 2, 2, 4);
+        const Extraction shrt = test_extraction({{1, 2, {"ACD", "ACD"}, {}}}, 2, 2, 2);
+        if (!sort_and_deduplicate_groups(tie, SR6).empty() || !sort_and_deduplicate_groups(low, SR6).empty() ||
+            !sort_and_deduplicate_groups(shrt, SR6).empty())
+            return "failed: group_sorting::length_filter_rejects_ties_low_support_and_short_blocks";
+    }
+    {   // sort_retains_original_raw_anchor_key_without_refinement (:606-615)
+        const Extraction ex = test_extraction({{31, 37, {"*AC**FGHIKL*", "*AC**DGHIKL*"}, {}}}, 2, 2, 2);
+        const std::vector<Candidate> v = sort_and_deduplicate_groups(ex, SR6);
+        if (v.size() != 1 || v[0].left != 31 || v[0].right != 37 || v[0].raw_len != 12) return "failed: group_sorting::sort_retains_original_raw_anchor_key_without_refinement";
+    }
+    {   // sort_nonoverlap_keeps_strongest_overlapping_group_deterministically (:618-637): equal strength, smaller key wins
+        const std::string shared = "ACDEFGHIKLMNPQRSTVWYA", ys(21, 'Y');
+        const Extraction ex = test_extraction({{50, 60, {shared, shared}, {}}, {10, 20, {shared, shared}, {}}, {30, 40, {ys}, {}}}, 10, 1, 2);
+        if (keys_of(sort_and_deduplicate_groups(ex, SR6)) != Keys{{10, 20}, {30, 40}}) return "failed: group_sorting::sort_nonoverlap_keeps_strongest_overlapping_group_deterministically";
+    }
+    {   // consensus_rows_by_isolate_uses_arena_backed_observations (:526-537), seen through filter_groups: two
+        // observations of one isolate collapse into one row, a disagreement becomes a sticky X
+        const Extraction ex = test_extraction({{1, 2, {"ACDA", "ACDA", "AEDA", "AEHA"}, {0, 0, 1, 1}}}, 1, 1, 2);
+        Candidate c;
+        c.left = 1; c.right = 2; c.coverage = 2; c.raw_len = 4;
+        c.rows = {0, 1, 2, 3};
+        const Alignment al = filter_groups(ex, {c}, 0.6f, 0, 0, SR6, 1);   // columns: C/E polymorphic, D/X
+        if (al.partitions.size() != 1 || std::string(al.concat[0].begin(), al.concat[0].end()) != "C" ||
+            std::string(al.concat[1].begin(), al.concat[1].end()) != "E")
+            return "failed: group_sorting::consensus_rows_by_isolate";
+    }
+    return std::string();
+}
+
 }  // namespace kh

@@ -62,6 +62,8 @@ void index_records(Proteome& p, const uint64_t* hdr, size_t n_rec, uint64_t base
 // protein_prediction.rs:265-294: `--genomes` — one predicted `<name>.faa` per nucleotide FASTA, written to tmp_dir.
 std::vector<SpeciesFile> predict_proteomes(const std::vector<SpeciesFile>& genomes, const std::string& tmp_dir, size_t threads);
 
+std::string extraction_self_test();   // group_extraction.rs protein-name / header checks; empty = passed
+std::string host_logic_self_test();   // group_filtering.rs / group_sorting.rs unit tests on the host functions; empty = passed
 std::string fasta_index_self_test();  // index_records vs parse_proteome on awkward FASTA texts; empty = passed
 std::string prediction_self_test();   // the reference's unit tests of protein_prediction.rs; empty = all passed
 

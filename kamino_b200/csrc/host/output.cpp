@@ -304,6 +304,10 @@ int cli(int argc, char** argv) {   // main.rs:5-9 + clap surface of lib.rs:119-1
             else if (a == "--self-test") {   // hidden: host-logic unit tests that need no GPU
                 const std::string r = prediction_self_test();
                 if (!r.empty()) throw std::runtime_error("protein prediction self-test " + r);
+                const std::string x = extraction_self_test();
+                if (!x.empty()) throw std::runtime_error("extraction self-test " + x);
+                const std::string h = host_logic_self_test();
+                if (!h.empty()) throw std::runtime_error("host logic self-test " + h);
                 const std::string f = fasta_index_self_test();
                 if (!f.empty()) throw std::runtime_error("FASTA record table self-test " + f);
                 std::printf("self-test ok\n");

@@ -51,9 +51,11 @@ def test_no_gpu_means_error_not_fallback(cli, tmp_path):
 GENOMES = ROOT / "tests" / "golden" / "test_genomes"
 
 
-def test_prediction_unit_tests_of_the_reference(cli):
-    """protein_prediction.rs:1152-1286 restated on the host functions (kamino-b200 --self-test); the same flag
-    checks the record bookkeeping of the device-framed FASTA path against the seq_io-style host parser."""
+def test_reference_unit_tests_on_the_host_logic(cli):
+    """The reference's own unit tests restated on the product's host functions (kamino-b200 --self-test, no GPU):
+    group_filtering.rs:484-693 (every filter_groups case), group_sorting.rs:486-638 (sort / non-overlap / length
+    selection), group_extraction.rs:666-677 (protein names), protein_prediction.rs:1152-1286; plus the record
+    bookkeeping of the device-framed FASTA path against the seq_io-style host parser."""
     r = _run(cli, "--self-test")
     assert r.returncode == 0 and "self-test ok" in r.stdout, r.stderr
 
