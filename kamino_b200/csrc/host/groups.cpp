@@ -218,6 +218,42 @@ std::string consensus_protein_name(const Extraction& ex, const Candidate& c) {
     return out;
 }
 
+// majority recoded state per column of the n x L row matrix, lowest state wins ties, -1 = no valid state
+// (group_filtering.rs:37-67)
+std::vector<int> majority_recoded_consensus(const uint8_t* rows, size_t n, size_t L, Scheme scheme) {
+    std::vector<int> cons(L, -1);
+    for (size_t col = 0; col < L; col++) {
+        size_t cnt[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t s = 0; s < n; s++) {
+            const uint8_t b = rows[s * L + col];
+            if (gap_or_x(b)) continue;
+            const uint8_t rc = recode(b, scheme);
+            if (rc != 255) cnt[rc]++;
+        }
+        size_t best = 0;
+        for (int st = 0; st < 6; st++) if (cnt[st] > best) { best = cnt[st]; cons[col] = st; }
+    }
+    return cons;
+}
+
+// rows with >= mask consecutive recoded mismatches against the consensus are blanked with 'X'
+// (group_filtering.rs:69-113); mask == 0 disables it
+void mask_rows_with_long_divergence(uint8_t* rows, size_t n, size_t L, const std::vector<int>& cons, size_t mask, Scheme scheme) {
+    if (mask == 0) return;
+    for (size_t s = 0; s < n; s++) {
+        uint8_t* row = rows + s * L;
+        size_t run = 0;
+        bool hit = false;
+        for (size_t col = 0; col < L; col++) {
+            if (cons[col] < 0 || gap_or_x(row[col])) { run = 0; continue; }
+            const uint8_t rc = recode(row[col], scheme);
+            if (rc == 255 || int(rc) == cons[col]) { run = 0; continue; }
+            if (++run >= mask) { hit = true; break; }
+        }
+        if (hit) std::memset(row, 'X', L);
+    }
+}
+
 struct Built { std::vector<uint8_t> rows; size_t kept = 0; std::string name; bool ok = false; };
 
 Built build_group(const Extraction& ex, const Candidate& c, size_t n, size_t k, size_t constant, float min_freq,
@@ -238,34 +274,7 @@ Built build_group(const Extraction& ex, const Candidate& c, size_t n, size_t k, 
     }
     if (L < k || L - k <= k) return out;
     const size_t mid0 = k, mid1 = L - k;
-    if (mask > 0) {
-        // majority recoded state per column, lowest state wins ties (group_filtering.rs:37-67)
-        std::vector<int> cons(L, -1);
-        for (size_t col = 0; col < L; col++) {
-            size_t cnt[6] = {0, 0, 0, 0, 0, 0};
-            for (size_t s = 0; s < n; s++) {
-                const uint8_t b = rows[s * L + col];
-                if (gap_or_x(b)) continue;
-                const uint8_t rc = recode(b, scheme);
-                if (rc != 255) cnt[rc]++;
-            }
-            size_t best = 0;
-            for (int st = 0; st < 6; st++) if (cnt[st] > best) { best = cnt[st]; cons[col] = st; }
-        }
-        // rows with >= mask consecutive recoded mismatches are blanked with 'X' (group_filtering.rs:69-113)
-        for (size_t s = 0; s < n; s++) {
-            uint8_t* row = rows.data() + s * L;
-            size_t run = 0;
-            bool hit = false;
-            for (size_t col = 0; col < L; col++) {
-                if (cons[col] < 0 || gap_or_x(row[col])) { run = 0; continue; }
-                const uint8_t rc = recode(row[col], scheme);
-                if (rc == 255 || int(rc) == cons[col]) { run = 0; continue; }
-                if (++run >= mask) { hit = true; break; }
-            }
-            if (hit) std::memset(row, 'X', L);
-        }
-    }
+    if (mask > 0) mask_rows_with_long_divergence(rows.data(), n, L, majority_recoded_consensus(rows.data(), n, L, scheme), mask, scheme);
     const float thresh = 1.0f - min_freq;   // f32 (group_filtering.rs:254,274)
     auto missing_ok = [&](size_t col) {
         size_t miss = 0;
@@ -422,6 +431,25 @@ std::string host_logic_self_test() {
         if (al.partitions.size() != 1 || al.partitions[0].start != 0 || al.partitions[0].end != len - 1 || al.partitions[0].len != len) return where;
         for (size_t s = 0; s < n; s++)
             if (std::string(al.concat[s].begin(), al.concat[s].end()) != fc.want[s]) return where;
+    }
+    {   // group_filtering.rs:414-481: majority_recoded_consensus and mask_rows_with_long_divergence
+        const std::string m = "AAXDDBD--";   // rows AAX / DDB / D--
+        const std::vector<int> got = majority_recoded_consensus(reinterpret_cast<const uint8_t*>(m.data()), 3, 3, SR6);
+        if (got != std::vector<int>{1, 0, -1}) return "failed: group_filtering::majority_recoded_consensus_ignores_missing_invalid_and_ties_by_state_value";
+        struct MaskCase { const char* name; std::string row; std::vector<int> cons; size_t mask; std::string want; };
+        const std::vector<MaskCase> mc = {
+            {"same_recoded_state_differences_are_not_masked", "PPPPP", {0, 0, 0, 0, 0}, 3, "PPPPP"},
+            {"fewer_than_mask_consecutive_recoded_differences_are_not_masked", "ADDAA", {0, 0, 0, 0, 0}, 3, "ADDAA"},
+            {"exactly_mask_consecutive_recoded_differences_mask_entire_row", "ADDDA", {0, 0, 0, 0, 0}, 3, "XXXXX"},
+            {"missing_ambiguous_and_invalid_positions_break_difference_runs", "DDAD-DXBD", {0, 0, 0, 0, 0, 0, 0, 0, 0}, 3, "DDAD-DXBD"},
+            {"consensus_positions_without_valid_recoded_state_break_difference_runs", "DDDDA", {0, 0, -1, 0, 0}, 3, "DDDDA"},
+            {"mask_zero_returns_without_changing_rows", "DDDDD", {0, 0, 0, 0, 0}, 0, "DDDDD"},
+        };
+        for (const MaskCase& c : mc) {
+            std::string row = c.row;
+            mask_rows_with_long_divergence(reinterpret_cast<uint8_t*>(row.data()), 1, row.size(), c.cons, c.mask, SR6);
+            if (row != c.want) return std::string("failed: group_filtering::") + c.name;
+        }
     }
     auto keys_of = [](const std::vector<Candidate>& v) {
         std::vector<std::pair<uint64_t, uint64_t>> k;

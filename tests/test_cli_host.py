@@ -53,7 +53,7 @@ GENOMES = ROOT / "tests" / "golden" / "test_genomes"
 
 def test_reference_unit_tests_on_the_host_logic(cli):
     """The reference's own unit tests restated on the product's host functions (kamino-b200 --self-test, no GPU):
-    group_filtering.rs:484-693 (every filter_groups case), group_sorting.rs:486-638 (sort / non-overlap / length
+    group_filtering.rs:414-693 (consensus, row masking and every filter_groups case), group_sorting.rs:486-638 (sort / non-overlap / length
     selection), group_extraction.rs:666-677 (protein names), protein_prediction.rs:1152-1286; plus the record
     bookkeeping of the device-framed FASTA path against the seq_io-style host parser."""
     r = _run(cli, "--self-test")
