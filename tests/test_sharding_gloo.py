@@ -154,3 +154,34 @@ def _pair_worker(rank, world, port, out_dir):
 def test_two_rank_gloo_pair_counts_gather(tmp_path):
     mp.spawn(_pair_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "pair.txt").read_text() == "ok"
+
+
+def test_row_blocks_and_species_shards_properties():
+    """Randomised invariants of the two partitioners (hypothesis): exact cover, alignment, balance."""
+    from hypothesis import given, settings, strategies as st
+    from kamino_b200 import sharding
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 70_000), st.integers(1, 16))
+    def rows(n, world):
+        blocks = sharding.pair_row_blocks(n, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == n
+        covered = 0
+        for b0, b1 in blocks:
+            assert b0 == covered and b1 >= b0 and b0 % 64 == 0 and (b1 % 64 == 0 or b1 == n)
+            covered = b1
+        nt = (n + 63) // 64
+        work = [sum(nt - t for t in range(b0 // 64, (b1 + 63) // 64)) for b0, b1 in blocks]
+        assert sum(work) == nt * (nt + 1) // 2
+        if nt >= 8 * world:                      # enough row tiles to balance: no rank above 1.5 x the mean
+            assert max(work) <= 1.5 * sum(work) / world
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 16))
+    def species(n, world):
+        parts = [sharding.shard_species(n, world, r) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+    rows()
+    species()
