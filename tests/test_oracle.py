@@ -209,3 +209,35 @@ def test_golden_genomes_with_the_python_predictor(oracle, golden_dir, tmp_path):
     assert pp.gc_model(pp.f32(0.5)) == (576, 400, 549)
     assert pp.length_score(270) == 31 and pp.calibrated_start_term(13, 600) == 6
     assert pp.translate_table11("GTGAAATAGNNN", True) == "MK*X"
+
+
+def test_fasta_reader_agrees_with_the_python_restatement(oracle, tmp_path):
+    """seq_io's record rules restated twice, independently (oracle/fasta_io.cpp and oracle/protein_prediction.py):
+    same records on awkward files.  (The crate itself is not available here: SURVEY 8c, 'parity unpinned'.)"""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import protein_prediction as pp
+    texts = [
+        b">a desc\nACDE\nFGH\n>b\nKLMN\n",
+        b"\n\r\n>a\r\nAC\r\nDE\r\n>b x y\r\n\r\nFG\r\n",
+        b">a\n>b\n\n>c d\nAC>DE\n \t\n>e",
+        b">only header",
+        b"",
+        b"\n\n",
+        b">x>y>z\nMKV\n>w\nLLL",
+        b">a\nAC\n\n\n>b\n\nDE",
+    ]
+    for i, t in enumerate(texts):
+        p = tmp_path / f"t{i}.fa"
+        p.write_bytes(t)
+        res, off = oracle.read_fasta(p)
+        got = [res[int(off[j]):int(off[j + 1])].tobytes() for j in range(len(off) - 1)]
+        want = [r.encode("latin-1") for r in pp.read_records(p)]
+        assert got == want, (i, got, want)
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b"ACDE\n>a\nAC\n")
+    with pytest.raises(Exception):
+        oracle.read_fasta(bad)
+    with pytest.raises(ValueError):
+        pp.read_records(bad)
