@@ -308,4 +308,14 @@ int orc_read_fasta(const char* path, uint8_t* residues, uint64_t cap_res, uint64
     } catch (const std::exception& e) { return fail(e); }
 }
 
+// The reference's unit tests of group_extraction / group_sorting / group_filtering on the oracle's functions
+// (selftest.cpp).  0 = all passed; otherwise the failing test's name is the error message.
+int orc_self_test(void) {
+    try {
+        const std::string r = self_test();
+        if (!r.empty()) throw std::runtime_error("reference unit test failed: " + r);
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 }  // extern "C"

@@ -224,4 +224,8 @@ std::string rs_parent(const std::string& p, bool* has_parent);
 std::string rs_extension(const std::string& file_name);   // "" when none
 std::string rs_file_stem(const std::string& file_name);
 
+// selftest.cpp: the reference's unit tests of the host logic on these functions; "" = all passed,
+// else the name of the first failing reference test
+std::string self_test();
+
 }  // namespace kmo

@@ -196,6 +196,11 @@ class Oracle:
         self._check(self.lib.orc_nj_newick(arr, n, _p(dist), buf, len(buf)))
         return buf.value.decode()
 
+    def self_test(self):
+        """The reference's unit tests of the host logic on the oracle's functions (oracle/selftest.cpp)."""
+        self.lib.orc_self_test.restype = C.c_int
+        self._check(self.lib.orc_self_test())
+
     def read_fasta(self, path):
         nres, nrec = C.c_uint64(), C.c_uint64()
         self._check(self.lib.orc_read_fasta(str(path).encode(), None, 0, C.byref(nres), None, 0, C.byref(nrec)))
