@@ -247,3 +247,44 @@ def test_reference_unit_tests_on_the_oracle(oracle):
     """group_extraction.rs:666-708, group_sorting.rs:438-659 and group_filtering.rs:413-693 — the reference's own
     unit tests of the host logic — restated on the oracle's functions (oracle/selftest.cpp): 36 tests."""
     oracle.self_test()
+
+
+def test_reference_unit_tests_on_the_python_predictor():
+    """protein_prediction.rs:1152-1286 on oracle/protein_prediction.py."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import protein_prediction as pp
+    # lookup_tables_encode_bases_complements_starts_and_stops
+    assert [pp.NT2.get(c) for c in "ACGTNa"] == [0, 1, 2, 3, None, None]
+    assert [pp.COMPLEMENT.get(c, "N") for c in "ATCGan"] == ["T", "A", "G", "C", "t", "N"]
+    assert {pp.codon_index(*c) for c in ("ATG", "GTG", "TTG")} == set(pp.START_BONUS) and pp.codon_index(*"ACG") not in pp.START_BONUS
+    assert {pp.codon_index(*c) for c in ("TAA", "TAG", "TGA")} == set(pp.STOPS) and pp.codon_index(*"TGG") not in pp.STOPS
+    gct, aaa = pp.codon_index(*"GCT"), pp.codon_index(*"AAA")
+
+    def orf(a, b, strand, score, p5=False):
+        return {"start": a, "end": b, "strand": strand, "scan_start": a, "scan_end": b, "p5": p5, "p3": False,
+                "has_start": True, "score": score}
+    # adaptive_model_training_uses_high_scoring_complete_orfs_and_background
+    fwd, orfs = "", []
+    for i in range(pp.ADAPTIVE_MIN_TRAIN_ORFS):
+        orfs.append(orf(len(fwd), len(fwd) + 390, 1, 10_000 - i))
+        fwd += "GCT" * 130
+    for i in range(pp.ADAPTIVE_MIN_TRAIN_ORFS):
+        orfs.append(orf(len(fwd), len(fwd) + 390, 1, i))
+        fwd += "AAA" * 130
+    model = pp.train_adaptive(orfs, fwd, "CCC" * (pp.ADAPTIVE_MIN_TRAIN_ORFS * 130))
+    assert model is not None and model[gct] > 0 and model[aaa] < 0
+    # adaptive_model_training_rejects_insufficient_or_partial_seed_orfs
+    n = pp.ADAPTIVE_MIN_TRAIN_ORFS * pp.ADAPTIVE_TRAIN_MIN_AA
+    assert pp.train_adaptive([orf(0, 360, 1, 0)] * (pp.ADAPTIVE_MIN_TRAIN_ORFS - 1), "ATG" * n, "CAT" * n) is None
+    assert pp.train_adaptive([orf(0, 360, 1, 0, p5=True)] * pp.ADAPTIVE_MIN_TRAIN_ORFS, "ATG" * n, "CAT" * n) is None
+    # adaptive_scores_are_clamped_and_added_per_strand
+    m = [0] * 64
+    m[gct], m[aaa] = 2200, -2200
+    assert pp.adaptive_coding_score("GCT" * 34, m) == 0 and pp.adaptive_coding_score("GCT" * 35, m) == 18
+    assert pp.adaptive_coding_score("AAA" * 35, m) == -18
+    # accumulate_codon_counts_counts_only_complete_valid_codons
+    counts = [0] * 64
+    pp.codon_counts("ATGGCTNNNT", counts)
+    assert counts[pp.codon_index(*"ATG")] == 1 and counts[gct] == 1 and sum(counts) == 2
