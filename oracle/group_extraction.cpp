@@ -132,7 +132,7 @@ void extract_from_valid_segment(const uint8_t* aa, const uint8_t* recoded, size_
     extract_bubble_pairs(aa, start_anchors, end_anchors, length_middle, sid, protein_id, groups, arena);
 }
 
-static void merge_species_extraction(SpeciesExtraction&& ex, RawDirectGroups& groups, BlockArena& arena,
+void merge_species_extraction(SpeciesExtraction&& ex, RawDirectGroups& groups, BlockArena& arena,
                                      std::vector<std::string>& protein_names) {  // :335-357
     size_t protein_offset = protein_names.size();
     if (protein_offset + ex.protein_names.size() > 0xFFFFFFFFull)

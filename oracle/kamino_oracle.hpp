@@ -130,6 +130,8 @@ struct SpeciesExtraction {                                                      
     size_t sid; BlockArena arena; RawDirectGroups groups; std::vector<std::string> protein_names;
 };
 std::string truncate_protein_name(const std::string& raw);                                    // :397-404
+void merge_species_extraction(SpeciesExtraction&& ex, RawDirectGroups& groups, BlockArena& arena,
+                              std::vector<std::string>& protein_names);                       // :335-357
 // Pass 1 for one species over already-parsed records (group_extraction.rs:359-395).
 // Returns the number of k-mers that passed the Bloom filter (CMS increments / CMS_DEPTH).
 uint64_t count_species_records(const std::vector<FastaRecord>& recs, size_t k, uint64_t k_mask,

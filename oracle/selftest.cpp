@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE — the reference's own unit tests of the host logic, restated on the oracle's functions:
-// /root/reference/src/group_extraction.rs:666-708, src/group_sorting.rs:438-659, src/group_filtering.rs:413-693.
+// /root/reference/src/group_extraction.rs:666-748, src/group_sorting.rs:438-659, src/group_filtering.rs:413-693.
 // They pin the oracle where the end-to-end goldens are blind (ties, masking, missingness order, ...).
 // orc_self_test (capi.cpp) returns the name of the first failing reference test, or an empty string.
 #include "kamino_oracle.hpp"
@@ -74,6 +74,45 @@ std::string self_test() {
         ORC_CHECK("group_extraction::block_arena_push_and_get_preserve_exact_bytes",
                   a.len == 3 && b.len == 4 && std::string(arena.get(a), arena.get(a) + 3) == "ACD" &&
                   std::string(arena.get(b), arena.get(b) + 4) == "EFGH");
+    }
+    {   // pending_species_merge_is_deterministic_when_results_arrive_out_of_order (:711-748): results are merged in
+        // species order whatever order they arrive in
+        auto extraction = [](size_t sid, const std::string& protein, const std::string& aa) {
+            SpeciesExtraction e;
+            e.sid = sid;
+            e.groups[{7, 11}] = {BlockObs{uint16_t(sid), 0, e.arena.push(reinterpret_cast<const uint8_t*>(aa.data()), aa.size())}};
+            e.protein_names = {protein};
+            return e;
+        };
+        RawDirectGroups groups;
+        BlockArena arena;
+        std::vector<std::string> names;
+        std::vector<SpeciesExtraction> arrivals;
+        arrivals.push_back(extraction(1, "protein_1", "BBBB"));
+        arrivals.push_back(extraction(0, "protein_0", "AAAA"));
+        arrivals.push_back(extraction(2, "protein_2", "CCCC"));
+        std::vector<std::pair<size_t, SpeciesExtraction>> pending;
+        size_t next_sid = 0;
+        for (SpeciesExtraction& a : arrivals) {
+            pending.emplace_back(a.sid, std::move(a));
+            for (bool merged = true; merged;) {
+                merged = false;
+                for (size_t i = 0; i < pending.size(); i++)
+                    if (pending[i].first == next_sid) {
+                        merge_species_extraction(std::move(pending[i].second), groups, arena, names);
+                        pending.erase(pending.begin() + i);
+                        next_sid++;
+                        merged = true;
+                        break;
+                    }
+            }
+        }
+        const std::vector<BlockObs>& o = groups[{7, 11}];
+        ORC_CHECK("group_extraction::pending_species_merge_is_deterministic_when_results_arrive_out_of_order",
+                  names == std::vector<std::string>{"protein_0", "protein_1", "protein_2"} && o.size() == 3 && o[0].sid == 0 && o[1].sid == 1 &&
+                  o[2].sid == 2 && o[0].protein_id == 0 && o[1].protein_id == 1 && o[2].protein_id == 2 &&
+                  std::string(arena.get(o[0].aa), arena.get(o[0].aa) + 4) == "AAAA" && std::string(arena.get(o[1].aa), arena.get(o[1].aa) + 4) == "BBBB" &&
+                  std::string(arena.get(o[2].aa), arena.get(o[2].aa) + 4) == "CCCC");
     }
     // ---- group_sorting.rs:438-659
     ORC_CHECK("group_sorting::direct_overlap_k_uses_minimum_block_length_below_k_11",

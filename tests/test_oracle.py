@@ -244,8 +244,8 @@ def test_fasta_reader_agrees_with_the_python_restatement(oracle, tmp_path):
 
 
 def test_reference_unit_tests_on_the_oracle(oracle):
-    """group_extraction.rs:666-708, group_sorting.rs:438-659 and group_filtering.rs:413-693 — the reference's own
-    unit tests of the host logic — restated on the oracle's functions (oracle/selftest.cpp): 36 tests."""
+    """group_extraction.rs:666-748, group_sorting.rs:438-659 and group_filtering.rs:413-693 — the reference's own
+    unit tests of the host logic — restated on the oracle's functions (oracle/selftest.cpp): 37 tests."""
     oracle.self_test()
 
 
