@@ -11,7 +11,11 @@
 //     Dayhoff6 + KGB6, alignment / missing / partitions, plus the checked-in NJ tree),
 //     copied as data fixtures under tests/golden/test_3diff;
 //   * the derived known-answer vectors of SURVEY.md §8c (mix64, first 13-mers,
-//     Bloom/CMS indices, 3diff CMS histogram, start/end anchors).
+//     Bloom/CMS indices, 3diff CMS histogram, start/end anchors);
+//   * the reference's own unit tests of the host logic (group_extraction.rs:666-748,
+//     group_sorting.rs:438-659, group_filtering.rs:413-693), restated in selftest.cpp;
+//   * for --genomes (protein_prediction.py, plain Python): the golden tests/data/test_genomes
+//     and the module's unit tests (protein_prediction.rs:1152-1286).
 // Collision / saturation / Bloom-order behaviour is not covered by any reference test
 // ("parity unpinned by the reference's own tests"); it follows the source literally.
 //
