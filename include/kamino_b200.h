@@ -72,10 +72,10 @@ typedef struct kmn_group {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);   /* currently 5 */
+uint32_t kmn_abi_version(void);   /* currently 6 */
 
 /* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
- * proba_filter.rs:129-143), the Bloom first-touch slots and all staged batches.
+ * proba_filter.rs:129-143), the scratch of the Bloom / count-min partition passes and all staged batches.
  * k in 1..=21 (lib.rs:208-218); scheme = KMN_*.  device = CUDA ordinal. */
 int  kmn_create(kmn_ctx** out, int device, int k, int scheme);
 void kmn_destroy(kmn_ctx* ctx);
@@ -167,6 +167,17 @@ int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
 int kmn_exchange_export(kmn_ctx* ctx, uint8_t* acc_handle64, uint8_t* table_handle64);
 int kmn_exchange_setup(kmn_ctx* ctx, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles);
 int kmn_exchange_reduce(kmn_ctx* ctx);
+/* Every in-kernel wait of the exchange is bounded (KMN_EXCHANGE_TIMEOUT_MS, default 30 000): when a peer does
+ * not arrive, kmn_exchange_reduce returns an error that names the rank instead of hanging the GPU; the ranks then
+ * re-run kmn_exchange_setup before exchanging again.  kmn_exchange_abort (callable from ANY host thread while
+ * kmn_exchange_reduce is blocked) makes the waiting kernel give up at once. */
+int kmn_exchange_abort(kmn_ctx* ctx);
+/* Row sums (4 x u64) and a position-sensitive 64-bit hash of the table (the finalized one once finalized):
+ * 40 bytes that let ranks, runs and implementations compare 512 MiB tables.  While no cell saturates,
+ * row_sums4[r] == the number of AtomicCountMinSketch::increment calls (proba_filter.rs:146-168), i.e. the
+ * sum of new_kmers_per_species over everything counted.  hash = sum over cells of cell * mix64(index + 0x51),
+ * index = row * 2^26 + column, arithmetic modulo 2^64 (mix64 = proba_filter.rs:30-37). */
+int kmn_table_checksum(kmn_ctx* ctx, uint64_t* row_sums4, uint64_t* hash);
 /* Block until all work queued on the context's stream has finished. */
 int kmn_synchronize(kmn_ctx* ctx);
 /* CUDA stream of the context (cudaStream_t as void*), for event timing by the caller. */

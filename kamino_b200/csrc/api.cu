@@ -132,7 +132,10 @@ struct kmn_ctx {
     bool exchange_planes = true;          // KMN_EXCHANGE_PLANES=0: exchange whole u16 cells instead
     bool peers_ready = false;
     uint32_t exchange_epoch = 0;          // exchanges run so far (every rank counts alike)
-    DevBuf<uint32_t> xsync;               // [0] go word, [1] finished-CTA counter of exchange_reduce_kernel
+    DevBuf<uint32_t> xsync;               // [0] go word, [1] finished-CTA counter, [2] error word of the exchange kernels
+    uint32_t* xabort_host = nullptr;      // host-mapped abort word (kmn_exchange_abort), read by the spinning kernels
+    uint32_t* xabort_dev = nullptr;
+    uint32_t exchange_timeout_ms = 30000; // KMN_EXCHANGE_TIMEOUT_MS: a rank waits this long for a peer before it gives up
     int exchange_grid = 0;
     std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
@@ -865,8 +868,31 @@ void alloc_exchange_buffers(kmn_ctx* c) {
     if (c->xtab.p) return;
     c->xtab.alloc(kXBytes / sizeof(uint16_t));
     KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
-    c->xsync.alloc(2);
-    KMN_CUDA(cudaMemset(c->xsync.p, 0, 2 * sizeof(uint32_t)));
+    c->xsync.alloc(4);
+    KMN_CUDA(cudaMemset(c->xsync.p, 0, 4 * sizeof(uint32_t)));
+    if (!c->xabort_host) {
+        KMN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->xabort_host), sizeof(uint32_t), cudaHostAllocMapped));
+        *c->xabort_host = 0;
+        KMN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->xabort_dev), c->xabort_host, 0));
+    }
+}
+ExchangeGuard exchange_guard(kmn_ctx* c) {
+    return ExchangeGuard{c->xsync.p + 2, c->xabort_dev, uint64_t(c->exchange_timeout_ms) * 1000000ull};
+}
+// after the exchange kernel has finished: turn a recorded timeout / abort into an error (and re-arm the word)
+void check_exchange_error(kmn_ctx* c) {
+    uint32_t err = 0;
+    KMN_CUDA(cudaMemcpyAsync(&err, c->xsync.p + 2, sizeof err, cudaMemcpyDeviceToHost, c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    if (!err) return;
+    KMN_CUDA(cudaMemsetAsync(c->xsync.p + 2, 0, sizeof(uint32_t), c->stream));
+    KMN_CUDA(cudaStreamSynchronize(c->stream));
+    const uint32_t who = (err & 0xFFu) - 1u;
+    std::string msg = (err & 0x200u) ? "table exchange aborted by the host while waiting for rank "
+                                     : "table exchange timed out after " + std::to_string(c->exchange_timeout_ms) + " ms waiting for rank ";
+    msg += std::to_string(who) + ((err & 0x100u) ? " to finish" : " to arrive");
+    msg += " (peer died or never launched?); call kmn_exchange_setup on every rank before exchanging again";
+    throw std::runtime_error(msg);
 }
 void set_peer_planes(PeerPlanes& pp, int p, void* xbuf) {
     uint8_t* b = static_cast<uint8_t*>(xbuf);
@@ -900,7 +926,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 5; }
+uint32_t kmn_abi_version(void) { return 6; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
@@ -945,6 +971,11 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         c->frame_carry.alloc(1);
         c->n_tiles_dev.alloc(2);
         if (const char* e = std::getenv("KMN_EXCHANGE_PLANES")) c->exchange_planes = std::strtol(e, nullptr, 10) != 0;
+        if (const char* e = std::getenv("KMN_EXCHANGE_TIMEOUT_MS")) {
+            const long v = std::strtol(e, nullptr, 10);
+            if (v < 1 || v > 3600000) throw std::runtime_error("KMN_EXCHANGE_TIMEOUT_MS must be in 1..3600000");
+            c->exchange_timeout_ms = uint32_t(v);
+        }
         if (const char* e = std::getenv("KMN_H2D_CHUNKS")) {   // tuning knob
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
@@ -989,6 +1020,7 @@ void kmn_destroy(kmn_ctx* c) {
     c->batches.clear();
     c->spare.clear();
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->xabort_host) cudaFreeHost(c->xabort_host);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1119,7 +1151,10 @@ int kmn_table_widen(kmn_ctx* c) {
 int kmn_table_device_ptr(kmn_ctx* c, void** ptr) {
     return guarded(c, [&] {
         if (!ptr) throw std::runtime_error("ptr must not be NULL");
-        materialize_table(c);
+        if (c->tab_zero) {   // the lazy zeroing runs on the library's stream: finish it before another stream may touch the table
+            materialize_table(c);
+            KMN_CUDA(cudaStreamSynchronize(c->stream));
+        }
         *ptr = const_cast<uint16_t*>(c->finalized ? c->final_tab : c->tab.p);
     });
 }
@@ -1169,6 +1204,10 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
             c->peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(ptr) + CMS_CELLS);
             set_peer_planes(c->planes, p, ptr);
         }
+        // a (re-)setup is collective: every rank starts again from epoch 0 with clean signal words
+        c->exchange_epoch = 0;
+        KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
+        KMN_CUDA(cudaMemset(c->xsync.p, 0, 4 * sizeof(uint32_t)));
         c->peers_ready = true;
     });
 }
@@ -1178,8 +1217,12 @@ int kmn_exchange_reduce(kmn_ctx* c) {
         if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
         const int world = c->peers.world;
         const bool planes = c->exchange_planes && (world == 2 || world == 4 || world == 8);
-        uint32_t epoch = ++c->exchange_epoch;
+        // the epoch only advances once this rank's kernel was launched: a failure before that must not leave
+        // this rank one exchange ahead of its peers
+        uint32_t epoch = c->exchange_epoch + 1;
         uint32_t* xs = c->xsync.p;
+        ExchangeGuard guard = exchange_guard(c);
+        *c->xabort_host = 0;
         materialize_table(c);
         KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if (planes) {
@@ -1191,7 +1234,7 @@ int kmn_exchange_reduce(kmn_ctx* c) {
                                                                      reinterpret_cast<uint32_t*>(xb + kXOffPBm));
             check_launch(c);
             uint64_t per = PLANE_BLOCKS / uint64_t(world), b0 = per * c->peers.rank, b1 = per * (c->peers.rank + 1);
-            void* args[] = {&c->planes, &b0, &b1, &epoch, &xs};
+            void* args[] = {&c->planes, &b0, &b1, &epoch, &xs, &guard};
             const void* fn = world == 2 ? reinterpret_cast<const void*>(exchange_planes_kernel<2>)
                            : world == 4 ? reinterpret_cast<const void*>(exchange_planes_kernel<4>)
                                         : reinterpret_cast<const void*>(exchange_planes_kernel<8>);
@@ -1203,6 +1246,7 @@ int kmn_exchange_reduce(kmn_ctx* c) {
             }
             KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
             check_launch(c);
+            c->exchange_epoch = epoch;
             planes_join_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(xb + kXOffFLo),
                                                                     reinterpret_cast<const uint4*>(xb + kXOffFHi),
                                                                     reinterpret_cast<const uint32_t*>(xb + kXOffFBm),
@@ -1210,7 +1254,7 @@ int kmn_exchange_reduce(kmn_ctx* c) {
         } else {
             const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(world);   // uint4 = 8 cells
             uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
-            void* args[] = {&c->peers, &v0, &v1, &epoch, &xs};
+            void* args[] = {&c->peers, &v0, &v1, &epoch, &xs, &guard};
             const void* fn;
             switch (world) {
                 case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
@@ -1225,13 +1269,37 @@ int kmn_exchange_reduce(kmn_ctx* c) {
                 c->exchange_grid = c->sm_count * std::min(per_sm, 8);
             }
             KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
+            c->exchange_epoch = epoch;
         }
         check_launch(c);
         KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        check_exchange_error(c);
         KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
         c->final_tab = c->xtab.p;
         c->finalized = true;   // valid once every rank's kernel has finished (caller barriers)
+    });
+}
+
+int kmn_exchange_abort(kmn_ctx* c) {
+    if (!c) { g_err = "NULL context"; return 1; }
+    if (c->xabort_host) *reinterpret_cast<volatile uint32_t*>(c->xabort_host) = 1u;   // any thread; no CUDA call
+    return 0;
+}
+
+int kmn_table_checksum(kmn_ctx* c, uint64_t* row_sums4, uint64_t* hash) {
+    return guarded(c, [&] {
+        if (!row_sums4 || !hash) throw std::runtime_error("NULL argument");
+        const uint16_t* t = c->finalized ? c->final_tab : c->tab.p;
+        if (!c->finalized) materialize_table(c);
+        c->new_counts.ensure(8);
+        KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, 5 * sizeof(unsigned long long), c->stream));
+        table_checksum_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(t), c->new_counts.p);
+        check_launch(c);
+        unsigned long long h[5];
+        KMN_CUDA(cudaMemcpyAsync(h, c->new_counts.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < 4; r++) row_sums4[r] = h[r];
+        *hash = h[4];
     });
 }
 

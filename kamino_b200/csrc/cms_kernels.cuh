@@ -261,6 +261,40 @@ cms_direct_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
     }
 }
 
+// Row sums + a position-sensitive 64-bit hash of the u16 table (sum of cell * mix64(cell index), wrapping):
+// lets ranks / runs compare 512 MiB tables through 40 bytes (kmn_table_checksum).  While nothing saturates,
+// row_sum[r] == number of AtomicCountMinSketch::increment calls (proba_filter.rs:146-168).
+__global__ void __launch_bounds__(256)
+table_checksum_kernel(const uint4* __restrict__ tab, unsigned long long* __restrict__ out /* [4] row sums, [4] hash */) {
+    constexpr uint64_t VEC_PER_ROW = (uint64_t(1) << CMS_WIDTH_LOG2) / 8;
+    unsigned long long sum[4] = {0, 0, 0, 0}, hash = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < CMS_CELLS / 8; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldcs(tab + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        unsigned long long s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+            s += lo + hi;
+            if (lo) hash += lo * mix64(i * 8 + 2 * j + 0x51ull);
+            if (hi) hash += hi * mix64(i * 8 + 2 * j + 1 + 0x51ull);
+        }
+        const int r = int(i / VEC_PER_ROW);
+        sum[0] += r == 0 ? s : 0; sum[1] += r == 1 ? s : 0; sum[2] += r == 2 ? s : 0; sum[3] += r == 3 ? s : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        for (int o = 16; o; o >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+    }
+    for (int o = 16; o; o >>= 1) hash += __shfl_xor_sync(0xffffffffu, hash, o);
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (sum[r]) atomicAdd(out + r, sum[r]);
+        atomicAdd(out + 4, hash);
+    }
+}
+
 // ---- multi-GPU -----------------------------------------------------------------------------------
 // NCCL variant: widen the u16 table to u32 (summable with ncclSum), then clamp the sum back.
 __global__ void __launch_bounds__(256)
@@ -298,6 +332,74 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+// Bounded spin on a signal word: returns false when `limit_ns` passed (or the host raised the abort word)
+// before *p reached `epoch`.  A rank that died, threw in pass 1 or never launched must not hang the other
+// GPUs inside a cooperative kernel: the waiter gives up, records who it waited for and the kernel drains.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct ExchangeGuard {
+    uint32_t* err;                 // device word: 0 = fine, else 1 + rank waited for (| 0x100 epilogue, 0x200 host abort)
+    const uint32_t* abort_flag;    // host-mapped word: non-zero = give up now (kmn_exchange_abort)
+    uint64_t limit_ns;
+};
+__device__ __forceinline__ bool wait_epoch(const uint32_t* p, uint32_t epoch, const ExchangeGuard& g, uint32_t who) {
+    if (ld_acquire_sys(p) >= epoch) return true;
+    const uint64_t t0 = global_ns();
+    for (uint32_t it = 1;; it++) {
+        if (ld_acquire_sys(p) >= epoch) return true;
+        if ((it & 63u) == 0) {
+            if (*reinterpret_cast<const volatile uint32_t*>(g.abort_flag)) { atomicCAS(g.err, 0u, 0x200u | (1u + who)); return false; }
+            if (global_ns() - t0 > g.limit_ns) { atomicCAS(g.err, 0u, 1u + who); return false; }
+            __nanosleep(200);
+        }
+    }
+}
+// prologue shared by both exchange kernels: CTA 0 publishes "my table is complete" to every peer, waits for
+// theirs and releases the other CTAs; returns false (CTA-uniform) when the exchange must be skipped.
+__device__ __forceinline__ bool exchange_prologue(uint32_t* const* flags, int world, int rank, uint32_t epoch,
+                                                  uint32_t* local_sync, const ExchangeGuard& g) {
+    if (blockIdx.x == 0) {
+        if (int(threadIdx.x) < world) {
+            const int q = (rank + int(threadIdx.x)) % world;
+            st_release_sys(flags[q] + rank, epoch);
+            wait_epoch(flags[rank] + q, epoch, g, uint32_t(q));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
+    } else {
+        if (threadIdx.x == 0) {
+            ExchangeGuard g2 = g;
+            g2.limit_ns = 2 * g.limit_ns;   // CTA 0 always releases, at the latest when its own waits give up
+            wait_epoch(local_sync, epoch, g2, uint32_t(rank));
+        }
+        __syncthreads();
+    }
+    return ld_acquire_sys(g.err) == 0;
+}
+// epilogue: the last CTA of this rank publishes "done" and waits for every peer's "done"
+__device__ __forceinline__ void exchange_epilogue(uint32_t* const* flags, int world, int rank, uint32_t epoch,
+                                                  uint32_t* local_sync, const ExchangeGuard& g, bool moved) {
+    __threadfence_system();   // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(local_sync + 1, 1u);
+        if (ticket == gridDim.x - 1) {   // last CTA of this rank
+            local_sync[1] = 0;
+            __threadfence_system();
+            if (!moved) return;          // a failed prologue: nothing was read or written, peers time out on their own
+            for (int p = 0; p < world; p++) st_release_sys(flags[(rank + p) % world] + MAX_PEERS + rank, epoch);
+            for (int p = 0; p < world; p++) {
+                ExchangeGuard g2 = g;
+                g2.err = g.err;
+                if (!wait_epoch(flags[rank] + MAX_PEERS + p, epoch, g2, 0x100u | uint32_t(p))) break;
+            }
+        }
+    }
+}
+
 // WORLD > 0: compile-time rank count; U vectors per thread and iteration, so that WORLD x U 16-byte loads
 // (all peers) are in flight per thread: NVLink round trips are ~2-3 us and one load at a time leaves the
 // links idle.  WORLD == 0: generic loop for other rank counts.
@@ -309,24 +411,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // written its slice into this rank's exchanged table.
 template <int WORLD, int U>
 __global__ void __launch_bounds__(256)
-exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end, uint32_t epoch, uint32_t* local_sync) {
+exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end, uint32_t epoch, uint32_t* local_sync,
+                       ExchangeGuard guard) {
     constexpr int W = WORLD > 0 ? WORLD : 1;
     const int world = pt.world;
-    if (blockIdx.x == 0) {
-        if (int(threadIdx.x) < world) {
-            const int q = (pt.rank + int(threadIdx.x)) % world;
-            st_release_sys(pt.flags[q] + pt.rank, epoch);
-            while (ld_acquire_sys(pt.flags[pt.rank] + q) < epoch) {}
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
-    } else {
-        if (threadIdx.x == 0)
-            while (ld_acquire_sys(local_sync) < epoch) {}
-        __syncthreads();
-    }
+    const bool go = exchange_prologue(pt.flags, world, pt.rank, epoch, local_sync, guard);
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t i0 = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < vec_end; i0 += stride * U) {
+    for (uint64_t i0 = vec_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; go && i0 < vec_end; i0 += stride * U) {
         if (WORLD > 0) {
             uint4 a[U][W];
 #pragma unroll
@@ -361,18 +452,7 @@ exchange_reduce_kernel(PeerTables pt, uint64_t vec_begin, uint64_t vec_end, uint
             }
         }
     }
-    __threadfence_system();   // this thread's peer stores are visible system-wide
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t ticket = atomicAdd(local_sync + 1, 1u);
-        if (ticket == gridDim.x - 1) {   // last CTA of this rank
-            local_sync[1] = 0;
-            __threadfence_system();
-            for (int p = 0; p < world; p++) st_release_sys(pt.flags[(pt.rank + p) % world] + MAX_PEERS + pt.rank, epoch);
-            for (int p = 0; p < world; p++)
-                while (ld_acquire_sys(pt.flags[pt.rank] + MAX_PEERS + p) < epoch) {}
-        }
-    }
+    exchange_epilogue(pt.flags, world, pt.rank, epoch, local_sync, guard, go);
 }
 
 // ---- byte-plane exchange ---------------------------------------------------------------------------
@@ -438,25 +518,15 @@ planes_join_kernel(const uint4* __restrict__ lo, const uint4* __restrict__ hi, c
 
 template <int WORLD>
 __global__ void __launch_bounds__(256)
-exchange_planes_kernel(PeerPlanes pt, uint64_t blk_begin, uint64_t blk_end, uint32_t epoch, uint32_t* local_sync) {
+exchange_planes_kernel(PeerPlanes pt, uint64_t blk_begin, uint64_t blk_end, uint32_t epoch, uint32_t* local_sync,
+                       ExchangeGuard guard) {
     constexpr int W = WORLD;
-    if (blockIdx.x == 0) {   // every rank's planes are complete before anybody loads them
-        if (int(threadIdx.x) < W) {
-            const int q = (pt.rank + int(threadIdx.x)) % W;
-            st_release_sys(pt.flags[q] + pt.rank, epoch);
-            while (ld_acquire_sys(pt.flags[pt.rank] + q) < epoch) {}
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
-    } else {
-        if (threadIdx.x == 0)
-            while (ld_acquire_sys(local_sync) < epoch) {}
-        __syncthreads();
-    }
+    // every rank's planes are complete before anybody loads them
+    const bool go = exchange_prologue(pt.flags, W, pt.rank, epoch, local_sync, guard);
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     // blk_begin, blk_end and stride are multiples of 32: a warp always owns 32 consecutive blocks (one bitmap word)
-    for (uint64_t i = blk_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < blk_end; i += stride) {
+    for (uint64_t i = blk_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; go && i < blk_end; i += stride) {
         uint4 l[W];
         uint32_t bits = 0;
 #pragma unroll
@@ -487,18 +557,7 @@ exchange_planes_kernel(PeerPlanes pt, uint64_t blk_begin, uint64_t blk_end, uint
             if (lane == 0) pt.f_bm[q][i >> 5] = m;
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t ticket = atomicAdd(local_sync + 1, 1u);
-        if (ticket == gridDim.x - 1) {   // last CTA of this rank
-            local_sync[1] = 0;
-            __threadfence_system();
-            for (int p = 0; p < W; p++) st_release_sys(pt.flags[(pt.rank + p) % W] + MAX_PEERS + pt.rank, epoch);
-            for (int p = 0; p < W; p++)
-                while (ld_acquire_sys(pt.flags[pt.rank] + MAX_PEERS + p) < epoch) {}
-        }
-    }
+    exchange_epilogue(pt.flags, W, pt.rank, epoch, local_sync, guard, go);
 }
 
 }  // namespace kmn

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_host_alloc", "kmn_host_free", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
-    "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
+    "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_exchange_abort", "kmn_table_checksum", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     lib.kmn_exchange_export.argtypes = [vp, vp, vp]
     lib.kmn_exchange_setup.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.kmn_exchange_reduce.argtypes = [vp]
+    lib.kmn_exchange_abort.argtypes = [vp]
+    lib.kmn_table_checksum.argtypes = [vp, vp, u64p]
     lib.kmn_synchronize.argtypes = [vp]
     lib.kmn_stream.argtypes = [vp, vpp]
     lib.kmn_scan_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
@@ -254,6 +256,15 @@ class Context:
 
     def exchange_reduce(self):
         self._check(self.lib.kmn_exchange_reduce(self._h))
+
+    def exchange_abort(self):
+        self._check(self.lib.kmn_exchange_abort(self._h))
+
+    def table_checksum(self) -> tuple[np.ndarray, int]:
+        """(row sums [4] u64, position-sensitive 64-bit hash) of the table, reduced on the device."""
+        rows, h = np.zeros(4, np.uint64), C.c_uint64()
+        self._check(self.lib.kmn_table_checksum(self._h, _ptr(rows), C.byref(h)))
+        return rows, int(h.value)
 
     def stream(self) -> int:
         p = C.c_void_p()

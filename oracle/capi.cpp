@@ -3,6 +3,7 @@
 // The batch layout mirrors the product ABI (include/kamino_b200.h) so that the parity tests
 // feed byte-identical inputs to both sides.
 #include "kamino_oracle.hpp"
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -277,6 +278,52 @@ int orc_nj_newick(const char* const* names, uint32_t n, const double* dist_nxn, 
         std::string s = nj_newick_from_matrix(nm, d);
         if (s.size() + 1 > cap) throw std::runtime_error("newick buffer too small");
         std::memcpy(out, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// merge_species_extraction (group_extraction.rs:335-357) + select_unique_best_supported_length
+// (group_sorting.rs:90-143) on n observations given in emission order (species-major): the checker of the
+// device grouping (kmn_group_observations).  Groups come out in ascending (left, right); per group:
+// observations, accepted (0/1), best length and coverage (only meaningful when accepted).
+// sel[] (n entries) lists, group after group, the emission indices of the SELECTED observations of the
+// accepted groups; n_sel = how many.
+int orc_group_observations(uint64_t n, const uint64_t* left, const uint64_t* right, const uint32_t* sid,
+                           const uint32_t* len, uint64_t n_species, uint32_t min_needed, int k,
+                           uint64_t* g_left, uint64_t* g_right, uint32_t* g_count, uint32_t* g_ok,
+                           uint32_t* g_len, uint32_t* g_cov, uint64_t cap_groups, uint64_t* n_groups,
+                           uint64_t* sel, uint64_t* n_sel) {
+    try {
+        RawDirectGroups groups;                       // the reference's HashMap<(u64,u64), Vec<BlockObs>>
+        for (uint64_t i = 0; i < n; i++) {
+            if (len[i] > 65535) throw std::runtime_error("block length exceeds u16");   // group_extraction.rs:92-94
+            BlockObs o{uint16_t(sid[i]), 0u, BlockAa{size_t(i), uint16_t(len[i])}};      // aa.start carries the emission index
+            groups[AnchorPair{left[i], right[i]}].push_back(o);
+        }
+        std::vector<AnchorPair> keys;
+        keys.reserve(groups.size());
+        for (auto& kv : groups) keys.push_back(kv.first);
+        std::sort(keys.begin(), keys.end(), [](const AnchorPair& a, const AnchorPair& b) {
+            return a.left != b.left ? a.left < b.left : a.right < b.right;
+        });
+        if (keys.size() > cap_groups) throw std::runtime_error("orc_group_observations: group buffers too small");
+        uint64_t ns = 0;
+        for (size_t g = 0; g < keys.size(); g++) {
+            const auto& obs = groups[keys[g]];
+            RawDirectCandidate c;
+            const bool ok = select_unique_best_supported_length(keys[g], obs, size_t(n_species), size_t(min_needed),
+                                                                size_t(k), c);
+            g_left[g] = keys[g].left;
+            g_right[g] = keys[g].right;
+            g_count[g] = uint32_t(obs.size());
+            g_ok[g] = ok ? 1u : 0u;
+            g_len[g] = ok ? uint32_t(c.raw_len) : 0u;
+            g_cov[g] = ok ? uint32_t(c.coverage) : 0u;
+            if (ok)
+                for (const BlockObs& o : c.selected) sel[ns++] = uint64_t(o.aa.start);
+        }
+        *n_groups = keys.size();
+        *n_sel = ns;
         return 0;
     } catch (const std::exception& e) { return fail(e); }
 }

@@ -175,6 +175,31 @@ class Oracle:
                                               min_needed, length_middle, _p(out), cap, C.byref(n)))
         return out[:n.value]
 
+    def group_observations(self, left, right, sid, length, n_species, min_needed, k):
+        """merge_species_extraction + select_unique_best_supported_length (group_sorting.rs:90-143) on
+        observations in emission order.  Returns (groups, selected): groups = structured array
+        (left, right, count, ok, best_len, coverage) in ascending (left, right); selected = emission
+        indices of the selected observations of the accepted groups, group after group."""
+        left = np.ascontiguousarray(left, np.uint64); right = np.ascontiguousarray(right, np.uint64)
+        sid = np.ascontiguousarray(sid, np.uint32); length = np.ascontiguousarray(length, np.uint32)
+        n = left.size
+        cap = max(n, 1)
+        gl, gr = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        gc, gok, glen, gcov = (np.zeros(cap, np.uint32) for _ in range(4))
+        sel = np.zeros(cap, np.uint64)
+        ng, ns = C.c_uint64(), C.c_uint64()
+        self.lib.orc_group_observations.argtypes = [C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint32, C.c_int] + \
+            [C.c_void_p] * 6 + [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.orc_group_observations(n, _p(left), _p(right), _p(sid), _p(length), n_species, min_needed, k,
+                                                    _p(gl), _p(gr), _p(gc), _p(gok), _p(glen), _p(gcov), cap,
+                                                    C.byref(ng), _p(sel), C.byref(ns)))
+        g = ng.value
+        groups = np.zeros(g, dtype=[("left", "<u8"), ("right", "<u8"), ("count", "<u4"), ("ok", "<u4"),
+                                    ("best_len", "<u4"), ("coverage", "<u4")])
+        groups["left"], groups["right"], groups["count"] = gl[:g], gr[:g], gc[:g]
+        groups["ok"], groups["best_len"], groups["coverage"] = gok[:g], glen[:g], gcov[:g]
+        return groups, sel[:ns.value].copy()
+
     # --nj
     def pair_counts(self, mapped: np.ndarray, threads=8):
         mapped = np.ascontiguousarray(mapped, np.uint8)

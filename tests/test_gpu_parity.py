@@ -375,6 +375,94 @@ def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
         _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
 
 
+def _host_threads():
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _check_pass2_species(ffi, oracle, ctx, bid, b, table, species_ids, k, scheme, min_needed, length_middle=35):
+    """Hits, occupancy and anchor pairs of some species of a scanned + paired batch against the oracle."""
+    cms = oracle.cms_from_table(table)
+    try:
+        for s in species_ids:
+            r0, r1 = int(b.sp_rec_off[s]), int(b.sp_rec_off[s + 1])
+            ws, we, wocc = oracle.scan_species(cms, b.residues, b.rec_off, r0, r1, k, scheme, min_needed)
+            gs, ge = ctx.fetch_hits(bid, s)
+            gocc = ctx.fetch_occupancy(bid, s)
+            assert np.array_equal(gocc, wocc[:len(gocc)]), f"occupancy differs (species {s})"
+            assert np.array_equal(gs, ws), f"start candidates differ (species {s})"
+            assert np.array_equal(ge, we), f"end anchors differ (species {s})"
+            wp = oracle.pair_species(cms, b.residues, b.rec_off, r0, r1, k, scheme, min_needed, length_middle)
+            assert np.array_equal(ctx.fetch_pairs(bid, s), wp), f"anchor pairs differ (species {s})"
+    finally:
+        oracle.cms_free(cms)
+
+
+def test_full_size_c1_equals_oracle(ffi, oracle):
+    """BASELINE.json configs[1] at FULL size (100 synthetic bacterial proteomes, 1.2e8 residues): the 512 MiB
+    count-min table, the per-species new-k-mer counts, and pass 2 (occupancy, boundary hits, anchor pairs) of
+    five species are bit-identical to the oracle's (extract_groups stages 1-4, group_extraction.rs:527-608)."""
+    species = synth.bacterial(100)
+    b = synth.stage(species)
+    k, scheme = 13, SR6
+    min_needed = oracle.min_needed(0.85, 100)
+    assert min_needed == 85
+    h = oracle.cmsa_new()
+    try:
+        want_new = oracle.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, k, scheme, threads=_host_threads())
+        want = oracle.cmsa_table(h)
+        with ffi.Context(k, scheme) as ctx:
+            bid, got_new = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+            ctx.finalize_table()
+            got = ctx.table_snapshot()
+            assert got_new.tolist() == want_new.tolist(), "per-species new k-mer counts differ from the oracle"
+            assert np.array_equal(got, want), "count-min table differs from the oracle at full size"
+            assert int(got.astype(np.uint64).sum()) == 4 * int(want_new.sum())       # nothing saturates at C1
+            ctx.scan_batch(bid, min_needed)
+            ctx.pair_batch(bid, 35)
+            _check_pass2_species(ffi, oracle, ctx, bid, b, want, (0, 1, 37, 63, 99), k, scheme, min_needed)
+    finally:
+        oracle.cmsa_free(h)
+
+
+def test_c3_shape_eukaryotic_multi_batch_equals_oracle(ffi, oracle):
+    """BASELINE.json configs[3] shape: eukaryotic proteomes (20 k proteins x ~500 aa, ~1e7 residues each: the
+    Bloom filter ends a proteome 15-25 % full, so false positives matter, proba_filter.rs:59-74) counted in
+    THREE batches that accumulate into one table (apply pass: overwrite, then read-modify-write twice).
+    24 species, 2.4e8 residues: table, counts and pass 2 of four species equal the oracle's."""
+    species = synth.eukaryotic(24)
+    k, scheme = 13, SR6
+    min_needed = oracle.min_needed(0.85, len(species))
+    cuts = [0, 9, 17, 24]
+    batches = [synth.stage(species[a:z]) for a, z in zip(cuts[:-1], cuts[1:])]
+    whole = synth.stage(species)
+    h = oracle.cmsa_new()
+    try:
+        want_new = oracle.count_batch(h, whole.residues, whole.rec_off, whole.sp_rec_off, k, scheme, threads=_host_threads())
+        want = oracle.cmsa_table(h)
+        # the regime this test is about: a visible share of the occurrences is filtered by the Bloom filter
+        assert int(want_new.sum()) < 0.93 * whole.n_residues
+        with ffi.Context(k, scheme) as ctx:
+            ids, got_new = [], []
+            for bt in batches:
+                bid, n = ctx.count_batch(bt.residues, bt.rec_off, bt.sp_rec_off)
+                ids.append(bid)
+                got_new.append(n)
+            ctx.finalize_table()
+            got = ctx.table_snapshot()
+            assert np.concatenate(got_new).tolist() == want_new.tolist()
+            assert np.array_equal(got, want), "count-min table differs from the oracle (3 accumulating batches)"
+            for bid, bt, sp_ids in ((ids[0], batches[0], (0, 8)), (ids[2], batches[2], (3, 6))):
+                ctx.scan_batch(bid, min_needed)
+                ctx.pair_batch(bid, 35)
+                _check_pass2_species(ffi, oracle, ctx, bid, bt, want, sp_ids, k, scheme, min_needed)
+    finally:
+        oracle.cmsa_free(h)
+
+
 def test_full_size_properties_100_proteomes(ffi, monkeypatch):
     """BASELINE.json configs[1] at full size (100 synthetic bacterial proteomes, 1.2e8 residues), checked
     through size-independent properties of the path instead of the (slow) oracle: the table is invariant
@@ -454,7 +542,7 @@ def _group_reference(left, right, sid, length, min_needed, k):
 
 
 @pytest.mark.parametrize("n,n_keys,seed", [(1, 1, 0), (5000, 40, 1), (200_000, 3000, 2), (70_000, 70_000, 3)])
-def test_group_observations(ffi, n, n_keys, seed):
+def test_group_observations(ffi, oracle, n, n_keys, seed):
     rng = np.random.default_rng(seed)
     k = 13
     pool_l = rng.integers(0, 1 << 39, n_keys, dtype=np.uint64)
@@ -470,6 +558,22 @@ def test_group_observations(ffi, n, n_keys, seed):
     want_perm, want = _group_reference(left, right, sid, length, 3, k)
     assert np.array_equal(perm, want_perm)
     assert len(groups) == len(want)
+    # the oracle's own merge + select_unique_best_supported_length (group_sorting.rs:90-143)
+    og, osel = oracle.group_observations(left, right, sid, length, 60, 3, k)
+    assert len(og) == len(groups)
+    first = groups["first"].astype(np.int64)
+    assert np.array_equal(left[perm[first]], og["left"]) and np.array_equal(right[perm[first]], og["right"])
+    assert np.array_equal(groups["count"], og["count"])
+    assert np.array_equal(groups["flags"] & ffi.GROUP_VALID, og["ok"])
+    ok = og["ok"] == 1
+    assert np.array_equal(groups["best_len"][ok], og["best_len"][ok]) and np.array_equal(groups["coverage"][ok], og["coverage"][ok])
+    # selected observations (block length == best length, emission order inside the group)
+    got_sel = []
+    for g in groups[ok]:
+        idx = perm[int(g["first"]):int(g["first"]) + int(g["count"])]
+        got_sel.append(idx[length[idx] == g["best_len"]])
+    got_sel = np.concatenate(got_sel) if got_sel else np.zeros(0, np.int64)
+    assert np.array_equal(got_sel.astype(np.uint64), osel)
     for g, w in zip(groups, want):
         assert not (int(g["flags"]) & ffi.GROUP_HOST)
         assert (int(g["first"]), int(g["count"])) == w[:2]

@@ -288,3 +288,43 @@ def test_reference_unit_tests_on_the_python_predictor():
     counts = [0] * 64
     pp.codon_counts("ATGGCTNNNT", counts)
     assert counts[pp.codon_index(*"ATG")] == 1 and counts[gct] == 1 and sum(counts) == 2
+
+
+def test_oracle_grouping_matches_a_numpy_restatement(oracle):
+    """orc_group_observations (the K7 checker: merge_species_extraction + select_unique_best_supported_length,
+    group_extraction.rs:335-357, group_sorting.rs:90-143) against an independent numpy/python restatement."""
+    rng = np.random.default_rng(5)
+    n, n_keys, k = 30_000, 900, 13
+    pool_l = rng.integers(0, 1 << 39, n_keys, dtype=np.uint64)
+    pool_r = rng.integers(0, 1 << 39, n_keys, dtype=np.uint64)
+    pick = rng.integers(0, n_keys, n)
+    sid = np.sort(rng.integers(0, 40, n)).astype(np.uint32)
+    length = (27 + rng.choice([0, 0, 0, 1, 5, 30], n)).astype(np.uint32)
+    length[rng.random(n) < 0.02] = 20
+    left, right = pool_l[pick], pool_r[pick]
+    groups, sel = oracle.group_observations(left, right, sid, length, 40, 3, k)
+    order = np.lexsort((np.arange(n), right, left))
+    heads = np.ones(n, bool)
+    heads[1:] = (left[order][1:] != left[order][:-1]) | (right[order][1:] != right[order][:-1])
+    firsts = np.flatnonzero(heads)
+    assert len(groups) == firsts.size
+    want_sel = []
+    for g, i0 in enumerate(firsts):
+        i1 = firsts[g + 1] if g + 1 < firsts.size else n
+        idx = order[i0:i1]
+        by_len = {}
+        for o in idx:
+            by_len.setdefault(int(length[o]), set()).add(int(sid[o]))
+        best_len, best_c, tie = 0, 0, False
+        for l, sp in by_len.items():
+            if len(sp) > best_c:
+                best_len, best_c, tie = l, len(sp), False
+            elif len(sp) == best_c:
+                tie = True
+        ok = (not tie) and best_c >= 3 and best_len >= 2 * k + 1
+        assert int(groups["count"][g]) == i1 - i0 and int(groups["ok"][g]) == int(ok)
+        assert (int(groups["left"][g]), int(groups["right"][g])) == (int(left[idx[0]]), int(right[idx[0]]))
+        if ok:
+            assert (int(groups["best_len"][g]), int(groups["coverage"][g])) == (best_len, best_c)
+            want_sel.append(idx[length[idx] == best_len])
+    assert np.array_equal(np.concatenate(want_sel).astype(np.uint64), sel)
