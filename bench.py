@@ -8,9 +8,15 @@
 A "step" is one pass of the hot path over one batch: 100 synthetic bacterial proteomes per GPU
 (BASELINE.json configs[1]) -> recode/frame, exact per-species Bloom, count-min build into the
 saturating u16 table (+ at N>1 the table exchange: fused NVLink peer kernel, or NCCL sum).
-  value : residues/s, inputs already resident in HBM (kmn_count_staged + kmn_finalize_table)
-  e2e   : residues/s through the C ABI from pinned HOST buffers (kmn_count_batch: H2D inside the
-          timed region) + finalize + D2H of the per-species new-k-mer counts
+  value     : residues/s, inputs already resident in HBM (kmn_count_staged + kmn_finalize_table)
+  e2e       : residues/s through the C ABI from pinned HOST buffers (kmn_count_batch: H2D inside the
+              timed region) + finalize + D2H of the per-species new-k-mer counts
+  roofline  : whole pass 1 against the measured HBM copy bandwidth: algorithmic fraction (frac), hardware DRAM
+              fraction (dram_fraction, from the committed ncu capture) and a per-kernel table
+  pass2, nj : BASELINE.md 3's secondary metrics (occupancy scan residues/s, --nj pair-columns/s), N = 1
+  checks    : asserted before timing: same table hash on every rank, row sums == new k-mers, and (N > 1) a
+              small sharded case equal to the oracle's table
+  strong_c2 : BASELINE.json configs[2] as ONE job (1,000 proteomes round-robin over the N GPUs, one exchange)
 The CPU oracle is only ever used here for the cpu_baseline / --impl reference legs.
 """
 from __future__ import annotations
@@ -33,6 +39,8 @@ METRIC = "residues/sec k-mer table build"
 UNIT = "residues/s"
 K, SCHEME_NAME, SCHEME = 13, "sr6", 1
 N_SPECIES = int(os.environ.get("KMN_BENCH_SPECIES", "100"))   # proteomes per GPU (weak scaling); 100 = BASELINE configs[1]
+WORKLOAD = f"{N_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa), k={K}, {SCHEME_NAME}"   # identical in both arms
+C2_SPECIES = int(os.environ.get("KMN_BENCH_C2_SPECIES", "1000"))   # BASELINE configs[2]: the strong-scaling job
 
 
 # stdout carries the ONE JSON line and nothing else: libraries that chat on fd 1 (NCCL prints its version
@@ -207,7 +215,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{N_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa), k={K}, {SCHEME_NAME}",
+        "config": {"workload": WORKLOAD,
                    "note": "C++ restatement of kamino 2.0.0 (not the Rust binary: no cargo/rustc in the image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,6 +229,180 @@ class _DevArray:
 
     def __init__(self, ptr: int, n: int, typestr: str):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def verify_table(ctx, world, rank, local_rank, new, exchange_and_finalize):
+    """Asserted BEFORE anything is timed (the table is the one the last warm-up step left behind):
+      * every rank holds the same table (64-bit position-sensitive hash, reduced on the device);
+      * per count-min row, sum(cells) == sum over all ranks of the new k-mers (proba_filter.rs:146-168 adds 1 to one
+        cell per row and new k-mer; holds while nothing saturates, which the bench workloads never do);
+      * N > 1: a small species set sharded over the ranks and exchanged equals the single-process oracle table."""
+    import torch
+    import torch.distributed as dist
+    rows, h = ctx.table_checksum()
+    total_new = int(new.sum())
+    hashes = [h]
+    if world > 1:
+        t = torch.tensor([total_new], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        total_new = int(t.item())
+        hashes = [None] * world
+        dist.all_gather_object(hashes, h)
+    assert len(set(hashes)) == 1, f"ranks hold different tables after the exchange: {hashes}"
+    assert [int(x) for x in rows] == [total_new] * 4, f"row sums {rows.tolist()} != new k-mers {total_new}"
+    out = {"table_hash": f"{h:016x}", "identical_on_all_ranks": True, "row_sums_equal_new_kmers": total_new}
+    if world > 1:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle_ffi
+        from kamino_b200 import sharding, synth
+        small = synth.stage(synth.bacterial(2 * world + 1, seed=99, n_prot=200, mean_len=150.0))
+        mine = sharding.shard_species(small.n_sp, world, rank)
+        res, rec, sp = sharding.select_species(small.residues, small.rec_off, small.sp_rec_off, mine)
+        ctx.reset_table()
+        ctx.count_batch(res, rec, sp)
+        exchange_and_finalize()
+        got = ctx.table_snapshot() if rank == 0 else None
+        _, h_small = ctx.table_checksum()
+        hs = [None] * world
+        dist.all_gather_object(hs, h_small)
+        assert len(set(hs)) == 1, "ranks hold different tables (small oracle case)"
+        if rank == 0:
+            orc = oracle_ffi.load()
+            hh = orc.cmsa_new()
+            try:
+                orc.count_batch(hh, small.residues, small.rec_off, small.sp_rec_off, K, SCHEME, threads=4)
+                assert np.array_equal(got, orc.cmsa_table(hh)), "exchanged table differs from the oracle's"
+            finally:
+                orc.cmsa_free(hh)
+        ctx.release_batches()
+        out["small_case_equals_oracle"] = f"{small.n_sp} species over {world} ranks"
+    log(f"[rank {rank}] table checks passed: {out}")
+    return out
+
+
+def secondary_legs(ctx, batch, h_res, h_rec, h_sp):
+    """BASELINE.md 3 secondary metrics in the same JSON line: pass-2 residues/s (occupancy scan + boundary hits,
+    then anchor pairing and grouping) on the bench workload and --nj pair-columns/s (n = 2000, L = 100000)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    ctx.reset_table()
+    bid, _ = ctx.count_batch(h_res, h_rec, h_sp)
+    ctx.finalize_table()
+    min_needed = int(np.ceil(np.float32(0.85) * np.float32(batch.n_sp)))
+    for _ in range(2):
+        ns, ne = ctx.scan_batch(bid, min_needed)
+    scan = []
+    for _ in range(5):
+        ctx.scan_batch(bid, min_needed)
+        scan.append(ctx.stage_ms("scan"))
+    pair = []
+    for _ in range(3):
+        n_pairs = ctx.pair_batch(bid, 35)
+        pair.append(ctx.stage_ms("pair_batch"))
+    grp_ms, n_groups, n_valid = None, None, None
+    if hasattr(ctx, "group_batches"):
+        for _ in range(3):
+            n_obs, n_groups, n_valid = ctx.group_batches([bid], min_needed)
+            grp_ms = ctx.stage_ms("group_observations")
+    scan_ms, pair_ms = float(np.median(scan)), float(np.median(pair))
+    pass2 = {"value": batch.n_residues / (scan_ms * 1e-3), "unit": UNIT, "scan_ms": scan_ms, "starts": int(ns), "ends": int(ne),
+             "pair_batch_ms": pair_ms, "anchor_pairs": int(n_pairs), "group_ms": grp_ms, "groups": n_groups,
+             "groups_passing_length_selection": n_valid, "min_needed": min_needed,
+             "algorithmic_bytes_per_residue": 1 + 8 * 0.96 + 2 * 0.96}
+    ctx.release_batches()
+    rng = np.random.default_rng(1)
+    n, L = 2000, 100_000
+    from kamino_b200 import synth
+    base = rng.choice(20, size=L, p=synth.LG_PI).astype(np.uint8)
+    m = np.tile(base, (n, 1))
+    mut = rng.random((n, L)) < 0.05
+    m[mut] = rng.integers(0, 20, int(mut.sum()), dtype=np.uint8)
+    m[rng.random((n, L)) < 0.05] = 20
+    ctx.pair_counts(m[:64])
+    ks, cs = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.pair_counts(m)
+        cs.append((time.perf_counter() - t0) * 1e3)
+        ks.append(ctx.stage_ms("pair_counts"))
+    k_ms, c_ms = float(np.median(ks)), float(np.median(cs))
+    pairs = n * (n - 1) // 2
+    nj = {"value": pairs * L / (k_ms * 1e-3), "unit": "pair-columns/s", "n": n, "L": L, "kernel_ms": k_ms, "call_ms": c_ms,
+          "call_value": pairs * L / (c_ms * 1e-3)}
+    return pass2, nj
+
+
+def strong_scaling_c2(ctx, world, rank, local_rank, barrier, exchange_and_finalize, args):
+    """BASELINE.json configs[2]: ONE job of 1,000 synthetic bacterial proteomes, species round-robin over the
+    ranks, one table exchange per job.  Reported next to the weak-scaling headline (driver: strong_c2.value at
+    N vs N = 1).  Every rank generates the same species set (same seed) and keeps its share."""
+    import torch
+    import torch.distributed as dist
+    from kamino_b200 import sharding, synth
+    t0 = time.time()
+    species = synth.bacterial(C2_SPECIES, seed=synth.SEED0 + 2)
+    mine = [species[i] for i in sharding.shard_species(len(species), world, rank)]
+    n_res_job = int(sum(int(s.lens.sum()) for s in species))
+    del species
+    batch = synth.stage(mine)
+    log(f"[rank {rank}] strong C2: {len(mine)} of {C2_SPECIES} species, {batch.n_residues} residues ({time.time() - t0:.0f}s to generate)")
+    pin_res = torch.empty(batch.residues.size, dtype=torch.uint8).pin_memory()
+    pin_res.numpy()[:] = batch.residues
+    h_res = pin_res.numpy()
+    h_rec, h_sp = batch.rec_off, batch.sp_rec_off
+    steps = max(1, min(args.steps, 5))
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        barrier()
+        ev0.record(lib_stream)
+        for _ in range(n):
+            fn()
+        ev1.record(lib_stream)
+        barrier()
+        dt = ev0.elapsed_time(ev1) * 1e-3
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    bid = ctx.stage_batch(h_res, h_rec, h_sp)
+    state = {}
+
+    def job_resident():
+        ctx.reset_table()
+        state["new"] = ctx.count_staged(bid, batch.n_sp)
+        exchange_and_finalize()
+
+    def job_e2e():
+        ctx.reset_table()
+        _, state["new"] = ctx.count_batch(h_res, h_rec, h_sp)
+        exchange_and_finalize()
+        ctx.release_batches()
+
+    job_resident()
+    # the job's table: identical on every rank, row sums == new k-mers of the whole job
+    rows, h = ctx.table_checksum()
+    tot = torch.tensor([int(state["new"].sum())], device="cuda", dtype=torch.int64)
+    hs = [h]
+    if world > 1:
+        dist.all_reduce(tot)
+        hs = [None] * world
+        dist.all_gather_object(hs, h)
+    assert len(set(hs)) == 1, "strong C2: ranks hold different tables"
+    assert [int(x) for x in rows] == [int(tot.item())] * 4, "strong C2: row sums != new k-mers"
+    dt = timed(job_resident, steps)
+    ctx.release_batches()
+    job_e2e()
+    dt_e2e = timed(job_e2e, steps)
+    return {"workload": f"{C2_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa), k={K}, {SCHEME_NAME}, "
+                        f"species round-robin over {world} GPU(s), one table exchange per job",
+            "scaling": "strong", "residues": n_res_job, "jobs_timed": steps,
+            "value": n_res_job * steps / dt, "unit": UNIT, "ms_per_job": 1e3 * dt / steps,
+            "e2e": {"value": n_res_job * steps / dt_e2e, "unit": UNIT, "ms_per_job": 1e3 * dt_e2e / steps,
+                    "h2d_bytes_per_job_per_gpu": int(batch.residues.size + h_rec.nbytes + h_sp.nbytes)},
+            "table_hash": f"{h:016x}", "row_sums_equal_new_kmers": int(tot.item())}
 
 
 def run_gpu(args):
@@ -302,11 +484,12 @@ def run_gpu(args):
     for _ in range(args.warmup):
         new = step_resident()
     u = float(new.sum()) / batch.n_residues
+    checks = verify_table(ctx, world, rank, local_rank, new, exchange_and_finalize)
     sampler.wait_first()
 
     # ---- timed: resident inputs
     stage_acc = {"frame": 0.0, "bloom": 0.0, "cms": 0.0, "finalize": 0.0, "cms_partition_kernel": 0.0,
-                 "bloom_bucket_kernel": 0.0}
+                 "bloom_bucket_kernel": 0.0, "bloom_partition_kernel": 0.0, "cms_apply_kernel": 0.0}
     launches0 = ctx.launch_count()
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -352,52 +535,86 @@ def run_gpu(args):
     h2d = int(batch.residues.size + batch.rec_off.nbytes + batch.sp_rec_off.nbytes)
     d2h = int(batch.n_sp * 8 + (batch.n_sp + 1) * 4)
 
-    # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream)
-    # cms_partition_kernel (one launch per step) is the longest kernel of pass 1: it hashes every k-mer that
-    # passed the Bloom filter into its 4 count-min cells and splits them over 4096 shared-memory-sized
-    # buckets.  SURVEY.md 8d: pass 1 moves B1 = 1 + 16u algorithmic bytes per residue (1 residue byte +
-    # 4 cells x (2 B read + 2 B write) per passing k-mer); the launch carries all of them for the batch.
+    # ---- roofline (BASELINE.md 3 / SURVEY.md 8d): the WHOLE pass over the measured copy bandwidth.
+    # Algorithmic bytes of pass 1: B1 = 1 + 16u per residue (1 residue byte + 4 cells x (2 B read + 2 B write) per
+    # k-mer that passes the Bloom filter; u measured).  frac = B1 * residues / step time / peak.  dram_fraction is
+    # the same with the bytes the DRAM actually moved (sum of ncu dram__bytes_{read,write}.sum over the step's
+    # kernels, captured once per code change: profiles/roofline_traffic.json).  The per-kernel table charges every
+    # kernel ITS OWN algorithmic bytes against ITS OWN time (CUDA events of the library around single launches).
     peak, peak_src = measured_peaks()
     stage_ms = {s: v / args.steps for s, v in stage_acc.items()}
-    alg_bytes = (1.0 + 16.0 * u) * batch.n_residues
-    dom_ms = stage_ms["cms_partition_kernel"]
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    pass1_ms = stage_ms["frame"] + stage_ms["bloom"] + stage_ms["cms"] + stage_ms["finalize"]
-    traffic = None
+    step_ms = 1e3 * elapsed / args.steps
+    n_res, n_pos = batch.n_residues, batch.n_residues + len(batch.rec_off) - 1
+    alg_bytes = (1.0 + 16.0 * u) * n_res
+    traffic_tab, traffic_src = {}, None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text())["cms_partition_kernel"]["dram_bytes_per_launch"]
+            traffic_tab = json.loads(tp.read_text())
+            traffic_src = traffic_tab.get("_source")
         except Exception:
-            traffic = None
-    roofline = {
-        "bound": "hbm", "kernel": "cms_partition_kernel", "launches_per_step": 1, "achieved": achieved,
-        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "algorithmic_bytes_per_launch": alg_bytes,
-        "new_kmer_fraction_u": u, "kernel_ms_per_launch": dom_ms, "stage_ms": stage_ms,
-        "whole_pass1_frac": alg_bytes / (pass1_ms * 1e-3) / 1e9 / peak,
-        "note": "integer path: every pass-1 kernel is bound by instruction issue / shared-memory atomics, not by "
-                "HBM bytes (ncu: issue slots 65-77 % busy, DRAM < 10 %); see DESIGN.md 4",
+            traffic_tab = {}
+    own = {   # algorithmic bytes of one launch of each kernel group (own inputs + own outputs, no sector rounding)
+        "frame": ("frame_count + frame_scatter (+ scans)", float(batch.residues.size) * 2 + n_pos),       # raw bytes read twice, codes written
+        "bloom_partition_kernel": ("bloom_partition_kernel", n_pos * (1 + 8.0)),                          # code in, 2 probes x 4 B out
+        "bloom_bucket_kernel": ("bloom_bucket_kernel", n_pos * (8.0 + 0.25)),                             # probes in, 2 lost bits out
+        "cms_partition_kernel": ("cms_partition_kernel", n_pos * 1.25 + 8.0 * u * n_res),                 # code + lost bits in, 4 x 2 B entries out
+        "cms_apply_kernel": ("cms_apply_kernel", 8.0 * u * n_res + 2.0 * ffi.CMS_CELLS),                  # entries in, every cell written (first batch after a reset)
     }
+    kernels = []
+    for key, (name, nbytes) in own.items():
+        ms = stage_ms[key]
+        tr = None
+        for part in name.replace("(+ scans)", "").replace("+", " ").split():
+            if part in traffic_tab:
+                tr = (tr or 0) + traffic_tab[part]["dram_bytes_per_launch"]
+        kernels.append({"kernel": name, "ms": ms, "share_of_step": ms / step_ms if step_ms else None,
+                        "algorithmic_bytes": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9 if ms else None,
+                        "frac": nbytes / (ms * 1e-3) / 1e9 / peak if ms else None, "traffic": tr,
+                        "dram_fraction": tr / (ms * 1e-3) / 1e9 / peak if (tr and ms) else None})
+    traffic = sum(k["traffic"] for k in kernels if k["traffic"]) if any(k["traffic"] for k in kernels) else None
+    dominant = max(kernels, key=lambda k: k["ms"])
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "pass 1: every kernel of a step (frame, Bloom partition + buckets, count-min partition + apply)",
+        "launches_per_step": int(launches // max(args.steps, 1)),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "dram_fraction": traffic / (step_ms * 1e-3) / 1e9 / peak if traffic else None,
+        "traffic_over_algorithmic": traffic / alg_bytes if traffic else None, "traffic_source": traffic_src,
+        "peak_source": peak_src, "algorithmic_bytes_per_residue": 1.0 + 16.0 * u, "algorithmic_bytes_per_step": alg_bytes,
+        "new_kmer_fraction_u": u, "ms_per_step": step_ms, "dominant_kernel": dominant["kernel"], "kernels": kernels,
+        "limiter": "instruction issue and shared-memory atomics, not DRAM bytes (ncu --set full summaries under profiles/): "
+                   "the roofline is stated against HBM because the path has no floating-point work",
+    }
+
+    # ---- secondary legs of BASELINE.md 3 (same process, after the timed regions): pass 2 and --nj
+    pass2 = nj = None
+    if world == 1 and not args.profile:
+        pass2, nj = secondary_legs(ctx, batch, h_res, h_rec, h_sp)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
         threads = host_threads()
-        n_res, dt, _, n_sp = cpu_pass1(batch, threads, n_species=8)
+        n_res_c, dt, _, n_sp = cpu_pass1(batch, threads, n_species=8)
         n_sample = int(max(8, min(N_SPECIES, 15.0 / max(dt / n_sp, 1e-6))))
-        n_res, dt, _, n_sp = cpu_pass1(batch, threads, n_species=n_sample)
-        cpu_baseline = {"value": n_res / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n_sp} of {N_SPECIES} species ({n_res} residues), pass 1 + snapshot, "
+        n_res_c, dt, _, n_sp = cpu_pass1(batch, threads, n_species=n_sample)
+        cpu_baseline = {"value": n_res_c / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n_sp} of {N_SPECIES} species ({n_res_c} residues), pass 1 + snapshot, "
                                   "C++ restatement of kamino 2.0.0"}
+
+    strong = None
+    if args.strong:
+        ctx.release_batches()
+        strong = strong_scaling_c2(ctx, world, rank, local_rank, barrier, exchange_and_finalize, args)
 
     if rank == 0:
         emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{N_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa) per GPU, k={K}, {SCHEME_NAME}",
+            "config": {"workload": WORKLOAD, "per_gpu": True,
                        "residues_per_gpu": batch.n_residues, "species_per_gpu": batch.n_sp,
-                       "l2": "per step the kernels stream 122 MB of residues, ~2 GB of partition lists and the 512 MiB "
+                       "l2": "per step the kernels stream 122 MB of residues, ~3 GB of partition slots and the 512 MiB "
                              "table: far beyond the 126 MB L2; no explicit flush",
                        "exchange": "none (1 GPU)" if world == 1 else (
                            ("fused NVLink peer kernel on byte planes: reduce-scatter + saturate + all-gather, in-kernel rank sync"
@@ -410,6 +627,10 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "pass2": pass2,
+            "nj": nj,
+            "checks": checks,
+            "strong_c2": strong,
         })
     ctx.close()
     if world > 1:
@@ -425,8 +646,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="resident leg only (for ncu): no e2e, no CPU baseline")
+    ap.add_argument("--strong", dest="strong", action="store_true", default=None,
+                    help="also run the strong-scaling job of BASELINE configs[2] (1,000 proteomes over the N GPUs); "
+                         "default: on (KMN_BENCH_STRONG=0 or --no-strong turns it off)")
+    ap.add_argument("--no-strong", dest="strong", action="store_false")
     args = ap.parse_args()
     claim_stdout()
+    if args.strong is None:
+        args.strong = os.environ.get("KMN_BENCH_STRONG", "1") != "0"
+    if args.profile:
+        args.strong = False
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)

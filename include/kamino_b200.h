@@ -167,6 +167,15 @@ int kmn_table_device_ptr(kmn_ctx* ctx, void** ptr);
 int kmn_exchange_export(kmn_ctx* ctx, uint8_t* acc_handle64, uint8_t* table_handle64);
 int kmn_exchange_setup(kmn_ctx* ctx, int world, int rank, const uint8_t* acc_handles, const uint8_t* table_handles);
 int kmn_exchange_reduce(kmn_ctx* ctx);
+/* The same exchange when ONE host process drives several GPUs (the drop-in for the reference's -t N species
+ * parallelism, group_extraction.rs:550-567 / :589-608: species shard over the devices, one exchange per job):
+ * ctxs[r] is the context of rank r, each created on its own device.  kmn_exchange_setup_local enables peer
+ * access between the devices and wires the ranks' buffers directly (no IPC handles); kmn_exchange_reduce_all
+ * queues every rank's exchange kernel and then waits for all of them (same kernels, same in-kernel rank
+ * synchronisation as kmn_exchange_reduce).  Calls on different contexts may otherwise run on different host
+ * threads at the same time (pass 1 and pass 2 of each device's own species). */
+int kmn_exchange_setup_local(kmn_ctx* const* ctxs, int world);
+int kmn_exchange_reduce_all(kmn_ctx* const* ctxs, int world);
 /* Every in-kernel wait of the exchange is bounded (KMN_EXCHANGE_TIMEOUT_MS, default 30 000): when a peer does
  * not arrive, kmn_exchange_reduce returns an error that names the rank instead of hanging the GPU; the ranks then
  * re-run kmn_exchange_setup before exchanging again.  kmn_exchange_abort (callable from ANY host thread while
@@ -240,7 +249,8 @@ int kmn_pair_counts_device(kmn_ctx* ctx, const uint32_t** valid, const uint32_t*
  * context, per stage, measured with CUDA events on the context's stream.
  * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts,
  *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1),
- *        8 pair_batch, 9 group_observations (kernels only). */
+ *        8 pair_batch, 9 group_observations (kernels only),
+ *        10 bloom_partition_kernel alone, 11 cms_apply_kernel (+ the idle spill / direct launches) alone. */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

@@ -47,6 +47,19 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Tuning builds (tools/ only): the same sources with -D overrides, as _lib/libkamino_b200_<name>.so
+    (loaded through the KAMINO_B200_LIB environment variable)."""
+    LIB_DIR.mkdir(exist_ok=True)
+    out = LIB_DIR / f"libkamino_b200_{name}.so"
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(INCLUDE), "-o", str(out), *map(str, sources())]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed building {out.name}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB_PATH

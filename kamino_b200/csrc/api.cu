@@ -156,17 +156,17 @@ struct kmn_ctx {
     DevBuf<uint32_t> fa_tile_hdr, fa_tile_base, fa_err;
     DevBuf<uint32_t> nj_valid, nj_mism;   // counts of the last pair_counts call (kmn_pair_counts_device)
     uint32_t nj_rows = 0, nj_n = 0;
-    float stage_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
     DevBuf<uint16_t> bl_cnt;
     uint32_t bloom_run_cap = RUN_CAP;     // test knob KMN_BLOOM_RUN_CAP: small slots force the slow exact path
-    DevBuf<uint16_t> cms_ent;             // bucket lists of the CMS partition (scratch of count_staged)
-    DevBuf<uint32_t> cms_cursor, cms_spill, cms_state, cms_tile_sp, cms_tile0;
+    DevBuf<uint16_t> cms_ent;             // (bucket, tile) slots of the CMS partition (scratch of count_staged)
+    DevBuf<uint32_t> cms_running, cms_spill, cms_state, cms_tile_sp, cms_tile0;
     int cms_force = 0;                    // test knob: 1 = exact (u32) redo in every bucket, 2 = direct fallback
-    uint32_t cms_cap_override = 0;        // test knob: bucket list capacity (forces the list-full fallback)
-    uint32_t cms_slot_limit = PART_SLOT;  // test knob: staged entries per bucket and tile (forces spills)
+    uint32_t cms_cap_override = 0;        // test knob: spill list capacity (forces the spill-full fallback)
+    uint32_t cms_slot_limit = PART_SLOT_CAP;  // test knob: staged entries per bucket and tile (forces spills)
 };
 
 namespace {
@@ -181,6 +181,32 @@ void check_launch(kmn_ctx* c) {
 }
 
 int grid_for(kmn_ctx* c, int ctas_per_sm) { return c->sm_count * ctas_per_sm; }
+
+// TMA descriptor of the partition's slot array ent[CMS_BUCKETS][tiles_cap][PART_SLOT] (u16): one box = the slots
+// of 256 consecutive buckets for one tile.  cuTensorMapEncodeTiled is resolved through the runtime, so the
+// library does not link against libcuda.
+CUtensorMap make_slots_map(uint16_t* ent, uint32_t tiles_cap) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        KMN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {PART_SLOT, tiles_cap, CMS_BUCKETS};
+    const cuuint64_t strides[2] = {PART_SLOT * sizeof(uint16_t), uint64_t(tiles_cap) * PART_SLOT * sizeof(uint16_t)};
+    const cuuint32_t box[3] = {PART_SLOT, 1, PART_BOX_BUCKETS};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ent, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+    return m;
+}
 
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total) on the context's stream: one CTA for short arrays,
 // per-tile sums + their scan + per-tile scans for long ones.
@@ -439,7 +465,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
 
     BloomRuns R{};
     CmsTiles T{};
-    CmsLists L{};
+    CmsSlots L{};
+    CUtensorMap slots_map{};
     if (!frame_only) {
         c->new_counts.ensure(size_t(b.n_sp) + 1);
         KMN_CUDA(cudaMemsetAsync(c->new_counts.p, 0, (size_t(b.n_sp) + 1) * sizeof(unsigned long long), c->stream));
@@ -473,20 +500,22 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         T.tile_sp = c->cms_tile_sp.p;
         T.sp_tile0 = c->cms_tile0.p;
         T.n_tiles = c->n_tiles_dev.p + 1;
-        // expected list length <= codes / 1024 (every position passes, uniform hashing); +25 % and a constant
-        // cover the correlation between species that share k-mers.  A full list is not an error: the batch
-        // then takes the exact direct path (cms_direct_kernel).
+        // one fixed slot per (bucket, tile): the tiles of all ranges of the batch, each range bounded like its grid.
+        // A slot that overflows spills single entries; a full spill list is not an error: the batch then takes
+        // the exact direct path (cms_direct_kernel).
         const uint64_t all_codes = b.n_raw + b.n_rec;
-        L.cap = c->cms_cap_override ? c->cms_cap_override
-                                    : uint32_t((all_codes / CMS_BUCKETS_PER_ROW * 5 / 4 + 4096 + 7) / 8 * 8);
-        L.spill_cap = uint32_t(all_codes / 64 + 65536);
-        c->cms_ent.ensure(size_t(CMS_BUCKETS) * L.cap);
+        uint64_t tiles_cap = 0;
+        for (const SpeciesRange& r : ranges) tiles_cap += r.codes_bound / PART_TILE + 2 * uint64_t(r.s1 - r.s0) + 2;
+        L.tiles_cap = uint32_t(tiles_cap);
+        L.spill_cap = c->cms_cap_override ? c->cms_cap_override : uint32_t(all_codes / 64 + 65536);
+        c->cms_ent.ensure(size_t(CMS_BUCKETS) * L.tiles_cap * PART_SLOT);
         c->cms_spill.ensure(L.spill_cap);
         L.ent = c->cms_ent.p;
-        L.cursor = c->cms_cursor.p;
+        L.running = c->cms_running.p;
         L.spill = c->cms_spill.p;
         L.state = c->cms_state.p;
-        KMN_CUDA(cudaMemsetAsync(L.cursor, 0, CMS_BUCKETS * sizeof(uint32_t), c->stream));
+        slots_map = make_slots_map(L.ent, L.tiles_cap);
+        KMN_CUDA(cudaMemsetAsync(c->cms_running.p, 0, 2 * sizeof(uint32_t), c->stream));
         KMN_CUDA(cudaMemsetAsync(L.state, 0, 2 * sizeof(uint32_t), c->stream));
     }
 
@@ -532,8 +561,9 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         const uint32_t n_sp_r = r.s1 - r.s0;
         const uint32_t bl_bound = uint32_t(r.codes_bound / BP_TILE) + 2 * n_sp_r + 2;
         species_tiles_kernel<<<2, 1024, 0, c->stream>>>(b.sp_cstart.p, r.s0, r.s1,
-                                                      TilesJob{BP_TILE_WT, c->bl_tile0.p, c->bl_tile_sp.p, c->n_tiles_dev.p},
-                                                      TilesJob{PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p, c->n_tiles_dev.p + 1});
+                                                      TilesJob{BP_TILE_WT, c->bl_tile0.p, c->bl_tile_sp.p, c->n_tiles_dev.p, nullptr},
+                                                      TilesJob{PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p, c->n_tiles_dev.p + 1,
+                                                               c->cms_running.p});
         check_launch(c);
         bloom_partition_kernel<<<bl_bound, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
         check_launch(c);
@@ -550,7 +580,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         const uint32_t cms_bound = uint32_t(r.codes_bound / PART_TILE) + 2 * n_sp_r + 2;
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[6], c->stream));
         cms_partition_kernel<<<std::min<uint32_t>(cms_bound, uint32_t(c->sm_count)), PART_THREADS, PART_SMEM, c->stream>>>(
-            b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
+            slots_map, b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[7], c->stream));
     }
@@ -593,7 +623,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     b.scanned = false;
     if (!frame_only && new_kmers_per_species)
         for (uint32_t s = 0; s < b.n_sp; s++) new_kmers_per_species[s] = counted ? h[s] : 0;
-    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = c->stage_ms[6] = c->stage_ms[7] = 0.f;
+    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = c->stage_ms[6] = c->stage_ms[7] = c->stage_ms[10] = c->stage_ms[11] = 0.f;
     if (timed && !frame_only) {
         KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]));
         if (counted) {
@@ -601,6 +631,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[2], c->ev[2], c->ev[3]));
             KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[6], c->ev[6], c->ev[7]));
             KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[7], c->ev[8], c->ev[9]));
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[10], c->ev[1], c->ev[8]));
+            KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[11], c->ev[7], c->ev[3]));
         }
     }
 }
@@ -954,12 +986,12 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         }
         if (const char* e = std::getenv("KMN_CMS_SLOT")) {    // test knob: small slots -> many spills
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 1 || v > PART_SLOT) throw std::runtime_error("KMN_CMS_SLOT must be in 1..32");
+            if (v < 1 || v > PART_SLOT_CAP) throw std::runtime_error("KMN_CMS_SLOT must be in 1..31");
             c->cms_slot_limit = uint32_t(v);
         }
-        if (const char* e = std::getenv("KMN_CMS_CAP")) {     // test knob: tiny bucket lists
+        if (const char* e = std::getenv("KMN_CMS_CAP")) {     // test knob: tiny spill list
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 8 || v > (1l << 30) || v % 8) throw std::runtime_error("KMN_CMS_CAP must be a multiple of 8");
+            if (v < 1 || v > (1l << 30)) throw std::runtime_error("KMN_CMS_CAP must be in 1..2^30");
             c->cms_cap_override = uint32_t(v);
         }
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -999,7 +1031,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BB_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BS_SMEM)));
         c->tab.alloc(CMS_CELLS);
-        c->cms_cursor.alloc(CMS_BUCKETS);
+        c->cms_running.alloc(2);
         c->cms_state.alloc(2);
         KMN_CUDA(cudaFuncSetAttribute(cms_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PART_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(cms_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(APPLY_SMEM)));
@@ -1208,76 +1240,168 @@ int kmn_exchange_setup(kmn_ctx* c, int world, int rank, const uint8_t* acc_handl
         c->exchange_epoch = 0;
         KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
         KMN_CUDA(cudaMemset(c->xsync.p, 0, 4 * sizeof(uint32_t)));
+        KMN_CUDA(cudaDeviceSynchronize());   // cudaMemset runs on the legacy stream, which the context's non-blocking streams do not wait for
         c->peers_ready = true;
     });
 }
 
+// The exchange of one rank in two halves, so that one host thread can drive several GPUs (kmn_exchange_reduce_all):
+// launch_exchange queues this rank's kernels (asynchronous: the kernel itself waits for the peers' kernels),
+// finish_exchange waits for them and turns a recorded timeout into an error.
+static void launch_exchange(kmn_ctx* c) {
+    if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
+    const int world = c->peers.world;
+    const bool planes = c->exchange_planes && (world == 2 || world == 4 || world == 8);
+    // the epoch only advances once this rank's kernel was launched: a failure before that must not leave
+    // this rank one exchange ahead of its peers
+    uint32_t epoch = c->exchange_epoch + 1;
+    uint32_t* xs = c->xsync.p;
+    ExchangeGuard guard = exchange_guard(c);
+    *c->xabort_host = 0;
+    materialize_table(c);
+    KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (planes) {
+        // byte planes: split this rank's table, reduce + scatter planes over NVLink, rebuild the u16 table
+        uint8_t* xb = reinterpret_cast<uint8_t*>(c->xtab.p);
+        planes_split_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->tab.p),
+                                                                 reinterpret_cast<uint4*>(xb + kXOffPLo),
+                                                                 reinterpret_cast<uint4*>(xb + kXOffPHi),
+                                                                 reinterpret_cast<uint32_t*>(xb + kXOffPBm));
+        check_launch(c);
+        uint64_t per = PLANE_BLOCKS / uint64_t(world), b0 = per * c->peers.rank, b1 = per * (c->peers.rank + 1);
+        void* args[] = {&c->planes, &b0, &b1, &epoch, &xs, &guard};
+        const void* fn = world == 2 ? reinterpret_cast<const void*>(exchange_planes_kernel<2>)
+                       : world == 4 ? reinterpret_cast<const void*>(exchange_planes_kernel<4>)
+                                    : reinterpret_cast<const void*>(exchange_planes_kernel<8>);
+        if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
+            int per_sm = 0;
+            KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+            if (per_sm < 1) throw std::runtime_error("exchange_planes_kernel does not fit on an SM");
+            c->exchange_grid = c->sm_count * std::min(per_sm, 8);
+        }
+        KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
+        check_launch(c);
+        c->exchange_epoch = epoch;
+        planes_join_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(xb + kXOffFLo),
+                                                                reinterpret_cast<const uint4*>(xb + kXOffFHi),
+                                                                reinterpret_cast<const uint32_t*>(xb + kXOffFBm),
+                                                                reinterpret_cast<uint4*>(c->xtab.p));
+    } else {
+        const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(world);   // uint4 = 8 cells
+        uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
+        void* args[] = {&c->peers, &v0, &v1, &epoch, &xs, &guard};
+        const void* fn;
+        switch (world) {
+            case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
+            case 4: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<4, 2>); break;
+            case 8: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<8, 2>); break;
+            default: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<0, 1>); break;
+        }
+        if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
+            int per_sm = 0;
+            KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+            if (per_sm < 1) throw std::runtime_error("exchange_reduce_kernel does not fit on an SM");
+            c->exchange_grid = c->sm_count * std::min(per_sm, 8);
+        }
+        KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
+        c->exchange_epoch = epoch;
+    }
+    check_launch(c);
+    KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+}
+
+static void finish_exchange(kmn_ctx* c) {
+    check_exchange_error(c);   // synchronises the stream
+    KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
+    c->final_tab = c->xtab.p;
+    c->finalized = true;       // valid once every rank's kernel has finished
+}
+
 int kmn_exchange_reduce(kmn_ctx* c) {
     return guarded(c, [&] {
-        if (!c->peers_ready) throw std::runtime_error("kmn_exchange_setup has not been called");
-        const int world = c->peers.world;
-        const bool planes = c->exchange_planes && (world == 2 || world == 4 || world == 8);
-        // the epoch only advances once this rank's kernel was launched: a failure before that must not leave
-        // this rank one exchange ahead of its peers
-        uint32_t epoch = c->exchange_epoch + 1;
-        uint32_t* xs = c->xsync.p;
-        ExchangeGuard guard = exchange_guard(c);
-        *c->xabort_host = 0;
-        materialize_table(c);
-        KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        if (planes) {
-            // byte planes: split this rank's table, reduce + scatter planes over NVLink, rebuild the u16 table
-            uint8_t* xb = reinterpret_cast<uint8_t*>(c->xtab.p);
-            planes_split_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->tab.p),
-                                                                     reinterpret_cast<uint4*>(xb + kXOffPLo),
-                                                                     reinterpret_cast<uint4*>(xb + kXOffPHi),
-                                                                     reinterpret_cast<uint32_t*>(xb + kXOffPBm));
-            check_launch(c);
-            uint64_t per = PLANE_BLOCKS / uint64_t(world), b0 = per * c->peers.rank, b1 = per * (c->peers.rank + 1);
-            void* args[] = {&c->planes, &b0, &b1, &epoch, &xs, &guard};
-            const void* fn = world == 2 ? reinterpret_cast<const void*>(exchange_planes_kernel<2>)
-                           : world == 4 ? reinterpret_cast<const void*>(exchange_planes_kernel<4>)
-                                        : reinterpret_cast<const void*>(exchange_planes_kernel<8>);
-            if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
-                int per_sm = 0;
-                KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
-                if (per_sm < 1) throw std::runtime_error("exchange_planes_kernel does not fit on an SM");
-                c->exchange_grid = c->sm_count * std::min(per_sm, 8);
-            }
-            KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
-            check_launch(c);
-            c->exchange_epoch = epoch;
-            planes_join_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(xb + kXOffFLo),
-                                                                    reinterpret_cast<const uint4*>(xb + kXOffFHi),
-                                                                    reinterpret_cast<const uint32_t*>(xb + kXOffFBm),
-                                                                    reinterpret_cast<uint4*>(c->xtab.p));
-        } else {
-            const uint64_t n_vec = CMS_CELLS / 8, per = n_vec / uint64_t(world);   // uint4 = 8 cells
-            uint64_t v0 = per * c->peers.rank, v1 = per * (c->peers.rank + 1);
-            void* args[] = {&c->peers, &v0, &v1, &epoch, &xs, &guard};
-            const void* fn;
-            switch (world) {
-                case 2: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<2, 4>); break;
-                case 4: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<4, 2>); break;
-                case 8: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<8, 2>); break;
-                default: fn = reinterpret_cast<const void*>(exchange_reduce_kernel<0, 1>); break;
-            }
-            if (c->exchange_grid == 0) {   // every CTA must be resident: the ranks synchronise inside the kernel
-                int per_sm = 0;
-                KMN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
-                if (per_sm < 1) throw std::runtime_error("exchange_reduce_kernel does not fit on an SM");
-                c->exchange_grid = c->sm_count * std::min(per_sm, 8);
-            }
-            KMN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->exchange_grid), dim3(256), args, 0, c->stream));
-            c->exchange_epoch = epoch;
-        }
-        check_launch(c);
-        KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
-        check_exchange_error(c);
-        KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
-        c->final_tab = c->xtab.p;
-        c->finalized = true;   // valid once every rank's kernel has finished (caller barriers)
+        launch_exchange(c);
+        finish_exchange(c);
     });
+}
+
+// ---- in-process multi-GPU: one host process drives `world` contexts, one per device -------------------------
+int kmn_exchange_setup_local(kmn_ctx* const* ctxs, int world) {
+    try {
+        if (!ctxs || world < 1 || world > MAX_PEERS) throw std::runtime_error("invalid context list");
+        if (CMS_CELLS / 8 % uint64_t(world)) throw std::runtime_error("world size must divide the table");
+        for (int r = 0; r < world; r++) {
+            if (!ctxs[r]) throw std::runtime_error("NULL context");
+            for (int q = 0; q < r; q++)
+                if (ctxs[q]->device == ctxs[r]->device) throw std::runtime_error("every rank needs its own device");
+        }
+        for (int r = 0; r < world; r++) {   // peer access in both directions, exchange buffers
+            DeviceGuard dg(ctxs[r]->device);
+            for (int q = 0; q < world; q++) {
+                if (q == r) continue;
+                int can = 0;
+                KMN_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device));
+                if (!can) throw std::runtime_error("device " + std::to_string(ctxs[r]->device) + " cannot access device " +
+                                                   std::to_string(ctxs[q]->device) + " (no peer path)");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+                else KMN_CUDA(e);
+            }
+            alloc_exchange_buffers(ctxs[r]);
+        }
+        for (int r = 0; r < world; r++) {
+            kmn_ctx* c = ctxs[r];
+            DeviceGuard dg(c->device);
+            for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+            c->ipc_opened.clear();
+            c->peers = PeerTables{};
+            c->peers.world = world;
+            c->peers.rank = r;
+            c->planes = PeerPlanes{};
+            c->planes.world = world;
+            c->planes.rank = r;
+            for (int p = 0; p < world; p++) {   // same address space: the peers' buffers are used as they are
+                c->peers.part[p] = reinterpret_cast<const uint4*>(ctxs[p]->tab.p);
+                c->peers.full[p] = reinterpret_cast<uint4*>(ctxs[p]->xtab.p);
+                c->peers.flags[p] = reinterpret_cast<uint32_t*>(ctxs[p]->xtab.p + CMS_CELLS);
+                set_peer_planes(c->planes, p, ctxs[p]->xtab.p);
+            }
+            c->exchange_epoch = 0;
+            KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
+            KMN_CUDA(cudaMemset(c->xsync.p, 0, 4 * sizeof(uint32_t)));
+            KMN_CUDA(cudaDeviceSynchronize());
+            c->peers_ready = true;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+int kmn_exchange_reduce_all(kmn_ctx* const* ctxs, int world) {
+    try {
+        if (!ctxs || world < 1) throw std::runtime_error("invalid context list");
+        // queue every rank's kernels first (each waits inside for the others), then wait for all of them
+        for (int r = 0; r < world; r++) {
+            if (!ctxs[r]) throw std::runtime_error("NULL context");
+            DeviceGuard dg(ctxs[r]->device);
+            launch_exchange(ctxs[r]);
+        }
+        std::string first_err;
+        for (int r = 0; r < world; r++) {
+            try {
+                DeviceGuard dg(ctxs[r]->device);
+                finish_exchange(ctxs[r]);
+            } catch (const std::exception& e) {
+                if (first_err.empty()) first_err = "rank " + std::to_string(r) + ": " + e.what();
+            }
+        }
+        if (!first_err.empty()) throw std::runtime_error(first_err);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
 }
 
 int kmn_exchange_abort(kmn_ctx* c) {
@@ -1417,7 +1541,7 @@ int kmn_pair_counts_device(kmn_ctx* c, const uint32_t** valid, const uint32_t** 
 
 int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
     return guarded(c, [&] {
-        if (which < 0 || which > 9 || !ms) throw std::runtime_error("invalid stage index");
+        if (which < 0 || which > 11 || !ms) throw std::runtime_error("invalid stage index");
         *ms = c->stage_ms[which];
     });
 }

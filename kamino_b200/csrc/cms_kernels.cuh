@@ -9,14 +9,16 @@
 //                         Bloom filter" from the lost map (count_kernels.cuh), keeps the k-mers in
 //                         registers for the four rows and splits the cell indices of one row at a time
 //                         over the row's 1024 buckets of 2^16 cells: rank = shared atomicAdd on the
-//                         bucket's fill counter, the low 16 index bits go to a fixed 32-entry slot in
-//                         shared memory, and each bucket's slot is appended to its global list as one
-//                         run (one global atomicAdd per bucket and tile reserves the space).  Also
-//                         counts the passes per species.
+//                         bucket's fill counter, the low 16 index bits go to the bucket's 32-entry slot of a
+//                         64 KiB staging buffer in shared memory (31 entries + their count), and the whole
+//                         buffer leaves for FIXED (bucket, tile) slots in global memory as four TMA tensor
+//                         stores issued by one thread while the next row is being ranked in the second
+//                         buffer: no reservation atomics, no copy-out instructions.  Also counts the passes
+//                         per species.
 //   cms_apply_kernel      one CTA per bucket: a 128 KiB shared-memory histogram (two u16 counters per
-//                         word) of the bucket's list, then  cell = min(cell + count, 65535)  on the
-//                         u16 table by the bucket's only owner — no global atomics, no u32
-//                         accumulators, no separate snapshot pass.
+//                         word) of the bucket's slots (contiguous over the tiles), then
+//                         cell = min(cell + count, 65535)  on the u16 table by the bucket's only owner —
+//                         no global atomics, no u32 accumulators, no separate snapshot pass.
 //
 // The table itself is the reference's saturating u16 table at all times: every update is +1 and
 // saturation is monotone, so adding a batch's exact per-cell count with a clamp is bit-identical to
@@ -25,35 +27,49 @@
 //
 // Rare paths, all exact: a slot that overflows inside a tile spills single entries to a global list
 // (cms_spill_kernel, CAS loop on the u16 cell); a shared counter that would pass 65535 inside one
-// batch makes the CTA redo its bucket with u32 counters in two halves; a bucket list or spill list
+// batch makes the CTA redo its bucket with u32 counters in two halves; a spill list
 // that runs out of space raises a flag that disables apply/spill and enables cms_direct_kernel,
 // which rebuilds the batch's increments with global CAS loops straight from codes[] + the lost map.
 #pragma once
 #include "kmn_device.cuh"
+#include <cuda.h>   // CUtensorMap (the driver entry point is resolved at run time, nothing links against libcuda)
 
 namespace kmn {
 
 constexpr uint32_t CMS_BUCKET_LOG2 = 16;                                             // cells per bucket
 constexpr uint32_t CMS_BUCKETS_PER_ROW = 1u << (CMS_WIDTH_LOG2 - CMS_BUCKET_LOG2);    // 1024
 constexpr uint32_t CMS_BUCKETS = CMS_DEPTH * CMS_BUCKETS_PER_ROW;                     // 4096
-constexpr int PART_THREADS = 1024;                   // == CMS_BUCKETS_PER_ROW: thread t reserves bucket t
+constexpr int PART_THREADS = 1024;                   // == CMS_BUCKETS_PER_ROW: thread t closes the slot of bucket t
 constexpr int PART_TILE = PART_THREADS * CHUNK;      // 16384 positions per CTA tile
 constexpr int PART_WTILES = PART_TILE / WARP_TILE;   // one warp tile per warp
-constexpr int PART_SLOT = 32;                        // staged entries per bucket and tile (mean 16)
-constexpr size_t PART_SMEM = size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * sizeof(uint16_t) +
-                             size_t(CMS_BUCKETS_PER_ROW) * sizeof(uint32_t);
+constexpr int PART_SLOT = 32;                        // u16 per (tile, bucket) slot: 31 entries (mean 15) + their count
+constexpr int PART_SLOT_CAP = PART_SLOT - 1;
+constexpr int PART_BOX_BUCKETS = 256;                // buckets per TMA store (box dimensions are limited to 256)
+constexpr size_t PART_STAGE_BYTES = size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * sizeof(uint16_t);   // 64 KiB per row
+constexpr size_t PART_SMEM = 2 * PART_STAGE_BYTES + 2 * size_t(CMS_BUCKETS_PER_ROW) * sizeof(uint32_t) + 16;
 constexpr int APPLY_THREADS = 1024;
 constexpr uint32_t APPLY_WORDS = 1u << (CMS_BUCKET_LOG2 - 1);   // 32768 u32 words = 2^16 u16 counters
-constexpr size_t APPLY_SMEM = size_t(APPLY_WORDS) * sizeof(uint32_t);
-static_assert(PART_THREADS == int(CMS_BUCKETS_PER_ROW), "one reserving thread per bucket");
-static_assert(PART_SLOT == 32, "copy-out moves one slot per warp instruction");
+static_assert(PART_THREADS == int(CMS_BUCKETS_PER_ROW), "one closing thread per bucket");
+static_assert(PART_SLOT * sizeof(uint16_t) == 64, "a slot is four 16-byte vectors");
 
-struct CmsLists {
-    uint16_t* ent;      // [CMS_BUCKETS][cap]  low 16 bits of the cell index, in arrival order
-    uint32_t* cursor;   // [CMS_BUCKETS]       entries appended so far
-    uint32_t* spill;    // [spill_cap]         flat cell offsets (row << 26 | idx) of slot overflows
-    uint32_t* state;    // [0] fallback flag, [1] spill entries
-    uint32_t cap, spill_cap;
+// Partition output: FIXED slots.  ent[bucket][tile][32]: the low 16 index bits of the entries of (bucket, tile)
+// in arrival order, entry 31 = their count.  A bucket's slots are contiguous over the tiles, so the apply pass
+// streams them; a tile's 1024 slots of one row leave shared memory as four TMA tensor stores (no reservation
+// atomics, no per-entry copy-out instructions).
+// A slot is a RING of 32 u16 that starts at slot_origin(bucket): ring position i < 31 holds the i-th entry, ring
+// position 31 the count.  Without the rotation the staging stores of a warp (random buckets, similar ranks) pile
+// up on a handful of shared-memory banks (ncu: 80 % of the kernel's shared-memory wavefronts were conflict
+// replays); with it the bank is a function of the bucket.  The apply pass owns one bucket per CTA, so the origin is
+// a CTA constant there.
+__host__ __device__ __forceinline__ uint32_t slot_origin(uint32_t bucket) { return bucket & 30u; }
+
+struct CmsSlots {
+    uint16_t* ent;             // [CMS_BUCKETS][tiles_cap][PART_SLOT]
+    uint32_t tiles_cap;        // slot columns allocated per bucket
+    const uint32_t* running;   // device: [0] first tile index of the current species range, [1] tiles written so far
+    uint32_t* spill;           // [spill_cap] flat cell offsets (row << 26 | idx) of slot overflows
+    uint32_t* state;           // [0] fallback flag, [1] spill entries
+    uint32_t spill_cap;
 };
 
 __host__ __device__ __forceinline__ uint64_t cms_seed(int r) {
@@ -81,17 +97,40 @@ struct CmsTiles {
     const uint32_t* n_tiles;    // device scalar
 };
 
+// ---- TMA (bulk tensor) store of one staged row: shared memory -> the fixed slots in global memory -----------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One CTA per SM, persistent over the tiles.  Per tile the k-mers stay in registers for the four rows; per row
+// every passing k-mer's cell index is ranked inside its bucket by a shared-memory atomicAdd and its low 16 bits
+// land in the bucket's slot of the row's staging buffer; thread b then closes slot b (writes the count) and one
+// elected thread hands the 64 KiB buffer to the TMA unit.  Two staging buffers: the store of row r drains while
+// row r+1 is being ranked.  Two CTA barriers per row.
 __global__ void __launch_bounds__(PART_THREADS, 1)
-cms_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, CmsTiles T,
-                     const uint32_t* __restrict__ lost2, int k, uint64_t k_mask, CmsLists L, uint32_t slot_limit,
-                     unsigned long long* __restrict__ new_per_species) {
-    extern __shared__ __align__(16) uint8_t part_smem[];
-    uint16_t* stage = reinterpret_cast<uint16_t*>(part_smem);                                   // [1024][32]
-    uint32_t* fill = reinterpret_cast<uint32_t*>(part_smem + size_t(CMS_BUCKETS_PER_ROW) * PART_SLOT * 2);   // [1024]
-    __shared__ uint32_t s_new;
+cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_t* __restrict__ codes,
+                     const uint32_t* __restrict__ sp_cstart, CmsTiles T, const uint32_t* __restrict__ lost2, int k,
+                     uint64_t k_mask, CmsSlots L, uint32_t slot_limit, unsigned long long* __restrict__ new_per_species) {
+    extern __shared__ __align__(1024) uint8_t part_smem[];   // TMA sources must be 128-byte aligned
+    uint16_t* stage = reinterpret_cast<uint16_t*>(part_smem);                          // [2][1024][32]
+    uint32_t* fill = reinterpret_cast<uint32_t*>(part_smem + 2 * PART_STAGE_BYTES);    // [2][1024]
+    uint32_t& s_new = fill[2 * CMS_BUCKETS_PER_ROW];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_new = 0;
+    if (threadIdx.x == 0) {
+        if (static_cast<uint32_t>(__cvta_generic_to_shared(part_smem)) & 127u) __trap();
+        s_new = 0;
+    }
+    fill[threadIdx.x] = 0;
+    fill[CMS_BUCKETS_PER_ROW + threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t n_tiles = *T.n_tiles;
+    const uint32_t tile0 = L.running[0];
+    uint32_t buf = 0;
     for (uint32_t tg = blockIdx.x; tg < n_tiles; tg += gridDim.x) {
         const uint32_t s = T.tile_sp[tg];
         const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
@@ -104,20 +143,24 @@ cms_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restri
             if (valid) new_bits = valid & ~both_lost_mask16(__ldcs(lost2 + c0 / CHUNK));
         }
         const uint32_t wn = __reduce_add_sync(0xffffffffu, uint32_t(__popc(new_bits)));
+        if (lane == 0 && wn) atomicAdd(&s_new, wn);
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) kmer[j] = fold30_keep(kmer[j]);   // the registers keep the folded k-mers for the four rows
 #pragma unroll 1
-        for (int r = 0; r < int(CMS_DEPTH); r++) {
-            fill[threadIdx.x] = 0;
-            __syncthreads();
-            if (r == 0 && lane == 0 && wn) atomicAdd(&s_new, wn);
-            const uint64_t seed = cms_seed(r);
+        for (int r = 0; r < int(CMS_DEPTH); r++, buf ^= 1u) {
+            uint16_t* st = stage + size_t(buf) * (PART_STAGE_BYTES / 2);
+            uint32_t* fl = fill + buf * CMS_BUCKETS_PER_ROW;
+            const uint64_t seed = fold30_keep(cms_seed(r));   // (kept: ptxas otherwise re-folds the seed next to every use)
+            // (a branch-free, predicated form of this loop — all 16 hashes first, then the atomics — was measured
+            // slower: 1.27 ms vs 1.05 ms per launch, 64 registers with spills vs 56)
 #pragma unroll
             for (int j = 0; j < CHUNK; j++) {
                 if (!((new_bits >> j) & 1u)) continue;
-                const uint32_t idx = cms_index(kmer[j], seed);
+                const uint32_t idx = cms_index_folded(kmer[j], seed);
                 const uint32_t b = idx >> CMS_BUCKET_LOG2;
-                const uint32_t rank = atomicAdd(&fill[b], 1u);
+                const uint32_t rank = atomicAdd(&fl[b], 1u);
                 if (rank < slot_limit) {
-                    stage[b * PART_SLOT + rank] = uint16_t(idx);
+                    st[b * PART_SLOT + ((slot_origin(b) + rank) & (PART_SLOT - 1))] = uint16_t(idx);
                 } else {   // slot full: rare single-entry spill
                     const uint32_t sp = atomicAdd(L.state + 1, 1u);
                     if (sp < L.spill_cap) L.spill[sp] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
@@ -125,27 +168,30 @@ cms_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restri
                 }
             }
             __syncthreads();
-            if (r == 0 && threadIdx.x == 0 && s_new) {   // this tile's adds precede the barrier above, the next tile's follow later ones
-                atomicAdd(new_per_species + s, static_cast<unsigned long long>(s_new));
-                s_new = 0;
-            }
-            // thread b reserves the run of bucket b; warp w then copies the slots of buckets 32w..32w+31
-            uint32_t n = min(fill[threadIdx.x], slot_limit), base = 0;
-            const uint32_t gb = uint32_t(r) * CMS_BUCKETS_PER_ROW + threadIdx.x;
-            if (n) {
-                base = atomicAdd(L.cursor + gb, n);
-                if (base + n > L.cap) { L.state[0] = 1u; n = 0; }   // list full: the batch falls back
-            }
-            uint16_t* out = L.ent + size_t(uint32_t(r) * CMS_BUCKETS_PER_ROW + warp * 32u) * L.cap + lane;
-#pragma unroll 4
-            for (int q = 0; q < 32; q++) {
-                const uint32_t nb = __shfl_sync(0xffffffffu, n, q);
-                const uint32_t bb = __shfl_sync(0xffffffffu, base, q);
-                if (lane < nb) out[size_t(q) * L.cap + bb] = stage[(warp * 32u + uint32_t(q)) * PART_SLOT + lane];
+            // thread b closes slot b; the other buffer's counters (read one row ago) are cleared for the next row
+            st[threadIdx.x * PART_SLOT + ((slot_origin(threadIdx.x) + PART_SLOT_CAP) & (PART_SLOT - 1))] =
+                uint16_t(min(fl[threadIdx.x], slot_limit));
+            fill[(buf ^ 1u) * CMS_BUCKETS_PER_ROW + threadIdx.x] = 0;
+            fence_proxy_async_smem();
+            if (threadIdx.x == 0) {
+                if (r == 0 && s_new) {   // this tile's adds precede the barrier above, the next tile's follow the one below
+                    atomicAdd(new_per_species + s, static_cast<unsigned long long>(s_new));
+                    s_new = 0;
+                }
+                tma_wait_read_all();     // the previous row's store has left the other buffer
             }
             __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(st));
+#pragma unroll
+                for (int q = 0; q < int(CMS_BUCKETS_PER_ROW) / PART_BOX_BUCKETS; q++)
+                    tma_store_3d(&slots_map, a + q * (PART_BOX_BUCKETS * PART_SLOT * 2), 0, int(tile0 + tg),
+                                 r * int(CMS_BUCKETS_PER_ROW) + q * PART_BOX_BUCKETS);
+                tma_commit();
+            }
         }
     }
+    if (threadIdx.x == 0) tma_wait_all();
 }
 
 __device__ __forceinline__ uint32_t sat_add_u16x2(uint32_t g, uint32_t d) {
@@ -154,44 +200,160 @@ __device__ __forceinline__ uint32_t sat_add_u16x2(uint32_t g, uint32_t d) {
     return lo | (hi << 16);
 }
 
+// ---- mbarrier / bulk-copy primitives (TMA loads of the apply pass) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// One CTA per bucket: histogram of the bucket's slots in 128 KiB of shared memory (two u16 counters per word),
+// then the saturating merge into the table.  The bucket's slot array is contiguous (ent[bucket][tile][32]); it is
+// streamed through a four-stage ring of 16 KiB shared-memory buffers by bulk async copies (one elected thread
+// issues them, mbarriers signal "landed" / "consumed"), so no thread ever waits on a global load.  Thread t reads
+// the t-th 16-byte vector of a stage (4 vectors per slot); the slot's count (ring position 31, see slot_origin)
+// reaches the slot's four lanes by shuffle.  The histogram atomics do not return a value; a counter that
+// wrapped or carried into its neighbour is detected afterwards (the histogram's total falls short of the number of
+// entries) and the bucket is then redone with u32 counters.
+constexpr int APPLY_STAGES = 4;
+constexpr uint32_t APPLY_STAGE_VEC = APPLY_THREADS;                        // one vector per thread and stage
+constexpr uint32_t APPLY_STAGE_BYTES = APPLY_STAGE_VEC * 16;               // 16 KiB
+constexpr size_t APPLY_SMEM = size_t(APPLY_WORDS) * sizeof(uint32_t) + size_t(APPLY_STAGES) * APPLY_STAGE_BYTES + 128;
+
+// Chunks carry a sequence number g that keeps counting over repeated passes (the exact redo streams the bucket
+// again): chunk g uses stage g % STAGES for the (g / STAGES)-th time, which fixes the barrier parities.
+struct ApplyRing {
+    uint32_t ring, full, empty;   // shared-memory addresses: stage buffers, "landed" barriers, "consumed" barriers
+    const uint4* src;
+    uint32_t n_vec, n_chunks;
+    uint32_t origin;              // slot_origin of the CTA's bucket
+    uint32_t issued;              // sequence number of the next chunk to issue (elected thread)
+    uint32_t done;                // sequence number of the first chunk of the current pass
+};
+
+__device__ __forceinline__ void apply_issue(ApplyRing& R) {   // elected thread only
+    const uint32_t g = R.issued++, st = g % APPLY_STAGES, use = g / APPLY_STAGES;
+    if (use > 0) mbar_wait(R.empty + 8 * st, (use - 1) & 1u);   // every thread has read the stage's previous content
+    const uint32_t v0 = (g - R.done) * APPLY_STAGE_VEC;
+    const uint32_t bytes = min(R.n_vec - v0, APPLY_STAGE_VEC) * 16u;
+    mbar_expect_tx(R.full + 8 * st, bytes);
+    bulk_load(R.ring + st * APPLY_STAGE_BYTES, R.src + v0, bytes, R.full + 8 * st);
+}
+
+// bump(c) for every live entry c of the bucket; returns this thread's number of live entries
+template <typename Bump>
+__device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
+    const unsigned lane = threadIdx.x & 31u;
+    // ring position of this lane's first entry (its vector holds slot positions 8 (lane & 3) ..+7) and where the
+    // count sits: vector cnt_vec of the slot, high half of word cnt_word (the origin is even)
+    const uint32_t first = (8u * (lane & 3u) - R.origin) & (PART_SLOT - 1);
+    const uint32_t cnt_pos = (R.origin + PART_SLOT_CAP) & (PART_SLOT - 1);
+    const int cnt_lane = int((lane & ~3u) | (cnt_pos >> 3));
+    const uint32_t cnt_word = (cnt_pos & 7u) >> 1;
+    uint32_t mine = 0;
+    if (threadIdx.x == 0)
+        for (uint32_t c = 0; c < min(R.n_chunks, uint32_t(APPLY_STAGES) - 1u); c++) apply_issue(R);
+    for (uint32_t c = 0; c < R.n_chunks; c++) {
+        if (threadIdx.x == 0 && c + APPLY_STAGES - 1 < R.n_chunks) apply_issue(R);
+        const uint32_t g = R.done + c, st = g % APPLY_STAGES;
+        mbar_wait(R.full + 8 * st, (g / APPLY_STAGES) & 1u);
+        const uint32_t i = c * APPLY_STAGE_VEC + threadIdx.x;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < R.n_vec) {
+            const uint32_t a = R.ring + st * APPLY_STAGE_BYTES + threadIdx.x * 16u;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+        }
+        mbar_arrive(R.empty + 8 * st);
+        const uint32_t cw = cnt_word == 0 ? v.x : cnt_word == 1 ? v.y : cnt_word == 2 ? v.z : v.w;
+        const uint32_t cnt = __shfl_sync(0xffffffffu, cw >> 16, cnt_lane);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (((first + uint32_t(j)) & (PART_SLOT - 1)) < cnt) {   // ring position 31 (the count) is never live: cnt <= 31
+                mine++;
+                bump((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+            }
+    }
+    R.done += R.n_chunks;
+    return mine;
+}
+
 __global__ void __launch_bounds__(APPLY_THREADS, 1)
-cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact, int fresh) {
+cms_apply_kernel(CmsSlots L, uint16_t* __restrict__ tab, int force_exact, int fresh) {
     // fresh: the table is logically zero (kmn_reset_table does not touch the 512 MiB; the first batch after it
     // overwrites every cell here instead of read-modify-writing it)
-    extern __shared__ __align__(16) uint32_t s_cnt[];   // APPLY_WORDS words
+    extern __shared__ __align__(128) uint32_t s_cnt[];   // APPLY_WORDS words, then the ring, then the barriers
+    __shared__ uint32_t s_tot[2];
     const uint32_t B = blockIdx.x;
     const bool fallback = L.state[0] != 0;              // cms_direct_kernel owns this batch
-    const uint32_t n = fallback ? 0u : min(L.cursor[B], L.cap);
-    if (n == 0) {
+    const uint32_t n_vec = fallback ? 0u : L.running[1] * 4u;
+    if (n_vec == 0) {
         if (fresh) {
             uint4* z4 = reinterpret_cast<uint4*>(tab + (size_t(B) << CMS_BUCKET_LOG2));
             for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) z4[i] = make_uint4(0, 0, 0, 0);
         }
         return;
     }
+    ApplyRing R;
+    R.ring = smem_u32(s_cnt + APPLY_WORDS);
+    R.full = R.ring + APPLY_STAGES * APPLY_STAGE_BYTES;
+    R.empty = R.full + 8 * APPLY_STAGES;
+    R.src = reinterpret_cast<const uint4*>(L.ent) + size_t(B) * L.tiles_cap * (PART_SLOT / 8);
+    R.n_vec = n_vec;
+    R.n_chunks = (n_vec + APPLY_STAGE_VEC - 1) / APPLY_STAGE_VEC;
+    R.origin = slot_origin(B & (CMS_BUCKETS_PER_ROW - 1));
+    R.issued = 0;
+    R.done = 0;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < APPLY_STAGES; st++) {
+            mbar_init(R.full + 8 * st, 1);
+            mbar_init(R.empty + 8 * st, APPLY_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_tot[0] = s_tot[1] = 0;
+    }
     uint4* s4 = reinterpret_cast<uint4*>(s_cnt);
     for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const uint16_t* __restrict__ e = L.ent + size_t(B) * L.cap;   // cap is a multiple of 8: 16-byte aligned
-    bool ovf = force_exact != 0;
-    auto bump = [&](uint32_t c) {
-        const uint32_t sh = (c & 1u) * 16u;
-        const uint32_t old = atomicAdd(&s_cnt[c >> 1], 1u << sh);
-        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) ovf = true;       // the counter wrapped / carried: redo exactly
-    };
-    const uint32_t n8 = n / 8;
-    for (uint32_t i = threadIdx.x; i < n8; i += APPLY_THREADS) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(e) + i);
-        bump(v.x & 0xFFFFu); bump(v.x >> 16);
-        bump(v.y & 0xFFFFu); bump(v.y >> 16);
-        bump(v.z & 0xFFFFu); bump(v.z >> 16);
-        bump(v.w & 0xFFFFu); bump(v.w >> 16);
+    const uint32_t mine = apply_stream(R, [&](uint32_t c) { atomicAdd(&s_cnt[c >> 1], 1u << ((c & 1u) * 16u)); });
+    {   // entries streamed by the CTA
+        const uint32_t w = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31u) == 0 && w) atomicAdd(&s_tot[0], w);
     }
-    for (uint32_t i = n8 * 8 + threadIdx.x; i < n; i += APPLY_THREADS) bump(e[i]);
+    __syncthreads();
     uint16_t* __restrict__ cells = tab + (size_t(B) << CMS_BUCKET_LOG2);   // B = row * 1024 + bucket
-    if (!__syncthreads_or(ovf)) {
+    {   // total of the histogram: falls short of the entries iff some counter wrapped or carried
+        uint32_t sum = 0;
+        for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) {
+            const uint4 d = s4[i];
+            sum += (d.x & 0xFFFFu) + (d.x >> 16) + (d.y & 0xFFFFu) + (d.y >> 16) + (d.z & 0xFFFFu) + (d.z >> 16) + (d.w & 0xFFFFu) + (d.w >> 16);
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if ((threadIdx.x & 31u) == 0 && sum) atomicAdd(&s_tot[1], sum);
+    }
+    __syncthreads();
+    const bool exact = force_exact != 0 || s_tot[0] != s_tot[1];   // CTA-uniform
+    if (!exact) {
         uint4* g4 = reinterpret_cast<uint4*>(cells);
-        if (fresh) {   // counters never passed 65535 (ovf is false): they are the cells
+        if (fresh) {   // no counter passed 65535: the counters are the cells
             for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) g4[i] = s4[i];
             return;
         }
@@ -212,10 +374,9 @@ cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact, int fr
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < APPLY_WORDS; i += APPLY_THREADS) s_cnt[i] = 0;
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += APPLY_THREADS) {
-            const uint32_t c = e[i];
+        apply_stream(R, [&](uint32_t c) {
             if ((c >> 15) == half) atomicAdd(&s_cnt[c & 0x7FFFu], 1u);
-        }
+        });
         __syncthreads();
         uint32_t* g32 = reinterpret_cast<uint32_t*>(cells + half * APPLY_WORDS);
         for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 2; i += APPLY_THREADS) {
@@ -231,7 +392,7 @@ cms_apply_kernel(CmsLists L, uint16_t* __restrict__ tab, int force_exact, int fr
 
 // slot overflows of the partition (after cms_apply_kernel in stream order)
 __global__ void __launch_bounds__(256)
-cms_spill_kernel(CmsLists L, uint16_t* __restrict__ tab) {
+cms_spill_kernel(CmsSlots L, uint16_t* __restrict__ tab) {
     if (L.state[0]) return;
     const uint32_t n = min(L.state[1], L.spill_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)

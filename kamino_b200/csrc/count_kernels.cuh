@@ -28,7 +28,7 @@
 //                           position.  A position whose k-mer equals the previous position's (a
 //                           homopolymer run) can never pass and is marked without probing.
 //   bloom_bucket_kernel     one CTA per (species, bucket): the bucket's 2^18 bits in shared memory,
-//                           runs consumed in file order, 16 tiles per step.  A probe whose bit was set
+//                           runs consumed in file order, 8 tiles per step (one per warp).  A probe whose bit was set
 //                           by an earlier step is lost.  Inside a step: every probe sets its bit with a
 //                           shared-memory atomicOr; a probe that finds the bit set by a probe of the
 //                           same step joins a small conflict list (and marks a 2048-bit mini filter);
@@ -55,7 +55,13 @@ constexpr uint32_t BB_WORDS = 1u << (BB_LOG2 - 5);
 constexpr uint32_t BB_MASK = (1u << BB_LOG2) - 1;
 constexpr uint32_t RUN_CAP = 208;                          // slots per (tile, bucket): mean 128, sigma 11
 constexpr uint32_t RUN_Q = (RUN_CAP + 31) / 32;            // entries per lane when a warp reads one run
-constexpr int BB_THREADS = 512;
+#ifndef KMN_BB_THREADS
+#define KMN_BB_THREADS 256
+#endif
+#ifndef KMN_BB_CTAS
+#define KMN_BB_CTAS 4
+#endif
+constexpr int BB_THREADS = KMN_BB_THREADS;
 constexpr uint32_t BB_STEP_RUNS = BB_THREADS / 32;         // runs (source tiles) per step: one per warp
 constexpr uint32_t BB_LIST_CAP = 2048;                     // conflict list of a step; overflow -> slow path (exact)
 constexpr uint32_t ENT_BIT_SHIFT = BP_POS_BITS + 1;         // entry = bit_in_bucket << 14 | pos_in_tile << 1 | probe
@@ -65,8 +71,10 @@ constexpr size_t BB_SMEM = size_t(BB_LIST_CAP) * sizeof(unsigned long long) + si
 static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
 static_assert(BB_LOG2 + ENT_BIT_SHIFT <= 32, "entry layout");
 static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
+// staging rows are cap + 1 words apart: an odd stride spreads the stores of a warp (random buckets, similar ranks)
+// over the shared-memory banks
 constexpr size_t bp_smem_for(uint32_t cap) {
-    return size_t(BB_BUCKETS) * cap * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
+    return size_t(BB_BUCKETS) * (cap + 1) * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
 }
 
 struct BloomRuns {
@@ -114,8 +122,9 @@ __global__ void __launch_bounds__(BP_THREADS, 2)
 bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k,
                        uint64_t k_mask, BloomRuns R) {
     extern __shared__ __align__(16) uint32_t bp_smem[];
-    uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap]
-    uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * R.cap;   // [BB_BUCKETS]
+    const uint32_t stride = R.cap + 1;
+    uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap + 1]
+    uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * stride;  // [BB_BUCKETS]
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tg = blockIdx.x;
     if (tg >= *R.n_tiles) return;
@@ -144,7 +153,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
             for (int pr = 0; pr < 2; pr++) {
                 const uint32_t b = idx[pr] >> BB_LOG2;
                 const uint32_t rank = atomicAdd(&fill[b], 1u);
-                if (rank < R.cap) stage[b * R.cap + rank] = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
+                if (rank < R.cap) stage[b * stride + rank] = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
                 else ovf = true;
             }
         }
@@ -159,7 +168,7 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
         const uint32_t b = warp * (BB_BUCKETS / BP_TILE_WT) + q;
         const uint32_t n = min(fill[b], R.cap);
         uint32_t* dst = R.ent + (size_t(tg) * BB_BUCKETS + b) * R.cap;
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = stage[b * R.cap + i];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = stage[b * stride + i];
     }
 }
 
@@ -303,7 +312,7 @@ __device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list
     return l;
 }
 
-__global__ void __launch_bounds__(BB_THREADS, 2)
+__global__ void __launch_bounds__(BB_THREADS, KMN_BB_CTAS)
 bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRuns R) {
     extern __shared__ __align__(16) unsigned long long bb_smem[];
     unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
@@ -374,8 +383,8 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
         }
         __syncthreads();
         // the other parity's scratch was last read in the previous step
-        if (threadIdx.x < MF_WORDS) s_mf[(par ^ 1u) * MF_WORDS + threadIdx.x] = 0;
-        if (threadIdx.x < MT_SLOTS) s_mt[(par ^ 1u) * MT_SLOTS + threadIdx.x] = ~0ull;
+        for (uint32_t i = threadIdx.x; i < MF_WORDS; i += BB_THREADS) s_mf[(par ^ 1u) * MF_WORDS + i] = 0;
+        for (uint32_t i = threadIdx.x; i < MT_SLOTS; i += BB_THREADS) s_mt[(par ^ 1u) * MT_SLOTS + i] = ~0ull;
         if (threadIdx.x == 0) s_n[par ^ 1u] = 0;
         // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
         uint32_t won = 0, member = 0;

@@ -326,7 +326,9 @@ __global__ void species_offsets_kernel(const uint32_t* __restrict__ rec_cstart,
 // Per-species source tiles of `tile_wt` warp tiles for the species [s0, s1) (count_kernels.cuh,
 // cms_kernels.cuh): sp_tile0[s] = first tile of species s (indices local to this range, sp_tile0[s0] = 0),
 // tile_sp[t] = species of tile t, *n_tiles = total.  One CTA; no host round trip.
-struct TilesJob { uint32_t tile_wt; uint32_t* sp_tile0; uint32_t* tile_sp; uint32_t* n_tiles; };
+// running (optional): [1] accumulates the tiles of the species ranges of one batch, [0] receives the value it had
+// before this range (= global index of the range's first tile).
+struct TilesJob { uint32_t tile_wt; uint32_t* sp_tile0; uint32_t* tile_sp; uint32_t* n_tiles; uint32_t* running; };
 
 __global__ void __launch_bounds__(1024)
 species_tiles_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t s1, TilesJob j0, TilesJob j1) {
@@ -378,6 +380,11 @@ species_tiles_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32
     if (threadIdx.x == 0) {
         sp_tile0[s1] = s_carry;
         *n_tiles = s_carry;
+        if (job.running) {
+            const uint32_t before = job.running[1];
+            job.running[0] = before;
+            job.running[1] = before + s_carry;
+        }
     }
 }
 

@@ -45,17 +45,70 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
+// The same function with fewer issue slots on the device.  mix64 is always applied to key ^ seed, and its first
+// step is linear over XOR:  (k ^ s) ^ ((k ^ s) >> 30) == (k ^ (k >> 30)) ^ (s ^ (s >> 30)).  A kernel that hashes
+// one k-mer with several seeds therefore folds the k-mer once (fold30) and pays two LOP3 per seed for the step.
+// The 64 x 64 -> 64 bit multiplies are spelled as one wide multiply-add plus two 32-bit ones (ptxas otherwise
+// emits a fourth instruction for the cross-term addition).
+__host__ __device__ constexpr uint64_t fold30(uint64_t x) { return x ^ (x >> 30); }
+// fold30 whose result the compiler must keep (it otherwise re-derives the fold from the raw key next to every use)
+__device__ __forceinline__ uint64_t fold30_keep(uint64_t x) {
+    uint64_t f = x ^ (x >> 30);
+    asm volatile("" : "+l"(f));
+    return f;
+}
+// (lo, hi) * c mod 2^64 in three issue slots: wide lo*clo, then both cross terms chained into the high word
+__device__ __forceinline__ void mul64c(uint32_t& lo, uint32_t& hi, uint64_t c) {
+    const uint32_t clo = uint32_t(c), chi = uint32_t(c >> 32);
+    uint32_t plo, phi;
+    asm("{\n\t.reg .u64 p;\n\t"
+        "mul.wide.u32 p, %2, %4;\n\t"
+        "mov.b64 {%0, %1}, p;\n\t"
+        "mad.lo.u32 %1, %3, %4, %1;\n\t"
+        "mad.lo.u32 %1, %2, %5, %1;\n\t}"
+        : "=&r"(plo), "=&r"(phi) : "r"(lo), "r"(hi), "r"(clo), "r"(chi));
+    lo = plo;
+    hi = phi;
+}
+// mix64(key ^ seed) from folded_key = fold30(key) and folded_seed = fold30(seed)
+__device__ __forceinline__ uint64_t mix64_folded(uint64_t folded_key, uint64_t folded_seed) {
+    const uint64_t x0 = folded_key ^ folded_seed;
+    uint32_t lo = uint32_t(x0), hi = uint32_t(x0 >> 32);
+    mul64c(lo, hi, 0xbf58476d1ce4e5b9ull);
+    lo ^= __funnelshift_r(lo, hi, 27);   // x ^= x >> 27
+    hi ^= hi >> 27;
+    mul64c(lo, hi, 0x94d049bb133111ebull);
+    lo ^= __funnelshift_r(lo, hi, 31);   // x ^ (x >> 31)
+    hi ^= hi >> 31;
+    return (uint64_t(hi) << 32) | lo;
+}
+// low 32 bits of the same (all the sketches need: indices are at most 26 bits wide)
+__device__ __forceinline__ uint32_t mix64_folded_lo(uint64_t folded_key, uint64_t folded_seed) {
+    const uint64_t x0 = folded_key ^ folded_seed;
+    uint32_t lo = uint32_t(x0), hi = uint32_t(x0 >> 32);
+    mul64c(lo, hi, 0xbf58476d1ce4e5b9ull);
+    lo ^= __funnelshift_r(lo, hi, 27);
+    hi ^= hi >> 27;
+    mul64c(lo, hi, 0x94d049bb133111ebull);
+    return lo ^ __funnelshift_r(lo, hi, 31);
+}
+
 // Bloom probe indices (proba_filter.rs:60-64): idx_i = (h1 + i*h2) & mask, h2 forced odd.
 __device__ __forceinline__ void bloom_indices(uint64_t kmer, uint32_t& i0, uint32_t& i1) {
-    uint64_t h1 = mix64(kmer ^ SEED_BLOOM_1);
-    uint64_t h2 = mix64(kmer ^ SEED_BLOOM_2) | 1ull;
-    i0 = uint32_t(h1) & BLOOM_MASK;
-    i1 = uint32_t(h1 + h2) & BLOOM_MASK;
+    const uint64_t fk = fold30_keep(kmer);
+    const uint32_t h1 = mix64_folded_lo(fk, fold30(SEED_BLOOM_1));        // only the low 25 bits of h1 and h1 + h2 are used
+    const uint32_t h2 = mix64_folded_lo(fk, fold30(SEED_BLOOM_2)) | 1u;
+    i0 = h1 & BLOOM_MASK;
+    i1 = (h1 + h2) & BLOOM_MASK;
 }
 
 // CMS cell index of row r (proba_filter.rs:107,148); flat offset = r * 2^26 + idx.
 __device__ __forceinline__ uint32_t cms_index(uint64_t kmer, uint64_t seed) {
-    return uint32_t(mix64(kmer ^ seed)) & CMS_MASK;
+    return mix64_folded_lo(fold30(kmer), fold30(seed)) & CMS_MASK;
+}
+// the same from a k-mer folded once for all rows
+__device__ __forceinline__ uint32_t cms_index_folded(uint64_t folded_kmer, uint64_t folded_seed) {
+    return mix64_folded_lo(folded_kmer, folded_seed) & CMS_MASK;
 }
 
 // Pack one 16-code chunk: symbol j (memory order) lands at bits [3*(15-j), 3*(15-j)+3) of P, so

@@ -26,6 +26,7 @@ occupancy_sweep_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int 
     const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
     const unsigned lane = threadIdx.x & 31u;
+    const uint64_t fseed = fold30_keep(seed);
     for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
         const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
         uint64_t kmer[CHUNK];
@@ -46,7 +47,7 @@ occupancy_sweep_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int 
         for (int j = 0; j < CHUNK; j++) {   // all gathers of the chunk in flight together
             v[j] = 0xFFFFu;
             if ((valid >> j) & 1u) {
-                const uint32_t idx = cms_index(kmer[j], seed);
+                const uint32_t idx = cms_index_folded(fold30_keep(kmer[j]), fseed);
                 if ((idx >> (CMS_WIDTH_LOG2 - 1)) == half) v[j] = __ldg(cms_row + idx);
             }
         }

@@ -16,7 +16,8 @@ DAYHOFF6, SR6, KGB6 = 0, 1, 2
 SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
 CMS_CELLS = 4 << 26
 STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5,
-          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8, "group_observations": 9}
+          "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8, "group_observations": 9,
+          "bloom_partition_kernel": 10, "cms_apply_kernel": 11}
 
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]
@@ -36,7 +37,7 @@ ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_host_alloc", "kmn_host_free", "kmn_count_batch",
     "kmn_stage_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
-    "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_exchange_abort", "kmn_table_checksum", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
+    "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_exchange_setup_local", "kmn_exchange_reduce_all", "kmn_exchange_abort", "kmn_table_checksum", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
@@ -49,7 +50,9 @@ _lib = None
 
 
 def library_path() -> Path:
-    return _build.LIB_PATH
+    import os
+    override = os.environ.get("KAMINO_B200_LIB")   # tuning builds of tools/ (same ABI, other -D constants)
+    return Path(override) if override else _build.LIB_PATH
 
 
 def load_library() -> C.CDLL:
@@ -88,6 +91,8 @@ def load_library() -> C.CDLL:
     lib.kmn_exchange_setup.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.kmn_exchange_reduce.argtypes = [vp]
     lib.kmn_exchange_abort.argtypes = [vp]
+    lib.kmn_exchange_setup_local.argtypes = [vpp, C.c_int]
+    lib.kmn_exchange_reduce_all.argtypes = [vpp, C.c_int]
     lib.kmn_table_checksum.argtypes = [vp, vp, u64p]
     lib.kmn_synchronize.argtypes = [vp]
     lib.kmn_stream.argtypes = [vp, vpp]
@@ -115,6 +120,22 @@ def _ptr(a: np.ndarray | None):
 
 def _as(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def exchange_setup_local(contexts: list["Context"]):
+    """Wire the exchange buffers of contexts that live in THIS process, one per device (kmn_exchange_setup_local)."""
+    lib = load_library()
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    if lib.kmn_exchange_setup_local(arr, len(contexts)) != 0:
+        raise KaminoError(lib.kmn_last_error().decode("utf-8", "replace"))
+
+
+def exchange_reduce_all(contexts: list["Context"]):
+    """One exchange over all the in-process contexts (kmn_exchange_reduce_all)."""
+    lib = load_library()
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    if lib.kmn_exchange_reduce_all(arr, len(contexts)) != 0:
+        raise KaminoError(lib.kmn_last_error().decode("utf-8", "replace"))
 
 
 class PinnedBuffer:

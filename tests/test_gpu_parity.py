@@ -271,7 +271,7 @@ def test_pair_counts_row_blocks(ffi, oracle):
 @pytest.mark.parametrize("knobs", [
     {"KMN_CMS_FORCE": "1"},                      # every bucket redone with u32 counters
     {"KMN_CMS_FORCE": "2"},                      # direct CAS path only
-    {"KMN_CMS_CAP": "8"},                        # bucket lists overflow -> fallback flag -> direct path
+    {"KMN_CMS_CAP": "8", "KMN_CMS_SLOT": "2"},   # spill list overflows -> fallback flag -> direct path
     {"KMN_CMS_SLOT": "1"},                       # almost every staged entry spills
     {"KMN_CMS_SLOT": "1", "KMN_CMS_FORCE": "1"},
 ])

@@ -1,4 +1,4 @@
-"""2-GPU parity (skipped unless >= 2 CUDA devices): species sharded over two ranks, tables merged by
+"""Multi-GPU parity at 2 / 4 / 8 ranks (each case skipped unless that many CUDA devices are visible): species sharded over two ranks, tables merged by
 the fused NVLink exchange kernel and by the NCCL all-reduce path; both must equal the single-process
 oracle table bit for bit."""
 import os
@@ -94,16 +94,64 @@ def _worker(rank, world, port, out_dir, planes):
 
 
 @pytest.mark.parametrize("planes", ["1", "0"])
-def test_two_gpu_exchange_matches_oracle(tmp_path, planes):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_exchange_matches_oracle(tmp_path, world, planes):
+    """exchange_planes_kernel<2/4/8> and exchange_reduce_kernel<2,4>/<4,2>/<8,2> against the single-process oracle."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), planes), nprocs=world, join=True)
+    for r in range(world):
+        txt = (tmp_path / f"rank{r}.txt").read_text()
+        assert txt.startswith("ok"), txt
+        print("rank", r, txt)
+
+
+def _timeout_worker(rank, world, port, out_dir):
+    import time
+    import torch
+    import torch.distributed as dist
+    from kamino_b200 import ffi, sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["KMN_EXCHANGE_TIMEOUT_MS"] = "1500"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        with ffi.Context(13, "sr6", device=rank) as ctx:
+            assert sharding.setup_fused_exchange(ctx)
+            msg = "not run"
+            if rank == 0:   # rank 1 never shows up: rank 0 must come back with an error, not hang
+                t0 = time.time()
+                try:
+                    ctx.exchange_reduce()
+                    msg = "no error"
+                except ffi.KaminoError as e:
+                    msg = f"{time.time() - t0:.1f}s {e}"
+            dist.barrier()
+            # both ranks set up again and a normal exchange works
+            assert sharding.setup_fused_exchange(ctx)
+            ctx.reset_table()
+            ctx.exchange_reduce()
+            rows, _ = ctx.table_checksum()
+            Path(out_dir, f"t{rank}.txt").write_text(f"{msg}|{int(rows.sum())}")
+            dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_timeout_names_the_missing_rank(tmp_path):
+    """A peer that never launches its exchange kernel must not hang the other GPUs (bounded in-kernel waits)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), planes), nprocs=2, join=True)
-    for r in range(2):
-        txt = (tmp_path / f"rank{r}.txt").read_text()
-        assert txt.startswith("ok"), txt
-        print("rank", r, txt)
+    mp.spawn(_timeout_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    msg, total = (tmp_path / "t0.txt").read_text().split("|")
+    assert "timed out" in msg and "rank 1" in msg, msg
+    assert total == "0" and (tmp_path / "t1.txt").read_text().endswith("|0")
 
 
 def _pair_worker(rank, world, port, out_dir):

@@ -32,7 +32,7 @@ def main():
     orc.cmsa_free(h)
     min_needed = orc.min_needed(0.85, len(species))
     knob_sets = [{}, {"KMN_BLOOM_RUN_CAP": "8"}, {"KMN_CMS_FORCE": "1"}, {"KMN_CMS_FORCE": "2"}, {"KMN_CMS_SLOT": "4"},
-                 {"KMN_CMS_CAP": "8"}, {"KMN_H2D_CHUNKS": "1"}]
+                 {"KMN_CMS_CAP": "8", "KMN_CMS_SLOT": "2"}, {"KMN_H2D_CHUNKS": "1"}]
     only = os.environ.get("SANITIZE_ONLY")
     if only is not None:
         knob_sets = [knob_sets[int(only)]]
