@@ -220,6 +220,13 @@ int kmn_fetch_pairs(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, kmn_pair* out,
 int kmn_group_observations(kmn_ctx* ctx, uint64_t n, const uint64_t* left, const uint64_t* right,
                            const uint32_t* sid, const uint32_t* len, uint32_t min_needed, uint32_t* perm,
                            kmn_group* groups, uint64_t cap_groups, uint64_t* n_groups);
+/* The same grouping straight from the anchor pairs kmn_pair_batch left on the device (no host arrays are
+ * uploaded): the observations are the pairs of the given batches, batch after batch and, inside a batch,
+ * species after species in emission order (== kmn_fetch_pairs order); species i of batch b carries the species
+ * index sid_base[b] + i * sid_stride.  perm indexes that concatenation.  With perm == NULL only *n_obs is set. */
+int kmn_group_batches(kmn_ctx* ctx, const uint32_t* batch_ids, uint32_t n_batches, const uint32_t* sid_base,
+                      uint32_t sid_stride, uint32_t min_needed, uint32_t* perm, uint64_t cap_perm, kmn_group* groups,
+                      uint64_t cap_groups, uint64_t* n_obs, uint64_t* n_groups);
 /* Occupancy per whitespace-stripped residue of species `sp` (records concatenated): estimate()
  * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues. */
 int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap,

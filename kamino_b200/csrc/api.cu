@@ -133,8 +133,7 @@ struct kmn_ctx {
     bool peers_ready = false;
     uint32_t exchange_epoch = 0;          // exchanges run so far (every rank counts alike)
     DevBuf<uint32_t> xsync;               // [0] go word, [1] finished-CTA counter, [2] error word of the exchange kernels
-    uint32_t* xabort_host = nullptr;      // host-mapped abort word (kmn_exchange_abort), read by the spinning kernels
-    uint32_t* xabort_dev = nullptr;
+    uint32_t* xabort_host = nullptr;      // pinned word (== 1): source of the copy that raises the device abort word xsync[3]
     uint32_t exchange_timeout_ms = 30000; // KMN_EXCHANGE_TIMEOUT_MS: a rank waits this long for a peer before it gives up
     int exchange_grid = 0;
     std::vector<void*> ipc_opened;
@@ -149,12 +148,14 @@ struct kmn_ctx {
     DevBuf<uint32_t> frame_carry, n_tiles_dev, scan_sums, scan_offs;
     // scratch of kmn_group_observations
     DevBuf<uint64_t> g_left, g_right;
-    DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first;
+    DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first, g_spoff;
     DevBuf<kmn_group> g_groups;
     DevBuf<uint64_t> fa_file_off;          // scratch of kmn_count_fasta
     DevBuf<uint8_t> fa_tile_sum, fa_tile_in;
     DevBuf<uint32_t> fa_tile_hdr, fa_tile_base, fa_err;
     DevBuf<uint32_t> nj_valid, nj_mism;   // counts of the last pair_counts call (kmn_pair_counts_device)
+    DevBuf<uint8_t> nj_mapped;            // scratch of the pair counts, kept between calls (no cudaMalloc per call)
+    DevBuf<uint32_t> nj_planes;
     uint32_t nj_rows = 0, nj_n = 0;
     float stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
@@ -777,29 +778,25 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
     if (n_pairs) *n_pairs = total;
 }
 
-void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const uint64_t* right, const uint32_t* sid,
-                        const uint32_t* len, uint32_t min_needed, uint32_t* perm, kmn_group* groups, uint64_t cap_groups,
-                        uint64_t* n_groups) {
-    if (n64 >= (1ull << 31)) throw std::runtime_error("too many observations for one grouping call");
-    const uint32_t n = uint32_t(n64);
-    if (n_groups) *n_groups = 0;
-    if (n == 0) return;
-    if (!left || !right || !sid || !len || !perm || !groups) throw std::runtime_error("NULL argument");
-    // scratch lives in the context (cudaMalloc / cudaFree per call would dominate the few ms of kernels)
+// scratch of the grouping, sized for n observations (lives in the context: cudaMalloc / cudaFree per call would
+// dominate the few ms of kernels)
+void group_scratch(kmn_ctx* c, uint32_t n) {
+    const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    c->g_left.ensure(n); c->g_right.ensure(n); c->g_sid.ensure(n); c->g_len.ensure(n);
+    c->g_perm[0].ensure(n); c->g_perm[1].ensure(n);
+    c->g_hist.ensure(size_t(RS_BINS) * n_blocks + 1); c->g_base.ensure(size_t(RS_BINS) * n_blocks + 2);
+    c->g_head.ensure(n); c->g_scan.ensure(size_t(n) + 1); c->g_first.ensure(size_t(n) + 1);
+}
+
+// Sort + run detection + length selection on the observation arrays already in g_left / g_right / g_sid / g_len.
+void group_core(kmn_ctx* c, uint32_t n, uint32_t min_needed, uint32_t* perm, kmn_group* groups, uint64_t cap_groups,
+                uint64_t* n_groups) {
     DevBuf<uint64_t>&d_left = c->g_left, &d_right = c->g_right;
     DevBuf<uint32_t>&d_sid = c->g_sid, &d_len = c->g_len, &d_hist = c->g_hist, &d_base = c->g_base, &d_head = c->g_head,
                     &d_scan = c->g_scan, &d_first = c->g_first;
     DevBuf<uint32_t>* d_perm = c->g_perm;
     DevBuf<kmn_group>& d_groups = c->g_groups;
     const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
-    d_left.ensure(n); d_right.ensure(n); d_sid.ensure(n); d_len.ensure(n);
-    d_perm[0].ensure(n); d_perm[1].ensure(n);
-    d_hist.ensure(size_t(RS_BINS) * n_blocks + 1); d_base.ensure(size_t(RS_BINS) * n_blocks + 2);
-    d_head.ensure(n); d_scan.ensure(size_t(n) + 1); d_first.ensure(size_t(n) + 1);
-    KMN_CUDA(cudaMemcpyAsync(d_left.p, left, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(d_right.p, right, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(d_sid.p, sid, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
-    KMN_CUDA(cudaMemcpyAsync(d_len.p, len, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     const uint32_t eb = (n + 255) / 256;
     iota_kernel<<<eb, 256, 0, c->stream>>>(d_perm[0].p, n);
@@ -809,12 +806,10 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     int cur = 0;
     for (int word = 0; word < 2; word++) {
         const uint64_t* key = word == 0 ? d_right.p : d_left.p;
-        for (uint32_t shift = 0; shift < bits; shift += 4) {
+        for (uint32_t shift = 0; shift < bits; shift += RS_BITS) {
             radix_hist_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(key, d_perm[cur].p, n, shift, d_hist.p);
             check_launch(c);
-            const ScanJob job{d_hist.p, d_base.p, RS_BINS * n_blocks, nullptr};
-            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
-            check_launch(c);
+            device_exclusive_scan(c, d_hist.p, d_base.p, RS_BINS * n_blocks);
             radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(key, d_perm[cur].p, n, shift, d_base.p, d_perm[cur ^ 1].p);
             check_launch(c);
             cur ^= 1;
@@ -842,6 +837,58 @@ void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const ui
     if (n_groups) *n_groups = ng;
 }
 
+void group_observations(kmn_ctx* c, uint64_t n64, const uint64_t* left, const uint64_t* right, const uint32_t* sid,
+                        const uint32_t* len, uint32_t min_needed, uint32_t* perm, kmn_group* groups, uint64_t cap_groups,
+                        uint64_t* n_groups) {
+    if (n64 >= (1ull << 31)) throw std::runtime_error("too many observations for one grouping call");
+    const uint32_t n = uint32_t(n64);
+    if (n_groups) *n_groups = 0;
+    if (n == 0) return;
+    if (!left || !right || !sid || !len || !perm || !groups) throw std::runtime_error("NULL argument");
+    group_scratch(c, n);
+    KMN_CUDA(cudaMemcpyAsync(c->g_left.p, left, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(c->g_right.p, right, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(c->g_sid.p, sid, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    KMN_CUDA(cudaMemcpyAsync(c->g_len.p, len, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    group_core(c, n, min_needed, perm, groups, cap_groups, n_groups);
+}
+
+// The same from the anchor pairs that kmn_pair_batch left on the device: nothing but a few offsets is uploaded.
+void group_batches(kmn_ctx* c, const uint32_t* batch_ids, uint32_t n_batches, const uint32_t* sid_base, uint32_t sid_stride,
+                   uint32_t min_needed, uint32_t* perm, uint64_t cap_perm, kmn_group* groups, uint64_t cap_groups,
+                   uint64_t* n_obs, uint64_t* n_groups) {
+    if (!batch_ids || !sid_base || !n_obs) throw std::runtime_error("NULL argument");
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_batches; i++) {
+        Batch& b = get_batch(c, batch_ids[i]);
+        if (!b.paired) throw std::runtime_error("batch has not been paired (kmn_pair_batch)");
+        total += b.h_sp_pairs_off[b.n_sp];
+    }
+    *n_obs = total;
+    if (n_groups) *n_groups = 0;
+    if (!perm || total == 0) return;   // size query
+    if (total >= (1ull << 31)) throw std::runtime_error("too many observations for one grouping call");
+    if (!groups) throw std::runtime_error("NULL argument");
+    if (cap_perm < total) throw std::runtime_error("perm buffer too small");
+    const uint32_t n = uint32_t(total);
+    group_scratch(c, n);
+    uint32_t at = 0;
+    for (uint32_t i = 0; i < n_batches; i++) {
+        Batch& b = get_batch(c, batch_ids[i]);
+        const uint32_t np = b.h_sp_pairs_off[b.n_sp];
+        if (np == 0) continue;
+        c->g_spoff.ensure(size_t(b.n_sp) + 1);
+        // (pageable source: the copy is staged before the call returns, so reusing g_spoff for the next batch is safe)
+        KMN_CUDA(cudaMemcpyAsync(c->g_spoff.p, b.h_sp_pairs_off.data(), (size_t(b.n_sp) + 1) * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, c->stream));
+        obs_from_pairs_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(b.pairs.p, np, c->g_spoff.p, b.n_sp, sid_base[i], sid_stride, at,
+                                                                     c->g_left.p, c->g_right.p, c->g_sid.p, c->g_len.p);
+        check_launch(c);
+        at += np;
+    }
+    group_core(c, n, min_needed, perm, groups, cap_groups, n_groups);
+}
+
 // rows [row0, row1) of the pair matrix (row0 a multiple of the 64-row tile; row1 a multiple or n): the
 // row block one rank computes when the matrix is sharded; the whole matrix is rows [0, n).
 void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint32_t row0, uint32_t row1, uint32_t* valid,
@@ -858,20 +905,23 @@ void pair_counts(kmn_ctx* c, const uint8_t* mapped, uint32_t n, uint64_t L, uint
     const uint32_t W = uint32_t((L + 31) / 32);
     const uint32_t t0 = row0 / PAIR_TILE, t1 = (row1 + PAIR_TILE - 1) / PAIR_TILE;
     const size_t out_cells = size_t(row1 - row0) * n;
-    DevBuf<uint8_t> d_mapped;
-    DevBuf<uint32_t> d_planes;
+    // scratch lives in the context; a row block only pairs rows >= row0 (columns j > i), so only those rows of the
+    // alignment are uploaded and bit-sliced (a rank of a sharded --nj moves its share, not the whole alignment)
+    DevBuf<uint8_t>& d_mapped = c->nj_mapped;
+    DevBuf<uint32_t>& d_planes = c->nj_planes;
     DevBuf<uint32_t>&d_valid = c->nj_valid, &d_mism = c->nj_mism;
-    d_mapped.alloc(std::max<size_t>(size_t(n) * L, 1));
-    d_planes.alloc(size_t(n_pad) * std::max<uint32_t>(W, 1) * PAIR_PLANES);
+    d_mapped.ensure(std::max<size_t>(size_t(n) * L, 1));
+    d_planes.ensure(size_t(n_pad) * std::max<uint32_t>(W, 1) * PAIR_PLANES);
     d_valid.ensure(out_cells);
     d_mism.ensure(out_cells);
-    if (L) KMN_CUDA(cudaMemcpyAsync(d_mapped.p, mapped, size_t(n) * L, cudaMemcpyHostToDevice, c->stream));
+    if (L) KMN_CUDA(cudaMemcpyAsync(d_mapped.p + size_t(row0) * L, mapped + size_t(row0) * L, size_t(n - row0) * L,
+                                    cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaMemsetAsync(d_valid.p, 0, out_cells * sizeof(uint32_t), c->stream));
     KMN_CUDA(cudaMemsetAsync(d_mism.p, 0, out_cells * sizeof(uint32_t), c->stream));
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (W) {
-        const uint64_t items = uint64_t(n_pad) * W;
-        pair_pack_kernel<<<uint32_t((items + 255) / 256), 256, 0, c->stream>>>(d_mapped.p, n, L, n_pad, W, d_planes.p);
+        const uint64_t items = uint64_t(n_pad - row0) * W;   // rows row0 .. n_pad
+        pair_pack_kernel<<<uint32_t((items + 255) / 256), 256, 0, c->stream>>>(d_mapped.p, n, L, n_pad, W, row0, d_planes.p);
         check_launch(c);
         // tile rows t0..t1-1 of the upper triangle: sum of (n_tiles - t)
         const uint64_t n_blocks = uint64_t(t1 - t0) * n_tiles - (uint64_t(t1) * (t1 - 1) / 2 - uint64_t(t0) * (t0 > 0 ? t0 - 1 : 0) / 2);
@@ -902,14 +952,13 @@ void alloc_exchange_buffers(kmn_ctx* c) {
     KMN_CUDA(cudaMemset(reinterpret_cast<uint8_t*>(c->xtab.p) + kXOffFlags, 0, 256));
     c->xsync.alloc(4);
     KMN_CUDA(cudaMemset(c->xsync.p, 0, 4 * sizeof(uint32_t)));
-    if (!c->xabort_host) {
-        KMN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->xabort_host), sizeof(uint32_t), cudaHostAllocMapped));
-        *c->xabort_host = 0;
-        KMN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->xabort_dev), c->xabort_host, 0));
+    if (!c->xabort_host) {   // pinned source word of kmn_exchange_abort's copy
+        KMN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->xabort_host), sizeof(uint32_t), cudaHostAllocPortable));
+        *c->xabort_host = 1;
     }
 }
 ExchangeGuard exchange_guard(kmn_ctx* c) {
-    return ExchangeGuard{c->xsync.p + 2, c->xabort_dev, uint64_t(c->exchange_timeout_ms) * 1000000ull};
+    return ExchangeGuard{c->xsync.p + 2, c->xsync.p + 3, uint64_t(c->exchange_timeout_ms) * 1000000ull};
 }
 // after the exchange kernel has finished: turn a recorded timeout / abort into an error (and re-arm the word)
 void check_exchange_error(kmn_ctx* c) {
@@ -1064,7 +1113,7 @@ int kmn_host_alloc(void** ptr, uint64_t bytes) {
     try {
         if (!ptr) throw std::runtime_error("ptr must not be NULL");
         *ptr = nullptr;
-        KMN_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+        KMN_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));   // pinned for every device of the process
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -1257,7 +1306,7 @@ static void launch_exchange(kmn_ctx* c) {
     uint32_t epoch = c->exchange_epoch + 1;
     uint32_t* xs = c->xsync.p;
     ExchangeGuard guard = exchange_guard(c);
-    *c->xabort_host = 0;
+    KMN_CUDA(cudaMemsetAsync(c->xsync.p + 3, 0, sizeof(uint32_t), c->stream));   // re-arm the abort word
     materialize_table(c);
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (planes) {
@@ -1405,9 +1454,12 @@ int kmn_exchange_reduce_all(kmn_ctx* const* ctxs, int world) {
 }
 
 int kmn_exchange_abort(kmn_ctx* c) {
-    if (!c) { g_err = "NULL context"; return 1; }
-    if (c->xabort_host) *reinterpret_cast<volatile uint32_t*>(c->xabort_host) = 1u;   // any thread; no CUDA call
-    return 0;
+    // any host thread: a 4-byte copy on the copy stream lands while the exchange kernel spins on the compute stream
+    return guarded(c, [&] {
+        if (!c->xabort_host || !c->xsync.p) return;   // no exchange has been set up
+        KMN_CUDA(cudaMemcpyAsync(c->xsync.p + 3, c->xabort_host, sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+        KMN_CUDA(cudaStreamSynchronize(c->copy_stream));
+    });
 }
 
 int kmn_table_checksum(kmn_ctx* c, uint64_t* row_sums4, uint64_t* hash) {
@@ -1492,6 +1544,14 @@ int kmn_group_observations(kmn_ctx* c, uint64_t n, const uint64_t* left, const u
                            const uint32_t* len, uint32_t min_needed, uint32_t* perm, kmn_group* groups,
                            uint64_t cap_groups, uint64_t* n_groups) {
     return guarded(c, [&] { group_observations(c, n, left, right, sid, len, min_needed, perm, groups, cap_groups, n_groups); });
+}
+
+int kmn_group_batches(kmn_ctx* c, const uint32_t* batch_ids, uint32_t n_batches, const uint32_t* sid_base, uint32_t sid_stride,
+                      uint32_t min_needed, uint32_t* perm, uint64_t cap_perm, kmn_group* groups, uint64_t cap_groups,
+                      uint64_t* n_obs, uint64_t* n_groups) {
+    return guarded(c, [&] {
+        group_batches(c, batch_ids, n_batches, sid_base, sid_stride, min_needed, perm, cap_perm, groups, cap_groups, n_obs, n_groups);
+    });
 }
 
 int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap, uint64_t* n) {

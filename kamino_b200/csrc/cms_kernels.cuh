@@ -503,18 +503,27 @@ __device__ __forceinline__ uint64_t global_ns() {
 }
 struct ExchangeGuard {
     uint32_t* err;                 // device word: 0 = fine, else 1 + rank waited for (| 0x100 epilogue, 0x200 host abort)
-    const uint32_t* abort_flag;    // host-mapped word: non-zero = give up now (kmn_exchange_abort)
+    const uint32_t* abort_flag;    // DEVICE word the host raises with a tiny copy on a side stream (kmn_exchange_abort).
+                                   // (A host-mapped word here cost 0.6-2 ms per exchange: ~1200 spinning CTAs polling
+                                   // it over PCIe delayed the very flags they were waiting for.)
     uint64_t limit_ns;
 };
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// SYS: the word is written by another GPU (system scope); otherwise by a CTA of this GPU
+template <bool SYS>
 __device__ __forceinline__ bool wait_epoch(const uint32_t* p, uint32_t epoch, const ExchangeGuard& g, uint32_t who) {
-    if (ld_acquire_sys(p) >= epoch) return true;
+    if ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) >= epoch) return true;
     const uint64_t t0 = global_ns();
     for (uint32_t it = 1;; it++) {
-        if (ld_acquire_sys(p) >= epoch) return true;
-        if ((it & 63u) == 0) {
-            if (*reinterpret_cast<const volatile uint32_t*>(g.abort_flag)) { atomicCAS(g.err, 0u, 0x200u | (1u + who)); return false; }
+        if ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) >= epoch) return true;
+        if (!SYS) __nanosleep(64);   // ~1200 CTAs poll the local go word: keep them off the memory system
+        if ((it & 255u) == 0) {
+            if (ld_acquire_gpu(g.abort_flag)) { atomicCAS(g.err, 0u, 0x200u | (1u + who)); return false; }
             if (global_ns() - t0 > g.limit_ns) { atomicCAS(g.err, 0u, 1u + who); return false; }
-            __nanosleep(200);
         }
     }
 }
@@ -526,7 +535,7 @@ __device__ __forceinline__ bool exchange_prologue(uint32_t* const* flags, int wo
         if (int(threadIdx.x) < world) {
             const int q = (rank + int(threadIdx.x)) % world;
             st_release_sys(flags[q] + rank, epoch);
-            wait_epoch(flags[rank] + q, epoch, g, uint32_t(q));
+            wait_epoch<true>(flags[rank] + q, epoch, g, uint32_t(q));
         }
         __syncthreads();
         if (threadIdx.x == 0) st_release_sys(local_sync, epoch);
@@ -534,11 +543,11 @@ __device__ __forceinline__ bool exchange_prologue(uint32_t* const* flags, int wo
         if (threadIdx.x == 0) {
             ExchangeGuard g2 = g;
             g2.limit_ns = 2 * g.limit_ns;   // CTA 0 always releases, at the latest when its own waits give up
-            wait_epoch(local_sync, epoch, g2, uint32_t(rank));
+            wait_epoch<false>(local_sync, epoch, g2, uint32_t(rank));
         }
         __syncthreads();
     }
-    return ld_acquire_sys(g.err) == 0;
+    return ld_acquire_gpu(g.err) == 0;
 }
 // epilogue: the last CTA of this rank publishes "done" and waits for every peer's "done"
 __device__ __forceinline__ void exchange_epilogue(uint32_t* const* flags, int world, int rank, uint32_t epoch,
@@ -555,7 +564,7 @@ __device__ __forceinline__ void exchange_epilogue(uint32_t* const* flags, int wo
             for (int p = 0; p < world; p++) {
                 ExchangeGuard g2 = g;
                 g2.err = g.err;
-                if (!wait_epoch(flags[rank] + MAX_PEERS + p, epoch, g2, 0x100u | uint32_t(p))) break;
+                if (!wait_epoch<true>(flags[rank] + MAX_PEERS + p, epoch, g2, 0x100u | uint32_t(p))) break;
             }
         }
     }

@@ -9,8 +9,8 @@
 // support of a block length = number of DISTINCT species observing it; the group survives iff exactly one
 // length attains the maximum support, support >= min_needed and length >= 2k+1.
 //
-// The sort is a plain 4-bit LSD radix sort (histogram / scan / stable scatter, 2048 elements per CTA):
-// a few million 78-bit keys, a few ms — nowhere near a bottleneck next to the host stages it replaces.
+// The sort is a stable LSD radix sort with 8-bit digits (histogram / scan / stable scatter, 2048 elements per
+// CTA): 2 x ceil(3k / 8) passes over a few million 3k-bit key halves.
 #pragma once
 #include "../../include/kamino_b200.h"
 #include "kmn_device.cuh"
@@ -20,15 +20,17 @@ namespace kmn {
 constexpr int RS_THREADS = 256;
 constexpr int RS_ROUNDS = 8;
 constexpr uint32_t RS_TILE = RS_THREADS * RS_ROUNDS;   // elements per CTA
-constexpr uint32_t RS_BINS = 16;                       // 4-bit digits
+constexpr uint32_t RS_BITS = 8;
+constexpr uint32_t RS_BINS = 1u << RS_BITS;            // 8-bit digits
 constexpr int GROUP_MAX_LENS = 12;                     // distinct block lengths tracked per group on the device
+static_assert(RS_BINS == RS_THREADS, "one thread per bin in the per-CTA tables");
 
 // per-CTA digit histogram of the current pass: block_hist[bin * n_blocks + block]
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ perm, uint32_t n, uint32_t shift,
                   uint32_t* __restrict__ block_hist) {
     __shared__ uint32_t s_h[RS_BINS];
-    if (threadIdx.x < RS_BINS) s_h[threadIdx.x] = 0;
+    s_h[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * RS_TILE;
 #pragma unroll
@@ -37,21 +39,24 @@ radix_hist_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__
         if (i < n) atomicAdd(&s_h[uint32_t(key[perm[i]] >> shift) & (RS_BINS - 1)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < RS_BINS) block_hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
+    block_hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
 }
 
 // stable scatter: element i goes to (scanned base of its digit and CTA) + (rank among the CTA's earlier
-// elements with the same digit)
+// elements with the same digit).  Inside a round the rank comes from a warp match (lanes with the same digit,
+// lower lane first) plus the counts of the earlier warps.
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ perm_in, uint32_t n, uint32_t shift,
                      const uint32_t* __restrict__ block_base, uint32_t* __restrict__ perm_out) {
+    constexpr int WARPS = RS_THREADS / 32;
     __shared__ uint32_t s_base[RS_BINS];
-    __shared__ uint32_t s_wcnt[RS_THREADS / 32][RS_BINS];
+    __shared__ uint16_t s_wcnt[WARPS][RS_BINS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (threadIdx.x < RS_BINS) s_base[threadIdx.x] = block_base[threadIdx.x * gridDim.x + blockIdx.x];
+    s_base[threadIdx.x] = block_base[threadIdx.x * gridDim.x + blockIdx.x];
     const uint32_t base = blockIdx.x * RS_TILE;
     for (int r = 0; r < RS_ROUNDS; r++) {
-        if (threadIdx.x < (RS_THREADS / 32) * RS_BINS) (&s_wcnt[0][0])[threadIdx.x] = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) s_wcnt[w][threadIdx.x] = 0;
         __syncthreads();
         const uint32_t i = base + r * RS_THREADS + threadIdx.x;
         const bool valid = i < n;
@@ -59,7 +64,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ key, const uint32_t* __restric
         const uint32_t d = valid ? (uint32_t(key[p] >> shift) & (RS_BINS - 1)) : RS_BINS;   // RS_BINS: padding lane
         const unsigned same = __match_any_sync(0xffffffffu, d);
         const uint32_t rank = __popc(same & ((1u << lane) - 1u));
-        if (valid && rank == 0) s_wcnt[warp][d] = __popc(same);
+        if (valid && rank == 0) s_wcnt[warp][d] = uint16_t(__popc(same));
         __syncthreads();
         if (valid) {
             uint32_t off = 0;
@@ -67,15 +72,35 @@ radix_scatter_kernel(const uint64_t* __restrict__ key, const uint32_t* __restric
             perm_out[s_base[d] + off + rank] = p;
         }
         __syncthreads();
-        if (threadIdx.x < RS_BINS) {
+        {
             uint32_t t = 0;
 #pragma unroll
-            for (int w = 0; w < RS_THREADS / 32; w++) t += s_wcnt[w][threadIdx.x];
+            for (int w = 0; w < WARPS; w++) t += s_wcnt[w][threadIdx.x];
             s_base[threadIdx.x] += t;
         }
         // the next round's zeroing is ordered after these reads by its barrier pair
         __syncthreads();
     }
+}
+
+// Observations straight from the anchor pairs kmn_pair_batch left on the device (kmn_group_batches): pair i of a
+// batch is observation out0 + i; its species is found in the batch's per-species pair offsets.
+__global__ void __launch_bounds__(256)
+obs_from_pairs_kernel(const kmn_pair* __restrict__ pairs, uint32_t n_pairs, const uint32_t* __restrict__ sp_pairs_off,
+                      uint32_t n_sp, uint32_t sid_base, uint32_t sid_stride, uint32_t out0, uint64_t* __restrict__ left,
+                      uint64_t* __restrict__ right, uint32_t* __restrict__ sid, uint32_t* __restrict__ len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const kmn_pair p = pairs[i];
+    uint32_t lo = 0, hi = n_sp;   // last species s with sp_pairs_off[s] <= i
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sp_pairs_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    left[out0 + i] = p.left;
+    right[out0 + i] = p.right;
+    sid[out0 + i] = sid_base + lo * sid_stride;
+    len[out0 + i] = p.len;
 }
 
 __global__ void iota_kernel(uint32_t* __restrict__ perm, uint32_t n) {

@@ -18,14 +18,9 @@ namespace kh {
 
 namespace {
 
-struct Ctx {   // RAII over kmn_ctx
-    kmn_ctx* p = nullptr;
-    Ctx(int device, int k, int scheme) {
-        if (kmn_create(&p, device, k, scheme) != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error());
-    }
-    ~Ctx() { kmn_destroy(p); }
-    void ok(int rc) const { if (rc != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error()); }
-};
+void gpu_ok(int rc) {
+    if (rc != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error());
+}
 
 bool valid_utf8(const std::string& s) {   // rec.id()? / rec.desc() fail on invalid UTF-8 (group_extraction.rs:429-430)
     const unsigned char* p = reinterpret_cast<const unsigned char*>(s.data());
@@ -90,20 +85,43 @@ std::string extraction_self_test() {
     return std::string();
 }
 
+GpuSet::~GpuSet() {
+    for (kmn_ctx* c : ctx) kmn_destroy(c);
+}
+
+// One context per device, created concurrently (each creation allocates and zeroes a 512 MiB table).
+void GpuSet::create(const std::vector<int>& devs, int k, int scheme) {
+    if (!ctx.empty()) return;
+    if (devs.empty()) throw std::runtime_error("no GPU device given");
+    for (size_t a = 0; a < devs.size(); a++)
+        for (size_t b = 0; b < a; b++)
+            if (devs[a] == devs[b]) throw std::runtime_error("--devices lists device " + std::to_string(devs[a]) + " twice");
+    devices = devs;
+    ctx.assign(devs.size(), nullptr);
+    std::vector<std::string> errs(devs.size());
+    std::vector<std::thread> pool;
+    for (size_t r = 0; r < devs.size(); r++)
+        pool.emplace_back([&, r] {
+            if (kmn_create(&ctx[r], devs[r], k, scheme) != 0) errs[r] = std::string("GPU front end: ") + kmn_last_error();
+        });
+    for (auto& t : pool) t.join();
+    for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+    if (devs.size() > 1) gpu_ok(kmn_exchange_setup_local(ctx.data(), int(devs.size())));
+}
+
 Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
-                          Scheme scheme, const Options& opt) {
+                          Scheme scheme, const Options& opt, GpuSet& gpus) {
     const size_t n = inputs.size();
     if (n > 0xFFFF)   // group_extraction.rs:538-543
         throw std::runtime_error("too many species (" + std::to_string(n) + ") for compact direct block observations; maximum is 65535");
     const float nf = float(n < 1 ? size_t(1) : n);
     volatile float prod = min_freq * nf;                       // f32 arithmetic, group_extraction.rs:544
     const uint32_t min_needed = uint32_t(std::ceil(float(prod)));
-    // the CUDA context and the 512 MiB table come up on a side thread while the host threads load the proteomes
-    std::unique_ptr<Ctx> gpu_holder;
+    // the CUDA contexts and their 512 MiB tables come up on a side thread while the host threads load the proteomes
     std::string gpu_err;
     std::thread gpu_init([&] {
         StageTimer t("kmn_create (overlaps the load)");
-        try { gpu_holder = std::make_unique<Ctx>(opt.device, int(k), int(scheme)); }
+        try { gpus.create(opt.devices, int(k), int(scheme)); }
         catch (const std::exception& e) { gpu_err = *e.what() ? e.what() : "GPU front end: error"; }
     });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } gpu_joiner{gpu_init};
@@ -133,95 +151,131 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     gpu_init.join();
     if (!gpu_err.empty()) throw std::runtime_error(gpu_err);
     for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);   // first error in species order (:569-571)
-    Ctx& gpu = *gpu_holder;
+    const size_t G = gpus.size();
 
-    // ---- pass 1: batches of whole species through kmn_count_batch
-    auto t_p1 = std::make_unique<StageTimer>("pass 1 (stage + count + finalize)");
-    struct BatchRef { uint32_t id; size_t sp0, sp1; };
-    std::vector<BatchRef> batches;
-    // the batch buffer is page-locked (kmn_host_alloc): its copies then overlap the kernels of kmn_count_batch
-    struct Pinned {
-        uint8_t* p = nullptr;
-        size_t cap = 0;
-        ~Pinned() { kmn_host_free(p); }
-        void ensure(size_t n, const Ctx& gpu) {
-            if (n <= cap) return;
-            kmn_host_free(p);
-            p = nullptr;
-            cap = 0;
-            void* q = nullptr;
-            gpu.ok(kmn_host_alloc(&q, n));
-            p = static_cast<uint8_t*>(q);
-            cap = n;
-        }
-    } buf;
-    std::vector<uint64_t> rec_off, sp_rec_off, hdr_off;
-    for (size_t s0 = 0; s0 < n;) {
-        size_t s1 = s0, bytes = 0, recs = 0;
-        while (s1 < n && (s1 == s0 || bytes + prot[s1].seq.size() <= opt.batch_bytes)) {
-            bytes += prot[s1].seq.size();
-            recs += prot[s1].n_rec();
-            s1++;
-        }
-        if (bytes + recs >= (uint64_t(1) << 31)) throw std::runtime_error("species " + inputs[s0].name + " is too large for one GPU batch");
-        buf.ensure(bytes, gpu);
-        rec_off.assign(1, 0);
-        sp_rec_off.assign(1, 0);
-        size_t at = 0;
-        std::vector<uint64_t> sp_at(s1 - s0 + 1);
-        for (size_t s = s0; s < s1; s++) {
-            sp_at[s - s0] = at;
-            for (size_t r = 0; r < prot[s].n_rec(); r++) rec_off.push_back(at + prot[s].rec_end[r]);
-            at += prot[s].seq.size();
-            sp_rec_off.push_back(rec_off.size() - 1);
-        }
-        sp_at[s1 - s0] = at;
-        auto on_threads = [&](auto&& per_species) {
-            std::atomic<size_t> next{s0};
-            auto work = [&] { for (size_t s; (s = next.fetch_add(1)) < s1;) per_species(s); };
-            std::vector<std::thread> pool;
-            for (size_t t = 0; t < std::max<size_t>(1, std::min(opt.threads, s1 - s0)); t++) pool.emplace_back(work);
-            for (auto& t : pool) t.join();
-        };
-        // gather the species into the pinned buffer on the host threads
-        on_threads([&](size_t s) {
-            if (!prot[s].seq.empty()) std::memcpy(buf.p + sp_at[s - s0], prot[s].seq.data(), prot[s].seq.size());
-        });
-        uint32_t id = 0;
-        if (device_fasta) {
-            uint64_t n_rec = 0;
-            if (kmn_count_fasta(gpu.p, buf.p, sp_at.data(), uint32_t(s1 - s0), nullptr, &id, &n_rec) != 0) {
-                const std::string gpu_msg = kmn_last_error();
-                // a format error: the host reader words it like the reference does, first bad file in species order
-                for (size_t s = s0; s < s1; s++) parse_proteome(prot[s].seq, inputs[s].path);
-                throw std::runtime_error("GPU front end: " + gpu_msg);
-            }
-            hdr_off.resize(n_rec);
-            sp_rec_off.assign(s1 - s0 + 1, 0);
-            uint64_t got = 0;
-            gpu.ok(kmn_fetch_records(gpu.p, id, hdr_off.data(), n_rec, &got, sp_rec_off.data()));
-            std::vector<std::string> idx_err(s1 - s0);
-            on_threads([&](size_t s) {   // headers and sequence ranges of the records the device found
-                try {
-                    index_records(prot[s], hdr_off.data() + sp_rec_off[s - s0], size_t(sp_rec_off[s - s0 + 1] - sp_rec_off[s - s0]),
-                                  sp_at[s - s0]);
-                } catch (const std::exception& e) { idx_err[s - s0] = e.what(); }
+    // ---- pass 1: species shard round-robin over the devices (sid mod G: a species never spans devices, so its
+    // Bloom filter stays device-local; the reference's par_iter over species, :557-567); every device counts its
+    // species in batches of whole species through kmn_count_fasta / kmn_count_batch on its own host thread, then
+    // ONE table exchange (the sketch is linear) gives every device the table of the whole job
+    auto t_p1 = std::make_unique<StageTimer>("pass 1 (stage + count + exchange)");
+    struct BatchRef { uint32_t id; std::vector<size_t> sids; };
+    std::vector<std::vector<BatchRef>> rank_batches(G);
+    struct RankError { size_t sid = SIZE_MAX; std::string msg; };
+    std::vector<RankError> rank_err(G);
+    const size_t helpers = std::max<size_t>(1, opt.threads / G);   // host threads of one device's gather / record indexing
+    auto on_rank_threads = [&](auto&& per_rank) {
+        std::vector<std::thread> pool;
+        for (size_t r = 0; r < G; r++)
+            pool.emplace_back([&, r] {
+                try { per_rank(r); }
+                catch (const std::exception& e) {
+                    if (rank_err[r].msg.empty()) rank_err[r] = {rank_batches[r].empty() ? r : rank_batches[r].back().sids.front(), e.what()};
+                }
             });
-            for (auto& e : idx_err) if (!e.empty()) throw std::runtime_error(e);
-        } else {
-            gpu.ok(kmn_count_batch(gpu.p, buf.p, rec_off.data(), rec_off.size() - 1, sp_rec_off.data(),
-                                   uint32_t(s1 - s0), nullptr, &id));
+        for (auto& t : pool) t.join();
+        const RankError* first = nullptr;
+        for (auto& e : rank_err)
+            if (!e.msg.empty() && (!first || e.sid < first->sid)) first = &e;
+        if (first) throw std::runtime_error(first->msg);   // first error in species order (:569-571)
+    };
+    on_rank_threads([&](size_t r) {
+        kmn_ctx* gpu = gpus.ctx[r];
+        std::vector<size_t> mine;
+        for (size_t sid = r; sid < n; sid += G) mine.push_back(sid);
+        // the batch buffer is page-locked (kmn_host_alloc): its copies then overlap the kernels of kmn_count_batch
+        struct Pinned {
+            uint8_t* p = nullptr;
+            size_t cap = 0;
+            ~Pinned() { kmn_host_free(p); }
+            void ensure(size_t n) {
+                if (n <= cap) return;
+                kmn_host_free(p);
+                p = nullptr;
+                cap = 0;
+                void* q = nullptr;
+                gpu_ok(kmn_host_alloc(&q, n));
+                p = static_cast<uint8_t*>(q);
+                cap = n;
+            }
+        } buf;
+        std::vector<uint64_t> rec_off, sp_rec_off, hdr_off;
+        for (size_t i0 = 0; i0 < mine.size();) {
+            size_t i1 = i0, bytes = 0, recs = 0;
+            while (i1 < mine.size() && (i1 == i0 || bytes + prot[mine[i1]].seq.size() <= opt.batch_bytes)) {
+                bytes += prot[mine[i1]].seq.size();
+                recs += prot[mine[i1]].n_rec();
+                i1++;
+            }
+            const size_t nb = i1 - i0;
+            if (bytes + recs >= (uint64_t(1) << 31)) throw std::runtime_error("species " + inputs[mine[i0]].name + " is too large for one GPU batch");
+            buf.ensure(bytes);
+            rec_off.assign(1, 0);
+            sp_rec_off.assign(1, 0);
+            size_t at = 0;
+            std::vector<uint64_t> sp_at(nb + 1);
+            for (size_t i = i0; i < i1; i++) {
+                const Proteome& pr = prot[mine[i]];
+                sp_at[i - i0] = at;
+                for (size_t q = 0; q < pr.n_rec(); q++) rec_off.push_back(at + pr.rec_end[q]);
+                at += pr.seq.size();
+                sp_rec_off.push_back(rec_off.size() - 1);
+            }
+            sp_at[nb] = at;
+            auto on_threads = [&](auto&& per_species) {   // per_species(index inside the batch)
+                std::atomic<size_t> next{0};
+                auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < nb;) per_species(i); };
+                std::vector<std::thread> pool;
+                for (size_t t = 0; t < std::max<size_t>(1, std::min(helpers, nb)); t++) pool.emplace_back(work);
+                for (auto& t : pool) t.join();
+            };
+            // gather the species into the pinned buffer on the host threads
+            on_threads([&](size_t i) {
+                const Proteome& pr = prot[mine[i0 + i]];
+                if (!pr.seq.empty()) std::memcpy(buf.p + sp_at[i], pr.seq.data(), pr.seq.size());
+            });
+            BatchRef ref;
+            ref.sids.assign(mine.begin() + i0, mine.begin() + i1);
+            uint32_t id = 0;
+            if (device_fasta) {
+                uint64_t n_rec = 0;
+                if (kmn_count_fasta(gpu, buf.p, sp_at.data(), uint32_t(nb), nullptr, &id, &n_rec) != 0) {
+                    const std::string gpu_msg = kmn_last_error();
+                    // a format error: the host reader words it like the reference does, first bad file in species order
+                    for (size_t i = i0; i < i1; i++) {
+                        try { parse_proteome(prot[mine[i]].seq, inputs[mine[i]].path); }
+                        catch (const std::exception& e) { rank_err[r] = {mine[i], e.what()}; return; }
+                    }
+                    rank_err[r] = {mine[i0], "GPU front end: " + gpu_msg};
+                    return;
+                }
+                hdr_off.resize(n_rec);
+                sp_rec_off.assign(nb + 1, 0);
+                uint64_t got = 0;
+                gpu_ok(kmn_fetch_records(gpu, id, hdr_off.data(), n_rec, &got, sp_rec_off.data()));
+                std::vector<std::string> idx_err(nb);
+                on_threads([&](size_t i) {   // headers and sequence ranges of the records the device found
+                    try {
+                        index_records(prot[mine[i0 + i]], hdr_off.data() + sp_rec_off[i], size_t(sp_rec_off[i + 1] - sp_rec_off[i]), sp_at[i]);
+                    } catch (const std::exception& e) { idx_err[i] = e.what(); }
+                });
+                for (size_t i = 0; i < nb; i++)
+                    if (!idx_err[i].empty()) { rank_err[r] = {mine[i0 + i], idx_err[i]}; return; }
+            } else {
+                gpu_ok(kmn_count_batch(gpu, buf.p, rec_off.data(), rec_off.size() - 1, sp_rec_off.data(), uint32_t(nb), nullptr, &id));
+            }
+            ref.id = id;
+            rank_batches[r].push_back(std::move(ref));
+            i0 = i1;
         }
-        batches.push_back({id, s0, s1});
-        s0 = s1;
-    }
-    gpu.ok(kmn_finalize_table(gpu.p));   // snapshot (:576)
+    });
+    if (G > 1) gpu_ok(kmn_exchange_reduce_all(gpus.ctx.data(), int(G)));   // one exchange per job: every device now holds the whole table
+    else gpu_ok(kmn_finalize_table(gpus.ctx[0]));                          // snapshot (:576)
     t_p1.reset();
     auto t_p2 = std::make_unique<StageTimer>("pass 2 (scan + pairing)");
 
-    // ---- pass 2: occupancy scan, boundary rule, anchor selection and bubble pairing on the device
-    // (kmn_scan_batch + kmn_pair_batch); the host slices the amino-acid blocks per species on its threads
-    // and merges them in sid order (:611-636)
+    // ---- pass 2: occupancy scan, boundary rule, anchor selection and bubble pairing on the device that holds
+    // the species (kmn_scan_batch + kmn_pair_batch; :589-608); the host slices the amino-acid blocks per species
+    // on its threads and merges them in sid order (:611-636)
     if (!opt.quiet) std::fprintf(stderr, " . pass 2: extract sequences\n");
     Extraction ex;
     ex.k = k;
@@ -237,17 +291,20 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
     };
     std::vector<SpeciesOut> outs(n);
     auto t_dev = std::make_unique<StageTimer>("  pass 2: device scan + pairing + fetch");
-    for (const BatchRef& b : batches) {
-        uint64_t ts = 0, te = 0, np = 0;
-        gpu.ok(kmn_scan_batch(gpu.p, b.id, min_needed, &ts, &te));
-        gpu.ok(kmn_pair_batch(gpu.p, b.id, uint32_t(std::min<size_t>(length_middle, 0xFFFFFFFFu)), &np));
-        for (size_t sid = b.sp0; sid < b.sp1; sid++) {   // calls on one context are serialised
-            uint64_t cnt = 0;
-            gpu.ok(kmn_fetch_pairs(gpu.p, b.id, uint32_t(sid - b.sp0), nullptr, 0, &cnt));
-            outs[sid].pairs.resize(cnt);
-            if (cnt) gpu.ok(kmn_fetch_pairs(gpu.p, b.id, uint32_t(sid - b.sp0), outs[sid].pairs.data(), cnt, &cnt));
+    on_rank_threads([&](size_t r) {
+        kmn_ctx* gpu = gpus.ctx[r];
+        for (const BatchRef& b : rank_batches[r]) {
+            uint64_t ts = 0, te = 0, np = 0;
+            gpu_ok(kmn_scan_batch(gpu, b.id, min_needed, &ts, &te));
+            gpu_ok(kmn_pair_batch(gpu, b.id, uint32_t(std::min<size_t>(length_middle, 0xFFFFFFFFu)), &np));
+            for (size_t i = 0; i < b.sids.size(); i++) {   // calls on one context are serialised
+                uint64_t cnt = 0;
+                gpu_ok(kmn_fetch_pairs(gpu, b.id, uint32_t(i), nullptr, 0, &cnt));
+                outs[b.sids[i]].pairs.resize(cnt);
+                if (cnt) gpu_ok(kmn_fetch_pairs(gpu, b.id, uint32_t(i), outs[b.sids[i]].pairs.data(), cnt, &cnt));
+            }
         }
-    }
+    });
     t_dev.reset();
     {
         StageTimer t_par("  pass 2: host block slicing (threads)");
@@ -357,8 +414,20 @@ Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, floa
         }
         ex.groups.resize(n_obs);
         uint64_t ng = 0;
-        gpu.ok(kmn_group_observations(gpu.p, n_obs, left.data(), right.data(), sid.data(), len.data(), min_needed,
-                                      perm.data(), ex.groups.data(), ex.groups.size(), &ng));
+        if (G == 1) {
+            // one device holds every batch's anchor pairs in emission order: the device groups them in place
+            std::vector<uint32_t> ids, base;
+            for (const BatchRef& b : rank_batches[0]) { ids.push_back(b.id); base.push_back(uint32_t(b.sids.front())); }
+            uint64_t n_dev = 0;
+            gpu_ok(kmn_group_batches(gpus.ctx[0], ids.data(), uint32_t(ids.size()), base.data(), 1, min_needed, perm.data(), perm.size(),
+                                     ex.groups.data(), ex.groups.size(), &n_dev, &ng));
+            if (n_dev != n_obs) throw std::runtime_error("GPU front end: the device grouped " + std::to_string(n_dev) +
+                                                         " observations, the host holds " + std::to_string(n_obs));
+        } else {
+            // the pairs live on several devices: the grouping device receives the observation keys from the host
+            gpu_ok(kmn_group_observations(gpus.ctx[0], n_obs, left.data(), right.data(), sid.data(), len.data(), min_needed,
+                                          perm.data(), ex.groups.data(), ex.groups.size(), &ng));
+        }
         ex.groups.resize(ng);
         ex.n_groups = ng;
         std::vector<Observation> sorted(n_obs);

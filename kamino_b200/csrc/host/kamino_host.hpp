@@ -30,12 +30,28 @@ struct Options {                     // src/lib.rs:119-175
     size_t length_middle = 35, mask = 5, threads = 1;
     Scheme recode = SR6;
     int device = 0;                  // new, non-breaking: CUDA ordinal (env KAMINO_DEVICE)
+    std::vector<int> devices;        // new, non-breaking: --devices 0,1,... (env KAMINO_DEVICES): the species shard round-robin
+                                     // over these GPUs, one table exchange per job; default: {device}
     size_t batch_bytes = size_t(1) << 30;   // residues per kmn_count_batch call
     bool quiet = false;
     std::string predict_only;        // new, hidden: with --genomes, write the predicted proteomes here and stop (no GPU)
 };
 
 struct SpeciesFile { std::string name, path; };      // src/io.rs:51-58
+
+// The GPUs of one run: one kmn_ctx per device (rank r = devices[r]), created once and shared by the stage
+// driver (both passes) and the --nj pair counts.  With several devices the contexts are wired for the
+// in-process table exchange (kmn_exchange_setup_local).
+struct GpuSet {
+    std::vector<kmn_ctx*> ctx;
+    std::vector<int> devices;
+    GpuSet() = default;
+    GpuSet(const GpuSet&) = delete;
+    GpuSet& operator=(const GpuSet&) = delete;
+    ~GpuSet();
+    void create(const std::vector<int>& devices, int k, int scheme);
+    size_t size() const { return ctx.size(); }
+};
 
 // io.rs
 std::vector<SpeciesFile> inputs_from_directory(const std::string& dir);   // io.rs:16-79
@@ -100,14 +116,14 @@ struct Alignment {                     // AlignmentResult, group_filtering.rs:12
 
 // group_extraction.rs:527-660 with both passes on the GPU (kmn_count_batch / kmn_scan_batch).
 Extraction extract_groups(const std::vector<SpeciesFile>& inputs, size_t k, float min_freq, size_t length_middle,
-                          Scheme scheme, const Options& opt);
+                          Scheme scheme, const Options& opt, GpuSet& gpus);
 // group_sorting.rs:329-380
 std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme scheme);
 // group_filtering.rs:292-363
 Alignment filter_groups(const Extraction& ex, const std::vector<Candidate>& cands, float min_freq, size_t constant,
                         size_t mask, Scheme scheme, size_t threads);
 // output.rs:32-95 (+ phylo.rs:274-301 with the pair counts from kmn_pair_counts)
-void write_outputs(const std::string& out_base, const Alignment& al, bool nj, int device, size_t* total_len,
+void write_outputs(const std::string& out_base, const Alignment& al, bool nj, GpuSet& gpus, size_t threads, size_t* total_len,
                    double* pct_missing);
 // lib.rs:206-298
 void run(const Options& opt);

@@ -5,6 +5,7 @@
 #include "../../../include/kamino_b200.h"
 #include "kamino_host.hpp"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -78,8 +79,8 @@ void emit(const std::vector<TreeNode>& t, const std::vector<std::string>& names,
     out += buf;
 }
 
-// phylo.rs:274-301: counts on the GPU, distances + classic NJ on the host
-std::string nj_newick(const std::vector<std::string>& names, const std::vector<std::vector<uint8_t>>& seqs, int device) {
+// phylo.rs:274-301: counts on the GPU(s) of the run, distances + classic NJ on the host
+std::string nj_newick(const std::vector<std::string>& names, const std::vector<std::vector<uint8_t>>& seqs, GpuSet& gpus, size_t threads) {
     const size_t n = names.size();
     if (n != seqs.size()) throw std::runtime_error("names and sequences length mismatch");
     if (n < 2) throw std::runtime_error("need at least 2 sequences");
@@ -91,15 +92,56 @@ std::string nj_newick(const std::vector<std::string>& names, const std::vector<s
     uint8_t map[256];
     std::memset(map, 20, sizeof map);
     for (int i = 0; i < 20; i++) map[uint8_t(order[i])] = uint8_t(i);
-    std::vector<uint8_t> mapped(n * L);
-    for (size_t i = 0; i < n; i++) for (size_t c = 0; c < L; c++) mapped[i * L + c] = map[seqs[i][c]];
+    // map_sequence (phylo.rs:75-79) on the host threads, straight into page-locked memory
+    if (gpus.size() == 0) throw std::runtime_error("GPU front end: no context for the pair counts");
+    struct PinnedBytes {
+        void* p = nullptr;
+        ~PinnedBytes() { kmn_host_free(p); }
+    } pin;
+    if (kmn_host_alloc(&pin.p, n * L) != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error());
+    uint8_t* mapped = static_cast<uint8_t*>(pin.p);
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t i; (i = next.fetch_add(1)) < n;)
+                for (size_t c = 0; c < L; c++) mapped[i * L + c] = map[seqs[i][c]];
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < std::max<size_t>(1, std::min(threads, n)); t++) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
     std::vector<uint32_t> valid(n * n, 0), mism(n * n, 0);
-    kmn_ctx* ctx = nullptr;
-    if (kmn_create(&ctx, device, 13, KMN_SR6) != 0) throw std::runtime_error(std::string("GPU front end: ") + kmn_last_error());
-    const int rc = kmn_pair_counts(ctx, mapped.data(), uint32_t(n), L, valid.data(), mism.data());
-    const std::string err = rc ? kmn_last_error() : "";
-    kmn_destroy(ctx);
-    if (rc) throw std::runtime_error("GPU front end: " + err);
+    // the rayon loop over rows i of compute_distance_matrix (phylo.rs:124-138), sharded over the run's GPUs as
+    // contiguous row blocks aligned to the kernel's 64-row tiles and balanced by upper-triangle tiles
+    const size_t G = gpus.size();
+    const size_t n_tiles = (n + 63) / 64, total = n_tiles * (n_tiles + 1) / 2;
+    std::vector<std::pair<uint32_t, uint32_t>> blocks;
+    {
+        size_t t = 0, done = 0;
+        for (size_t r = 0; r < G; r++) {
+            const size_t target = total * (r + 1) / G, t0 = t;
+            auto dist = [](size_t a, size_t b) { return a > b ? a - b : b - a; };
+            while (t < n_tiles && (r == G - 1 || dist(done + (n_tiles - t), target) <= dist(done, target))) {
+                done += n_tiles - t;
+                t++;
+            }
+            blocks.emplace_back(uint32_t(std::min(t0 * 64, n)), uint32_t(std::min(t * 64, n)));
+        }
+    }
+    std::vector<std::string> errs(G);
+    {
+        std::vector<std::thread> pool;
+        for (size_t r = 0; r < G; r++)
+            pool.emplace_back([&, r] {
+                const uint32_t b0 = blocks[r].first, b1 = blocks[r].second;
+                if (b1 <= b0) return;
+                if (kmn_pair_counts_rows(gpus.ctx[r], mapped, uint32_t(n), L, b0, b1, valid.data() + size_t(b0) * n,
+                                         mism.data() + size_t(b0) * n) != 0)
+                    errs[r] = kmn_last_error();
+            });
+        for (auto& t : pool) t.join();
+    }
+    for (auto& e : errs) if (!e.empty()) throw std::runtime_error("GPU front end: " + e);
 
     const size_t dim = 2 * n - 1;
     std::vector<double> d(dim * dim, 0.0);
@@ -170,7 +212,7 @@ std::string nj_newick(const std::vector<std::string>& names, const std::vector<s
 
 }  // namespace
 
-void write_outputs(const std::string& out_base, const Alignment& al, bool nj, int device, size_t* total_len,
+void write_outputs(const std::string& out_base, const Alignment& al, bool nj, GpuSet& gpus, size_t threads, size_t* total_len,
                    double* pct_missing) {   // output.rs:32-95
     const auto& sp = al.species_names;
     const size_t len = al.concat.empty() ? 0 : al.concat[0].size();
@@ -203,7 +245,7 @@ void write_outputs(const std::string& out_base, const Alignment& al, bool nj, in
                      al.partition_names[i].c_str());
     std::fclose(f);
     if (nj) {
-        const std::string tree = nj_newick(sp, al.concat, device);
+        const std::string tree = nj_newick(sp, al.concat, gpus, threads);
         f = create(derive_path(out_base, "_NJ", "tree"));
         std::fprintf(f, "%s\n", tree.c_str());
         std::fclose(f);
@@ -251,7 +293,12 @@ void run(const Options& o) {   // lib.rs:206-298
     }
     if (inputs.empty()) throw std::runtime_error("At least one input source with files must be provided.");
     StageTimer t_all("total");
-    Extraction ex = extract_groups(inputs, k, o.min_freq, o.length_middle, o.recode, o);
+    Options opt = o;
+    if (opt.devices.empty()) opt.devices.push_back(opt.device);
+    if (opt.devices.size() != 1 && opt.devices.size() != 2 && opt.devices.size() != 4 && opt.devices.size() != 8 && opt.devices.size() != 16)
+        throw std::runtime_error("--devices takes 1, 2, 4, 8 or 16 devices (the table splits evenly over them)");
+    GpuSet gpus;   // lives until the outputs are written: --nj reuses the contexts of the passes
+    Extraction ex = extract_groups(inputs, k, o.min_freq, o.length_middle, o.recode, opt, gpus);
     if (!o.quiet) std::fprintf(stderr, "# analyse variant groups\n . raw variant groups: %zu\n", ex.n_groups);
     std::vector<Candidate> cands;
     { StageTimer t("sort_and_deduplicate_groups"); cands = sort_and_deduplicate_groups(ex, o.recode); }
@@ -261,14 +308,34 @@ void run(const Options& o) {   // lib.rs:206-298
     if (!o.quiet) std::fprintf(stderr, " . filtered variant groups: %zu\n", al.partitions.size());
     size_t alen = 0;
     double amiss = 0;
-    { StageTimer t("write_outputs (+NJ)"); write_outputs(o.output, al, o.nj, o.device, &alen, &amiss); }
+    { StageTimer t("write_outputs (+NJ)"); write_outputs(o.output, al, o.nj, gpus, o.threads, &alen, &amiss); }
     if (!o.quiet) std::fprintf(stderr, "# output files\n . alignment: length=%zu missing=%.1f%%\n", alen, amiss);
     if (o.nj && !o.quiet) std::fprintf(stderr, " . NJ tree\n");
+}
+
+static std::vector<int> parse_devices(const std::string& v) {   // "0,1,2,3"
+    std::vector<int> out;
+    size_t pos = 0;
+    while (pos <= v.size()) {
+        const size_t comma = std::min(v.find(',', pos), v.size());
+        const std::string tok = v.substr(pos, comma - pos);
+        if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos)
+            throw std::runtime_error("invalid value '" + v + "' for '--devices' (comma-separated CUDA ordinals)");
+        out.push_back(std::stoi(tok));
+        pos = comma + 1;
+    }
+    return out;
 }
 
 int cli(int argc, char** argv) {   // main.rs:5-9 + clap surface of lib.rs:119-175
     Options o;
     if (const char* d = std::getenv("KAMINO_DEVICE")) o.device = std::atoi(d);
+    try {
+        if (const char* d = std::getenv("KAMINO_DEVICES")) o.devices = parse_devices(d);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
     try {
         for (int i = 1; i < argc; i++) {
             std::string a = argv[i], val;
@@ -299,6 +366,7 @@ int cli(int argc, char** argv) {   // main.rs:5-9 + clap surface of lib.rs:119-1
             }
             else if (a == "--nj" || a == "--NJ") o.nj = true;           // README spells it --NJ, clap accepts --nj
             else if (a == "--device") o.device = std::stoi(need());
+            else if (a == "--devices") o.devices = parse_devices(need());
             else if (a == "--batch-bytes") o.batch_bytes = std::stoull(need());
             else if (a == "--predict-only") o.predict_only = need();
             else if (a == "--self-test") {   // hidden: host-logic unit tests that need no GPU

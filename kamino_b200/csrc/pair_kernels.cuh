@@ -22,9 +22,9 @@ constexpr size_t PAIR_COUNT_SMEM = size_t(4) * PAIR_TILE * PAIR_ROW_STRIDE * siz
 
 // planes[(i * W + w) * 8 + p]; columns >= L and rows >= n are "invalid" (valid plane 0).
 __global__ void __launch_bounds__(256)
-pair_pack_kernel(const uint8_t* __restrict__ mapped, uint32_t n, uint64_t L, uint32_t n_pad, uint32_t W,
+pair_pack_kernel(const uint8_t* __restrict__ mapped, uint32_t n, uint64_t L, uint32_t n_pad, uint32_t W, uint32_t row0,
                  uint32_t* __restrict__ planes) {
-    const uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t idx = uint64_t(row0) * W + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // rows below row0 are not needed
     if (idx >= uint64_t(n_pad) * W) return;
     const uint32_t i = uint32_t(idx / W), w = uint32_t(idx % W);
     uint32_t p[6] = {0, 0, 0, 0, 0, 0};

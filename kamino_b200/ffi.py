@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "kmn_stage_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_exchange_setup_local", "kmn_exchange_reduce_all", "kmn_exchange_abort", "kmn_table_checksum", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
-    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
+    "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_group_batches", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.kmn_pair_batch.argtypes = [vp, C.c_uint32, C.c_uint32, u64p]
     lib.kmn_group_observations.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.kmn_fetch_pairs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.kmn_group_batches.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]
     lib.kmn_pair_counts.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, vp]
     lib.kmn_count_fasta.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(C.c_uint32), u64p]
     lib.kmn_fetch_records.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p, vp]
@@ -333,6 +334,26 @@ class Context:
         self._check(self.lib.kmn_group_observations(self._h, n, _ptr(left), _ptr(right), _ptr(sid), _ptr(length),
                                                     min_needed, _ptr(perm), _ptr(groups), groups.size, C.byref(ng)))
         return perm, groups[:ng.value]
+
+    def group_batches(self, batch_ids, min_needed: int, sid_base=None, sid_stride: int = 1, full: bool = False):
+        """Grouping of the anchor pairs of paired batches, read in place on the device (kmn_group_batches).
+        Returns (n_obs, n_groups, n_valid), or (perm, groups) with full=True."""
+        ids = _as(batch_ids, np.uint32)
+        if sid_base is None:
+            sid_base = np.zeros(ids.size, np.uint32)
+        base = _as(sid_base, np.uint32)
+        n_obs, ng = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kmn_group_batches(self._h, _ptr(ids), ids.size, _ptr(base), sid_stride, min_needed, None, 0, None, 0,
+                                               C.byref(n_obs), C.byref(ng)))
+        n = int(n_obs.value)
+        perm = np.zeros(max(n, 1), dtype=np.uint32)
+        groups = np.zeros(max(n, 1), dtype=GROUP_DTYPE)
+        self._check(self.lib.kmn_group_batches(self._h, _ptr(ids), ids.size, _ptr(base), sid_stride, min_needed, _ptr(perm), perm.size,
+                                               _ptr(groups), groups.size, C.byref(n_obs), C.byref(ng)))
+        groups = groups[:ng.value]
+        if full:
+            return perm[:n], groups
+        return n, int(ng.value), int(np.count_nonzero(groups["flags"] & GROUP_VALID))
 
     def fetch_occupancy(self, batch_id: int, sp: int) -> np.ndarray:
         n = C.c_uint64()

@@ -81,6 +81,29 @@ def test_synthetic_matches_oracle_cli(product_cli, oracle, synthetic_dir, tmp_pa
     assert len(aln) >= 48 and len(aln[1]) > 0, "expected a non-empty alignment on related proteomes"
 
 
+@pytest.mark.parametrize("n_dev", [2, 4, 8])
+def test_multi_device_cli_matches_oracle_cli(product_cli, oracle, synthetic_dir, tmp_path, n_dev):
+    """`--devices 0,1,...`: the species shard round-robin over the GPUs of ONE process (the reference's rayon
+    loops over species, group_extraction.rs:558-567 / :589-608), one in-process table exchange, pass 2 and the
+    --nj row blocks on every device: byte-identical to the oracle CLI and to the one-GPU run."""
+    import torch
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    want, got, one = tmp_path / "want", tmp_path / "got", tmp_path / "one"
+    for d in (want, got, one):
+        d.mkdir()
+    for extra in ([], ["-r", "dayhoff6", "-k", 11, "--batch-bytes", 700000]):
+        common = ["-i", synthetic_dir / "in", "--nj", "-t", 4, *extra]
+        ref_args = [a for i, a in enumerate(common) if a != "--batch-bytes" and (i == 0 or common[i - 1] != "--batch-bytes")]
+        r = oracle.run_cli([*ref_args, "-o", want / "kamino"])
+        assert r.returncode == 0, r.stderr
+        _run(product_cli, [*common, "-o", one / "kamino"])
+        _run(product_cli, [*common, "--devices", ",".join(map(str, range(n_dev))), "-o", got / "kamino"])
+        for f in FILES:
+            assert (got / f).read_bytes() == (want / f).read_bytes(), (f, n_dev, extra)
+            assert (got / f).read_bytes() == (one / f).read_bytes(), (f, n_dev, extra)
+
+
 def test_awkward_fasta_files_match_oracle_cli(product_cli, oracle, synthetic_dir, tmp_path):
     """CRLF files, leading empty lines, a missing final line feed, '>' inside headers and a file whose first
     line is not a header: same outputs / same error text as the oracle CLI, with the records found on the device."""

@@ -131,6 +131,29 @@ def _timeout_worker(rank, world, port, out_dir):
                 except ffi.KaminoError as e:
                     msg = f"{time.time() - t0:.1f}s {e}"
             dist.barrier()
+            # the host can also break the wait at once (kmn_exchange_abort from another thread)
+            amsg = "not run"
+            assert sharding.setup_fused_exchange(ctx)
+            if rank == 0:
+                import threading
+                box = {}
+
+                def blocked():
+                    t0 = time.time()
+                    try:
+                        ctx.exchange_reduce()
+                        box["msg"] = "no error"
+                    except ffi.KaminoError as e:
+                        box["msg"] = f"{time.time() - t0:.2f}s {e}"
+
+                th = threading.Thread(target=blocked)
+                th.start()
+                time.sleep(0.3)
+                ctx.exchange_abort()
+                th.join()
+                amsg = box["msg"]
+            dist.barrier()
+            Path(out_dir, f"a{rank}.txt").write_text(amsg)
             # both ranks set up again and a normal exchange works
             assert sharding.setup_fused_exchange(ctx)
             ctx.reset_table()
@@ -151,6 +174,8 @@ def test_exchange_timeout_names_the_missing_rank(tmp_path):
     mp.spawn(_timeout_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     msg, total = (tmp_path / "t0.txt").read_text().split("|")
     assert "timed out" in msg and "rank 1" in msg, msg
+    amsg = (tmp_path / "a0.txt").read_text()
+    assert "aborted by the host" in amsg and float(amsg.split("s ")[0]) < 1.2, amsg
     assert total == "0" and (tmp_path / "t1.txt").read_text().endswith("|0")
 
 

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--nj", action="store_true")
     ap.add_argument("--workdir", default="/tmp/kamino_e2e")
     ap.add_argument("--skip-oracle", action="store_true")
+    ap.add_argument("--devices", default="", help="comma-separated CUDA ordinals for kamino-b200 --devices")
     args = ap.parse_args()
     import oracle_ffi
     from kamino_b200 import build, synth
@@ -45,13 +46,16 @@ def main():
     threads = len(os.sched_getaffinity(0))
     common = ["-i", str(work / "in"), "-t", str(threads)] + (["--nj"] if args.nj else [])
     t0 = time.time()
-    r = subprocess.run([str(cli), *common, "-o", str(work / "got" / "kamino")], capture_output=True, text=True)
+    dev = ["--devices", args.devices] if args.devices else []
+    env = dict(os.environ, KAMINO_TIMING="1")
+    r = subprocess.run([str(cli), *common, *dev, "-o", str(work / "got" / "kamino")], capture_output=True, text=True, env=env)
     gpu_s = time.time() - t0
     if r.returncode != 0:
         print(r.stderr, file=sys.stderr)
         raise SystemExit("kamino-b200 failed")
     out = {"what": "e2e_cli", "species": args.species, "kind": args.kind, "residues": n_res, "threads": threads,
-           "generate_s": round(gen_s, 1), "gpu_cli_s": round(gpu_s, 2), "gpu_stderr_tail": r.stderr.strip().splitlines()[-4:]}
+           "generate_s": round(gen_s, 1), "gpu_cli_s": round(gpu_s, 2), "devices": args.devices or "0",
+           "gpu_stage_times": [l for l in r.stderr.splitlines() if l.startswith("[time]")]}
     if not args.skip_oracle:
         t0 = time.time()
         r = subprocess.run([str(oracle_ffi.CLI), *common, "-o", str(work / "want" / "kamino")], capture_output=True, text=True)
