@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""kmn_count_batch from pinned host memory (the e2e leg of bench.py) for several copy/compute range schedules
+(KMN_H2D_CHUNKS x KMN_H2D_MODE); one JSON line per setting."""
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    from kamino_b200 import ffi, synth
+    b = synth.stage(synth.bacterial(100, seed=synth.SEED0 + 1))
+    pin = ffi.PinnedBuffer(b.residues.size)
+    pin.array[:] = b.residues
+    for mode in ("doubling", "equal"):
+        for chunks in (1, 2, 3, 4, 5, 8):
+            os.environ["KMN_H2D_CHUNKS"] = str(chunks)
+            os.environ["KMN_H2D_MODE"] = mode
+            with ffi.Context(13, "sr6") as ctx:
+                ts = []
+                for i in range(9):
+                    ctx.reset_table()
+                    ctx.synchronize()
+                    t0 = time.perf_counter()
+                    ctx.count_batch(pin.array, b.rec_off, b.sp_rec_off)
+                    ctx.finalize_table()
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                    ctx.release_batches()
+                print(json.dumps({"mode": mode, "chunks": chunks, "ms": round(float(np.median(ts[3:])), 3)}), flush=True)
+    pin.free()
+
+
+if __name__ == "__main__":
+    main()
