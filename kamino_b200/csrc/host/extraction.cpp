@@ -47,26 +47,15 @@ bool valid_utf8(const std::string& s) {   // rec.id()? / rec.desc() fail on inva
     return true;
 }
 
-bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
-std::string trim(const std::string& s) {
-    size_t b = 0, e = s.size();
-    while (b < e && is_ws((unsigned char)s[b])) b++;
-    while (e > b && is_ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
-
-// "id desc" with both parts trimmed, cut at the first " [" (group_extraction.rs:397-404, :429-436)
+// "id desc" with both parts trimmed (Unicode White_Space, like str::trim), cut at the first " ["
+// (group_extraction.rs:397-404, :429-436)
 std::string protein_name_of(const std::string& head) {
-    const size_t sp = head.find(' ');
-    const std::string id = trim(sp == std::string::npos ? head : head.substr(0, sp));
-    const std::string desc = sp == std::string::npos ? std::string() : trim(head.substr(sp + 1));
-    std::string name = trim(desc.empty() ? id : id + " " + desc);
+    const size_t sp = head.find(' ');   // seq_io splits id / desc at the first SPACE byte
+    const std::string id = uws::trim(sp == std::string::npos ? head : head.substr(0, sp));
+    const std::string desc = sp == std::string::npos ? std::string() : uws::trim(head.substr(sp + 1));
+    const std::string name = uws::trim(desc.empty() ? id : id + " " + desc);
     const size_t cut = name.find(" [");
-    if (cut != std::string::npos) {
-        name.resize(cut);
-        while (!name.empty() && is_ws((unsigned char)name.back())) name.pop_back();
-    }
-    return name;
+    return cut == std::string::npos ? name : uws::trim_end(name.substr(0, cut));
 }
 
 }  // namespace
@@ -82,6 +71,11 @@ std::string extraction_self_test() {
         return "failed: group_extraction::protein names (id only / inner spaces)";
     if (!valid_utf8("caf\xc3\xa9") || valid_utf8("bad\xff") || valid_utf8("\xc3") || valid_utf8("\xed\xa0\x80"))
         return "failed: group_extraction::header UTF-8 validation";
+    // str::trim follows Unicode White_Space: NEL, NBSP, EN QUAD, LINE SEPARATOR, IDEOGRAPHIC SPACE around the fields
+    if (protein_name_of("id1 \xc2\xa0\xe2\x80\x80kinase\xe3\x80\x80 [Homo\xc2\x85]") != "id1 kinase" ||
+        protein_name_of("\xc2\x85id2\xe2\x80\xa8 desc\xe2\x81\x9f") != "id2 desc" ||
+        protein_name_of("id3 caf\xc3\xa9\xc2\xa0") != "id3 caf\xc3\xa9")
+        return "failed: group_extraction::protein names (Unicode white space)";
     return std::string();
 }
 

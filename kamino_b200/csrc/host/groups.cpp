@@ -163,13 +163,6 @@ std::vector<Candidate> sort_and_deduplicate_groups(const Extraction& ex, Scheme 
 
 namespace {
 
-inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
-std::string trim(const std::string& s) {
-    size_t b = 0, e = s.size();
-    while (b < e && is_ws((unsigned char)s[b])) b++;
-    while (e > b && is_ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
 
 // Majority-rule label over the descriptions of the supporting proteins (group_filtering.rs:143-221).
 std::string consensus_protein_name(const Extraction& ex, const Candidate& c) {
@@ -177,11 +170,11 @@ std::string consensus_protein_name(const Extraction& ex, const Candidate& c) {
     for (uint32_t r : c.rows) {
         const uint32_t pid = ex.obs[r].protein;
         if (pid >= ex.protein_names.size()) continue;
-        const std::string t = trim(ex.protein_names[pid]);
-        size_t p = 0;
-        while (p < t.size() && !is_ws((unsigned char)t[p])) p++;
+        const std::string t = uws::trim(ex.protein_names[pid]);
+        size_t p = 0, wl = 0;   // split_once(char::is_whitespace): first white-space CHARACTER (Unicode), :153-155
+        while (p < t.size() && (wl = uws::at(t, p)) == 0) p++;
         if (p >= t.size()) continue;
-        std::string d = trim(t.substr(p + 1));
+        std::string d = uws::trim(t.substr(p + wl));
         if (!d.empty()) names.push_back(std::move(d));
     }
     if (names.empty()) return "";
@@ -191,11 +184,11 @@ std::string consensus_protein_name(const Extraction& ex, const Candidate& c) {
     for (const std::string& nm : names) {
         std::unordered_set<std::string> in_name;
         size_t pos = 0;
-        for (size_t i = 0; i < nm.size();) {
-            while (i < nm.size() && is_ws((unsigned char)nm[i])) i++;
+        for (size_t i = 0; i < nm.size();) {   // split_whitespace (:179)
+            for (size_t l; i < nm.size() && (l = uws::at(nm, i)) != 0;) i += l;
             if (i >= nm.size()) break;
             size_t j = i;
-            while (j < nm.size() && !is_ws((unsigned char)nm[j])) j++;
+            while (j < nm.size() && uws::at(nm, j) == 0) j++;
             std::string w = nm.substr(i, j - i);
             i = j;
             const size_t at = pos++;

@@ -71,13 +71,7 @@ std::vector<SpeciesFile> inputs_from_directory(const std::string& dir) {   // io
     return out;
 }
 
-static bool ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
-static std::string trimmed(const std::string& s) {
-    size_t b = 0, e = s.size();
-    while (b < e && ws((unsigned char)s[b])) b++;
-    while (e > b && ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
+static std::string trimmed(const std::string& s) { return uws::trim(s); }   // str::trim (Unicode White_Space), io.rs:122-123
 
 std::vector<SpeciesFile> inputs_from_table(const std::string& tsv) {   // io.rs:82-162
     std::ifstream f(tsv, std::ios::binary);
@@ -87,7 +81,7 @@ std::vector<SpeciesFile> inputs_from_table(const std::string& tsv) {   // io.rs:
     std::set<std::string> seen;
     std::string line;
     for (size_t no = 1; std::getline(f, line); no++) {
-        while (!line.empty() && ws((unsigned char)line.back())) line.pop_back();   // strip CR + trim_end
+        line = uws::trim_end(line);   // strip CR + trim_end
         if (line.empty()) continue;
         std::vector<std::string> cols;
         size_t s = 0;

@@ -157,6 +157,49 @@ void parallel_sort(std::vector<T>& v, Cmp cmp, size_t threads) {
     }
 }
 
+// Rust's str::trim / trim_end / split_whitespace / char::is_whitespace follow the Unicode White_Space property
+// (group_extraction.rs:398-402,429-430; group_filtering.rs:153-155,179; io.rs:122-123), not just ASCII.  On valid
+// UTF-8 the white-space characters are exactly these byte sequences:
+//   09..0D, 20 | C2 85, C2 A0 | E1 9A 80 | E2 80 80..8A, E2 80 A8, E2 80 A9, E2 80 AF | E2 81 9F | E3 80 80
+namespace uws {
+// length in bytes of the white-space character that STARTS at s[i], 0 if none does
+inline size_t at(const std::string& s, size_t i) {
+    const size_t n = s.size();
+    const unsigned char c = (unsigned char)s[i];
+    if (c == 0x20 || (c >= 0x09 && c <= 0x0D)) return 1;
+    if (c == 0xC2 && i + 1 < n) {
+        const unsigned char d = (unsigned char)s[i + 1];
+        return (d == 0x85 || d == 0xA0) ? 2 : 0;
+    }
+    if (i + 2 >= n) return 0;
+    const unsigned char d = (unsigned char)s[i + 1], e = (unsigned char)s[i + 2];
+    if (c == 0xE1) return (d == 0x9A && e == 0x80) ? 3 : 0;
+    if (c == 0xE2) {
+        if (d == 0x80) return ((e >= 0x80 && e <= 0x8A) || e == 0xA8 || e == 0xA9 || e == 0xAF) ? 3 : 0;
+        return (d == 0x81 && e == 0x9F) ? 3 : 0;
+    }
+    if (c == 0xE3) return (d == 0x80 && e == 0x80) ? 3 : 0;
+    return 0;
+}
+// length in bytes of the white-space character that ENDS just before s[e], 0 if none does
+inline size_t before(const std::string& s, size_t e) {
+    for (size_t len = 1; len <= 3 && len <= e; len++)
+        if (at(s, e - len) == len) return len;
+    return 0;
+}
+inline std::string trim_end(const std::string& s) {
+    size_t e = s.size();
+    for (size_t l; e > 0 && (l = before(s, e)) != 0;) e -= l;
+    return s.substr(0, e);
+}
+inline std::string trim(const std::string& s) {
+    size_t b = 0, e = s.size();
+    for (size_t l; b < e && (l = at(s, b)) != 0;) b += l;
+    for (size_t l; e > b && (l = before(s, e)) != 0;) e -= l;
+    return s.substr(b, e - b);
+}
+}  // namespace uws
+
 // Wall-clock stage timer: prints "[time] <what>: <s>" to stderr when KAMINO_TIMING is set.
 struct StageTimer {
     const char* what;

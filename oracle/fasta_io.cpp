@@ -141,19 +141,9 @@ std::vector<SpeciesInput> collect_species_inputs_from_dir(const std::string& dir
     return inputs;
 }
 
-// str::trim / trim_end on ASCII input (Rust trims Unicode White_Space; ASCII subset here).
-static bool rs_is_ws(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); }
-static std::string trim_end(const std::string& s) {
-    size_t e = s.size();
-    while (e > 0 && rs_is_ws((unsigned char)s[e - 1])) e--;
-    return s.substr(0, e);
-}
-static std::string trim(const std::string& s) {
-    size_t b = 0, e = s.size();
-    while (b < e && rs_is_ws((unsigned char)s[b])) b++;
-    while (e > b && rs_is_ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
+// str::trim / trim_end (Unicode White_Space, kamino_oracle.hpp)
+static std::string trim_end(const std::string& s) { return rs_trim_end(s); }
+static std::string trim(const std::string& s) { return rs_trim(s); }
 
 std::vector<SpeciesInput> collect_species_inputs_from_table(const std::string& table) {  // io.rs:82-162
     std::ifstream f(table, std::ios::binary);

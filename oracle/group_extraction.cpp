@@ -167,20 +167,6 @@ uint64_t count_species_records(const std::vector<FastaRecord>& recs, size_t k, u
     return n_new;
 }
 
-static std::string rs_trim(const std::string& s) {
-    auto ws = [](unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); };
-    size_t b = 0, e = s.size();
-    while (b < e && ws((unsigned char)s[b])) b++;
-    while (e > b && ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
-static std::string rs_trim_end(const std::string& s) {
-    auto ws = [](unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); };
-    size_t e = s.size();
-    while (e > 0 && ws((unsigned char)s[e - 1])) e--;
-    return s.substr(0, e);
-}
-
 std::string truncate_protein_name(const std::string& raw) {  // :397-404
     std::string t = rs_trim(raw);
     size_t p = t.find(" [");

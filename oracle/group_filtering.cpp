@@ -12,13 +12,7 @@
 namespace kmo {
 
 static inline bool is_missing_or_ambiguous(uint8_t b) { return b == '-' || b == 'X'; }  // :32-35
-static inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); }
-static std::string trim(const std::string& s) {
-    size_t b = 0, e = s.size();
-    while (b < e && is_ws((unsigned char)s[b])) b++;
-    while (e > b && is_ws((unsigned char)s[e - 1])) e--;
-    return s.substr(b, e - b);
-}
+static std::string trim(const std::string& s) { return rs_trim(s); }   // str::trim: Unicode White_Space
 
 std::vector<int> majority_recoded_consensus(const std::vector<std::vector<uint8_t>>& rows, size_t len,
                                             RecodeScheme s) {  // :37-67
@@ -91,10 +85,10 @@ std::string consensus_protein_name(const std::vector<BlockObs>& observations,
     for (const BlockObs& obs : observations) {
         if (size_t(obs.protein_id) >= protein_names.size()) continue;
         std::string t = trim(protein_names[obs.protein_id]);
-        size_t p = 0;
-        while (p < t.size() && !is_ws((unsigned char)t[p])) p++;
-        if (p >= t.size()) continue;  // split_once found no whitespace
-        std::string desc = trim(t.substr(p + 1));
+        size_t p = 0, wl = 0;
+        while (p < t.size() && (wl = rs_ws_len(t, p)) == 0) p++;
+        if (p >= t.size()) continue;  // split_once(char::is_whitespace) found no whitespace
+        std::string desc = trim(t.substr(p + wl));
         if (!desc.empty()) names.push_back(desc);
     }
     if (names.empty()) return "";
@@ -105,10 +99,10 @@ std::string consensus_protein_name(const std::vector<BlockObs>& observations,
         std::unordered_set<std::string> seen_in_name;
         size_t position = 0, i = 0;
         while (i < name.size()) {
-            while (i < name.size() && is_ws((unsigned char)name[i])) i++;
+            for (size_t l; i < name.size() && (l = rs_ws_len(name, i)) != 0;) i += l;
             if (i >= name.size()) break;
             size_t j = i;
-            while (j < name.size() && !is_ws((unsigned char)name[j])) j++;
+            while (j < name.size() && rs_ws_len(name, j) == 0) j++;
             std::string word = name.substr(i, j - i);
             i = j;
             size_t pos = position++;

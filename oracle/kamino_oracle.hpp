@@ -30,6 +30,48 @@
 
 namespace kmo {
 
+// char::is_whitespace / str::trim / split_whitespace of Rust's std follow the Unicode White_Space property.
+// Decodes the scalar value that starts at s[i] (the callers hold valid UTF-8) and tests the property's ranges;
+// returns the character's byte length when it is white space, else 0.
+inline size_t rs_ws_len(const std::string& s, size_t i) {
+    const unsigned char b0 = (unsigned char)s[i];
+    uint32_t cp;
+    size_t len;
+    if (b0 < 0x80) { cp = b0; len = 1; }
+    else if ((b0 >> 5) == 0x6 && i + 1 < s.size()) { cp = ((b0 & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu); len = 2; }
+    else if ((b0 >> 4) == 0xE && i + 2 < s.size()) {
+        cp = ((b0 & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
+        len = 3;
+    } else return 0;   // 4-byte characters: none is white space
+    const bool ws = (cp >= 0x09 && cp <= 0x0D) || cp == 0x20 || cp == 0x85 || cp == 0xA0 || cp == 0x1680 ||
+                    (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+    return ws ? len : 0;
+}
+inline std::string rs_trim_start(const std::string& s) {
+    size_t b = 0;
+    while (b < s.size()) {
+        const size_t l = rs_ws_len(s, b);
+        if (!l) break;
+        b += l;
+    }
+    return s.substr(b);
+}
+inline std::string rs_trim_end(const std::string& s) {
+    size_t e = s.size();
+    for (;;) {
+        // the last character starts at the last byte that is not a UTF-8 continuation byte
+        size_t st = e;
+        while (st > 0 && (((unsigned char)s[st - 1]) & 0xC0) == 0x80) st--;
+        if (st == 0) break;
+        st--;
+        if (rs_ws_len(s, st) != e - st || e == st) break;
+        e = st;
+    }
+    return s.substr(0, e);
+}
+inline std::string rs_trim(const std::string& s) { return rs_trim_end(rs_trim_start(s)); }
+
+
 // ---------------------------------------------------------------- recode.rs
 constexpr uint32_t RECODE_BITS_PER_SYMBOL = 3;          // src/recode.rs:5
 enum RecodeScheme : int { Dayhoff6 = 0, SR6 = 1, KGB6 = 2 };  // src/recode.rs:9-16

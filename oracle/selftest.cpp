@@ -68,6 +68,11 @@ std::string self_test() {
     ORC_CHECK("group_extraction::truncate_protein_name_keeps_record_id_and_removes_organism_suffix",
               truncate_protein_name("WP_012345.1 hypothetical protein [Escherichia coli]") == "WP_012345.1 hypothetical protein" &&
               truncate_protein_name("WP_012345.1 hypothetical protein") == "WP_012345.1 hypothetical protein");
+    // not a reference test: str::trim / trim_end follow Unicode White_Space (NBSP, NEL, EN QUAD, IDEOGRAPHIC SPACE ...)
+    ORC_CHECK("oracle::unicode_white_space_in_str_trim",
+              truncate_protein_name("\xc2\xa0id kinase\xe2\x80\x80 [Homo]\xe3\x80\x80") == "id kinase" &&
+              rs_trim("\xc2\x85 x\xe2\x80\xa8") == "x" && rs_trim("caf\xc3\xa9") == "caf\xc3\xa9" &&
+              rs_ws_len(std::string("\xe2\x81\x9f"), 0) == 3 && rs_ws_len(std::string("\xe2\x80\x8b"), 0) == 0);
     {
         BlockArena arena;
         const BlockAa a = arena.push(reinterpret_cast<const uint8_t*>("ACD"), 3), b = arena.push(reinterpret_cast<const uint8_t*>("EFGH"), 4);

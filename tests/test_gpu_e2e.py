@@ -122,6 +122,10 @@ def test_awkward_fasta_files_match_oracle_cli(product_cli, oracle, synthetic_dir
             data = data.replace(b" hypothetical", b" >hypo>thetical")
         elif i == 5:
             data = data.replace(b"\n", b"\n\n", 50)
+        elif i == 7:   # Unicode white space around / inside the header fields (str::trim, split_whitespace)
+            data = data.replace(b" hypothetical protein ", "\u00a0 hypothetical\u2003protein\u3000 ".encode())
+        elif i == 8:
+            data = data.replace(b" [Synth sp]", "\u2028 [Synth sp]\u0085".encode())
         (d / f.name).write_bytes(data)
     want, got = tmp_path / "want", tmp_path / "got"
     want.mkdir(); got.mkdir()
