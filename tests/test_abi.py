@@ -52,3 +52,11 @@ def test_product_never_references_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")):
         txt = p.read_text()
         assert "oracle_ffi" not in txt and "kamino_oracle" not in txt and "orc_" not in txt, p
+
+
+def test_integration_doc_lists_every_export():
+    """INTEGRATION.md's Rust extern "C" block is a complete mirror of the header."""
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    block = doc[doc.index('#[link(name = "kamino_b200")]'):doc.index("pub fn check(rc: c_int)")]
+    declared = set(re.findall(r"pub fn (kmn_[a-z0-9_]+)\(", block))
+    assert declared == set(_header_symbols()), sorted(set(_header_symbols()) ^ declared)
