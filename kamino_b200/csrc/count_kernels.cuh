@@ -288,23 +288,32 @@ __device__ __forceinline__ uint32_t atoms_or_u32(uint32_t a, uint32_t v) {
     return o;
 }
 
+// The bucket kernel's conflict table in 32 bits (a 64-bit shared-memory atomicMin is a CAS loop; ncu showed the
+// conflict path, run by one or two lanes in almost every step, taking a quarter of the kernel's instructions):
+// slot = low 8 bits of the bit index, key = remaining bit-index bits << 18 | order inside the step.  The minimum
+// of a slot is the smallest bit that maps to it and, for that bit, its first toucher in file order.
+constexpr uint32_t MT32_ORDER_BITS = 18;   // order = warp << 14 | position inside the tile << 1 | probe
+static_assert((BB_THREADS / 32) <= (1 << (MT32_ORDER_BITS - ENT_BIT_SHIFT)), "order field");
+static_assert(BB_LOG2 - 8 + MT32_ORDER_BITS <= 32, "key layout");
+__device__ __forceinline__ uint32_t mt32_slot(uint32_t bit) { return bit & (MT_SLOTS - 1); }
+__device__ __forceinline__ uint32_t mt32_key(uint32_t bit, uint32_t order) { return ((bit >> 8) << MT32_ORDER_BITS) | order; }
+
 // rare: a probe of this step found its bit set by another probe of the same step
-__device__ __noinline__ void bucket_conflict_join(unsigned long long* list, unsigned long long* mt, uint32_t* mf,
+__device__ __noinline__ void bucket_conflict_join(unsigned long long* list, uint32_t* mt, uint32_t* mf,
                                                   uint32_t* n_list, uint32_t bit, uint32_t p, bool mark) {
-    const unsigned long long key = (static_cast<unsigned long long>(bit) << 32) | p;
     const uint32_t slot = atomicAdd(n_list, 1u);
-    if (slot < BB_LIST_CAP) list[slot] = key;
-    atomicMin(&mt[mt_slot(bit)], key);
+    if (slot < BB_LIST_CAP) list[slot] = (static_cast<unsigned long long>(bit) << 32) | p;
+    atomicMin(&mt[mt32_slot(bit)], mt32_key(bit, p));
     if (mark) atomicOr(&mf[(bit >> 5) & (MF_WORDS - 1)], 1u << (bit & 31u));
 }
 
 // rare: is a member of the conflict list beaten by a smaller file position of the same bit?
-__device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list, const unsigned long long* mt, uint32_t n,
+__device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list, const uint32_t* mt, uint32_t n,
                                                   uint32_t bit, uint32_t p) {
+    const uint32_t best = mt[mt32_slot(bit)];
+    if ((best >> MT32_ORDER_BITS) == (bit >> 8)) return best != mt32_key(bit, p);
     const unsigned long long lo = static_cast<unsigned long long>(bit) << 32, me = lo | p;
-    const unsigned long long best = mt[mt_slot(bit)];
-    if ((best >> 32) == bit) return best != me;
-    bool l = false;   // the hash slot belongs to a smaller bit: scan the list
+    bool l = false;   // the slot belongs to a smaller bit: scan the list
     for (uint32_t i = 0; i < n; i++) {
         const unsigned long long o = list[i];
         l |= (o >= lo) && (o < me);
@@ -317,7 +326,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
     extern __shared__ __align__(16) unsigned long long bb_smem[];
     unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(bb_smem + BB_LIST_CAP);       // BB_WORDS
-    __shared__ unsigned long long s_mt[2 * MT_SLOTS];
+    __shared__ uint32_t s_mt[2 * MT_SLOTS];
     __shared__ uint32_t s_mf[2 * MF_WORDS];
     __shared__ uint32_t s_n[2];
     const uint32_t s = s0 + blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
@@ -328,7 +337,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
     const uint32_t cb = sp_cstart[s];
     for (uint32_t i = threadIdx.x; i < BB_WORDS; i += BB_THREADS) s_bits[i] = 0;
     for (uint32_t i = threadIdx.x; i < 2 * MF_WORDS; i += BB_THREADS) s_mf[i] = 0;
-    for (uint32_t i = threadIdx.x; i < 2 * MT_SLOTS; i += BB_THREADS) s_mt[i] = ~0ull;
+    for (uint32_t i = threadIdx.x; i < 2 * MT_SLOTS; i += BB_THREADS) s_mt[i] = ~0u;
     if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t a_bits = smem_addr(s_bits);
@@ -368,7 +377,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
                 if ((lv >> q) & 1u) raw[q] = __ldcs(e + 32 * q);
         }
         n_next2 = run_len(t + 2 * BB_STEP_RUNS);
-        unsigned long long* mt = s_mt + par * MT_SLOTS;
+        uint32_t* mt = s_mt + par * MT_SLOTS;
         uint32_t* mf = s_mf + par * MF_WORDS;
         const uint32_t a_mf = smem_addr(mf);
         // phase 1: bits set by earlier steps (= by smaller file positions)
@@ -384,7 +393,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
         __syncthreads();
         // the other parity's scratch was last read in the previous step
         for (uint32_t i = threadIdx.x; i < MF_WORDS; i += BB_THREADS) s_mf[(par ^ 1u) * MF_WORDS + i] = 0;
-        for (uint32_t i = threadIdx.x; i < MT_SLOTS; i += BB_THREADS) s_mt[(par ^ 1u) * MT_SLOTS + i] = ~0ull;
+        for (uint32_t i = threadIdx.x; i < MT_SLOTS; i += BB_THREADS) s_mt[(par ^ 1u) * MT_SLOTS + i] = ~0u;
         if (threadIdx.x == 0) s_n[par ^ 1u] = 0;
         // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
         uint32_t won = 0, member = 0;

@@ -119,11 +119,18 @@ def species_set(n_species: int, n_prot: int, mean_len: float, seed: int = SEED0,
 
 
 # Per-branch substitution probabilities of the named configurations, with the root-to-tip sum capped so that the
-# pairwise identity span does not depend on the number of species: bacterial sets ~92.5-99.9 % identical, eukaryotic
-# ones ~89-99.8 %.  SURVEY.md 8d asks for 80-99 %; measured with the oracle CLI, spans that reach down to 80-85 %
-# leave NO variant group at >= 300 species (a group needs a 13-mer shared by 85 % of the species), which would make
-# the output parity of configs[2..4] vacuous — so the span stops where 1,000 species still align.
-BACTERIAL_P_SUB, BACTERIAL_MAX_DEPTH = (0.0005, 0.02), 0.04
+# pairwise identity span does not depend on the number of species.  kamino's subject is sets of ISOLATES (north_star:
+# "per-isolate k-mer table"): the bacterial sets are ~97.7-99.9 % identical (root-to-tip <= 1.2 %), the eukaryotic
+# "within-phylum" sets ~89-99.8 %.  SURVEY.md 8d suggests 80-99 %; measured with the oracle CLI (400 proteins per
+# proteome, default flags), wider spans leave nothing to compare at the sizes of configs[2] and configs[4], because a
+# variant group needs a 13-mer shared by 85 % of the species:
+#     root-to-tip cap   identity        100 species            1000 species
+#     8 %  (p <= 3 %)   85-99.9 %       0 groups               0 groups
+#     4 %  (p <= 2 %)   92.5-99.9 %     978 groups, 13.5 kaa   3 groups, 14 aa
+#     2 %  (p <= 1 %)   96-99.9 %       1545 groups, 20.7 kaa  68 groups, 587 aa
+#     1.2 % (p <= 0.6%) 97.7-99.9 %     1882 groups, 20.0 kaa  187 groups, 1.4 kaa
+# so the cap is set where 1,000 and 5,000 proteomes still give an alignment worth checking bit for bit.
+BACTERIAL_P_SUB, BACTERIAL_MAX_DEPTH = (0.0003, 0.006), 0.012
 EUKARYOTIC_P_SUB, EUKARYOTIC_MAX_DEPTH = (0.001, 0.03), 0.06
 
 
