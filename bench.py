@@ -555,17 +555,18 @@ def run_gpu(args):
         except Exception:
             traffic_tab = {}
     own = {   # algorithmic bytes of one launch of each kernel group (own inputs + own outputs, no sector rounding)
-        "frame": ("frame_count + frame_scatter (+ scans)", float(batch.residues.size) * 2 + n_pos),       # raw bytes read twice, codes written
-        "bloom_partition_kernel": ("bloom_partition_kernel", n_pos * (1 + 8.0)),                          # code in, 2 probes x 4 B out
-        "bloom_bucket_kernel": ("bloom_bucket_kernel", n_pos * (8.0 + 0.25)),                             # probes in, 2 lost bits out
-        "cms_partition_kernel": ("cms_partition_kernel", n_pos * 1.25 + 8.0 * u * n_res),                 # code + lost bits in, 4 x 2 B entries out
-        "cms_apply_kernel": ("cms_apply_kernel", 8.0 * u * n_res + 2.0 * ffi.CMS_CELLS),                  # entries in, every cell written (first batch after a reset)
+        "frame": ("frame_count + frame_scatter (+ scans)", float(batch.residues.size) * 2 + n_pos,        # raw bytes read twice, codes written
+                  ["frame_count_kernel", "frame_scatter_kernel"]),
+        "bloom_partition_kernel": ("bloom_partition_kernel", n_pos * (1 + 8.0), ["bloom_partition_kernel"]),          # code in, 2 probes x 4 B out
+        "bloom_bucket_kernel": ("bloom_bucket_kernel", n_pos * (8.0 + 0.25), ["bloom_bucket_kernel"]),                # probes in, 2 lost bits out
+        "cms_partition_kernel": ("cms_partition_kernel", n_pos * 1.25 + 8.0 * u * n_res, ["cms_partition_kernel"]),   # code + lost bits in, 4 x 2 B entries out
+        "cms_apply_kernel": ("cms_apply_kernel", 8.0 * u * n_res + 2.0 * ffi.CMS_CELLS, ["cms_apply_kernel"]),        # entries in, every cell written (first batch after a reset)
     }
     kernels = []
-    for key, (name, nbytes) in own.items():
+    for key, (name, nbytes, parts) in own.items():
         ms = stage_ms[key]
         tr = None
-        for part in name.replace("(+ scans)", "").replace("+", " ").split():
+        for part in parts:
             if part in traffic_tab:
                 tr = (tr or 0) + traffic_tab[part]["dram_bytes_per_launch"]
         kernels.append({"kernel": name, "ms": ms, "share_of_step": ms / step_ms if step_ms else None,
@@ -614,7 +615,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu": True,
                        "residues_per_gpu": batch.n_residues, "species_per_gpu": batch.n_sp,
-                       "l2": "per step the kernels stream 122 MB of residues, ~3 GB of partition slots and the 512 MiB "
+                       "l2": "per step the kernels stream 121 MB of residues, ~5.5 GB of partition runs / slots and the 512 MiB "
                              "table: far beyond the 126 MB L2; no explicit flush",
                        "exchange": "none (1 GPU)" if world == 1 else (
                            ("fused NVLink peer kernel on byte planes: reduce-scatter + saturate + all-gather, in-kernel rank sync"
