@@ -139,6 +139,8 @@ struct kmn_ctx {
     std::vector<void*> ipc_opened;
     std::vector<std::unique_ptr<Batch>> spare;   // released batches whose buffers get reused
     cudaStream_t copy_stream = nullptr;   // host -> device copies of kmn_count_batch, overlapped with the kernels
+    cudaStream_t frame_stream = nullptr;  // K0 of range j+1 runs here, beside the Bloom / count-min kernels of range j
+    cudaEvent_t ev_frame[1 + kMaxH2dChunks] = {};
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
     uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
@@ -449,7 +451,19 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     const bool timed = ranges.size() == 1;   // per-stage events only make sense without the pipeline
     const int grid = grid_for(c, 8);
 
+    // KMN_TRACE_RANGES=1: device timeline of the copy / frame / compute streams of this call on stderr (tuning aid)
+    static const bool trace = std::getenv("KMN_TRACE_RANGES") != nullptr;
+    struct Mark { cudaEvent_t e; const char* what; size_t j; };
+    std::vector<Mark> marks;
+    auto mark = [&](cudaStream_t st, const char* what, size_t j) {
+        if (!trace) return;
+        cudaEvent_t e;
+        KMN_CUDA(cudaEventCreate(&e));
+        KMN_CUDA(cudaEventRecord(e, st));
+        marks.push_back({e, what, j});
+    };
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    mark(c->stream, "start", 0);
     if (from_host) {
         KMN_CUDA(cudaMemcpyAsync(b.rec_off.p, host_rec_off, (size_t(b.n_rec) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         KMN_CUDA(cudaMemcpyAsync(b.sp_rec_off.p, host_sp_rec_off, (size_t(b.n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
@@ -522,9 +536,17 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
 
     if (from_host)   // pad with spaces: skipped like any whitespace (disjoint from the range copies)
         KMN_CUDA(cudaMemsetAsync(b.raw.p + b.n_raw, 0x20, b.raw_pad - b.n_raw, c->copy_stream));
+    // With several ranges the frame kernels (K0: a chain of small launches around two streaming kernels) run on
+    // their own stream: range j+1 is framed while the Bloom / count-min kernels of range j keep the SMs busy, so
+    // the serial tail of the small launches disappears behind them.  fs == c->stream when there is one range.
+    cudaStream_t fs = ranges.size() > 1 ? c->frame_stream : c->stream;
+    if (fs != c->stream) {   // everything queued so far (offset copies, memsets of codes / carry / scratch) precedes the first frame
+        KMN_CUDA(cudaEventRecord(c->ev_frame[0], c->stream));
+        KMN_CUDA(cudaStreamWaitEvent(fs, c->ev_frame[0], 0));
+    }
     for (size_t j = 0; j < ranges.size(); j++) {
         const SpeciesRange& r = ranges[j];
-        if (from_host) {   // copy stream: this range's raw bytes, then the compute stream may frame them
+        if (from_host) {   // copy stream: this range's raw bytes, then the frame stream may frame them
             if (j == 0) KMN_CUDA(cudaEventRecord(c->ev_h2d[0], c->copy_stream));
             if (r.copy_end > r.copy_begin)
                 KMN_CUDA(cudaMemcpyAsync(b.raw.p + r.copy_begin, host_residues + r.copy_begin, r.copy_end - r.copy_begin,
@@ -532,30 +554,39 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             if (j + 1 == ranges.size()) KMN_CUDA(cudaEventRecord(c->ev_h2d[1], c->copy_stream));
             cudaEvent_t e = c->ev_copy[1 + j % (kMaxH2dChunks)];
             KMN_CUDA(cudaEventRecord(e, c->copy_stream));
-            KMN_CUDA(cudaStreamWaitEvent(c->stream, e, 0));
+            KMN_CUDA(cudaStreamWaitEvent(fs, e, 0));
+            mark(c->copy_stream, "copy done", j);
         }
+        mark(fs, "frame begins", j);
         // ---- K0 frame on the range's tiles (running total of kept bytes carried on the device)
         const uint32_t nt = r.tile_end - r.tile_begin;
         if (b.n_rec > 0 && nt > 0) {
-            frame_count_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, c->lut, r.tile_begin, c->tile_cnt.p);
+            frame_count_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, c->lut, r.tile_begin, c->tile_cnt.p);
             check_launch(c);
             const ScanJob job{c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt, c->frame_carry.p};
-            exclusive_scan_kernel<<<1, 1024, 0, c->stream>>>(job, job);
+            exclusive_scan_kernel<<<1, 1024, 0, fs>>>(job, job);
             check_launch(c);
-            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p);
+            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, fs>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p);
             check_launch(c);
-            frame_scatter_kernel<<<nt, FRAME_THREADS, 0, c->stream>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
-                                                                   b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin, c->tile_rec.p);
+            frame_scatter_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
+                                                            b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin, c->tile_rec.p);
             check_launch(c);
         }
         {
             const uint32_t s_begin = j == 0 ? 0 : r.s0 + 1, s_end = r.s1;   // boundary s0 was written by the previous range
             if (s_end >= s_begin) {
-                species_offsets_kernel<<<(s_end - s_begin + 1 + 255) / 256, 256, 0, c->stream>>>(b.rec_cstart.p, b.sp_rec_off.p,
-                                                                                              s_begin, s_end, b.sp_cstart.p);
+                species_offsets_kernel<<<(s_end - s_begin + 1 + 255) / 256, 256, 0, fs>>>(b.rec_cstart.p, b.sp_rec_off.p,
+                                                                                       s_begin, s_end, b.sp_cstart.p);
                 check_launch(c);
             }
         }
+        mark(fs, "frame done", j);
+        if (fs != c->stream) {   // the Bloom / count-min kernels of this range follow its frame
+            cudaEvent_t e = c->ev_frame[1 + j % kMaxH2dChunks];
+            KMN_CUDA(cudaEventRecord(e, fs));
+            KMN_CUDA(cudaStreamWaitEvent(c->stream, e, 0));
+        }
+        mark(c->stream, "bloom begins", j);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
         if (frame_only || r.s1 == r.s0) continue;
         // ---- K2 Bloom: probe partition, per-bucket shared-memory bitsets, slow exact path
@@ -584,6 +615,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             slots_map, b.codes.p, b.sp_cstart.p, T, c->bl_lost2.p, c->k, c->k_mask, L, c->cms_slot_limit, c->new_counts.p);
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[7], c->stream));
+        mark(c->stream, "partition done", j);
     }
     const bool counted = !frame_only && b.n_sp > 0;
     if (counted) {
@@ -603,6 +635,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         check_launch(c);
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    mark(c->stream, "apply done", 0);
     b.h_sp_cstart.resize(size_t(b.n_sp) + 1);
     KMN_CUDA(cudaMemcpyAsync(b.h_sp_cstart.data(), b.sp_cstart.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
                              cudaMemcpyDeviceToHost, c->stream));
@@ -618,6 +651,15 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         } else {
             (void)cudaGetLastError();   // a failed measurement must not surface as the next launch's error
         }
+    }
+    if (trace && !marks.empty()) {
+        for (const Mark& m : marks) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, marks[0].e, m.e) != cudaSuccess) (void)cudaGetLastError();
+            std::fprintf(stderr, "[kmn trace] %8.3f ms  range %zu  %s\n", ms, m.j, m.what);
+            if (&m != &marks[0]) cudaEventDestroy(m.e);
+        }
+        cudaEventDestroy(marks[0].e);
     }
     b.n_codes = b.h_sp_cstart[b.n_sp];
     b.framed = true;
@@ -1046,6 +1088,8 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         KMN_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         KMN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        KMN_CUDA(cudaStreamCreateWithFlags(&c->frame_stream, cudaStreamNonBlocking));
+        for (auto& ev : c->ev_frame) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
         for (auto& ev : c->ev_copy) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c->ev_h2d) KMN_CUDA(cudaEventCreate(&ev));
@@ -1105,6 +1149,8 @@ void kmn_destroy(kmn_ctx* c) {
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& ev : c->ev_frame) if (ev) cudaEventDestroy(ev);
+    if (c->frame_stream) cudaStreamDestroy(c->frame_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

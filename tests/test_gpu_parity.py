@@ -724,3 +724,63 @@ def test_count_fasta_full_size(ffi, oracle):
         assert n_rec == len(b.rec_off) - 1
         assert new_a.tolist() == new_b.tolist()
         assert np.array_equal(ctx.table_snapshot(), table_a)
+
+
+def test_group_batches_reads_the_device_pairs_in_place(ffi, oracle):
+    """kmn_group_batches (observations = the anchor pairs kmn_pair_batch left on the device, two batches) against
+    kmn_group_observations on the fetched pairs and against the oracle's merge + length selection
+    (group_extraction.rs:335-357, group_sorting.rs:90-143)."""
+    species = synth.species_set(12, 400, 250.0, seed=5)
+    k, scheme = 13, SR6
+    min_needed = oracle.min_needed(0.6, len(species))
+    a, b = synth.stage(species[:7]), synth.stage(species[7:])
+    with ffi.Context(k, scheme) as ctx:
+        ids = []
+        for bt in (a, b):
+            bid, _ = ctx.count_batch(bt.residues, bt.rec_off, bt.sp_rec_off)
+            ids.append(bid)
+        ctx.finalize_table()
+        pairs, sids = [], []
+        for bid, bt, base in ((ids[0], a, 0), (ids[1], b, 7)):
+            ctx.scan_batch(bid, min_needed)
+            ctx.pair_batch(bid, 35)
+            for s in range(bt.n_sp):
+                p = ctx.fetch_pairs(bid, s)
+                pairs.append(p)
+                sids.append(np.full(len(p), base + s, np.uint32))
+        pairs, sids = np.concatenate(pairs), np.concatenate(sids)
+        assert len(pairs) > 1000
+        perm_d, groups_d = ctx.group_batches(ids, min_needed, sid_base=[0, 7], full=True)
+        perm_h, groups_h = ctx.group_observations(pairs["left"], pairs["right"], sids, pairs["len"], min_needed)
+    assert np.array_equal(perm_d, perm_h)
+    assert np.array_equal(groups_d, groups_h)
+    og, osel = oracle.group_observations(pairs["left"], pairs["right"], sids, pairs["len"], len(species), min_needed, k)
+    assert len(og) == len(groups_d)
+    assert np.array_equal(groups_d["count"], og["count"])
+    assert np.array_equal(groups_d["flags"] & ffi.GROUP_VALID, og["ok"])
+    ok = og["ok"] == 1
+    assert ok.any(), "expected some accepted groups"
+    assert np.array_equal(groups_d["best_len"][ok], og["best_len"][ok])
+    assert np.array_equal(groups_d["coverage"][ok], og["coverage"][ok])
+
+
+def test_table_checksum_matches_the_snapshot(ffi, oracle):
+    """kmn_table_checksum (row sums + position-sensitive hash, reduced on the device) against numpy on the snapshot."""
+    b = synth.stage(synth.bacterial(3, seed=77, n_prot=200, mean_len=150.0))
+    with ffi.Context(13, SR6) as ctx:
+        ctx.reset_table()
+        rows0, h0 = ctx.table_checksum()                     # a reset table that nothing was counted into: all zero
+        assert rows0.tolist() == [0, 0, 0, 0] and h0 == 0
+        _, new = ctx.count_batch(b.residues, b.rec_off, b.sp_rec_off)
+        rows_live, h_live = ctx.table_checksum()             # before finalize: the live table
+        ctx.finalize_table()
+        rows, h = ctx.table_checksum()
+        t = ctx.table_snapshot()
+    assert (rows_live.tolist(), h_live) == (rows.tolist(), h)
+    assert rows.tolist() == [int(new.sum())] * 4
+    assert rows.tolist() == [int(t[r << 26:(r + 1) << 26].astype(np.uint64).sum()) for r in range(4)]
+    nz = np.flatnonzero(t)
+    want = 0
+    for i in nz.tolist():
+        want = (want + int(t[i]) * oracle.mix64(i + 0x51)) & 0xFFFFFFFFFFFFFFFF
+    assert h == want
