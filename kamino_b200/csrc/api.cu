@@ -107,7 +107,7 @@ struct Batch {
 }  // namespace
 
 constexpr uint32_t kMaxH2dChunks = 16;
-constexpr float kSlowLinkGBs = 40.f;   // below this measured host-to-device rate the copies, not the kernels, pace pass 1
+constexpr float kKernelGBs = 36.f;     // raw bytes per second the frame / Bloom / partition kernels of a (small) range consume
 
 struct kmn_ctx {
     int device = 0;
@@ -143,10 +143,11 @@ struct kmn_ctx {
     cudaEvent_t ev_frame[1 + kMaxH2dChunks] = {};
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
-    uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS)
+    uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS): every range costs ~50 us of launch gaps and tails
+    float h2d_ratio = 0.f;                // KMN_H2D_RATIO: growth of consecutive ranges (0: from the measured link rate)
     cudaEvent_t ev_h2d[2] = {};           // first / last host-to-device range copy of the last kmn_count_batch
     float h2d_gbs = 0.f;                  // measured link rate of that call (0: not measured yet)
-    int h2d_mode = 0;                     // KMN_H2D_MODE: 0 adaptive, 1 doubling ranges, 2 equal ranges
+    int h2d_mode = 0;                     // KMN_H2D_MODE: 0 adaptive (geometric ranges), 1 doubling ranges, 2 equal ranges
     DevBuf<uint32_t> frame_carry, n_tiles_dev, scan_sums, scan_offs;
     // scratch of kmn_group_observations
     DevBuf<uint64_t> g_left, g_right;
@@ -389,7 +390,7 @@ struct SpeciesRange {
     uint64_t codes_bound;           // upper bound of the codes[] positions of the range
 };
 
-std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, bool equal) {
+std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double ratio) {
     std::vector<SpeciesRange> out;
     const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
     if (b.n_sp == 0) {   // records without species cannot exist (sp_rec_off spans them); frame only
@@ -397,13 +398,18 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, bool equal)
         return out;
     }
     want = std::max<uint32_t>(1, std::min<uint32_t>(want, b.n_sp));
-    // Only the first range's copy is exposed, and the link moves bytes about twice as fast as the kernels
-    // consume them: every range may be twice as large as the one before it (weights 1, 2, 4, ...), which keeps
-    // the first copy tiny without multiplying the number of ranges.
-    // On a slow link (several ranks sharing the host's PCIe / memory path) the copies are the critical path and
-    // the kernels of the LAST range are what is left after them: equal, more numerous ranges keep that tail short.
-    const uint64_t weight_sum = (uint64_t(1) << want) - 1;
-    auto range_bytes = [&](size_t j) { return equal ? b.n_raw / want + 1 : b.n_raw / weight_sum * (uint64_t(1) << j) + 1; };
+    // Geometric ranges, each `ratio` times the one before.  Only the first range's copy is exposed, so it should be
+    // small; after that the copy of range j+1 has to land while the kernels of range j run, or the GPU idles: the
+    // ranges may grow by at most (link rate / rate at which the kernels consume raw bytes).  Measured (KMN_TRACE_RANGES,
+    // 55 GB/s link): doubling ranges left the GPU idle for 0.5 ms of a 4.8 ms call waiting for the last two copies;
+    // 5 ranges growing by 1.5 take 4.69 ms, by 2.0 4.86 ms, equal ones 4.86 ms, 12 ranges > 5.0 ms
+    // (profiles/r02_e2e_range_schedules.jsonl).  Ratio 1 (equal ranges) is right when the link is the slower side
+    // (several ranks sharing the host's PCIe / memory path): then the kernels of the LAST range are what is left
+    // after the copies.
+    std::vector<double> w(want);
+    double wsum = 0;
+    for (uint32_t j = 0; j < want; j++) { w[j] = j == 0 ? 1.0 : w[j - 1] * ratio; wsum += w[j]; }
+    auto range_bytes = [&](size_t j) { return uint64_t(double(b.n_raw) * w[std::min<size_t>(j, want - 1)] / wsum) + 1; };
     uint32_t s0 = 0;
     uint64_t copied = 0;
     uint32_t tiled = 0;
@@ -444,10 +450,13 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     const bool from_host = host_rec_off != nullptr;
     // range schedule: doubling sizes while the link outruns the kernels (~27 GB/s of raw bytes), equal sizes and
     // more of them when the previous call measured a slower link
-    const bool equal = from_host && (c->h2d_mode == 2 || (c->h2d_mode == 0 && c->h2d_gbs > 0.f && c->h2d_gbs < kSlowLinkGBs));
-    const uint32_t chunks = equal && c->h2d_mode == 0 ? std::max<uint32_t>(c->h2d_chunks, 8) : c->h2d_chunks;
+    // range schedule: growth ratio from the link rate the previous call measured (55 GB/s when none has been)
+    double ratio = c->h2d_ratio > 0.f ? c->h2d_ratio : std::min(2.0, std::max(1.0, double(c->h2d_gbs > 0.f ? c->h2d_gbs : 55.f) / kKernelGBs));
+    if (c->h2d_mode == 1) ratio = 2.0;
+    if (c->h2d_mode == 2) ratio = 1.0;
+    const uint32_t chunks = c->h2d_chunks;
     const uint32_t want = from_host ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, uint32_t(b.n_raw >> 22))) : 1;
-    const std::vector<SpeciesRange> ranges = plan_ranges(b, want, equal);
+    const std::vector<SpeciesRange> ranges = plan_ranges(b, want, ratio);
     const bool timed = ranges.size() == 1;   // per-stage events only make sense without the pipeline
     const int grid = grid_for(c, 8);
 
@@ -1105,6 +1114,11 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
             c->h2d_chunks = uint32_t(v);
+        }
+        if (const char* e = std::getenv("KMN_H2D_RATIO")) {    // tuning knob: growth of consecutive ranges
+            const double v = std::strtod(e, nullptr);
+            if (!(v >= 1.0 && v <= 4.0)) throw std::runtime_error("KMN_H2D_RATIO must be in 1..4");
+            c->h2d_ratio = float(v);
         }
         if (const char* e = std::getenv("KMN_H2D_MODE")) {     // tuning knob: adaptive / doubling / equal
             const std::string m = e;

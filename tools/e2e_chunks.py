@@ -18,10 +18,15 @@ def main():
     b = synth.stage(synth.bacterial(100, seed=synth.SEED0 + 1))
     pin = ffi.PinnedBuffer(b.residues.size)
     pin.array[:] = b.residues
-    for mode in ("doubling", "equal"):
-        for chunks in (1, 2, 3, 4, 5, 8):
-            os.environ["KMN_H2D_CHUNKS"] = str(chunks)
-            os.environ["KMN_H2D_MODE"] = mode
+    settings = [("adaptive", None, None)]
+    settings += [("ratio", r, n) for r in ("1.0", "1.2", "1.35", "1.5", "2.0") for n in (5, 8, 12)]
+    for mode, ratio, chunks in settings:
+        for _ in (0,):
+            for k in ("KMN_H2D_CHUNKS", "KMN_H2D_RATIO", "KMN_H2D_MODE"):
+                os.environ.pop(k, None)
+            if ratio is not None:
+                os.environ["KMN_H2D_RATIO"] = ratio
+                os.environ["KMN_H2D_CHUNKS"] = str(chunks)
             with ffi.Context(13, "sr6") as ctx:
                 ts = []
                 for i in range(9):
@@ -32,7 +37,7 @@ def main():
                     ctx.finalize_table()
                     ts.append((time.perf_counter() - t0) * 1e3)
                     ctx.release_batches()
-                print(json.dumps({"mode": mode, "chunks": chunks, "ms": round(float(np.median(ts[3:])), 3)}), flush=True)
+                print(json.dumps({"mode": mode, "ratio": ratio, "chunks": chunks, "ms": round(float(np.median(ts[3:])), 3)}), flush=True)
     pin.free()
 
 
