@@ -56,11 +56,11 @@ static_assert(PART_SLOT * sizeof(uint16_t) == 64, "a slot is four 16-byte vector
 // in arrival order, entry 31 = their count.  A bucket's slots are contiguous over the tiles, so the apply pass
 // streams them; a tile's 1024 slots of one row leave shared memory as four TMA tensor stores (no reservation
 // atomics, no per-entry copy-out instructions).
-// A slot is a RING of 32 u16 that starts at slot_origin(bucket): ring position i < 31 holds the i-th entry, ring
-// position 31 the count.  Without the rotation the staging stores of a warp (random buckets, similar ranks) pile
-// up on a handful of shared-memory banks (ncu: 80 % of the kernel's shared-memory wavefronts were conflict
-// replays); with it the bank is a function of the bucket.  The apply pass owns one bucket per CTA, so the origin is
-// a CTA constant there.
+// Inside a slot of 32 u16 the i-th entry (i < 31) sits at position i ^ slot_origin(bucket) and the count at
+// position 31 ^ slot_origin(bucket).  Without the permutation the staging stores of a warp (random buckets, similar
+// ranks) pile up on a handful of shared-memory banks (ncu: 80 % of the kernel's shared-memory wavefronts were
+// conflict replays); with it the bank is a function of the bucket.  The apply pass owns one bucket per CTA, so the
+// origin is a CTA constant there: position p is live iff (p ^ origin) < count.
 __host__ __device__ __forceinline__ uint32_t slot_origin(uint32_t bucket) { return bucket & 30u; }
 
 struct CmsSlots {
@@ -151,8 +151,9 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
             uint16_t* st = stage + size_t(buf) * (PART_STAGE_BYTES / 2);
             uint32_t* fl = fill + buf * CMS_BUCKETS_PER_ROW;
             const uint64_t seed = fold30_keep(cms_seed(r));   // (kept: ptxas otherwise re-folds the seed next to every use)
-            // (a branch-free, predicated form of this loop — all 16 hashes first, then the atomics — was measured
-            // slower: 1.27 ms vs 1.05 ms per launch, 64 registers with spills vs 56)
+            // (Two branch-free forms of this loop were measured slower: all 16 hashes hoisted ahead of predicated atomics
+            // and stores, 64 registers with spills: 1.27 ms; straight-line entries with a dummy bucket for dead lanes
+            // and min(rank, cap) stores, 64 registers: 1.03 ms; this branchy form, 56 registers: 0.92 ms.)
 #pragma unroll
             for (int j = 0; j < CHUNK; j++) {
                 if (!((new_bits >> j) & 1u)) continue;
@@ -160,7 +161,7 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
                 const uint32_t b = idx >> CMS_BUCKET_LOG2;
                 const uint32_t rank = atomicAdd(&fl[b], 1u);
                 if (rank < slot_limit) {
-                    st[b * PART_SLOT + ((slot_origin(b) + rank) & (PART_SLOT - 1))] = uint16_t(idx);
+                    st[b * PART_SLOT + (slot_origin(b) ^ rank)] = uint16_t(idx);
                 } else {   // slot full: rare single-entry spill
                     const uint32_t sp = atomicAdd(L.state + 1, 1u);
                     if (sp < L.spill_cap) L.spill[sp] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
@@ -169,8 +170,7 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
             }
             __syncthreads();
             // thread b closes slot b; the other buffer's counters (read one row ago) are cleared for the next row
-            st[threadIdx.x * PART_SLOT + ((slot_origin(threadIdx.x) + PART_SLOT_CAP) & (PART_SLOT - 1))] =
-                uint16_t(min(fl[threadIdx.x], slot_limit));
+            st[threadIdx.x * PART_SLOT + (slot_origin(threadIdx.x) ^ PART_SLOT_CAP)] = uint16_t(min(fl[threadIdx.x], slot_limit));
             fill[(buf ^ 1u) * CMS_BUCKETS_PER_ROW + threadIdx.x] = 0;
             fence_proxy_async_smem();
             if (threadIdx.x == 0) {
@@ -229,7 +229,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 // then the saturating merge into the table.  The bucket's slot array is contiguous (ent[bucket][tile][32]); it is
 // streamed through a four-stage ring of 16 KiB shared-memory buffers by bulk async copies (one elected thread
 // issues them, mbarriers signal "landed" / "consumed"), so no thread ever waits on a global load.  Thread t reads
-// the t-th 16-byte vector of a stage (4 vectors per slot); the slot's count (ring position 31, see slot_origin)
+// the t-th 16-byte vector of a stage (4 vectors per slot); the slot's count (position 31 ^ slot_origin)
 // reaches the slot's four lanes by shuffle.  The histogram atomics do not return a value; a counter that
 // wrapped or carried into its neighbour is detected afterwards (the histogram's total falls short of the number of
 // entries) and the bucket is then redone with u32 counters.
@@ -262,10 +262,11 @@ __device__ __forceinline__ void apply_issue(ApplyRing& R) {   // elected thread 
 template <typename Bump>
 __device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
     const unsigned lane = threadIdx.x & 31u;
-    // ring position of this lane's first entry (its vector holds slot positions 8 (lane & 3) ..+7) and where the
-    // count sits: vector cnt_vec of the slot, high half of word cnt_word (the origin is even)
-    const uint32_t first = (8u * (lane & 3u) - R.origin) & (PART_SLOT - 1);
-    const uint32_t cnt_pos = (R.origin + PART_SLOT_CAP) & (PART_SLOT - 1);
+    // rank of the entry at this lane's first position (its vector holds slot positions 8 (lane & 3) ..+7; position p
+    // holds rank p ^ origin, and origin is even and < 32, so position first_pos + j holds rank (first ^ j)) and
+    // where the count sits: vector cnt_pos >> 3 of the slot, high half of word cnt_word
+    const uint32_t first = (8u * (lane & 3u)) ^ R.origin;
+    const uint32_t cnt_pos = R.origin ^ PART_SLOT_CAP;
     const int cnt_lane = int((lane & ~3u) | (cnt_pos >> 3));
     const uint32_t cnt_word = (cnt_pos & 7u) >> 1;
     uint32_t mine = 0;
@@ -288,7 +289,7 @@ __device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const bool live = ((first + uint32_t(j)) & (PART_SLOT - 1)) < cnt;   // ring position 31 (the count) is never live: cnt <= 31
+            const bool live = (first ^ uint32_t(j)) < cnt;   // rank 31 (the count's position) is never live: cnt <= 31
             bump((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, live);
         }
     }

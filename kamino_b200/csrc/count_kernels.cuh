@@ -443,15 +443,19 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRu
                     lost |= 1u << q;
             }
         }
-        // lost probes -> lost map (atomicOr: idempotent)
+        // lost probes -> lost map (atomicOr: idempotent).  About one probe in ten is lost: the loop runs over the set
+        // bits (once or twice per warp) instead of over all RUN_Q entries with three lanes in 32 active each time.
         if (lost) {
             const uint32_t c_tile = tile_c0(cb, t);
+            while (lost) {
+                const int q = __ffs(lost) - 1;
+                lost &= lost - 1;
+                uint32_t e = 0;
 #pragma unroll
-            for (int q = 0; q < int(RUN_Q); q++)
-                if ((lost >> q) & 1u) {
-                    const uint32_t c = c_tile + ((cur[q] >> 1) & (BP_TILE - 1));
-                    atomicOr(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK) + (cur[q] & 1u)));
-                }
+                for (int i = 0; i < int(RUN_Q); i++) e = i == q ? cur[i] : e;
+                const uint32_t c = c_tile + ((e >> 1) & (BP_TILE - 1));
+                atomicOr(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK) + (e & 1u)));
+            }
         }
     }
 }
