@@ -75,7 +75,7 @@ RecodeLut make_lut(int scheme) {
 struct Batch {
     uint64_t n_raw = 0;
     uint32_t n_rec = 0, n_sp = 0;
-    size_t raw_pad = 0;      // n_raw rounded up to FRAME_TILE
+    size_t raw_pad = 0;      // n_raw rounded up to FR_TILE
     size_t codes_cap = 0;    // allocated codes bytes (multiple of WARP_TILE)
     uint32_t n_codes = 0;    // stripped residues + n_rec separators (known after framing)
     bool framed = false;
@@ -148,7 +148,8 @@ struct kmn_ctx {
     cudaEvent_t ev_h2d[2] = {};           // first / last host-to-device range copy of the last kmn_count_batch
     float h2d_gbs = 0.f;                  // measured link rate of that call (0: not measured yet)
     int h2d_mode = 0;                     // KMN_H2D_MODE: 0 adaptive (geometric ranges), 1 doubling ranges, 2 equal ranges
-    DevBuf<uint32_t> frame_carry, n_tiles_dev, scan_sums, scan_offs;
+    DevBuf<uint32_t> frame_ticket, tile_blo, n_tiles_dev, scan_sums, scan_offs;
+    DevBuf<unsigned long long> tile_state;
     // scratch of kmn_group_observations
     DevBuf<uint64_t> g_left, g_right;
     DevBuf<uint32_t> g_sid, g_len, g_perm[2], g_hist, g_base, g_head, g_scan, g_first, g_spoff;
@@ -165,6 +166,8 @@ struct kmn_ctx {
     // Bloom stage scratch (count_kernels.cuh): probe runs per (source tile, bucket), tile tables, flags
     DevBuf<uint32_t> bl_ent, bl_tile_sp, bl_tile0, bl_slow, bl_lost2, bl_scratch;
     DevBuf<uint16_t> bl_cnt;
+    DevBuf<unsigned long long> bl_ovf;
+    DevBuf<uint32_t> bl_ovf_n;
     uint32_t bloom_run_cap = RUN_CAP;     // test knob KMN_BLOOM_RUN_CAP: small slots force the slow exact path
     DevBuf<uint16_t> cms_ent;             // (bucket, tile) slots of the CMS partition (scratch of count_staged)
     DevBuf<uint32_t> cms_running, cms_spill, cms_state, cms_tile_sp, cms_tile0;
@@ -276,7 +279,7 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     b->n_raw = n_raw;
     b->n_rec = uint32_t(n_rec);
     b->n_sp = n_sp;
-    b->raw_pad = (size_t(n_raw) / FRAME_TILE + 1) * FRAME_TILE;   // at least one pad byte: offset n_raw has a chunk
+    b->raw_pad = (size_t(n_raw) / FR_TILE + 1) * FR_TILE;   // at least one pad byte: offset n_raw has a chunk
     b->raw.ensure(b->raw_pad);
     b->rec_off.ensure(n_rec + 1);
     b->sp_rec_off.ensure(size_t(n_sp) + 1);
@@ -320,7 +323,7 @@ std::unique_ptr<Batch> frame_fasta(kmn_ctx* c, const uint8_t* bytes, const uint6
     b->from_fasta = true;
     b->n_raw = n_raw;
     b->n_sp = n_files;
-    b->raw_pad = (size_t(n_raw) / FRAME_TILE + 1) * FRAME_TILE;
+    b->raw_pad = (size_t(n_raw) / FR_TILE + 1) * FR_TILE;
     b->raw.ensure(b->raw_pad);
     const uint32_t n_tiles = uint32_t(b->raw_pad / FRAME_TILE);
     c->fa_file_off.ensure(size_t(n_files) + 1);
@@ -386,13 +389,13 @@ std::unique_ptr<Batch> frame_fasta(kmn_ctx* c, const uint8_t* bytes, const uint6
 struct SpeciesRange {
     uint32_t s0, s1;                // species [s0, s1)
     uint64_t copy_begin, copy_end;  // raw bytes that must be resident before this range is framed
-    uint32_t tile_begin, tile_end;  // frame tiles (4096 raw bytes) processed with this range
+    uint32_t tile_begin, tile_end;  // frame tiles (FR_TILE raw bytes) processed with this range
     uint64_t codes_bound;           // upper bound of the codes[] positions of the range
 };
 
 std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double ratio) {
     std::vector<SpeciesRange> out;
-    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
+    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FR_TILE);
     if (b.n_sp == 0) {   // records without species cannot exist (sp_rec_off spans them); frame only
         out.push_back({0, 0, 0, b.n_raw, 0, n_frame_tiles, 0});
         return out;
@@ -427,10 +430,10 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double rati
         const uint64_t end_byte = b.h_sp_raw_off[s1];
         const bool last = s1 == b.n_sp;
         r.copy_begin = copied;
-        r.copy_end = last ? b.n_raw : std::min<uint64_t>(b.n_raw, (end_byte / FRAME_TILE + 1) * FRAME_TILE);
+        r.copy_end = last ? b.n_raw : std::min<uint64_t>(b.n_raw, (end_byte / FR_TILE + 1) * FR_TILE);
         r.copy_end = std::max(r.copy_end, r.copy_begin);
         r.tile_begin = tiled;
-        r.tile_end = last ? n_frame_tiles : std::max<uint32_t>(tiled, uint32_t(r.copy_end / FRAME_TILE));
+        r.tile_end = last ? n_frame_tiles : std::max<uint32_t>(tiled, uint32_t(r.copy_end / FR_TILE));
         if (r.copy_end == b.n_raw) r.tile_end = n_frame_tiles;   // the pad tile carries the boundaries at n_raw
         const uint64_t recs = b.h_sp_rec_off[s1] - b.h_sp_rec_off[s0];
         r.codes_bound = (b.h_sp_raw_off[s1] - b.h_sp_raw_off[s0]) + recs;
@@ -480,11 +483,14 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));   // the raw buffer's previous users are done
     }
     KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));
-    KMN_CUDA(cudaMemsetAsync(c->frame_carry.p, 0, sizeof(uint32_t), c->stream));
-    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FRAME_TILE);
-    c->tile_cnt.ensure(n_frame_tiles + 1);
-    c->tile_base.ensure(n_frame_tiles + 2);
+    const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FR_TILE);
     c->tile_rec.ensure(n_frame_tiles + 2);
+    c->tile_blo.ensure(n_frame_tiles + 2);
+    c->tile_state.ensure(n_frame_tiles + 2);
+    // look-back states of the frame tiles (the chain of kept bytes runs through all ranges of the call) and one
+    // ticket counter per range
+    KMN_CUDA(cudaMemsetAsync(c->tile_state.p, 0, (size_t(n_frame_tiles) + 2) * sizeof(unsigned long long), c->stream));
+    KMN_CUDA(cudaMemsetAsync(c->frame_ticket.p, 0, (kMaxH2dChunks + 1) * sizeof(uint32_t), c->stream));
     if (b.n_rec == 0) KMN_CUDA(cudaMemsetAsync(b.rec_cstart.p, 0, sizeof(uint32_t), c->stream));
 
     BloomRuns R{};
@@ -509,6 +515,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         c->bl_slow.ensure(size_t(b.n_sp) + 1);
         c->bl_ent.ensure(size_t(bl_tiles) * BB_BUCKETS * R.cap);
         c->bl_cnt.ensure(size_t(bl_tiles) * BB_BUCKETS);
+        c->bl_ovf.ensure(size_t(bl_tiles) * OVF_CAP);
+        c->bl_ovf_n.ensure(bl_tiles);
         c->bl_lost2.ensure(b.codes_cap / CHUNK);
         c->cms_tile_sp.ensure(cms_tiles);
         c->cms_tile0.ensure(size_t(b.n_sp) + 1);
@@ -516,6 +524,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         KMN_CUDA(cudaMemsetAsync(c->bl_lost2.p, 0, (b.codes_cap / CHUNK) * sizeof(uint32_t), c->stream));
         R.ent = c->bl_ent.p;
         R.cnt = c->bl_cnt.p;
+        R.ovf = c->bl_ovf.p;
+        R.ovf_n = c->bl_ovf_n.p;
         R.tile_sp = c->bl_tile_sp.p;
         R.sp_tile0 = c->bl_tile0.p;
         R.n_tiles = c->n_tiles_dev.p;
@@ -570,15 +580,12 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         // ---- K0 frame on the range's tiles (running total of kept bytes carried on the device)
         const uint32_t nt = r.tile_end - r.tile_begin;
         if (b.n_rec > 0 && nt > 0) {
-            frame_count_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, c->lut, r.tile_begin, c->tile_cnt.p);
+            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, fs>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p,
+                                                                            c->tile_blo.p);
             check_launch(c);
-            const ScanJob job{c->tile_cnt.p + r.tile_begin, c->tile_base.p + r.tile_begin, nt, c->frame_carry.p};
-            exclusive_scan_kernel<<<1, 1024, 0, fs>>>(job, job);
-            check_launch(c);
-            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, fs>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p);
-            check_launch(c);
-            frame_scatter_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, b.n_raw, c->lut, c->tile_base.p, b.rec_off.p,
-                                                            b.n_rec, b.codes.p, b.rec_cstart.p, r.tile_begin, c->tile_rec.p);
+            frame_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, b.n_raw, c->lut, b.rec_off.p, b.n_rec, b.codes.p, b.rec_cstart.p,
+                                                    r.tile_begin, c->tile_rec.p, c->tile_blo.p, c->tile_state.p,
+                                                    c->frame_ticket.p + j % (kMaxH2dChunks + 1));
             check_launch(c);
         }
         {
@@ -609,8 +616,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         bloom_partition_kernel<<<bl_bound, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
-        // one CTA per (species, bucket); the grid's x dimension holds up to 2^31-1 CTAs
-        bloom_bucket_kernel<<<n_sp_r * BB_BUCKETS, BB_THREADS, BB_SMEM, c->stream>>>(b.sp_cstart.p, r.s0, R);
+        // one warp per (species, bucket), persistent CTAs of BW_WARPS warps
+        const uint32_t bb_items = n_sp_r * BB_BUCKETS;
+        bloom_bucket_kernel<<<std::min<uint32_t>(uint32_t(c->sm_count), (bb_items + BW_WARPS - 1) / BW_WARPS), BW_THREADS, BW_SMEM, c->stream>>>(
+            b.sp_cstart.p, r.s0, bb_items, R);
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[9], c->stream));
         bloom_slow_kernel<<<std::min<uint32_t>(n_sp_r, BS_MAX_CTAS), BS_THREADS, BS_SMEM, c->stream>>>(
@@ -1102,7 +1111,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         for (auto& ev : c->ev) KMN_CUDA(cudaEventCreate(&ev));
         for (auto& ev : c->ev_copy) KMN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c->ev_h2d) KMN_CUDA(cudaEventCreate(&ev));
-        c->frame_carry.alloc(1);
+        c->frame_ticket.alloc(kMaxH2dChunks + 1);
         c->n_tiles_dev.alloc(2);
         if (const char* e = std::getenv("KMN_EXCHANGE_PLANES")) c->exchange_planes = std::strtol(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("KMN_EXCHANGE_TIMEOUT_MS")) {
@@ -1129,13 +1138,13 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         }
         if (const char* e = std::getenv("KMN_BLOOM_RUN_CAP")) {   // test knob
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 1 || v > long(RUN_CAP)) throw std::runtime_error("KMN_BLOOM_RUN_CAP must be in 1..208");
+            if (v < 1 || v > long(RUN_CAP)) throw std::runtime_error("KMN_BLOOM_RUN_CAP must be in 1.." + std::to_string(RUN_CAP));
             c->bloom_run_cap = uint32_t(v);
         }
         c->bl_scratch.alloc(size_t(BS_MAX_CTAS) << (BLOOM_BITS_LOG2 - 5));
         KMN_CUDA(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PAIR_COUNT_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
-        KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BB_SMEM)));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BW_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BS_SMEM)));
         c->tab.alloc(CMS_CELLS);
         c->cms_running.alloc(2);

@@ -21,19 +21,20 @@
 // filter bits never live in global memory:
 //
 //   bloom_partition_kernel  one CTA per source tile (8 Ki positions of ONE species): hashes every
-//                           k-mer once and splits its two probes over the 128 buckets of 2^18 filter
+//                           k-mer once and splits its two probes over the 256 buckets of 2^17 filter
 //                           bits; entry = (bit inside the bucket, position inside the tile).  Each
-//                           (tile, bucket) run has a FIXED slot in global memory, so there are no
-//                           global atomics and the runs of a bucket are ordered by tile = by file
-//                           position.  A position whose k-mer equals the previous position's (a
+//                           (tile, bucket) run has a FIXED slot in global memory (96 entries, mean 64), so
+//                           there are no global atomics and the runs of a bucket are ordered by tile = by
+//                           file position; the few probes that do not fit their slot go to the tile's
+//                           overflow list.  A position whose k-mer equals the previous position's (a
 //                           homopolymer run) can never pass and is marked without probing.
-//   bloom_bucket_kernel     one CTA per (species, bucket): the bucket's 2^18 bits in shared memory,
-//                           runs consumed in file order, 8 tiles per step (one per warp).  A probe whose bit was set
-//                           by an earlier step is lost.  Inside a step: every probe sets its bit with a
-//                           shared-memory atomicOr; a probe that finds the bit set by a probe of the
-//                           same step joins a small conflict list (and marks a 2048-bit mini filter);
-//                           the probes that set a marked bit join it too; inside the list the smallest
-//                           file position wins.  A lost probe sets its bit (2 per position) in the lost map.
+//   bloom_bucket_kernel     one WARP per (species, bucket): the bucket's 2^17 bits in the warp's own 16 KiB of
+//                           shared memory (14 warps per SM, one persistent CTA), runs consumed in file order,
+//                           one run (= one source tile) per step, no CTA barrier anywhere.  A probe whose bit
+//                           was set by an earlier step is lost.  Inside a step every probe sets its bit with a
+//                           shared-memory atomicOr; two probes of one step on the same bit (1.6 % of the steps)
+//                           are settled by the warp itself: the smallest file position wins.  A lost probe
+//                           sets its bit (2 per position) in the lost map.
 //   bloom_slow_kernel       same step logic on a 4 MiB global bitset, one CTA per species, straight from
 //                           codes[]: only for species whose probes overflow a run slot (massively
 //                           repeated k-mers) — exact for every input, fast for natural ones.
@@ -41,6 +42,7 @@
 // count-min partition (cms_kernels.cuh) reads the map directly.  The map is written with atomicOr only,
 // so redoing a species on the slow path is idempotent.
 #pragma once
+#include <type_traits>
 #include "kmn_device.cuh"
 
 namespace kmn {
@@ -49,28 +51,37 @@ constexpr int BP_THREADS = 512;
 constexpr uint32_t BP_TILE_WT = BP_THREADS / 32;          // warp tiles per source tile (one per warp)
 constexpr uint32_t BP_TILE = BP_TILE_WT * WARP_TILE;       // 8192 positions
 constexpr uint32_t BP_POS_BITS = 13;
-constexpr uint32_t BB_LOG2 = 18;                           // filter bits per bucket (32 KiB of shared memory)
-constexpr uint32_t BB_BUCKETS = 1u << (BLOOM_BITS_LOG2 - BB_LOG2);   // 128
+#ifndef KMN_BB_LOG2
+#define KMN_BB_LOG2 17
+#endif
+constexpr uint32_t BB_LOG2 = KMN_BB_LOG2;                  // filter bits per bucket (16 KiB of shared memory per warp)
+constexpr uint32_t BB_BUCKETS = 1u << (BLOOM_BITS_LOG2 - BB_LOG2);   // 256
 constexpr uint32_t BB_WORDS = 1u << (BB_LOG2 - 5);
 constexpr uint32_t BB_MASK = (1u << BB_LOG2) - 1;
-constexpr uint32_t RUN_CAP = 208;                          // slots per (tile, bucket): mean 128, sigma 11
+// slots per (tile, bucket): the probes of a tile land in a bucket's run as Binomial(16 Ki, 1 / buckets): mean 64,
+// sigma 8 at 256 buckets.  4 sigma of head room; what does not fit (3e-5 of the runs) goes to the tile's overflow list.
+#ifndef KMN_RUN_CAP
+#define KMN_RUN_CAP (BB_LOG2 == 17 ? 96 : BB_LOG2 == 16 ? 52 : 176)
+#endif
+constexpr uint32_t RUN_CAP = KMN_RUN_CAP;
 constexpr uint32_t RUN_Q = (RUN_CAP + 31) / 32;            // entries per lane when a warp reads one run
-#ifndef KMN_BB_THREADS
-#define KMN_BB_THREADS 256
-#endif
-#ifndef KMN_BB_CTAS
-#define KMN_BB_CTAS 4
-#endif
-constexpr int BB_THREADS = KMN_BB_THREADS;
-constexpr uint32_t BB_STEP_RUNS = BB_THREADS / 32;         // runs (source tiles) per step: one per warp
-constexpr uint32_t BB_LIST_CAP = 2048;                     // conflict list of a step; overflow -> slow path (exact)
+constexpr uint32_t OVF_CAP = 64;                           // overflow entries per source tile; more -> slow path (exact)
+constexpr uint32_t OVF_Q = OVF_CAP / 32;
+constexpr uint32_t CNT_OVF = 0x8000u;                      // flag in a run's count: part of the run sits in the overflow list
+constexpr uint32_t BW_NQ = RUN_Q + OVF_Q;                  // probes per lane and step, overflow entries included
+constexpr uint32_t BW_WARPS = (227u * 1024u - 2048u) / (BB_WORDS * 4u);   // 14 warps, each with its own bucket
+constexpr int BW_THREADS = int(BW_WARPS) * 32;
+constexpr size_t BW_SMEM = size_t(BW_WARPS) * BB_WORDS * sizeof(uint32_t);
+constexpr uint32_t BW_DEPTH = 4;                           // runs in flight per warp (global-load latency is hidden by depth, not by occupancy)
+constexpr uint32_t BB_LIST_CAP = 2048;                     // (bloom_slow_kernel) conflict list of a step
 constexpr uint32_t ENT_BIT_SHIFT = BP_POS_BITS + 1;         // entry = bit_in_bucket << 14 | pos_in_tile << 1 | probe
-constexpr uint32_t MF_WORDS = 256;                         // 8192-bit mini filter of a step's conflicting bits
-constexpr uint32_t MT_SLOTS = 256;                         // hashed min table of a step's conflict list
-constexpr size_t BB_SMEM = size_t(BB_LIST_CAP) * sizeof(unsigned long long) + size_t(BB_WORDS) * sizeof(uint32_t);
+constexpr uint32_t ENT_ORDER_MASK = (1u << ENT_BIT_SHIFT) - 1;
+constexpr uint32_t MF_WORDS = 256;                         // (bloom_slow_kernel) 8192-bit mini filter of a step's conflicting bits
+constexpr uint32_t MT_SLOTS = 256;                         // (bloom_slow_kernel) hashed min table of a step's conflict list
 static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
 static_assert(BB_LOG2 + ENT_BIT_SHIFT <= 32, "entry layout");
 static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
+static_assert(RUN_CAP < CNT_OVF && BW_WARPS >= 1 && BW_THREADS <= 1024, "bucket kernel shape");
 // staging rows are cap + 1 words apart: an odd stride spreads the stores of a warp (random buckets, similar ranks)
 // over the shared-memory banks
 constexpr size_t bp_smem_for(uint32_t cap) {
@@ -79,8 +90,10 @@ constexpr size_t bp_smem_for(uint32_t cap) {
 
 struct BloomRuns {
     uint32_t* ent;              // [n_tiles][BB_BUCKETS][cap] bit_in_bucket << 14 | pos_in_tile << 1 | probe
-    uint16_t* cnt;              // per species: [BB_BUCKETS][tiles of the species] (a bucket's counts are contiguous)
+    uint16_t* cnt;              // per species: [BB_BUCKETS][tiles of the species] (a bucket's counts are contiguous); | CNT_OVF
     uint32_t cap;               // RUN_CAP (smaller only under the test knob)
+    unsigned long long* ovf;    // [n_tiles][OVF_CAP] (bucket << 32) | entry: probes that did not fit their run slot
+    uint32_t* ovf_n;            // [n_tiles] entries in the tile's overflow list
     const uint32_t* tile_sp;    // [n_tiles] species (index inside the batch) of every source tile
     const uint32_t* sp_tile0;   // [n_sp + 1] first source tile of every species (species_tiles_kernel)
     const uint32_t* n_tiles;    // device scalar: source tiles of this launch (the grid is an upper bound)
@@ -125,9 +138,11 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
     const uint32_t stride = R.cap + 1;
     uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap + 1]
     uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * stride;  // [BB_BUCKETS]
+    __shared__ uint32_t s_ovf_n;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tg = blockIdx.x;
     if (tg >= *R.n_tiles) return;
+    if (threadIdx.x == 0) s_ovf_n = 0;
     const uint32_t s = R.tile_sp[tg];
     const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
     const uint32_t tg0 = R.sp_tile0[s], nt = R.sp_tile0[s + 1] - tg0;
@@ -153,16 +168,25 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
             for (int pr = 0; pr < 2; pr++) {
                 const uint32_t b = idx[pr] >> BB_LOG2;
                 const uint32_t rank = atomicAdd(&fill[b], 1u);
-                if (rank < R.cap) stage[b * stride + rank] = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
-                else ovf = true;
+                const uint32_t entry = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
+                if (rank < R.cap) {
+                    stage[b * stride + rank] = entry;
+                } else {   // rare: the run slot is full
+                    const uint32_t o = atomicAdd(&s_ovf_n, 1u);
+                    if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
+                    else ovf = true;
+                }
             }
         }
         if (ovf) R.slow[s] = 1u;
     }
     __syncthreads();
-    if (threadIdx.x < BB_BUCKETS)
-        R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(min(fill[threadIdx.x], R.cap));
-    // warp w copies the runs of buckets 8w .. 8w+7 to their fixed slots
+    if (threadIdx.x < BB_BUCKETS) {
+        const uint32_t f = fill[threadIdx.x];
+        R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(f > R.cap ? (R.cap | CNT_OVF) : f);
+    }
+    if (threadIdx.x == 0) R.ovf_n[tg] = min(s_ovf_n, OVF_CAP);
+    // warp w copies the runs of its BB_BUCKETS / 16 buckets to their fixed slots
 #pragma unroll 1
     for (uint32_t q = 0; q < BB_BUCKETS / BP_TILE_WT; q++) {
         const uint32_t b = warp * (BB_BUCKETS / BP_TILE_WT) + q;
@@ -273,7 +297,7 @@ __device__ __forceinline__ bool bloom_step(uint32_t* bitset, const StepShared& S
     return true;
 }
 
-// ---- bloom_bucket_kernel: the same step, hand-scheduled for shared memory ---------------------------
+// ---- bloom_bucket_kernel: one warp per (species, bucket) --------------------------------------------
 // (32-bit shared addresses and explicit ld/atom.shared keep the per-probe instruction count low: this
 // kernel is bound by instruction issue, not by memory.)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -288,175 +312,219 @@ __device__ __forceinline__ uint32_t atoms_or_u32(uint32_t a, uint32_t v) {
     return o;
 }
 
-// The bucket kernel's conflict table in 32 bits (a 64-bit shared-memory atomicMin is a CAS loop; ncu showed the
-// conflict path, run by one or two lanes in almost every step, taking a quarter of the kernel's instructions):
-// slot = low 8 bits of the bit index, key = remaining bit-index bits << 18 | order inside the step.  The minimum
-// of a slot is the smallest bit that maps to it and, for that bit, its first toucher in file order.
-constexpr uint32_t MT32_ORDER_BITS = 18;   // order = warp << 14 | position inside the tile << 1 | probe
-static_assert((BB_THREADS / 32) <= (1 << (MT32_ORDER_BITS - ENT_BIT_SHIFT)), "order field");
-static_assert(BB_LOG2 - 8 + MT32_ORDER_BITS <= 32, "key layout");
-__device__ __forceinline__ uint32_t mt32_slot(uint32_t bit) { return bit & (MT_SLOTS - 1); }
-__device__ __forceinline__ uint32_t mt32_key(uint32_t bit, uint32_t order) { return ((bit >> 8) << MT32_ORDER_BITS) | order; }
-
-// rare: a probe of this step found its bit set by another probe of the same step
-__device__ __noinline__ void bucket_conflict_join(unsigned long long* list, uint32_t* mt, uint32_t* mf,
-                                                  uint32_t* n_list, uint32_t bit, uint32_t p, bool mark) {
-    const uint32_t slot = atomicAdd(n_list, 1u);
-    if (slot < BB_LIST_CAP) list[slot] = (static_cast<unsigned long long>(bit) << 32) | p;
-    atomicMin(&mt[mt32_slot(bit)], mt32_key(bit, p));
-    if (mark) atomicOr(&mf[(bit >> 5) & (MF_WORDS - 1)], 1u << (bit & 31u));
+__device__ __forceinline__ void red_or_if(uint32_t* p, uint32_t v, bool pred) {   // predicated, no branch
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.or.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(uint32_t(pred)) : "memory");
 }
 
-// rare: is a member of the conflict list beaten by a smaller file position of the same bit?
-__device__ __noinline__ bool bucket_conflict_lost(const unsigned long long* list, const uint32_t* mt, uint32_t n,
-                                                  uint32_t bit, uint32_t p) {
-    const uint32_t best = mt[mt32_slot(bit)];
-    if ((best >> MT32_ORDER_BITS) == (bit >> 8)) return best != mt32_key(bit, p);
-    const unsigned long long lo = static_cast<unsigned long long>(bit) << 32, me = lo | p;
-    bool l = false;   // the slot belongs to a smaller bit: scan the list
-    for (uint32_t i = 0; i < n; i++) {
-        const unsigned long long o = list[i];
-        l |= (o >= lo) && (o < me);
+// Rare (1.6 % of the steps): probes of ONE step share a bit.  `conf` marks this lane's probes that found their bit
+// set by another probe of the step; all probes of that bit (the one that set it included) are compared and every
+// one but the first in file order is lost.  All 32 lanes call this.
+template <int NQ>
+__device__ __forceinline__ uint32_t warp_step_conflicts(const uint32_t (&cur)[NQ], uint32_t todo, uint32_t conf) {
+    uint32_t lost = 0;
+    for (;;) {
+        const uint32_t open = __ballot_sync(0xffffffffu, conf != 0);
+        if (!open) break;
+        uint32_t mine = 0;
+        if (conf) {
+            const int q = __ffs(conf) - 1;
+#pragma unroll
+            for (int i = 0; i < NQ; i++) mine = i == q ? (cur[i] >> ENT_BIT_SHIFT) : mine;
+        }
+        const uint32_t bit = __shfl_sync(0xffffffffu, mine, __ffs(open) - 1);
+        uint32_t match = 0, best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+            if (((todo >> q) & 1u) && (cur[q] >> ENT_BIT_SHIFT) == bit) {
+                match |= 1u << q;
+                best = min(best, cur[q] & ENT_ORDER_MASK);
+            }
+        const uint32_t first = __reduce_min_sync(0xffffffffu, best);
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+            if (((match >> q) & 1u) && (cur[q] & ENT_ORDER_MASK) != first) lost |= 1u << q;
+        conf &= ~match;
     }
-    return l;
+    return lost;
 }
 
-__global__ void __launch_bounds__(BB_THREADS, KMN_BB_CTAS)
-bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, BloomRuns R) {
-    extern __shared__ __align__(16) unsigned long long bb_smem[];
-    unsigned long long* s_list = bb_smem;                                        // BB_LIST_CAP
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(bb_smem + BB_LIST_CAP);       // BB_WORDS
-    __shared__ uint32_t s_mt[2 * MT_SLOTS];
-    __shared__ uint32_t s_mf[2 * MF_WORDS];
-    __shared__ uint32_t s_n[2];
-    const uint32_t s = s0 + blockIdx.x / BB_BUCKETS, beta = blockIdx.x % BB_BUCKETS;
-    if (R.slow[s]) return;
+// One step on a run whose tail sits in the tile's overflow list (3e-5 of the runs; every run under the
+// KMN_BLOOM_RUN_CAP test knob): the run's entries are read again here, the overflow entries of this bucket join
+// them, same three phases with plain branches.  `lost2_tile` = lost-map word of the tile's first position.
+__device__ __noinline__ void bucket_step_overflow(uint32_t a_bits, const uint32_t* __restrict__ run, uint32_t n,
+                                                  const unsigned long long* __restrict__ ovf, uint32_t n_ovf,
+                                                  uint32_t beta, uint32_t* __restrict__ lost2_tile) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t cur[BW_NQ], live = 0;
+#pragma unroll
+    for (int q = 0; q < int(RUN_Q); q++) {
+        cur[q] = 0;
+        if (lane + 32u * q < n) {
+            cur[q] = __ldcs(run + 32 * q);
+            live |= 1u << q;
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < int(OVF_Q); x++) {
+        cur[RUN_Q + x] = 0;
+        const uint32_t j = lane + 32u * uint32_t(x);
+        if (j < n_ovf) {
+            const unsigned long long e = ovf[j];
+            if (uint32_t(e >> 32) == beta) {
+                cur[RUN_Q + x] = uint32_t(e);
+                live |= 1u << (RUN_Q + x);
+            }
+        }
+    }
+    uint32_t pre = 0;
+#pragma unroll
+    for (int q = 0; q < int(BW_NQ); q++)
+        if ((live >> q) & 1u) {
+            const uint32_t bit = cur[q] >> ENT_BIT_SHIFT;
+            pre |= ((lds_u32(a_bits + ((bit >> 5) << 2)) >> (bit & 31u)) & 1u) << q;
+        }
+    __syncwarp();
+    uint32_t conf = 0;
+    const uint32_t todo = live & ~pre;
+#pragma unroll
+    for (int q = 0; q < int(BW_NQ); q++)
+        if ((todo >> q) & 1u) {
+            const uint32_t bit = cur[q] >> ENT_BIT_SHIFT, m = 1u << (bit & 31u);
+            if (atoms_or_u32(a_bits + ((bit >> 5) << 2), m) & m) conf |= 1u << q;
+        }
+    __syncwarp();
+    uint32_t lost = pre;
+    if (__any_sync(0xffffffffu, conf != 0)) lost |= warp_step_conflicts<int(BW_NQ)>(cur, todo, conf);
+#pragma unroll
+    for (int q = 0; q < int(BW_NQ); q++)
+        if ((lost >> q) & 1u) atomicOr(lost2_tile + ((cur[q] >> 5) & (BP_TILE / CHUNK - 1)), 1u << (cur[q] & 31u));
+}
+
+// One persistent CTA per SM; every warp owns BB_WORDS of shared memory and takes (species, bucket) items on its
+// own.  With 14 warps per SM there is little occupancy to hide global-load latency behind: a warp keeps the
+// entries of BW_DEPTH runs in flight in registers, and the run lengths of the next 32 .. 64 tiles in two registers
+// (lane l holds tile blk + l; a shuffle hands a length to the warp).  The step itself is branch-free: a dead lane
+// slot ORs a zero mask into some word of the warp's own bitset, a lost probe's lost-map update is a predicated RED;
+// the only branches are warp-uniform (third lane slot in use? overflow run? conflict inside the step?).
+// Entry e = bit << 14 | pos << 1 | probe: its bitset word is (e >> 19), its bit (e >> 14) & 31; its lost-map word
+// (2 bits per position, 16 positions per word) is tile_word + ((e >> 5) & 511), its lost-map bit e & 31.
+__global__ void __launch_bounds__(BW_THREADS, 1)
+bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_t n_items, BloomRuns R) {
+    extern __shared__ __align__(16) uint32_t bw_smem[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tg0 = R.sp_tile0[s], n_tiles = R.sp_tile0[s + 1] - tg0;
-    if (n_tiles == 0) return;
-    const uint32_t cb = sp_cstart[s];
-    for (uint32_t i = threadIdx.x; i < BB_WORDS; i += BB_THREADS) s_bits[i] = 0;
-    for (uint32_t i = threadIdx.x; i < 2 * MF_WORDS; i += BB_THREADS) s_mf[i] = 0;
-    for (uint32_t i = threadIdx.x; i < 2 * MT_SLOTS; i += BB_THREADS) s_mt[i] = ~0u;
-    if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t a_bits = smem_addr(s_bits);
-    // this bucket's run lengths are contiguous; warp w owns run t0 + w of every step
-    const uint16_t* __restrict__ cnt = R.cnt + size_t(tg0) * BB_BUCKETS + size_t(beta) * n_tiles;
-    const uint32_t* __restrict__ ent = R.ent + (size_t(tg0) * BB_BUCKETS + beta) * R.cap + lane;
+    uint32_t* bits = bw_smem + size_t(warp) * BB_WORDS;
+    const uint32_t a_bits = smem_addr(bits);
     const size_t run_stride = size_t(BB_BUCKETS) * R.cap;
-    auto run_len = [&](uint32_t t) -> uint32_t { return t < n_tiles ? uint32_t(__ldg(cnt + t)) : 0u; };
-    auto lane_live = [&](uint32_t n) -> uint32_t {   // bit q set <=> lane + 32 q < n
-        return n > lane ? (2u << ((n - lane - 1u) >> 5)) - 1u : 0u;
-    };
-    // software pipeline: entries one step ahead, run lengths two steps ahead
-    uint32_t raw[RUN_Q];
-    uint32_t n_next = run_len(warp);
-    {
-        const uint32_t lv = lane_live(n_next);
-        const uint32_t* e = ent + size_t(warp) * run_stride;
-#pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++)
-            if ((lv >> q) & 1u) raw[q] = __ldcs(e + 32 * q);
-    }
-    uint32_t n_next2 = run_len(BB_STEP_RUNS + warp);
-    uint32_t par = 0;
-    for (uint32_t t0 = 0; t0 < n_tiles; t0 += BB_STEP_RUNS, par ^= 1u) {
-        const uint32_t t = t0 + warp;
-        const uint32_t n = n_next;
-        const uint32_t live = lane_live(n);
-        uint32_t cur[RUN_Q];
-#pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++) cur[q] = raw[q];
-        n_next = n_next2;
-        {
-            const uint32_t lv = lane_live(n_next);
-            const uint32_t* e = ent + size_t(t + BB_STEP_RUNS) * run_stride;
+    for (uint32_t item = blockIdx.x * BW_WARPS + warp; item < n_items; item += gridDim.x * BW_WARPS) {
+        const uint32_t s = s0 + item / BB_BUCKETS, beta = item % BB_BUCKETS;
+        if (R.slow[s]) continue;   // warp-uniform
+        const uint32_t tg0 = R.sp_tile0[s], n_tiles = R.sp_tile0[s + 1] - tg0;
+        if (n_tiles == 0) continue;
+        const uint32_t cb = sp_cstart[s];
+        __syncwarp();
+        for (uint32_t i = lane; i < BB_WORDS / 4; i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        // this bucket's run lengths are contiguous over the tiles
+        const uint16_t* __restrict__ cnt = R.cnt + size_t(tg0) * BB_BUCKETS + size_t(beta) * n_tiles;
+        const uint32_t* __restrict__ ent0 = R.ent + (size_t(tg0) * BB_BUCKETS + beta) * R.cap + lane;
+        auto cnt_block = [&](uint32_t t) -> uint32_t { return t + lane < n_tiles ? uint32_t(__ldg(cnt + t + lane)) : 0u; };
+        uint32_t blk = 0, c_cur = cnt_block(0), c_nxt = cnt_block(32);
+        auto run_len = [&](uint32_t t) -> uint32_t {   // t in [blk, blk + 64); 0 past the last tile
+            return __shfl_sync(0xffffffffu, t - blk < 32u ? c_cur : c_nxt, int(t & 31u));
+        };
+        uint32_t raw[BW_DEPTH][RUN_Q], n_raw[BW_DEPTH];
+        const uint32_t* ent[BW_DEPTH];
+        auto load_run = [&](const uint32_t* e, uint32_t n, uint32_t (&dst)[RUN_Q]) {
+            const uint32_t nn = n & ~CNT_OVF;
 #pragma unroll
             for (int q = 0; q < int(RUN_Q); q++)
-                if ((lv >> q) & 1u) raw[q] = __ldcs(e + 32 * q);
-        }
-        n_next2 = run_len(t + 2 * BB_STEP_RUNS);
-        uint32_t* mt = s_mt + par * MT_SLOTS;
-        uint32_t* mf = s_mf + par * MF_WORDS;
-        const uint32_t a_mf = smem_addr(mf);
-        // phase 1: bits set by earlier steps (= by smaller file positions)
-        uint32_t pre = 0;
+                if (lane + 32u * q < nn) dst[q] = __ldcs(e + 32 * q);
+        };
 #pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++) {
-            if (32u * q >= n) break;   // warp-uniform
-            if ((live >> q) & 1u) {
-                const uint32_t bit = cur[q] >> ENT_BIT_SHIFT;
-                pre |= ((lds_u32(a_bits + ((bit >> 5) << 2)) >> (bit & 31u)) & 1u) << q;
+        for (int i = 0; i < int(BW_DEPTH); i++) {
+#pragma unroll
+            for (int q = 0; q < int(RUN_Q); q++) raw[i][q] = 0;
+            n_raw[i] = run_len(uint32_t(i));
+            ent[i] = ent0 + size_t(i) * run_stride;
+            load_run(ent[i], n_raw[i], raw[i]);
+        }
+        uint32_t* lost2_tile = R.lost2 + tile_c0(cb, 0) / CHUNK;
+        // one step: the run of tile t sits in (e_raw, n_run, run); PREFETCH: the run BW_DEPTH tiles ahead takes its place
+        auto step = [&](uint32_t t, uint32_t (&e_raw)[RUN_Q], uint32_t& n_run, const uint32_t*& run, auto prefetch) {
+            const uint32_t nr = n_run;
+            uint32_t cur[RUN_Q];
+#pragma unroll
+            for (int q = 0; q < int(RUN_Q); q++) cur[q] = e_raw[q];
+            const uint32_t* this_run = run;
+            if (decltype(prefetch)::value) {
+                n_run = run_len(t + BW_DEPTH);
+                run += size_t(BW_DEPTH) * run_stride;
+                load_run(run, n_run, e_raw);
             }
-        }
-        __syncthreads();
-        // the other parity's scratch was last read in the previous step
-        for (uint32_t i = threadIdx.x; i < MF_WORDS; i += BB_THREADS) s_mf[(par ^ 1u) * MF_WORDS + i] = 0;
-        for (uint32_t i = threadIdx.x; i < MT_SLOTS; i += BB_THREADS) s_mt[(par ^ 1u) * MT_SLOTS + i] = ~0u;
-        if (threadIdx.x == 0) s_n[par ^ 1u] = 0;
-        // phase 2: every remaining probe sets its bit; the loser of a same-step race joins the conflict list
-        uint32_t won = 0, member = 0;
-        const uint32_t todo = live & ~pre;
+            if (nr & CNT_OVF) {   // rare: the rest of this run sits in the tile's overflow list
+                const uint32_t tile = tg0 + t;
+                bucket_step_overflow(a_bits, this_run, nr & ~CNT_OVF, R.ovf + size_t(tile) * OVF_CAP, min(R.ovf_n[tile], OVF_CAP), beta,
+                                     lost2_tile);
+            } else {
+                const int nq = int((nr + 31u) >> 5);   // warp-uniform: lane slots in use
+                uint32_t a[RUN_Q], m[RUN_Q];
+                bool pre[RUN_Q];
+                // phase 1: bits set by earlier steps (= by smaller file positions)
 #pragma unroll
-        for (int q = 0; q < int(RUN_Q); q++) {
-            if (32u * q >= n) break;
-            if ((todo >> q) & 1u) {
-                const uint32_t bit = cur[q] >> ENT_BIT_SHIFT, m = 1u << (bit & 31u);
-                if (atoms_or_u32(a_bits + ((bit >> 5) << 2), m) & m) {
-                    member |= 1u << q;
-                    bucket_conflict_join(s_list, mt, mf, &s_n[par], bit, (warp << ENT_BIT_SHIFT) | (cur[q] & ((1u << ENT_BIT_SHIFT) - 1)), true);
-                } else {
-                    won |= 1u << q;
+                for (int q = 0; q < int(RUN_Q); q++) {
+                    if (q >= 2 && q >= nq) break;   // warp-uniform
+                    a[q] = a_bits + ((cur[q] >> (ENT_BIT_SHIFT + 3)) & (BB_WORDS * 4u - 4u));
+                    m[q] = lane + 32u * q < nr ? 1u << ((cur[q] >> ENT_BIT_SHIFT) & 31u) : 0u;
+                    pre[q] = (lds_u32(a[q]) & m[q]) != 0u;
                 }
-            }
-        }
-        __syncthreads();
-        uint32_t lost = pre;
-        if (s_n[par] != 0) {   // CTA-uniform: same-step conflicts exist
-            // phase 3a: the probes that set a marked bit join the list
+                __syncwarp();
+                // phase 2: every remaining probe sets its bit; finding it set now means a probe of this very step did it
+                bool conf[RUN_Q], any_conf = false;
 #pragma unroll
-            for (int q = 0; q < int(RUN_Q); q++) {
-                if (32u * q >= n) break;
-                if ((won >> q) & 1u) {
-                    const uint32_t bit = cur[q] >> ENT_BIT_SHIFT;
-                    if ((lds_u32(a_mf + (((bit >> 5) & (MF_WORDS - 1)) << 2)) >> (bit & 31u)) & 1u) {
-                        member |= 1u << q;
-                        bucket_conflict_join(s_list, mt, mf, &s_n[par], bit, (warp << ENT_BIT_SHIFT) | (cur[q] & ((1u << ENT_BIT_SHIFT) - 1)), false);
+                for (int q = 0; q < int(RUN_Q); q++) {
+                    if (q >= 2 && q >= nq) break;
+                    const uint32_t m2 = pre[q] ? 0u : m[q];
+                    conf[q] = (atoms_or_u32(a[q], m2) & m2) != 0u;
+                    any_conf |= conf[q];
+                }
+                __syncwarp();
+                uint32_t extra = 0;
+                if (__any_sync(0xffffffffu, any_conf)) {   // rare
+                    uint32_t todo = 0, cm = 0;
+#pragma unroll
+                    for (int q = 0; q < int(RUN_Q); q++) {
+                        if (q >= 2 && q >= nq) break;
+                        if (m[q] && !pre[q]) todo |= 1u << q;
+                        if (conf[q]) cm |= 1u << q;
                     }
+                    extra = warp_step_conflicts<int(RUN_Q)>(cur, todo, cm);
+                }
+                // lost probes -> lost map (idempotent OR); about one probe in ten
+#pragma unroll
+                for (int q = 0; q < int(RUN_Q); q++) {
+                    if (q >= 2 && q >= nq) break;
+                    red_or_if(lost2_tile + ((cur[q] >> 5) & (BP_TILE / CHUNK - 1)), 1u << (cur[q] & 31u),
+                              pre[q] || ((extra >> q) & 1u));
                 }
             }
-            __syncthreads();
-            // phase 3b: inside the list the smallest file position of a bit wins
-            const uint32_t nl = s_n[par];
-            if (nl > BB_LIST_CAP) {   // conflict list too small: bloom_slow_kernel redoes the species
-                if (threadIdx.x == 0) R.slow[s] = 1u;
-                return;
+            lost2_tile += BP_TILE / CHUNK;
+        };
+        // full groups of BW_DEPTH steps: no exit inside the unrolled body, so each of its copies keeps its own registers
+        // (an exit test per step made ptxas rotate the prefetched entries through one register set at the end of every
+        // step, i.e. wait for the loads it had just issued)
+        const uint32_t n_full = n_tiles - n_tiles % BW_DEPTH;
+        for (uint32_t t0 = 0; t0 < n_full; t0 += BW_DEPTH) {
+            if (t0 == blk + 32u) {
+                blk += 32u;
+                c_cur = c_nxt;
+                c_nxt = cnt_block(blk + 32u);
             }
-            while (member) {
-                const int q = __ffs(member) - 1;
-                member &= member - 1;
-                uint32_t c = 0;
 #pragma unroll
-                for (int i = 0; i < int(RUN_Q); i++) c = i == q ? cur[i] : c;
-                if (bucket_conflict_lost(s_list, mt, nl, c >> ENT_BIT_SHIFT, (warp << ENT_BIT_SHIFT) | (c & ((1u << ENT_BIT_SHIFT) - 1))))
-                    lost |= 1u << q;
-            }
+            for (int i = 0; i < int(BW_DEPTH); i++) step(t0 + uint32_t(i), raw[i], n_raw[i], ent[i], std::true_type{});
         }
-        // lost probes -> lost map (atomicOr: idempotent).  About one probe in ten is lost: the loop runs over the set
-        // bits (once or twice per warp) instead of over all RUN_Q entries with three lanes in 32 active each time.
-        if (lost) {
-            const uint32_t c_tile = tile_c0(cb, t);
-            while (lost) {
-                const int q = __ffs(lost) - 1;
-                lost &= lost - 1;
-                uint32_t e = 0;
 #pragma unroll
-                for (int i = 0; i < int(RUN_Q); i++) e = i == q ? cur[i] : e;
-                const uint32_t c = c_tile + ((e >> 1) & (BP_TILE - 1));
-                atomicOr(R.lost2 + c / CHUNK, 1u << (2u * (c % CHUNK) + (e & 1u)));
-            }
-        }
+        for (int i = 0; i < int(BW_DEPTH) - 1; i++)
+            if (n_full + uint32_t(i) < n_tiles) step(n_full + uint32_t(i), raw[i], n_raw[i], ent[i], std::false_type{});
     }
 }
 

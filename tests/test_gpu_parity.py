@@ -332,7 +332,7 @@ def test_bloom_repeats_and_conflicts(ffi, oracle):
         _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 2, scan_species=[0])
 
 
-@pytest.mark.parametrize("cap", ["1", "16", "120"])
+@pytest.mark.parametrize("cap", ["1", "16", "80"])
 def test_bloom_slow_path(ffi, oracle, cap, monkeypatch):
     """Run slots too small for the probes of a tile: the species take bloom_slow_kernel (global bitset)."""
     monkeypatch.setenv("KMN_BLOOM_RUN_CAP", cap)
