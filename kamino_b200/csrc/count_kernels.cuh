@@ -72,7 +72,10 @@ constexpr uint32_t BW_NQ = RUN_Q + OVF_Q;                  // probes per lane an
 constexpr uint32_t BW_WARPS = (227u * 1024u - 2048u) / (BB_WORDS * 4u);   // 14 warps, each with its own bucket
 constexpr int BW_THREADS = int(BW_WARPS) * 32;
 constexpr size_t BW_SMEM = size_t(BW_WARPS) * BB_WORDS * sizeof(uint32_t);
-constexpr uint32_t BW_DEPTH = 4;                           // runs in flight per warp (global-load latency is hidden by depth, not by occupancy)
+#ifndef KMN_BW_DEPTH
+#define KMN_BW_DEPTH 4
+#endif
+constexpr uint32_t BW_DEPTH = KMN_BW_DEPTH;                           // runs in flight per warp (global-load latency is hidden by depth, not by occupancy)
 constexpr uint32_t BB_LIST_CAP = 2048;                     // (bloom_slow_kernel) conflict list of a step
 constexpr uint32_t ENT_BIT_SHIFT = BP_POS_BITS + 1;         // entry = bit_in_bucket << 14 | pos_in_tile << 1 | probe
 constexpr uint32_t ENT_ORDER_MASK = (1u << ENT_BIT_SHIFT) - 1;
@@ -81,7 +84,7 @@ constexpr uint32_t MT_SLOTS = 256;                         // (bloom_slow_kernel
 static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
 static_assert(BB_LOG2 + ENT_BIT_SHIFT <= 32, "entry layout");
 static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
-static_assert(RUN_CAP < CNT_OVF && BW_WARPS >= 1 && BW_THREADS <= 1024, "bucket kernel shape");
+static_assert(RUN_CAP < CNT_OVF && BW_WARPS >= 1 && BW_THREADS <= 1024 && 32 % BW_DEPTH == 0, "bucket kernel shape");
 // staging rows are cap + 1 words apart: an odd stride spreads the stores of a warp (random buckets, similar ranks)
 // over the shared-memory banks
 constexpr size_t bp_smem_for(uint32_t cap) {
@@ -477,8 +480,9 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
                     m[q] = lane + 32u * q < nr ? 1u << ((cur[q] >> ENT_BIT_SHIFT) & 31u) : 0u;
                     pre[q] = (lds_u32(a[q]) & m[q]) != 0u;
                 }
-                __syncwarp();
                 // phase 2: every remaining probe sets its bit; finding it set now means a probe of this very step did it
+                // (no __syncwarp between the phases: the step is branch-free, the warp converged, and a warp's
+                // shared-memory accesses execute in program order)
                 bool conf[RUN_Q], any_conf = false;
 #pragma unroll
                 for (int q = 0; q < int(RUN_Q); q++) {
@@ -487,7 +491,6 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
                     conf[q] = (atoms_or_u32(a[q], m2) & m2) != 0u;
                     any_conf |= conf[q];
                 }
-                __syncwarp();
                 uint32_t extra = 0;
                 if (__any_sync(0xffffffffu, any_conf)) {   // rare
                     uint32_t todo = 0, cm = 0;

@@ -159,22 +159,25 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t* __restrict__ rec_o
 // ---- K0 in one pass ------------------------------------------------------------------------------------
 // Output index of a kept raw byte i = (#kept bytes before i) + (index of the record containing i)   [one separator
 // per earlier record];  rec_cstart[b] = (#kept bytes before rec_off[b]) + b, and record b-1's separator (0xFF) sits
-// right before it.  One CTA per tile of 16 KiB raw bytes (4 chunks of 16 bytes per thread, a warp's four loads are
-// 512 contiguous bytes each): raw is read ONCE; the running number of kept bytes travels from tile to tile by a
-// decoupled look-back over `state` (tiles are taken in ticket order, so a tile only ever waits for tiles that are
-// already running; the chain continues across the launches of one call because finished tiles keep their
-// inclusive prefix).  The record boundaries that fall into the tile are staged in shared memory once (offsets
-// relative to the tile), every chunk finds its record there, and the tile that contains raw offset rec_off[b]
+// right before it.  One CTA per tile of 16 KiB raw bytes, one thread per 64 contiguous bytes: raw is read ONCE; the
+// running number of kept bytes travels from tile to tile by a decoupled look-back over `state` (tiles are taken in
+// ticket order, so a tile only ever waits for tiles that are already running; the chain continues across the
+// launches of one call because finished tiles keep their inclusive prefix).  The record boundaries that fall into
+// the tile are staged in shared memory once (offsets relative to the tile); a thread finds its first boundary there
+// and then walks its 64 bytes and its boundaries together; the thread whose bytes contain raw offset rec_off[b]
 // owns boundary b.  The codes of a tile (residues + separators) form one contiguous range of codes[]: they are
-// staged in shared memory at the same 16-byte alignment (words swizzled so that the byte stores of a warp, 16 bytes
-// apart, spread over the banks) and leave as 16-byte vectors (bytes only at the two ragged ends); a tile with
-// thousands of empty records reads its boundaries from global memory and stores bytes directly.
-constexpr int FR_CHUNKS = 4;
-constexpr int FR_TILE = FRAME_THREADS * FR_CHUNKS * CHUNK;                 // 16384 raw bytes per CTA
-constexpr int FR_TILE_CHUNKS = FR_TILE / CHUNK;
+// assembled in a zeroed shared-memory image of that range — a 16-byte chunk without an inner boundary is placed
+// run by run of kept bytes, each run as five funnel-shifted words OR-ed in (`red.shared.or`), never byte by byte —
+// and leave as 16-byte vectors (bytes only at the two ragged ends).  Words of the image are XOR-swizzled so that
+// the threads of a warp, 64 bytes apart, hit different banks.  A tile with thousands of empty records reads its
+// boundaries from global memory and stores bytes directly.
+constexpr int FR_SEG = 64;                                                  // raw bytes per thread (4 chunks of 16)
+constexpr int FR_TILE = FRAME_THREADS * FR_SEG;                             // 16384 raw bytes per CTA
 constexpr uint32_t FR_MAX_BOUNDS = 2048;                                    // record boundaries staged per tile
-constexpr uint32_t FR_STAGE = FR_TILE + FR_MAX_BOUNDS + 32;
+constexpr uint32_t FR_SLACK = 16;                                           // image bytes before the tile's first code
+constexpr uint32_t FR_STAGE = FR_TILE + FR_MAX_BOUNDS + 64;                 // + alignment, slack and the 5-word overhang
 constexpr unsigned long long FR_AGGREGATE = 1ull << 32, FR_INCLUSIVE = 2ull << 32;
+static_assert(FR_STAGE % 64 == 0, "the swizzle permutes words inside 64-byte groups");
 
 // tile_rec[t] = record_of(rec_off, 0, n_rec, t * FR_TILE); tile_blo[t] = first boundary that may belong to tile t
 // (empty records that end exactly at the tile's first byte share its offset).  One thread per tile, so the ~19
@@ -200,12 +203,30 @@ __device__ __forceinline__ unsigned long long ld_state(const unsigned long long*
 __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void reds_or(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
-// byte x of the staging buffer: words are XOR-swizzled inside their 16-byte vector by the 128-byte row
-__device__ __forceinline__ uint32_t fr_swz(uint32_t x) { return x ^ (((x >> 7) & 3u) << 2); }
+// word w of the image lives at word w ^ ((w >> 5) & 15): a permutation inside every 16-word group
+__device__ __forceinline__ uint32_t fr_swz(uint32_t w) { return w ^ ((w >> 5) & 15u); }
+// the low 4 bits of n -> a byte mask
+__device__ __forceinline__ uint32_t nib_to_bytes(uint32_t n) { return (((n & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+// OR the chunk bytes selected by the bit mask pm (c[0..3] = the 16 codes) into the image so that chunk byte i lands
+// at image byte off0 + i
+__device__ __forceinline__ void fr_place(uint32_t a_stage, const uint32_t (&c)[4], uint32_t pm, uint32_t off0) {
+    const uint32_t m0 = c[0] & nib_to_bytes(pm), m1 = c[1] & nib_to_bytes(pm >> 4), m2 = c[2] & nib_to_bytes(pm >> 8),
+                   m3 = c[3] & nib_to_bytes(pm >> 12);
+    const uint32_t sh = (off0 & 3u) * 8u, w0 = off0 >> 2;
+    reds_or(a_stage + (fr_swz(w0) << 2), m0 << sh);
+    reds_or(a_stage + (fr_swz(w0 + 1) << 2), __funnelshift_l(m0, m1, sh));
+    reds_or(a_stage + (fr_swz(w0 + 2) << 2), __funnelshift_l(m1, m2, sh));
+    reds_or(a_stage + (fr_swz(w0 + 3) << 2), __funnelshift_l(m2, m3, sh));
+    reds_or(a_stage + (fr_swz(w0 + 4) << 2), __funnelshift_l(m3, 0u, sh));
+}
 
 #ifndef KMN_FRAME_CTAS
-#define KMN_FRAME_CTAS 3
+#define KMN_FRAME_CTAS 4
 #endif
 __global__ void __launch_bounds__(FRAME_THREADS, KMN_FRAME_CTAS)
 frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, const uint64_t* __restrict__ rec_off,
@@ -215,72 +236,62 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_w[FRAME_WARPS];
     __shared__ uint32_t s_tile, s_tb, s_first, s_last;
-    __shared__ uint16_t s_cpre[FR_TILE_CHUNKS], s_kept[FR_TILE_CHUNKS];
-    __shared__ int32_t s_boff[FR_MAX_BOUNDS];
-    __shared__ __align__(16) uint8_t s_stage[FR_STAGE];
+    __shared__ int32_t s_boff[FR_MAX_BOUNDS + 1];
+    __shared__ __align__(16) uint32_t s_stage[FR_STAGE / 4];
     if (threadIdx.x == 0) {
         s_tile = tile_begin + atomicAdd(ticket, 1u);
         s_first = 0xFFFFFFFFu;
         s_last = 0;
     }
+    for (uint32_t i = threadIdx.x; i < FR_STAGE / 16; i += FRAME_THREADS) reinterpret_cast<uint4*>(s_stage)[i] = make_uint4(0u, 0u, 0u, 0u);
     load_lut(s_lut, lut);   // (barrier inside)
     const uint32_t tile = s_tile;
     const uint64_t tile0 = uint64_t(tile) * FR_TILE;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // ---- load + recode: chunk ci = warp * 128 + i * 32 + lane
-    uint4 v[FR_CHUNKS];
+    const int32_t x_base = int32_t(threadIdx.x) * FR_SEG;
+    // ---- load + recode this thread's 64 bytes
+    uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < FR_CHUNKS; i++)
-        v[i] = __ldcs(reinterpret_cast<const uint4*>(raw + tile0) + (warp * (FR_CHUNKS * 32) + i * 32 + lane));
+    for (int i = 0; i < 4; i++) v[i] = __ldg(reinterpret_cast<const uint4*>(raw + tile0 + x_base) + i);
     const uint32_t rhi = tile_rec[tile + 1], blo = tile_blo[tile];
-    // boundaries blo .. rhi + 1 (the last one is a sentinel at or beyond the tile's end)
-    const uint32_t nb = rhi + 2u - blo;
+    // boundaries blo .. min(rhi + 1, n_rec), then a sentinel
+    const uint32_t nb = min(rhi + 1u, n_rec) + 1u - blo;
     const bool staged = nb <= FR_MAX_BOUNDS;   // CTA-uniform
-    auto boff_global = [&](uint32_t j) -> int32_t {
-        const uint32_t b = blo + j;
-        if (b > n_rec) return FR_TILE + 1;
-        const uint64_t x = rec_off[b];
+    auto boff_global = [&](uint32_t j) -> int32_t {   // offset of boundary blo + j relative to the tile, clamped
+        if (j >= nb) return 0x7FFFFFFF;
+        const uint64_t x = rec_off[blo + j];
         return x < tile0 ? -1 : (x - tile0 > uint64_t(FR_TILE) ? FR_TILE + 1 : int32_t(x - tile0));
     };
     if (staged)
-        for (uint32_t j = threadIdx.x; j < nb; j += FRAME_THREADS) s_boff[j] = boff_global(j);
+        for (uint32_t j = threadIdx.x; j <= nb; j += FRAME_THREADS) s_boff[j] = boff_global(j);
     auto boff = [&](uint32_t j) -> int32_t { return staged ? s_boff[j] : boff_global(j); };
-    uint32_t cw[FR_CHUNKS][4], kept[FR_CHUNKS], n_kept[FR_CHUNKS];
+    uint32_t cw[4][4], kept[4], nk = 0;
 #pragma unroll
-    for (int i = 0; i < FR_CHUNKS; i++) {
+    for (int i = 0; i < 4; i++) {
         const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-        const uint64_t i0 = tile0 + uint64_t(warp * (FR_CHUNKS * 32) + i * 32 + lane) * CHUNK;
         uint32_t k = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            uint32_t o = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t c = s_lut[(w[q] >> (8 * j)) & 0xFFu];
-                o |= c << (8 * j);
-                if (c != CODE_SKIP) k |= 1u << (4 * q + j);
-            }
+            const uint32_t o = uint32_t(s_lut[w[q] & 0xFFu]) | (uint32_t(s_lut[(w[q] >> 8) & 0xFFu]) << 8) |
+                               (uint32_t(s_lut[(w[q] >> 16) & 0xFFu]) << 16) | (uint32_t(s_lut[w[q] >> 24]) << 24);
             cw[i][q] = o;
+            // a byte is whitespace iff it is CODE_SKIP = 0xFE: bit 7 set and bit 0 clear (classes are < 0x80, a reset is 0xFF)
+            const uint32_t skip = (o >> 7) & ~o & 0x01010101u;
+            k |= (((skip * 0x01020408u) >> 24) ^ 0xFu) << (4 * q);
         }
+        const uint64_t i0 = tile0 + uint64_t(x_base + 16 * i);
         if (i0 + CHUNK > n_raw) k &= i0 < n_raw ? (1u << uint32_t(n_raw - i0)) - 1u : 0u;   // nothing beyond the data
         kept[i] = k;
-        n_kept[i] = __popc(k);
+        nk += __popc(k);
     }
-    // ---- exclusive prefix of the kept bytes inside the tile (order: warp, i, lane)
-    uint32_t p01 = n_kept[0] | (n_kept[1] << 16), p23 = n_kept[2] | (n_kept[3] << 16);
+    // ---- exclusive prefix of the kept bytes inside the tile
+    uint32_t incl = nk;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y01 = __shfl_up_sync(0xffffffffu, p01, d), y23 = __shfl_up_sync(0xffffffffu, p23, d);
-        if (lane >= unsigned(d)) { p01 += y01; p23 += y23; }
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= unsigned(d)) incl += y;
     }
-    const uint32_t t01 = __shfl_sync(0xffffffffu, p01, 31), t23 = __shfl_sync(0xffffffffu, p23, 31);
-    const uint32_t tot[4] = {t01 & 0xFFFFu, t01 >> 16, t23 & 0xFFFFu, t23 >> 16};
-    uint32_t excl[FR_CHUNKS];
-    excl[0] = (p01 & 0xFFFFu) - n_kept[0];
-    excl[1] = tot[0] + (p01 >> 16) - n_kept[1];
-    excl[2] = tot[0] + tot[1] + (p23 & 0xFFFFu) - n_kept[2];
-    excl[3] = tot[0] + tot[1] + tot[2] + (p23 >> 16) - n_kept[3];
-    if (lane == 0) s_w[warp] = tot[0] + tot[1] + tot[2] + tot[3];
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     uint32_t woff = 0, agg = 0;
 #pragma unroll
@@ -288,13 +299,7 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
         woff += (i < int(warp)) ? s_w[i] : 0u;
         agg += s_w[i];
     }
-#pragma unroll
-    for (int i = 0; i < FR_CHUNKS; i++) {
-        excl[i] += woff;
-        const uint32_t ci = warp * (FR_CHUNKS * 32) + i * 32 + lane;
-        s_cpre[ci] = uint16_t(excl[i]);
-        s_kept[ci] = uint16_t(kept[i]);
-    }
+    const uint32_t excl = woff + incl - nk;
     // ---- decoupled look-back (warp 0): kept bytes before this tile
     if (warp == 0) {
         if (lane == 0) st_state(state + tile, (tile == 0 ? FR_INCLUSIVE : FR_AGGREGATE) | agg);
@@ -303,12 +308,12 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
             int64_t look = int64_t(tile) - 1;
             for (;;) {
                 const int64_t idx = look - int64_t(lane);
-                unsigned long long sv = idx >= 0 ? ld_state(state + idx) : FR_INCLUSIVE;   // before tile 0: nothing
+                const unsigned long long sv = idx >= 0 ? ld_state(state + idx) : FR_INCLUSIVE;   // before tile 0: nothing
                 const uint32_t invalid = __ballot_sync(0xffffffffu, (sv >> 32) == 0ull);
-                const uint32_t incl = __ballot_sync(0xffffffffu, (sv >> 32) == 2ull);
-                const int f = incl ? __ffs(incl) - 1 : 32;             // nearest predecessor with an inclusive prefix
+                const uint32_t inclusive = __ballot_sync(0xffffffffu, (sv >> 32) == 2ull);
+                const int f = inclusive ? __ffs(inclusive) - 1 : 32;   // nearest predecessor with an inclusive prefix
                 const uint32_t need = f >= 31 ? 0xffffffffu : (2u << f) - 1u;   // lanes 0 .. f
-                if (invalid & need) continue;                           // a predecessor has not published yet: look again
+                if (invalid & need) continue;                            // a predecessor has not published yet: look again
                 before += __reduce_add_sync(0xffffffffu, ((need >> lane) & 1u) ? uint32_t(sv) : 0u);
                 if (f < 32) break;
                 look -= 32;
@@ -319,56 +324,67 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
     }
     __syncthreads();
     const uint32_t tb = s_tb;
-    // staging origin: no code of this tile lies before q0; smem index = position - g0, g0 16-byte aligned
+    // image origin: no code of this tile lies before q0; image byte = position - g0; g0 is 16-byte aligned and leaves
+    // FR_SLACK bytes in front (a run of kept bytes behind dropped ones is placed from up to 15 bytes before its chunk)
     const uint32_t q0 = tb + max(blo, 1u) - 1u;
-    const uint32_t g0 = q0 & ~15u;
+    const uint32_t g0 = (q0 & ~15u) - FR_SLACK;
+    const uint32_t a_stage = uint32_t(__cvta_generic_to_shared(s_stage));
     uint32_t my_first = 0xFFFFFFFFu, my_last = 0;
-    auto put = [&](uint32_t pos, uint32_t val) {
-        if (staged) s_stage[fr_swz(pos - g0)] = uint8_t(val);
-        else codes[pos] = uint8_t(val);
-    };
-    // ---- residues
-#pragma unroll
-    for (int i = 0; i < FR_CHUNKS; i++) {
-        if (!kept[i]) continue;
-        const int32_t x0 = int32_t((warp * (FR_CHUNKS * 32) + i * 32 + lane) * CHUNK);
-        // j = last boundary at or before x0 (boundary 0 of the stage list is never after the tile's first byte)
-        uint32_t lo = 0, hi = nb - 1;
-        while (lo < hi) {
-            const uint32_t mid = lo + (hi - lo + 1) / 2;
-            if (boff(mid) <= x0) lo = mid; else hi = mid - 1;
-        }
-        uint32_t j = lo;
-        uint32_t out = tb + excl[i] + blo + j;       // position of the chunk's first kept byte
-        my_first = min(my_first, out);
-        int32_t next = boff(j + 1);
-        if (next >= x0 + CHUNK) {   // the whole chunk lies in one record
-#pragma unroll
-            for (int q = 0; q < 16; q++)
-                if ((kept[i] >> q) & 1u) put(out++, (cw[i][q >> 2] >> (8 * (q & 3))) & 0xFFu);
+    auto put = [&](uint32_t pos, uint32_t val) {   // one byte
+        if (staged) {
+            const uint32_t off = pos - g0;
+            reds_or(a_stage + (fr_swz(off >> 2) << 2), val << (8u * (off & 3u)));
         } else {
-#pragma unroll
-            for (int q = 0; q < 16; q++)
-                if ((kept[i] >> q) & 1u) {
-                    while (x0 + q >= next) { j++; out++; next = boff(j + 1); }
-                    put(out++, (cw[i][q >> 2] >> (8 * (q & 3))) & 0xFFu);
-                }
+            codes[pos] = uint8_t(val);
         }
-        my_last = max(my_last, out);
+        my_first = min(my_first, pos);
+        my_last = max(my_last, pos + 1u);
+    };
+    // ---- this thread's first boundary: the first one at or after x_base
+    uint32_t jn;
+    {
+        uint32_t lo = 0, hi = nb;   // boff(nb) is the sentinel
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (boff(mid) < x_base) lo = mid + 1; else hi = mid;
+        }
+        jn = lo;
     }
-    // ---- record boundaries that fall into this tile: rec_cstart and the previous record's separator
-    for (uint32_t j = threadIdx.x; j < nb; j += FRAME_THREADS) {
-        const uint32_t b = blo + j;
-        if (b > n_rec) break;
-        const int32_t x = boff(j);
-        if (x < 0 || x >= FR_TILE) continue;
-        const uint32_t ci = uint32_t(x) / CHUNK;
-        const uint32_t cs = tb + s_cpre[ci] + __popc(uint32_t(s_kept[ci]) & ((1u << (uint32_t(x) % CHUNK)) - 1u)) + b;
-        rec_cstart[b] = cs;
-        if (b > 0) {
-            put(cs - 1, CODE_INVALID);
-            my_first = min(my_first, cs - 1);
-            my_last = max(my_last, cs);
+    uint32_t kb = tb + excl;   // kept bytes before the next byte
+    int32_t next = boff(jn);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int32_t x0 = x_base + 16 * i;
+        if (staged && next >= x0 + CHUNK) {   // no boundary inside the chunk: blo + jn - 1 is the record of all its bytes
+            if (kept[i]) {
+                const uint32_t out = kb + blo + jn - 1u;
+                my_first = min(my_first, out);
+                uint32_t rem = kept[i];
+                do {   // one run of kept bytes per turn (one turn, or two around a line break)
+                    const uint32_t a = __ffs(rem) - 1u, len = __ffs(~(rem >> a)) - 1u;
+                    const uint32_t pm = ((1u << len) - 1u) << a;
+                    fr_place(a_stage, cw[i], pm, out - g0 + __popc(kept[i] & ((1u << a) - 1u)) - a);
+                    rem &= ~pm;
+                } while (rem);
+                kb += __popc(kept[i]);
+                my_last = max(my_last, kb + blo + jn - 1u);
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < CHUNK; q++) {
+                while (next <= x0 + q) {   // boundary blo + jn sits at this byte: its record starts with the next kept byte
+                    const uint32_t b = blo + jn, cs = kb + b;
+                    rec_cstart[b] = cs;
+                    if (b > 0) put(cs - 1u, CODE_INVALID);
+                    jn++;
+                    next = boff(jn);
+                }
+                if ((kept[i] >> q) & 1u) {
+                    const uint32_t wq = q < 4 ? cw[i][0] : q < 8 ? cw[i][1] : q < 12 ? cw[i][2] : cw[i][3];   // (no indexed register array)
+                    put(kb + blo + jn - 1u, (wq >> (8 * (q & 3))) & 0xFFu);
+                    kb++;
+                }
+            }
         }
     }
     if (!staged) return;
@@ -382,19 +398,22 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
     __syncthreads();
     const uint32_t first = s_first, last = s_last;
     if (last <= first) return;
-    const uint32_t v_lo = (first - g0 + 15u) & ~15u, v_hi = (last - g0) & ~15u;   // whole vectors in smem coordinates
+    const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
+    auto image_byte = [&](uint32_t x) -> uint8_t { return s_bytes[(fr_swz(x >> 2) << 2) | (x & 3u)]; };
+    const uint32_t v_lo = (first - g0 + 15u) & ~15u, v_hi = (last - g0) & ~15u;   // whole vectors in image coordinates
     if (v_hi > v_lo) {
         for (uint32_t x = v_lo + threadIdx.x * 16u; x < v_hi; x += FRAME_THREADS * 16u) {
-            uint4 o = *reinterpret_cast<const uint4*>(s_stage + x);
-            const uint32_t sw = (x >> 7) & 3u;
+            // logical words x/4 .. x/4+3 share (w >> 5): they sit in vector (x/16) ^ (sw >> 2), permuted by sw & 3
+            const uint32_t sw = (x >> 7) & 15u;
+            uint4 o = *reinterpret_cast<const uint4*>(s_bytes + ((((x >> 4) ^ (sw >> 2))) << 4));
             if (sw & 1u) { uint32_t t = o.x; o.x = o.y; o.y = t; t = o.z; o.z = o.w; o.w = t; }
             if (sw & 2u) { uint32_t t = o.x; o.x = o.z; o.z = t; t = o.y; o.y = o.w; o.w = t; }
-            *reinterpret_cast<uint4*>(codes + g0 + x) = o;
+            *reinterpret_cast<uint4*>(codes + uint32_t(g0 + x)) = o;   // g0 may be "negative" (tile 0): wrap in 32 bits
         }
-        for (uint32_t x = first - g0 + threadIdx.x; x < v_lo; x += FRAME_THREADS) codes[g0 + x] = s_stage[fr_swz(x)];
-        for (uint32_t x = v_hi + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[g0 + x] = s_stage[fr_swz(x)];
+        for (uint32_t x = first - g0 + threadIdx.x; x < v_lo; x += FRAME_THREADS) codes[uint32_t(g0 + x)] = image_byte(x);
+        for (uint32_t x = v_hi + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[uint32_t(g0 + x)] = image_byte(x);
     } else {
-        for (uint32_t x = first - g0 + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[g0 + x] = s_stage[fr_swz(x)];
+        for (uint32_t x = first - g0 + threadIdx.x; x < last - g0; x += FRAME_THREADS) codes[uint32_t(g0 + x)] = image_byte(x);
     }
 }
 

@@ -358,9 +358,9 @@ def test_bloom_natural_overflow_takes_slow_path(ffi, oracle):
 
 
 def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
-    """Record boundaries exactly on the 4096-byte frame tiles, empty records on both sides of them, and
-    thousands of empty records inside one tile (the staged write-out of frame_scatter_kernel falls back
-    to direct stores there)."""
+    """Record boundaries exactly on 4096- and 16384-byte offsets (the frame tiles), empty records on both sides of
+    them, and thousands of empty records inside one tile (frame_kernel then reads its boundaries from global memory
+    and stores bytes directly)."""
     rng = np.random.default_rng(41)
     aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
 
@@ -372,6 +372,38 @@ def test_frame_tile_boundaries_and_empty_records(ffi, oracle):
     sp2 = [prot(30) + b"\n" + prot(30) + b" \t" + prot(4036 - 63)] + [b"", prot(4096)]
     residues, rec_off, sp = _batch_from_records([sp0, sp1, [], sp2])
     for k in (13, 5):
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
+
+
+def test_frame_whitespace_runs_and_chunk_edges(ffi, oracle):
+    """frame_kernel places the kept bytes of a 16-byte chunk run by run: chunks with several holes (single
+    residues between line breaks), CRLF, whitespace runs longer than a chunk and longer than a thread's 64 bytes,
+    invalid letters, records that start / end on 16-, 64- and 16384-byte edges, the whole thing across many tiles."""
+    rng = np.random.default_rng(43)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXBZ*acdefghiklmnpqrstvwy", np.uint8)
+    ws = [b"\n", b"\r\n", b" ", b"\t", b"\n\n\n", b" " * 17, b"\n" * 70, b"\x0c"]
+
+    def noisy(n_res, p_ws):
+        out = bytearray()
+        while n_res > 0:
+            run = int(min(n_res, rng.integers(1, 90)))
+            out += aa[rng.integers(0, len(aa), run)].tobytes()
+            n_res -= run
+            if rng.random() < p_ws:
+                out += ws[int(rng.integers(0, len(ws)))]
+        return bytes(out)
+
+    def exact(n):   # exactly n raw bytes, line breaks every 60
+        body = bytearray(aa[rng.integers(0, 20, n)].tobytes())
+        body[60::61] = b"\n" * len(body[60::61])
+        return bytes(body)
+
+    sp0 = [noisy(int(rng.integers(0, 700)), 0.9) for _ in range(400)]
+    sp1 = [exact(16), exact(48), exact(64), b"", exact(64), exact(128 - 1), exact(1), exact(16384 - 321), exact(16384), b"",
+           exact(16384 + 16), b"A\nC\nD\nE\nF\nG\nH\nI\n" * 40, b"\r\n".join([b"ACDEFGHIKLMNPQ"] * 300)]
+    sp2 = [noisy(50000, 0.5), b"\n" * 20000, noisy(3000, 1.0), b" "]
+    residues, rec_off, sp = _batch_from_records([sp0, sp1, sp2])
+    for k in (13, 4):
         _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, SR6, 1)
 
 
