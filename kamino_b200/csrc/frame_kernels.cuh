@@ -355,31 +355,46 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int32_t x0 = x_base + 16 * i;
-        if (staged && next >= x0 + CHUNK) {   // no boundary inside the chunk: blo + jn - 1 is the record of all its bytes
-            if (kept[i]) {
+        const uint32_t k = kept[i];
+        if (staged) {
+            // The boundaries inside the chunk cut it into segments; every segment lies in one record (blo + jn - 1 while
+            // boundary jn is the next one) and is placed run by run of kept bytes.  Chunk byte q lands at
+            // kb + (#kept chunk bytes before q) + record.  Usually one turn; two in the chunk where a record ends.
+            uint32_t lo = 0;
+            for (;;) {
+                const uint32_t hi = next < x0 + CHUNK ? uint32_t(next - x0) : uint32_t(CHUNK);
+                uint32_t rem = k & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
                 const uint32_t out = kb + blo + jn - 1u;
-                my_first = min(my_first, out);
-                uint32_t rem = kept[i];
-                do {   // one run of kept bytes per turn (one turn, or two around a line break)
+                while (rem) {   // one run of kept bytes per turn (one turn, or two around a line break)
                     const uint32_t a = __ffs(rem) - 1u, len = __ffs(~(rem >> a)) - 1u;
                     const uint32_t pm = ((1u << len) - 1u) << a;
-                    fr_place(a_stage, cw[i], pm, out - g0 + __popc(kept[i] & ((1u << a) - 1u)) - a);
+                    const uint32_t pos = out + __popc(k & ((1u << a) - 1u));   // of chunk byte a
+                    fr_place(a_stage, cw[i], pm, pos - g0 - a);
+                    my_first = min(my_first, pos);
+                    my_last = max(my_last, pos + len);
                     rem &= ~pm;
-                } while (rem);
-                kb += __popc(kept[i]);
-                my_last = max(my_last, kb + blo + jn - 1u);
+                }
+                if (hi == uint32_t(CHUNK)) break;
+                // boundary blo + jn sits at chunk byte hi: its record starts with the next kept byte
+                const uint32_t b = blo + jn, cs = kb + __popc(k & ((1u << hi) - 1u)) + b;
+                rec_cstart[b] = cs;
+                if (b > 0) put(cs - 1u, CODE_INVALID);
+                jn++;
+                next = boff(jn);
+                lo = hi;
             }
+            kb += __popc(k);
         } else {
 #pragma unroll 1
             for (int q = 0; q < CHUNK; q++) {
-                while (next <= x0 + q) {   // boundary blo + jn sits at this byte: its record starts with the next kept byte
+                while (next <= x0 + q) {
                     const uint32_t b = blo + jn, cs = kb + b;
                     rec_cstart[b] = cs;
                     if (b > 0) put(cs - 1u, CODE_INVALID);
                     jn++;
                     next = boff(jn);
                 }
-                if ((kept[i] >> q) & 1u) {
+                if ((k >> q) & 1u) {
                     const uint32_t wq = q < 4 ? cw[i][0] : q < 8 ? cw[i][1] : q < 12 ? cw[i][2] : cw[i][3];   // (no indexed register array)
                     put(kb + blo + jn - 1u, (wq >> (8 * (q & 3))) & 0xFFu);
                     kb++;
