@@ -482,7 +482,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         KMN_CUDA(cudaEventRecord(c->ev_copy[0], c->stream));
         KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));   // the raw buffer's previous users are done
     }
-    KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));
+    if (b.n_rec == 0) KMN_CUDA(cudaMemsetAsync(b.codes.p, CODE_INVALID, b.codes_cap, c->stream));   // else: frame_kernel + codes_tail_kernel write every byte
     const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FR_TILE);
     c->tile_rec.ensure(n_frame_tiles + 2);
     c->tile_blo.ensure(n_frame_tiles + 2);
@@ -588,6 +588,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                                                     c->frame_ticket.p + j % (kMaxH2dChunks + 1));
             check_launch(c);
         }
+        if (b.n_rec > 0 && j + 1 == ranges.size()) {   // rec_cstart[n_rec] = number of codes
+            codes_tail_kernel<<<grid_for(c, 2), 256, 0, fs>>>(b.codes.p, b.rec_cstart.p + b.n_rec, b.codes_cap);
+            check_launch(c);
+        }
         {
             const uint32_t s_begin = j == 0 ? 0 : r.s0 + 1, s_end = r.s1;   // boundary s0 was written by the previous range
             if (s_end >= s_begin) {
@@ -613,7 +617,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                                                       TilesJob{PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p, c->n_tiles_dev.p + 1,
                                                                c->cms_running.p});
         check_launch(c);
-        bloom_partition_kernel<<<bl_bound, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+        bloom_partition_kernel<<<std::min<uint32_t>(bl_bound, 2u * uint32_t(c->sm_count)), BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
         // one warp per (species, bucket), persistent CTAs of BW_WARPS warps

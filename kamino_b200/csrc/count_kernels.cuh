@@ -85,10 +85,8 @@ static_assert(BP_TILE == (1u << BP_POS_BITS), "entry layout");
 static_assert(BB_LOG2 + ENT_BIT_SHIFT <= 32, "entry layout");
 static_assert(BB_BUCKETS % BP_TILE_WT == 0 && BB_BUCKETS <= BP_THREADS, "bucket ownership");
 static_assert(RUN_CAP < CNT_OVF && BW_WARPS >= 1 && BW_THREADS <= 1024 && 32 % BW_DEPTH == 0, "bucket kernel shape");
-// staging rows are cap + 1 words apart: an odd stride spreads the stores of a warp (random buckets, similar ranks)
-// over the shared-memory banks
 constexpr size_t bp_smem_for(uint32_t cap) {
-    return size_t(BB_BUCKETS) * (cap + 1) * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
+    return size_t(BB_BUCKETS) * cap * sizeof(uint32_t) + BB_BUCKETS * sizeof(uint32_t);
 }
 
 struct BloomRuns {
@@ -134,69 +132,92 @@ __device__ __forceinline__ uint32_t tile_c0(uint32_t cb, uint32_t t) {
     return (cb / WARP_TILE + t * BP_TILE_WT) * WARP_TILE;
 }
 
+// The staging buffer IS the tile's slot array ([bucket][cap], the layout of R.ent): when a tile is ranked, one
+// elected thread hands the whole buffer to the bulk-copy engine (cp.async.bulk.global.shared::cta, SASS UBLKCP) and
+// the CTA — persistent, two per SM — moves on to load and hash its next tile while the copy drains; it only waits
+// for the copy to have READ the buffer right before it ranks into it again.  No thread copies entries out.
+// Position of rank r inside a run: r ^ (bucket & 31) when the slot size is a multiple of 32 (bank = function of
+// the bucket: the stores of a warp — random buckets, similar ranks — would otherwise pile up on a few banks); the
+// bucket kernel reads a run in whatever order it lies.
+__device__ __forceinline__ void bulk_store_group(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t run_swizzle(uint32_t cap, uint32_t bucket) { return (cap & 31u) ? 0u : (bucket & 31u); }
+
 __global__ void __launch_bounds__(BP_THREADS, 2)
 bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k,
                        uint64_t k_mask, BloomRuns R) {
-    extern __shared__ __align__(16) uint32_t bp_smem[];
-    const uint32_t stride = R.cap + 1;
-    uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap + 1]
+    extern __shared__ __align__(128) uint32_t bp_smem[];
+    const uint32_t stride = R.cap;
+    uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap]
     uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * stride;  // [BB_BUCKETS]
     __shared__ uint32_t s_ovf_n;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tg = blockIdx.x;
-    if (tg >= *R.n_tiles) return;
-    if (threadIdx.x == 0) s_ovf_n = 0;
-    const uint32_t s = R.tile_sp[tg];
-    const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
-    const uint32_t tg0 = R.sp_tile0[s], nt = R.sp_tile0[s + 1] - tg0;
-    const uint32_t base = tile_c0(cb, tg - tg0);
-    if (threadIdx.x < BB_BUCKETS) fill[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
-    if (base + warp * WARP_TILE < ce) {   // warp-uniform
+    const uint32_t n_tiles = *R.n_tiles;
+    const uint32_t stage_bytes = BB_BUCKETS * stride * uint32_t(sizeof(uint32_t));
+    for (uint32_t tg = blockIdx.x; tg < n_tiles; tg += gridDim.x) {
+        const uint32_t s = R.tile_sp[tg];
+        const uint32_t cb = sp_cstart[s], ce = sp_cstart[s + 1];
+        const uint32_t tg0 = R.sp_tile0[s], nt = R.sp_tile0[s + 1] - tg0;
+        const uint32_t base = tile_c0(cb, tg - tg0);
+        const uint32_t c0 = base + warp * WARP_TILE + lane * CHUNK;
+        const bool active = base + warp * WARP_TILE < ce;   // warp-uniform
         uint64_t kmer[CHUNK];
-        const uint32_t valid_all = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer);
-        const uint32_t valid = valid_all & range_mask16(c0, cb, ce);
-        const uint32_t dup = dup_mask16(kmer, valid_all) & valid;
-        if (dup) atomicOr(R.lost2 + c0 / CHUNK, spread2(dup, 3u));
-        const uint32_t todo = valid & ~dup;
-        bool ovf = false;
+        uint32_t todo = 0;
+        if (active) {
+            const uint32_t valid_all = load_chunk_kmers<true>(codes, base + warp * WARP_TILE, k, k_mask, kmer);
+            const uint32_t valid = valid_all & range_mask16(c0, cb, ce);
+            const uint32_t dup = dup_mask16(kmer, valid_all) & valid;
+            if (dup) atomicOr(R.lost2 + c0 / CHUNK, spread2(dup, 3u));
+            todo = valid & ~dup;
+        }
+        // the previous tile's copy has read the staging buffer; its counters were consumed before the copy was issued
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            s_ovf_n = 0;
+        }
+        if (threadIdx.x < BB_BUCKETS) fill[threadIdx.x] = 0;
+        __syncthreads();
+        if (active) {
+            bool ovf = false;
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++) {
-            if (!((todo >> j) & 1u)) continue;
-            uint32_t idx[2];
-            bloom_indices(kmer[j], idx[0], idx[1]);
-            const uint32_t pos = warp * WARP_TILE + lane * CHUNK + j;
+            for (int j = 0; j < CHUNK; j++) {
+                if (!((todo >> j) & 1u)) continue;
+                uint32_t idx[2];
+                bloom_indices(kmer[j], idx[0], idx[1]);
+                const uint32_t pos = warp * WARP_TILE + lane * CHUNK + j;
 #pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                const uint32_t b = idx[pr] >> BB_LOG2;
-                const uint32_t rank = atomicAdd(&fill[b], 1u);
-                const uint32_t entry = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
-                if (rank < R.cap) {
-                    stage[b * stride + rank] = entry;
-                } else {   // rare: the run slot is full
-                    const uint32_t o = atomicAdd(&s_ovf_n, 1u);
-                    if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
-                    else ovf = true;
+                for (int pr = 0; pr < 2; pr++) {
+                    const uint32_t b = idx[pr] >> BB_LOG2;
+                    const uint32_t rank = atomicAdd(&fill[b], 1u);
+                    const uint32_t entry = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
+                    if (rank < R.cap) {
+                        stage[b * stride + (rank ^ run_swizzle(R.cap, b))] = entry;
+                    } else {   // rare: the run slot is full
+                        const uint32_t o = atomicAdd(&s_ovf_n, 1u);
+                        if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
+                        else ovf = true;
+                    }
                 }
             }
+            if (ovf) R.slow[s] = 1u;
         }
-        if (ovf) R.slow[s] = 1u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's staging stores, before the bulk copy reads them
+        __syncthreads();
+        if (threadIdx.x < BB_BUCKETS) {
+            const uint32_t f = fill[threadIdx.x];
+            R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(f > R.cap ? (R.cap | CNT_OVF) : f);
+        }
+        if (threadIdx.x == 0) {
+            R.ovf_n[tg] = min(s_ovf_n, OVF_CAP);
+            // the whole slot array of the tile (dead positions included) in pieces of at most 32 KiB
+            uint8_t* dst = reinterpret_cast<uint8_t*>(R.ent + size_t(tg) * BB_BUCKETS * R.cap);
+            const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
+            for (uint32_t o = 0; o < stage_bytes; o += 32768u) bulk_store_group(dst + o, src + o, min(stage_bytes - o, 32768u));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < BB_BUCKETS) {
-        const uint32_t f = fill[threadIdx.x];
-        R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(f > R.cap ? (R.cap | CNT_OVF) : f);
-    }
-    if (threadIdx.x == 0) R.ovf_n[tg] = min(s_ovf_n, OVF_CAP);
-    // warp w copies the runs of its BB_BUCKETS / 16 buckets to their fixed slots
-#pragma unroll 1
-    for (uint32_t q = 0; q < BB_BUCKETS / BP_TILE_WT; q++) {
-        const uint32_t b = warp * (BB_BUCKETS / BP_TILE_WT) + q;
-        const uint32_t n = min(fill[b], R.cap);
-        uint32_t* dst = R.ent + (size_t(tg) * BB_BUCKETS + b) * R.cap;
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = stage[b * stride + i];
-    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- one step of exact first-touch resolution on a set of probes -----------------------------------
@@ -356,13 +377,14 @@ __device__ __forceinline__ uint32_t warp_step_conflicts(const uint32_t (&cur)[NQ
 // them, same three phases with plain branches.  `lost2_tile` = lost-map word of the tile's first position.
 __device__ __noinline__ void bucket_step_overflow(uint32_t a_bits, const uint32_t* __restrict__ run, uint32_t n,
                                                   const unsigned long long* __restrict__ ovf, uint32_t n_ovf,
-                                                  uint32_t beta, uint32_t* __restrict__ lost2_tile) {
+                                                  uint32_t beta, uint32_t* __restrict__ lost2_tile, uint32_t cap) {
     const unsigned lane = threadIdx.x & 31u;
+    const uint32_t rlane = lane ^ run_swizzle(cap, beta);
     uint32_t cur[BW_NQ], live = 0;
 #pragma unroll
     for (int q = 0; q < int(RUN_Q); q++) {
         cur[q] = 0;
-        if (lane + 32u * q < n) {
+        if (rlane + 32u * q < n) {
             cur[q] = __ldcs(run + 32 * q);
             live |= 1u << q;
         }
@@ -430,6 +452,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
         // this bucket's run lengths are contiguous over the tiles
         const uint16_t* __restrict__ cnt = R.cnt + size_t(tg0) * BB_BUCKETS + size_t(beta) * n_tiles;
         const uint32_t* __restrict__ ent0 = R.ent + (size_t(tg0) * BB_BUCKETS + beta) * R.cap + lane;
+        const uint32_t rlane = lane ^ run_swizzle(R.cap, beta);   // this lane's slot positions hold ranks rlane + 32 q
         auto cnt_block = [&](uint32_t t) -> uint32_t { return t + lane < n_tiles ? uint32_t(__ldg(cnt + t + lane)) : 0u; };
         uint32_t blk = 0, c_cur = cnt_block(0), c_nxt = cnt_block(32);
         auto run_len = [&](uint32_t t) -> uint32_t {   // t in [blk, blk + 64); 0 past the last tile
@@ -441,7 +464,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
             const uint32_t nn = n & ~CNT_OVF;
 #pragma unroll
             for (int q = 0; q < int(RUN_Q); q++)
-                if (lane + 32u * q < nn) dst[q] = __ldcs(e + 32 * q);
+                if (rlane + 32u * q < nn) dst[q] = __ldcs(e + 32 * q);
         };
 #pragma unroll
         for (int i = 0; i < int(BW_DEPTH); i++) {
@@ -467,7 +490,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
             if (nr & CNT_OVF) {   // rare: the rest of this run sits in the tile's overflow list
                 const uint32_t tile = tg0 + t;
                 bucket_step_overflow(a_bits, this_run, nr & ~CNT_OVF, R.ovf + size_t(tile) * OVF_CAP, min(R.ovf_n[tile], OVF_CAP), beta,
-                                     lost2_tile);
+                                     lost2_tile, R.cap);
             } else {
                 const int nq = int((nr + 31u) >> 5);   // warp-uniform: lane slots in use
                 uint32_t a[RUN_Q], m[RUN_Q];
@@ -477,7 +500,7 @@ bloom_bucket_kernel(const uint32_t* __restrict__ sp_cstart, uint32_t s0, uint32_
                 for (int q = 0; q < int(RUN_Q); q++) {
                     if (q >= 2 && q >= nq) break;   // warp-uniform
                     a[q] = a_bits + ((cur[q] >> (ENT_BIT_SHIFT + 3)) & (BB_WORDS * 4u - 4u));
-                    m[q] = lane + 32u * q < nr ? 1u << ((cur[q] >> ENT_BIT_SHIFT) & 31u) : 0u;
+                    m[q] = rlane + 32u * q < nr ? 1u << ((cur[q] >> ENT_BIT_SHIFT) & 31u) : 0u;
                     pre[q] = (lds_u32(a[q]) & m[q]) != 0u;
                 }
                 // phase 2: every remaining probe sets its bit; finding it set now means a probe of this very step did it

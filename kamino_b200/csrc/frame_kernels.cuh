@@ -432,6 +432,15 @@ frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, con
     }
 }
 
+// codes[] behind the last separator: 0xFF up to the end of the buffer (consumers read whole warp tiles and scan
+// the whole capacity).  Everything before *n_codes is written by frame_kernel, so the buffer needs no memset.
+__global__ void __launch_bounds__(256) codes_tail_kernel(uint8_t* __restrict__ codes, const uint32_t* __restrict__ n_codes, size_t cap) {
+    const size_t n = *n_codes, v0 = min((n + 15) & ~size_t(15), cap);
+    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = size_t(gridDim.x) * blockDim.x;
+    if (n + tid < v0) codes[n + tid] = CODE_INVALID;   // at most 15 bytes
+    for (size_t i = v0 / 16 + tid; i < cap / 16; i += nth) reinterpret_cast<uint4*>(codes)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+}
+
 // species -> codes[] offsets for the species boundaries [s_begin, s_end]: sp_cstart[s] = rec_cstart[sp_rec_off[s]]
 __global__ void species_offsets_kernel(const uint32_t* __restrict__ rec_cstart,
                                        const uint64_t* __restrict__ sp_rec_off, uint32_t s_begin, uint32_t s_end,
