@@ -19,7 +19,7 @@ def main():
     pin = ffi.PinnedBuffer(b.residues.size)
     pin.array[:] = b.residues
     settings = [("adaptive", None, None)]
-    settings += [("ratio", r, n) for r in ("1.0", "1.2", "1.35", "1.5", "2.0") for n in (5, 8, 12)]
+    settings += [("ratio", r, n) for r in ("1.0", "1.5", "2.0", "3.0") for n in (3, 4, 5, 8)]
     for mode, ratio, chunks in settings:
         for _ in (0,):
             for k in ("KMN_H2D_CHUNKS", "KMN_H2D_RATIO", "KMN_H2D_MODE"):
