@@ -106,7 +106,7 @@ struct Batch {
 
 }  // namespace
 
-constexpr uint32_t kMaxH2dChunks = 16;
+constexpr uint32_t kMaxH2dChunks = 32;
 constexpr float kKernelGBs = 36.f;     // raw bytes per second the frame / Bloom / partition kernels of a (small) range consume
 
 struct kmn_ctx {
@@ -143,6 +143,7 @@ struct kmn_ctx {
     cudaEvent_t ev_frame[1 + kMaxH2dChunks] = {};
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_copy[1 + kMaxH2dChunks] = {};
+    bool h2d_chunks_forced = false;       // KMN_H2D_CHUNKS given: no automatic schedule for long batches
     uint32_t h2d_chunks = 5;              // species ranges per kmn_count_batch (KMN_H2D_CHUNKS): every range costs ~50 us of launch gaps and tails
     float h2d_ratio = 0.f;                // KMN_H2D_RATIO: growth of consecutive ranges (0: from the measured link rate)
     cudaEvent_t ev_h2d[2] = {};           // first / last host-to-device range copy of the last kmn_count_batch
@@ -393,7 +394,7 @@ struct SpeciesRange {
     uint64_t codes_bound;           // upper bound of the codes[] positions of the range
 };
 
-std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double ratio) {
+std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double ratio, bool long_schedule) {
     std::vector<SpeciesRange> out;
     const uint32_t n_frame_tiles = uint32_t(b.raw_pad / FR_TILE);
     if (b.n_sp == 0) {   // records without species cannot exist (sp_rec_off spans them); frame only
@@ -409,10 +410,26 @@ std::vector<SpeciesRange> plan_ranges(const Batch& b, uint32_t want, double rati
     // (profiles/r02_e2e_range_schedules.jsonl).  Ratio 1 (equal ranges) is right when the link is the slower side
     // (several ranks sharing the host's PCIe / memory path): then the kernels of the LAST range are what is left
     // after the copies.
-    std::vector<double> w(want);
+    // Long batches (> 160 MB: a 1000-proteome job in one call) keep that ramp — 9 MB, then `ratio` times more each —
+    // up to 48 MB and continue with ranges of that size: with 5 ranges the last one alone would be 38 % of the
+    // batch, and its kernels would only start when the whole batch has been copied.
+    std::vector<double> w;
+    if (long_schedule) {
+        double size = 9e6, left = double(b.n_raw);
+        while (left > 0 && w.size() < kMaxH2dChunks) {
+            w.push_back(size);
+            left -= size;
+            size = std::min(size * std::max(ratio, 1.0), 48e6);
+        }
+        if (left > 0) w.back() += left;   // (more than kMaxH2dChunks ranges: the last one takes the rest)
+        want = std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(w.size()), b.n_sp));
+    } else {
+        w.resize(want);
+        for (uint32_t j = 0; j < want; j++) w[j] = j == 0 ? 1.0 : w[j - 1] * ratio;
+    }
     double wsum = 0;
-    for (uint32_t j = 0; j < want; j++) { w[j] = j == 0 ? 1.0 : w[j - 1] * ratio; wsum += w[j]; }
-    auto range_bytes = [&](size_t j) { return uint64_t(double(b.n_raw) * w[std::min<size_t>(j, want - 1)] / wsum) + 1; };
+    for (double x : w) wsum += x;
+    auto range_bytes = [&](size_t j) { return uint64_t(double(b.n_raw) * w[std::min<size_t>(j, w.size() - 1)] / wsum) + 1; };
     uint32_t s0 = 0;
     uint64_t copied = 0;
     uint32_t tiled = 0;
@@ -459,7 +476,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     if (c->h2d_mode == 2) ratio = 1.0;
     const uint32_t chunks = c->h2d_chunks;
     const uint32_t want = from_host ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, uint32_t(b.n_raw >> 22))) : 1;
-    const std::vector<SpeciesRange> ranges = plan_ranges(b, want, ratio);
+    const bool long_schedule = from_host && !c->h2d_chunks_forced && c->h2d_mode == 0 && b.n_raw > (uint64_t(160) << 20);
+    const std::vector<SpeciesRange> ranges = plan_ranges(b, want, ratio, long_schedule);
     const bool timed = ranges.size() == 1;   // per-stage events only make sense without the pipeline
     const int grid = grid_for(c, 8);
 
@@ -1125,7 +1143,8 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         }
         if (const char* e = std::getenv("KMN_H2D_CHUNKS")) {   // tuning knob
             const long v = std::strtol(e, nullptr, 10);
-            if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1..16");
+            if (v < 1 || v > long(kMaxH2dChunks)) throw std::runtime_error("KMN_H2D_CHUNKS must be in 1.." + std::to_string(kMaxH2dChunks));
+            c->h2d_chunks_forced = true;
             c->h2d_chunks = uint32_t(v);
         }
         if (const char* e = std::getenv("KMN_H2D_RATIO")) {    // tuning knob: growth of consecutive ranges
