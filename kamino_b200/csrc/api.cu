@@ -635,7 +635,13 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                                                       TilesJob{PART_WTILES, c->cms_tile0.p, c->cms_tile_sp.p, c->n_tiles_dev.p + 1,
                                                                c->cms_running.p});
         check_launch(c);
-        bloom_partition_kernel<<<std::min<uint32_t>(bl_bound, 2u * uint32_t(c->sm_count)), BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+        {
+            const uint32_t bp_grid = std::min<uint32_t>(bl_bound, 2u * uint32_t(c->sm_count));
+            if (R.cap == RUN_CAP)
+                bloom_partition_kernel<RUN_CAP><<<bp_grid, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+            else   // test knob KMN_BLOOM_RUN_CAP
+                bloom_partition_kernel<0><<<bp_grid, BP_THREADS, bp_smem_for(R.cap), c->stream>>>(b.codes.p, b.sp_cstart.p, c->k, c->k_mask, R);
+        }
         check_launch(c);
         if (timed) KMN_CUDA(cudaEventRecord(c->ev[8], c->stream));
         // one warp per (species, bucket), persistent CTAs of BW_WARPS warps
@@ -1166,7 +1172,8 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
         }
         c->bl_scratch.alloc(size_t(BS_MAX_CTAS) << (BLOOM_BITS_LOG2 - 5));
         KMN_CUDA(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PAIR_COUNT_SMEM)));
-        KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel<RUN_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
+        KMN_CUDA(cudaFuncSetAttribute(bloom_partition_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bp_smem_for(RUN_CAP))));
         KMN_CUDA(cudaFuncSetAttribute(bloom_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BW_SMEM)));
         KMN_CUDA(cudaFuncSetAttribute(bloom_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BS_SMEM)));
         c->tab.alloc(CMS_CELLS);

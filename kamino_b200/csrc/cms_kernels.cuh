@@ -154,10 +154,7 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
             // (Two branch-free forms of this loop were measured slower: all 16 hashes hoisted ahead of predicated atomics
             // and stores, 64 registers with spills: 1.27 ms; straight-line entries with a dummy bucket for dead lanes
             // and min(rank, cap) stores, 64 registers: 1.03 ms; this branchy form, 56 registers: 0.92 ms.)
-#pragma unroll
-            for (int j = 0; j < CHUNK; j++) {
-                if (!((new_bits >> j) & 1u)) continue;
-                const uint32_t idx = cms_index_folded(kmer[j], seed);
+            auto emit = [&](uint32_t idx) {
                 const uint32_t b = idx >> CMS_BUCKET_LOG2;
                 const uint32_t rank = atomicAdd(&fl[b], 1u);
                 if (rank < slot_limit) {
@@ -167,7 +164,28 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
                     if (sp < L.spill_cap) L.spill[sp] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
                     else L.state[0] = 1u;
                 }
+            };
+#if KMN_PART_ILP > 1
+            // the hashes of KMN_PART_ILP neighbouring positions are computed together (independent dependency chains),
+            // dead positions included; only the rank / store part is conditional
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += KMN_PART_ILP) {
+                uint32_t idx[KMN_PART_ILP];
+#pragma unroll
+                for (int u = 0; u < KMN_PART_ILP; u++) idx[u] = cms_index_folded(kmer[j + u], seed);
+#pragma unroll
+                for (int u = 0; u < KMN_PART_ILP; u++) asm volatile("" : "+r"(idx[u]));
+#pragma unroll
+                for (int u = 0; u < KMN_PART_ILP; u++)
+                    if ((new_bits >> (j + u)) & 1u) emit(idx[u]);
             }
+#else
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                if (!((new_bits >> j) & 1u)) continue;
+                emit(cms_index_folded(kmer[j], seed));
+            }
+#endif
             __syncthreads();
             // thread b closes slot b; the other buffer's counters (read one row ago) are cleared for the next row
             st[threadIdx.x * PART_SLOT + (slot_origin(threadIdx.x) ^ PART_SLOT_CAP)] = uint16_t(min(fl[threadIdx.x], slot_limit));
@@ -233,10 +251,20 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 // reaches the slot's four lanes by shuffle.  The histogram atomics do not return a value; a counter that
 // wrapped or carried into its neighbour is detected afterwards (the histogram's total falls short of the number of
 // entries) and the bucket is then redone with u32 counters.
-constexpr int APPLY_STAGES = 4;
-constexpr uint32_t APPLY_STAGE_VEC = APPLY_THREADS;                        // one vector per thread and stage
-constexpr uint32_t APPLY_STAGE_BYTES = APPLY_STAGE_VEC * 16;               // 16 KiB
-constexpr size_t APPLY_SMEM = size_t(APPLY_WORDS) * sizeof(uint32_t) + size_t(APPLY_STAGES) * APPLY_STAGE_BYTES + 128;
+#ifndef KMN_PART_ILP
+#define KMN_PART_ILP 2
+#endif
+#ifndef KMN_APPLY_VPT
+#define KMN_APPLY_VPT 2
+#endif
+#ifndef KMN_APPLY_STAGES
+#define KMN_APPLY_STAGES 3
+#endif
+constexpr int APPLY_STAGES = KMN_APPLY_STAGES;
+constexpr uint32_t APPLY_VPT = KMN_APPLY_VPT;                              // vectors per thread and stage
+constexpr uint32_t APPLY_STAGE_VEC = APPLY_THREADS * APPLY_VPT;
+constexpr uint32_t APPLY_STAGE_BYTES = APPLY_STAGE_VEC * 16;               // 16 KiB per vector and thread
+constexpr size_t APPLY_SMEM = size_t(APPLY_WORDS) * sizeof(uint32_t) + size_t(APPLY_STAGES) * APPLY_STAGE_BYTES + 256;   // + barriers (64 B) + one dummy word per lane
 
 // Chunks carry a sequence number g that keeps counting over repeated passes (the exact redo streams the bucket
 // again): chunk g uses stage g % STAGES for the (g / STAGES)-th time, which fixes the barrier parities.
@@ -276,21 +304,28 @@ __device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
         if (threadIdx.x == 0 && c + APPLY_STAGES - 1 < R.n_chunks) apply_issue(R);
         const uint32_t g = R.done + c, st = g % APPLY_STAGES;
         mbar_wait(R.full + 8 * st, (g / APPLY_STAGES) & 1u);
-        const uint32_t i = c * APPLY_STAGE_VEC + threadIdx.x;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < R.n_vec) {
-            const uint32_t a = R.ring + st * APPLY_STAGE_BYTES + threadIdx.x * 16u;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+        uint4 v[APPLY_VPT];
+#pragma unroll
+        for (uint32_t u = 0; u < APPLY_VPT; u++) {
+            const uint32_t i = c * APPLY_STAGE_VEC + u * APPLY_THREADS + threadIdx.x;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (i < R.n_vec) {
+                const uint32_t a = R.ring + st * APPLY_STAGE_BYTES + (u * APPLY_THREADS + threadIdx.x) * 16u;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(a) : "memory");
+            }
         }
         mbar_arrive(R.empty + 8 * st);
-        const uint32_t cw = cnt_word == 0 ? v.x : cnt_word == 1 ? v.y : cnt_word == 2 ? v.z : v.w;
-        const uint32_t cnt = __shfl_sync(0xffffffffu, cw >> 16, cnt_lane);
-        if ((lane & 3u) == 0) mine += cnt;   // one lane per slot books the slot's entries
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const bool live = (first ^ uint32_t(j)) < cnt;   // rank 31 (the count's position) is never live: cnt <= 31
-            bump((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, live);
+        for (uint32_t u = 0; u < APPLY_VPT; u++) {
+            const uint32_t cw = cnt_word == 0 ? v[u].x : cnt_word == 1 ? v[u].y : cnt_word == 2 ? v[u].z : v[u].w;
+            const uint32_t cnt = __shfl_sync(0xffffffffu, cw >> 16, cnt_lane);
+            if ((lane & 3u) == 0) mine += cnt;   // one lane per slot books the slot's entries
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool live = (first ^ uint32_t(j)) < cnt;   // rank 31 (the count's position) is never live: cnt <= 31
+                bump((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, live);
+            }
         }
     }
     R.done += R.n_chunks;
@@ -334,13 +369,16 @@ cms_apply_kernel(CmsSlots L, uint16_t* __restrict__ tab, int force_exact, int fr
     uint4* s4 = reinterpret_cast<uint4*>(s_cnt);
     for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    // predicated shared-memory reduction (no branch around it: half of the slot positions are dead, and a branch per
-    // entry made the loop ~40 % longer): counter word c >> 1, low or high half by c & 1
+    // No branch around the histogram atomic (half of the slot positions are dead): a dead position adds to the
+    // lane's own dummy word instead (bank = lane; the dummy words collect garbage, nothing reads them).  ptxas turns
+    // a predicated red.shared back into BSSY / BRA / ATOMS / BSYNC, and the branch per entry cost 11 % of the kernel
+    // (0.76 -> 0.675 ms; its top stall reason was branch resolving).  Counter word c >> 1, low or high half by c & 1.
     const uint32_t a_cnt = smem_u32(s_cnt);
+    const uint32_t off_dummy = R.full + 128u + 4u * (threadIdx.x & 31u) - a_cnt;
     const uint32_t mine = apply_stream(R, [&](uint32_t c, bool live) {
-        const uint32_t addr = a_cnt + ((c << 1) & 0x3FFFCu), val = (c & 1u) ? 0x10000u : 1u;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
-                     ::"r"(addr), "r"(val), "r"(uint32_t(live)) : "memory");
+        const uint32_t off = live ? ((c << 1) & 0x3FFFCu) : off_dummy;
+        const uint32_t val = (c & 1u) ? 0x10000u : 1u;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_cnt + off), "r"(val) : "memory");
     });
     {   // entries streamed by the CTA
         const uint32_t w = __reduce_add_sync(0xffffffffu, mine);

@@ -47,6 +47,9 @@
 
 namespace kmn {
 
+#ifndef KMN_BP_ILP
+#define KMN_BP_ILP 1
+#endif
 constexpr int BP_THREADS = 512;
 constexpr uint32_t BP_TILE_WT = BP_THREADS / 32;          // warp tiles per source tile (one per warp)
 constexpr uint32_t BP_TILE = BP_TILE_WT * WARP_TILE;       // 8192 positions
@@ -144,11 +147,15 @@ __device__ __forceinline__ void bulk_store_group(void* dst_global, uint32_t src_
 }
 __device__ __forceinline__ uint32_t run_swizzle(uint32_t cap, uint32_t bucket) { return (cap & 31u) ? 0u : (bucket & 31u); }
 
+// CAP: the run slot size as a compile-time constant (RUN_CAP: the slot address and the swizzle then cost 6 instead
+// of 11 instructions per probe); 0: R.cap at run time (test knob KMN_BLOOM_RUN_CAP).
+template <uint32_t CAP>
 __global__ void __launch_bounds__(BP_THREADS, 2)
 bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ sp_cstart, int k,
                        uint64_t k_mask, BloomRuns R) {
     extern __shared__ __align__(128) uint32_t bp_smem[];
-    const uint32_t stride = R.cap;
+    const uint32_t cap = CAP ? CAP : R.cap;
+    const uint32_t stride = cap;
     uint32_t* stage = bp_smem;                               // [BB_BUCKETS][cap]
     uint32_t* fill = bp_smem + size_t(BB_BUCKETS) * stride;  // [BB_BUCKETS]
     __shared__ uint32_t s_ovf_n;
@@ -180,38 +187,57 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
         __syncthreads();
         if (active) {
             bool ovf = false;
+            auto emit = [&](uint32_t i, uint32_t pos, uint32_t pr) {
+                const uint32_t b = i >> BB_LOG2;
+                const uint32_t rank = atomicAdd(&fill[b], 1u);
+                const uint32_t entry = ((i & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | pr;
+                if (rank < cap) {
+                    stage[b * stride + (rank ^ run_swizzle(cap, b))] = entry;
+                } else {   // rare: the run slot is full
+                    const uint32_t o = atomicAdd(&s_ovf_n, 1u);
+                    if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
+                    else ovf = true;
+                }
+            };
+#if KMN_BP_ILP > 1
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += KMN_BP_ILP) {
+                uint32_t idx[KMN_BP_ILP][2];
+#pragma unroll
+                for (int u = 0; u < KMN_BP_ILP; u++) bloom_indices(kmer[j + u], idx[u][0], idx[u][1]);
+#pragma unroll
+                for (int u = 0; u < KMN_BP_ILP; u++) asm volatile("" : "+r"(idx[u][0]), "+r"(idx[u][1]));
+#pragma unroll
+                for (int u = 0; u < KMN_BP_ILP; u++) {
+                    if (!((todo >> (j + u)) & 1u)) continue;
+                    const uint32_t pos = warp * WARP_TILE + lane * CHUNK + j + u;
+                    emit(idx[u][0], pos, 0u);
+                    emit(idx[u][1], pos, 1u);
+                }
+            }
+#else
 #pragma unroll
             for (int j = 0; j < CHUNK; j++) {
                 if (!((todo >> j) & 1u)) continue;
                 uint32_t idx[2];
                 bloom_indices(kmer[j], idx[0], idx[1]);
                 const uint32_t pos = warp * WARP_TILE + lane * CHUNK + j;
-#pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                    const uint32_t b = idx[pr] >> BB_LOG2;
-                    const uint32_t rank = atomicAdd(&fill[b], 1u);
-                    const uint32_t entry = ((idx[pr] & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | uint32_t(pr);
-                    if (rank < R.cap) {
-                        stage[b * stride + (rank ^ run_swizzle(R.cap, b))] = entry;
-                    } else {   // rare: the run slot is full
-                        const uint32_t o = atomicAdd(&s_ovf_n, 1u);
-                        if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
-                        else ovf = true;
-                    }
-                }
+                emit(idx[0], pos, 0u);
+                emit(idx[1], pos, 1u);
             }
+#endif
             if (ovf) R.slow[s] = 1u;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's staging stores, before the bulk copy reads them
         __syncthreads();
         if (threadIdx.x < BB_BUCKETS) {
             const uint32_t f = fill[threadIdx.x];
-            R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(f > R.cap ? (R.cap | CNT_OVF) : f);
+            R.cnt[size_t(tg0) * BB_BUCKETS + size_t(threadIdx.x) * nt + (tg - tg0)] = uint16_t(f > cap ? (cap | CNT_OVF) : f);
         }
         if (threadIdx.x == 0) {
             R.ovf_n[tg] = min(s_ovf_n, OVF_CAP);
             // the whole slot array of the tile (dead positions included) in pieces of at most 32 KiB
-            uint8_t* dst = reinterpret_cast<uint8_t*>(R.ent + size_t(tg) * BB_BUCKETS * R.cap);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(R.ent + size_t(tg) * BB_BUCKETS * cap);
             const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
             for (uint32_t o = 0; o < stage_bytes; o += 32768u) bulk_store_group(dst + o, src + o, min(stage_bytes - o, 32768u));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -191,33 +191,78 @@ __device__ __forceinline__ void for_each_kmer_in_warp_tile(const uint8_t* __rest
     }
 }
 
-// Register-resident variant: the lane ends up with the k-mers ENDING at its 16 positions (kmer[j],
-// garbage where invalid) and returns the validity mask (bit j: position c0+j carries a valid k-mer).
-// Lets the caller issue all of a chunk's memory operations before consuming any result
-// (memory-level parallelism instead of one exposed round trip per position).
+// Pack one 16-code chunk like pack_chunk; inv = bit j set <=> code j is 0xFF (a reset).
+__device__ __forceinline__ void pack_chunk_mask(const uint4& v, uint64_t& P, uint32_t& inv) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint64_t p = 0;
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t x = w[i];
+        const uint32_t t = ((x & 7u) << 9) | (((x >> 8) & 7u) << 6) | (((x >> 16) & 7u) << 3) | ((x >> 24) & 7u);
+        p = (p << 12) | t;
+        // bit 7 of the four bytes -> bits 24..27 of the product (the other partial products stay below bit 24)
+        m |= ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+    }
+    P = p;
+    inv = m;
+}
+
+// Register-resident k-mers of one warp tile: the lane ends up with the k-mers ENDING at its 16 positions
+// (kmer[j], garbage where invalid) and returns the validity mask (bit j: position c0+j carries a valid k-mer,
+// i.e. the reference's loop has have == k there, group_extraction.rs:373-388).  Lets the caller issue all of a
+// chunk's memory operations before consuming any result.
+// No rolling: the packed symbols of the lane's chunk and of the two chunks before it (previous lanes by shuffle;
+// lanes 0 / 1 load the two chunks before the tile) form one bit string, and the k-mer ending at symbol j is the
+// window of that string at bit offset 3 (15 - j) — two funnel shifts and the mask, 4 instructions per position
+// instead of the ~12 of the roll / have recurrence.  A window is valid iff none of its k symbols is a reset:
+// the reset bits of the three chunks are OR-ed over windows of k by log2(k) shift steps, once per chunk.
+// "Before the buffer" counts as a reset.  k <= 21 (3 k <= 63 bits; 20 symbols of history <= the 32 available).
+// ALL 32 lanes must call this (shuffles inside).  STREAM: evict-first loads.
 template <bool STREAM = false>
 __device__ __forceinline__ uint32_t load_chunk_kmers(const uint8_t* __restrict__ codes, uint32_t tile_base,
                                                      int k, uint64_t k_mask, uint64_t (&kmer)[CHUNK]) {
-    uint4 v;
-    uint64_t roll;
-    int have;
-    warp_tile_seed<STREAM>(codes, tile_base, k, k_mask, v, roll, have);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t valid = 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t c0 = tile_base + lane * CHUNK;
+    const uint4 v = STREAM ? __ldcs(reinterpret_cast<const uint4*>(codes + c0))
+                           : __ldg(reinterpret_cast<const uint4*>(codes + c0));
+    uint64_t P;
+    uint32_t I;
+    pack_chunk_mask(v, P, I);
+    // history chunks for lanes 0 and 1: chunk (tile - 2) on lane 0, chunk (tile - 1) on lane 1
+    uint64_t E = 0;
+    uint32_t EI = 0x8000u;   // a chunk before the buffer: its last symbol is a reset
+    if (lane < 2 && tile_base >= (2 - lane) * CHUNK) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4*>(codes + tile_base - (2 - lane) * CHUNK));
+        pack_chunk_mask(e, E, EI);
+    }
+    uint64_t P1 = __shfl_up_sync(0xffffffffu, P, 1);
+    uint32_t P2 = __shfl_up_sync(0xffffffffu, uint32_t(P), 2);   // 5 symbols of history from the chunk before the previous one
+    uint32_t I1 = __shfl_up_sync(0xffffffffu, I, 1), I2 = __shfl_up_sync(0xffffffffu, I, 2);
+    const uint64_t E1 = __shfl_sync(0xffffffffu, E, 1);
+    const uint32_t E0 = __shfl_sync(0xffffffffu, uint32_t(E), 0);
+    const uint32_t EI0 = __shfl_sync(0xffffffffu, EI, 0), EI1 = __shfl_sync(0xffffffffu, EI, 1);
+    if (lane == 0) { P1 = E1; I1 = EI1; P2 = E0; I2 = EI0; }
+    if (lane == 1) { P2 = uint32_t(E1); I2 = EI1; }
+    // the symbol string, low bits first: P (48 bits), P1 (48 bits), low 32 bits of the chunk before
+    const uint32_t S[4] = {uint32_t(P), uint32_t(P >> 32) | (uint32_t(P1) << 16), uint32_t(P1 >> 16), P2};
+    const uint32_t mlo = uint32_t(k_mask), mhi = uint32_t(k_mask >> 32);
 #pragma unroll
     for (int j = 0; j < CHUNK; j++) {
-        const uint32_t code = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        if (code == CODE_INVALID) {
-            roll = 0;
-            have = 0;
-        } else {
-            roll = ((roll << 3) | uint64_t(code)) & k_mask;
-            if (have < k) have++;
-            if (have == k) valid |= 1u << j;
-        }
-        kmer[j] = roll;
+        const int o = 3 * (15 - j), w = o >> 5, sh = o & 31;
+        const uint32_t lo = sh ? __funnelshift_r(S[w], S[w + 1], sh) : S[w];
+        const uint32_t hi = sh ? __funnelshift_r(S[w + 1], S[w + 2], sh) : S[w + 1];
+        kmer[j] = (uint64_t(hi & mhi) << 32) | (lo & mlo);
     }
-    return valid;
+    // resets OR-ed over windows of k symbols (bit t of J: symbol t of the 48, oldest first)
+    uint64_t acc = uint64_t(I2) | (uint64_t(I1) << 16) | (uint64_t(I) << 32);
+    int w = 1;
+    while (2 * w <= k) {
+        acc |= acc << w;
+        w *= 2;
+    }
+    if (k > w) acc |= acc << (k - w);
+    return ~uint32_t(acc >> 32) & 0xFFFFu;
 }
 
 // bit j set <=> position c0+j lies inside [cb, ce)
