@@ -36,6 +36,9 @@
 
 namespace kmn {
 
+#ifndef KMN_PART_ILP
+#define KMN_PART_ILP 2   // positions whose hashes cms_partition_kernel computes together
+#endif
 constexpr uint32_t CMS_BUCKET_LOG2 = 16;                                             // cells per bucket
 constexpr uint32_t CMS_BUCKETS_PER_ROW = 1u << (CMS_WIDTH_LOG2 - CMS_BUCKET_LOG2);    // 1024
 constexpr uint32_t CMS_BUCKETS = CMS_DEPTH * CMS_BUCKETS_PER_ROW;                     // 4096
@@ -61,7 +64,7 @@ static_assert(PART_SLOT * sizeof(uint16_t) == 64, "a slot is four 16-byte vector
 // ranks) pile up on a handful of shared-memory banks (ncu: 80 % of the kernel's shared-memory wavefronts were
 // conflict replays); with it the bank is a function of the bucket.  The apply pass owns one bucket per CTA, so the
 // origin is a CTA constant there: position p is live iff (p ^ origin) < count.
-__host__ __device__ __forceinline__ uint32_t slot_origin(uint32_t bucket) { return bucket & 30u; }
+__host__ __device__ __forceinline__ uint32_t slot_origin(uint32_t bucket) { return bucket & 31u; }
 
 struct CmsSlots {
     uint16_t* ent;             // [CMS_BUCKETS][tiles_cap][PART_SLOT]
@@ -96,6 +99,8 @@ struct CmsTiles {
     const uint32_t* sp_tile0;   // [n_sp + 1] first tile of every species (species_tiles_kernel)
     const uint32_t* n_tiles;    // device scalar
 };
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // ---- TMA (bulk tensor) store of one staged row: shared memory -> the fixed slots in global memory -----------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -154,11 +159,18 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
             // (Two branch-free forms of this loop were measured slower: all 16 hashes hoisted ahead of predicated atomics
             // and stores, 64 registers with spills: 1.27 ms; straight-line entries with a dummy bucket for dead lanes
             // and min(rank, cap) stores, 64 registers: 1.03 ms; this branchy form, 56 registers: 0.92 ms.)
+            // Entry index inside the staging buffer = b * 32 + ((b & 31) ^ rank) = Tq ^ rank with Tq one LOP3 of two
+            // shifts of the index (idx < 2^26, so idx >> 16 is the bucket itself); explicit shared-memory addresses so
+            // that neither the counter nor the store address is re-derived from generic pointers per entry.
+            const uint32_t a_fl = smem_addr_u32(fl), a_st = smem_addr_u32(st);
             auto emit = [&](uint32_t idx) {
                 const uint32_t b = idx >> CMS_BUCKET_LOG2;
-                const uint32_t rank = atomicAdd(&fl[b], 1u);
+                uint32_t Tq;   // ((idx >> 11) & 0x7FE0) | (b & 31) as one LOP3: (x & c) | (b & ~c), c = 0x7FE0 (b < 1024)
+                asm("lop3.b32 %0, %1, %2, 0x7FE0, 0xE4;" : "=r"(Tq) : "r"(idx >> (CMS_BUCKET_LOG2 - 5)), "r"(b));
+                uint32_t rank;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(a_fl + 4u * b) : "memory");
                 if (rank < slot_limit) {
-                    st[b * PART_SLOT + (slot_origin(b) ^ rank)] = uint16_t(idx);
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_st + 2u * (Tq ^ rank)), "h"(uint16_t(idx)) : "memory");
                 } else {   // slot full: rare single-entry spill
                     const uint32_t sp = atomicAdd(L.state + 1, 1u);
                     if (sp < L.spill_cap) L.spill[sp] = (uint32_t(r) << CMS_WIDTH_LOG2) | idx;
@@ -251,9 +263,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 // reaches the slot's four lanes by shuffle.  The histogram atomics do not return a value; a counter that
 // wrapped or carried into its neighbour is detected afterwards (the histogram's total falls short of the number of
 // entries) and the bucket is then redone with u32 counters.
-#ifndef KMN_PART_ILP
-#define KMN_PART_ILP 2
-#endif
 #ifndef KMN_APPLY_VPT
 #define KMN_APPLY_VPT 2
 #endif
@@ -291,8 +300,8 @@ template <typename Bump>
 __device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
     const unsigned lane = threadIdx.x & 31u;
     // rank of the entry at this lane's first position (its vector holds slot positions 8 (lane & 3) ..+7; position p
-    // holds rank p ^ origin, and origin is even and < 32, so position first_pos + j holds rank (first ^ j)) and
-    // where the count sits: vector cnt_pos >> 3 of the slot, high half of word cnt_word
+    // holds rank p ^ origin, and origin < 32, so position first_pos + j holds rank (first ^ j)) and
+    // where the count sits: vector cnt_pos >> 3 of the slot, word cnt_word, its high half iff cnt_pos is odd
     const uint32_t first = (8u * (lane & 3u)) ^ R.origin;
     const uint32_t cnt_pos = R.origin ^ PART_SLOT_CAP;
     const int cnt_lane = int((lane & ~3u) | (cnt_pos >> 3));
@@ -318,7 +327,7 @@ __device__ __forceinline__ uint32_t apply_stream(ApplyRing& R, Bump&& bump) {
 #pragma unroll
         for (uint32_t u = 0; u < APPLY_VPT; u++) {
             const uint32_t cw = cnt_word == 0 ? v[u].x : cnt_word == 1 ? v[u].y : cnt_word == 2 ? v[u].z : v[u].w;
-            const uint32_t cnt = __shfl_sync(0xffffffffu, cw >> 16, cnt_lane);
+            const uint32_t cnt = __shfl_sync(0xffffffffu, (cnt_pos & 1u) ? cw >> 16 : cw & 0xFFFFu, cnt_lane);
             if ((lane & 3u) == 0) mine += cnt;   // one lane per slot books the slot's entries
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll

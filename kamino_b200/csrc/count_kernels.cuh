@@ -186,17 +186,26 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
         if (threadIdx.x < BB_BUCKETS) fill[threadIdx.x] = 0;
         __syncthreads();
         if (active) {
-            bool ovf = false;
+            // explicit shared-memory addresses; with a compile-time slot size the slot address is
+            // (stage + b * 4 CAP + 4 rank) ^ 4 (b & 31): the base is 128-byte aligned and a slot a multiple of 128 bytes,
+            // so the swizzle only touches bits the sum leaves alone, and everything but one LEA and one LOP3 is
+            // computed while the rank atomic is in flight
+            const uint32_t a_fill = static_cast<uint32_t>(__cvta_generic_to_shared(fill));
+            const uint32_t a_stage = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
             auto emit = [&](uint32_t i, uint32_t pos, uint32_t pr) {
                 const uint32_t b = i >> BB_LOG2;
-                const uint32_t rank = atomicAdd(&fill[b], 1u);
+                uint32_t rank;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(a_fill + 4u * b) : "memory");
                 const uint32_t entry = ((i & BB_MASK) << ENT_BIT_SHIFT) | (pos << 1) | pr;
                 if (rank < cap) {
-                    stage[b * stride + (rank ^ run_swizzle(cap, b))] = entry;
+                    uint32_t a;
+                    if (CAP && CAP % 32u == 0) a = (a_stage + b * (4u * CAP) + 4u * rank) ^ ((i >> (BB_LOG2 - 2)) & 0x7Cu);
+                    else a = a_stage + 4u * (b * stride + (rank ^ run_swizzle(cap, b)));
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(entry) : "memory");
                 } else {   // rare: the run slot is full
                     const uint32_t o = atomicAdd(&s_ovf_n, 1u);
                     if (o < OVF_CAP) R.ovf[size_t(tg) * OVF_CAP + o] = (static_cast<unsigned long long>(b) << 32) | entry;
-                    else ovf = true;
+                    else R.slow[s] = 1u;
                 }
             };
 #if KMN_BP_ILP > 1
@@ -226,7 +235,6 @@ bloom_partition_kernel(const uint8_t* __restrict__ codes, const uint32_t* __rest
                 emit(idx[1], pos, 1u);
             }
 #endif
-            if (ovf) R.slow[s] = 1u;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's staging stores, before the bulk copy reads them
         __syncthreads();
