@@ -351,7 +351,9 @@ def strong_scaling_c2(ctx, world, rank, local_rank, barrier, exchange_and_finali
     pin_res = torch.empty(batch.residues.size, dtype=torch.uint8).pin_memory()
     pin_res.numpy()[:] = batch.residues
     h_res = pin_res.numpy()
-    h_rec, h_sp = batch.rec_off, batch.sp_rec_off
+    pin_rec = torch.from_numpy(batch.rec_off.astype(np.int64)).pin_memory()
+    pin_sp = torch.from_numpy(batch.sp_rec_off.astype(np.int64)).pin_memory()
+    h_rec, h_sp = pin_rec.numpy().view(np.uint64), pin_sp.numpy().view(np.uint64)
     steps = max(1, min(args.steps, 5))
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -107,7 +107,7 @@ struct Batch {
 }  // namespace
 
 constexpr uint32_t kMaxH2dChunks = 32;
-constexpr float kKernelGBs = 36.f;     // raw bytes per second the frame / Bloom / partition kernels of a (small) range consume
+constexpr float kKernelGBs = 41.f;     // raw bytes per second the frame / Bloom / partition kernels of a (small) range consume
 
 struct kmn_ctx {
     int device = 0;
@@ -495,7 +495,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     KMN_CUDA(cudaEventRecord(c->ev[0], c->stream));
     mark(c->stream, "start", 0);
     if (from_host) {
-        KMN_CUDA(cudaMemcpyAsync(b.rec_off.p, host_rec_off, (size_t(b.n_rec) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        // (rec_off — 8 bytes per record, 3 MB per 100 proteomes — travels in slices with the ranges' raw bytes)
         KMN_CUDA(cudaMemcpyAsync(b.sp_rec_off.p, host_sp_rec_off, (size_t(b.n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         KMN_CUDA(cudaEventRecord(c->ev_copy[0], c->stream));
         KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));   // the raw buffer's previous users are done
@@ -581,9 +581,19 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         KMN_CUDA(cudaEventRecord(c->ev_frame[0], c->stream));
         KMN_CUDA(cudaStreamWaitEvent(fs, c->ev_frame[0], 0));
     }
+    uint64_t rec_copied = 0;   // rec_off[0, rec_copied) is on its way
     for (size_t j = 0; j < ranges.size(); j++) {
         const SpeciesRange& r = ranges[j];
-        if (from_host) {   // copy stream: this range's raw bytes, then the frame stream may frame them
+        // the range's frame kernels read rec_off up to the first boundary behind the range's last raw byte
+        uint32_t rec_hi = b.n_rec;
+        if (from_host) {   // copy stream: this range's record offsets and raw bytes, then the frame stream may frame them
+            if (j + 1 < ranges.size())
+                rec_hi = uint32_t(std::min<uint64_t>(b.n_rec, uint64_t(std::upper_bound(host_rec_off, host_rec_off + b.n_rec + 1, r.copy_end) - host_rec_off)));
+            if (uint64_t(rec_hi) + 1 > rec_copied) {
+                KMN_CUDA(cudaMemcpyAsync(b.rec_off.p + rec_copied, host_rec_off + rec_copied, (uint64_t(rec_hi) + 1 - rec_copied) * sizeof(uint64_t),
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+                rec_copied = uint64_t(rec_hi) + 1;
+            }
             if (j == 0) KMN_CUDA(cudaEventRecord(c->ev_h2d[0], c->copy_stream));
             if (r.copy_end > r.copy_begin)
                 KMN_CUDA(cudaMemcpyAsync(b.raw.p + r.copy_begin, host_residues + r.copy_begin, r.copy_end - r.copy_begin,
@@ -598,7 +608,7 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
         // ---- K0 frame on the range's tiles (running total of kept bytes carried on the device)
         const uint32_t nt = r.tile_end - r.tile_begin;
         if (b.n_rec > 0 && nt > 0) {
-            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, fs>>>(b.rec_off.p, b.n_rec, r.tile_begin, nt + 1, c->tile_rec.p,
+            frame_tile_records_kernel<<<(nt + 1 + 255) / 256, 256, 0, fs>>>(b.rec_off.p, rec_hi, r.tile_begin, nt + 1, c->tile_rec.p,
                                                                             c->tile_blo.p);
             check_launch(c);
             frame_kernel<<<nt, FRAME_THREADS, 0, fs>>>(b.raw.p, b.n_raw, c->lut, b.rec_off.p, b.n_rec, b.codes.p, b.rec_cstart.p,

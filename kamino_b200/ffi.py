@@ -155,6 +155,17 @@ class PinnedBuffer:
             self.lib.kmn_host_free(self._p)
             self._p = None
 
+    @classmethod
+    def copy_of(cls, a: np.ndarray) -> tuple["PinnedBuffer", np.ndarray]:
+        """A page-locked copy of `a`: (buffer to free, view with a's dtype and shape).  cudaMemcpyAsync from pageable
+        memory is staged by the driver and blocks the calling thread; offsets handed to kmn_count_batch should be
+        pinned like the residues."""
+        a = np.ascontiguousarray(a)
+        buf = cls(a.nbytes)
+        view = buf.array[: a.nbytes].view(a.dtype).reshape(a.shape)
+        view[...] = a
+        return buf, view
+
 
 class Context:
     """One kmn_ctx: one GPU, one table (mirrors AtomicCountMinSketch + CountMinSketch ownership)."""

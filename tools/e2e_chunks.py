@@ -18,8 +18,12 @@ def main():
     b = synth.stage(synth.bacterial(100, seed=synth.SEED0 + 1))
     pin = ffi.PinnedBuffer(b.residues.size)
     pin.array[:] = b.residues
+    pin_rec, h_rec = ffi.PinnedBuffer.copy_of(b.rec_off)
+    pin_sp, h_sp = ffi.PinnedBuffer.copy_of(b.sp_rec_off)
     settings = [("adaptive", None, None)]
-    settings += [("ratio", r, n) for r in ("1.0", "1.5", "2.0", "3.0") for n in (3, 4, 5, 8)]
+    ratios = os.environ.get("E2E_RATIOS", "1.0,1.5,2.0,3.0").split(",")
+    chunks = [int(x) for x in os.environ.get("E2E_CHUNKS", "3,4,5,8").split(",")]
+    settings += [("ratio", r, n) for r in ratios for n in chunks]
     for mode, ratio, chunks in settings:
         for _ in (0,):
             for k in ("KMN_H2D_CHUNKS", "KMN_H2D_RATIO", "KMN_H2D_MODE"):
@@ -33,7 +37,7 @@ def main():
                     ctx.reset_table()
                     ctx.synchronize()
                     t0 = time.perf_counter()
-                    ctx.count_batch(pin.array, b.rec_off, b.sp_rec_off)
+                    ctx.count_batch(pin.array, h_rec, h_sp)
                     ctx.finalize_table()
                     ts.append((time.perf_counter() - t0) * 1e3)
                     ctx.release_batches()
