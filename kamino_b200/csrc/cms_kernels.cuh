@@ -357,6 +357,8 @@ cms_apply_kernel(CmsSlots L, uint16_t* __restrict__ tab, int force_exact, int fr
         }
         return;
     }
+    if (!fresh)   // the merge at the end reads the bucket's 128 KiB of cells: one 128-byte line per thread, into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + (size_t(B) << CMS_BUCKET_LOG2) + size_t(threadIdx.x) * 64) : "memory");
     ApplyRing R;
     R.ring = smem_u32(s_cnt + APPLY_WORDS);
     R.full = R.ring + APPLY_STAGES * APPLY_STAGE_BYTES;
@@ -412,15 +414,20 @@ cms_apply_kernel(CmsSlots L, uint16_t* __restrict__ tab, int force_exact, int fr
             for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) g4[i] = s4[i];
             return;
         }
-        for (uint32_t i = threadIdx.x; i < APPLY_WORDS / 4; i += APPLY_THREADS) {
-            const uint4 d = s4[i];
+        // all of the thread's cell vectors in flight together (they were prefetched into L2 when the CTA started)
+        constexpr uint32_t NV = APPLY_WORDS / 4 / APPLY_THREADS;   // 8
+        uint4 g[NV];
+#pragma unroll
+        for (uint32_t u = 0; u < NV; u++) g[u] = g4[u * APPLY_THREADS + threadIdx.x];
+#pragma unroll
+        for (uint32_t u = 0; u < NV; u++) {
+            const uint4 d = s4[u * APPLY_THREADS + threadIdx.x];
             if (!(d.x | d.y | d.z | d.w)) continue;
-            uint4 g = g4[i];
-            g.x = sat_add_u16x2(g.x, d.x);
-            g.y = sat_add_u16x2(g.y, d.y);
-            g.z = sat_add_u16x2(g.z, d.z);
-            g.w = sat_add_u16x2(g.w, d.w);
-            g4[i] = g;
+            g[u].x = sat_add_u16x2(g[u].x, d.x);
+            g[u].y = sat_add_u16x2(g[u].y, d.y);
+            g[u].z = sat_add_u16x2(g[u].z, d.z);
+            g[u].w = sat_add_u16x2(g[u].w, d.w);
+            g4[u * APPLY_THREADS + threadIdx.x] = g[u];
         }
         return;
     }

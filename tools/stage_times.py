@@ -22,13 +22,18 @@ def main():
         bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
         acc = {n: [] for n in names}
         new = None
+        accumulate = os.environ.get("KMN_STAGE_ACCUMULATE") == "1"   # batches 2.. of a job: cms_apply merges into a live table
         for i in range(3 + steps):
-            ctx.reset_table()
+            if not (accumulate and i > 0):
+                ctx.reset_table()
             new = ctx.count_staged(bid, b.n_sp)
-            ctx.finalize_table()
+            if not accumulate:
+                ctx.finalize_table()
             if i >= 3:
                 for n in names:
                     acc[n].append(ctx.stage_ms(n))
+        if accumulate:
+            ctx.finalize_table()
         rows, h = ctx.table_checksum()
     med = {n: round(float(np.median(v)), 4) for n, v in acc.items()}
     med["pass1_sum"] = round(med["frame"] + med["bloom"] + med["cms"], 4)
