@@ -89,6 +89,7 @@ struct Batch {
     std::vector<uint64_t> h_sp_raw_off;  // raw byte offset of each species (plans the copy / compute ranges)
     // pass 2 results
     bool scanned = false;
+    bool occ_narrow = false;                 // occ[] came from the narrow table: exact where >= min_needed, 0 below
     DevBuf<uint16_t> occ;
     DevBuf<uint32_t> inv_pos;
     uint32_t n_inv = 0;
@@ -122,6 +123,14 @@ struct kmn_ctx {
     DevBuf<uint32_t> wide;                // u32 widening of the table for the NCCL variant (allocated on demand)
     bool widened = false;
     const uint16_t* final_tab = nullptr;  // what pass 2 reads once finalized (tab or xtab)
+    // narrow copy of the finalized table for pass 2 (scan_kernels.cuh): valid for (tab8_src, tab8_base); tab_max_src: the
+    // table whose largest cell is tab_max.  Both are forgotten whenever final_tab is (re)assigned.
+    DevBuf<uint8_t> tab8;
+    DevBuf<uint32_t> tab_max_dev;
+    const uint16_t* tab8_src = nullptr;
+    const uint16_t* tab_max_src = nullptr;
+    uint32_t tab8_base = 0, tab_max = 0;
+    bool scan_wide = false;               // test / tuning knob KMN_SCAN_WIDE: pass 2 always reads the u16 table (8 sweeps)
     bool tab_zero = false;                // kmn_reset_table: tab is LOGICALLY zero, its memory is stale (materialize_table)
     bool finalized = false;
     DevBuf<unsigned long long> new_counts;
@@ -757,8 +766,46 @@ void finalize_table(kmn_ctx* c) {
     KMN_CUDA(cudaEventRecord(c->ev[1], c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
-    c->final_tab = c->tab.p;
+    c->final_tab = c->tab.p; c->tab8_src = c->tab_max_src = nullptr;
     c->finalized = true;
+}
+
+// 8 L2-sized sweeps over the u16 table: (row, half-row)
+void wide_occupancy_sweeps(kmn_ctx* c, Batch& b, uint32_t n_tiles) {
+    const int grid = grid_for(c, 8);
+    for (uint32_t r = 0; r < CMS_DEPTH; r++)
+        for (uint32_t half = 0; half < 2; half++) {
+            occupancy_sweep_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(
+                b.codes.p, n_tiles, c->k, c->k_mask, c->final_tab + (size_t(r) << CMS_WIDTH_LOG2), cms_seed(int(r)), half,
+                r == 0 && half == 0, b.occ.p);
+            check_launch(c);
+        }
+}
+
+// Pass 2 may read the narrow (one byte per cell) copy of the finalized table when every cell fits the byte window
+// above min_needed - 1 (scan_kernels.cuh).  Builds / reuses the copy; false: use the u16 table.
+bool narrow_table_for(kmn_ctx* c, uint32_t min_needed) {
+    if (c->scan_wide || min_needed < 1) return false;
+    if (c->tab_max_src != c->final_tab) {
+        c->tab_max_dev.ensure(1);
+        KMN_CUDA(cudaMemsetAsync(c->tab_max_dev.p, 0, sizeof(uint32_t), c->stream));
+        table_max_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->final_tab), CMS_CELLS / 8, c->tab_max_dev.p);
+        check_launch(c);
+        KMN_CUDA(cudaMemcpyAsync(&c->tab_max, c->tab_max_dev.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        c->tab_max_src = c->final_tab;
+    }
+    const uint32_t base = min_needed - 1;
+    if (c->tab_max > base + 255u) return false;
+    if (c->tab8_src != c->final_tab || c->tab8_base != base) {
+        c->tab8.ensure(CMS_CELLS);
+        narrow_table_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->final_tab),
+                                                                  reinterpret_cast<uint2*>(c->tab8.p), CMS_CELLS / 8, base);
+        check_launch(c);
+        c->tab8_src = c->final_tab;
+        c->tab8_base = base;
+    }
+    return true;
 }
 
 void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, uint64_t* n_ends) {
@@ -768,14 +815,16 @@ void scan_batch(kmn_ctx* c, Batch& b, uint32_t min_needed, uint64_t* n_starts, u
     const uint32_t n_tiles = uint32_t((size_t(b.n_codes) + WARP_TILE - 1) / WARP_TILE);
     b.occ.ensure(size_t(n_tiles + 1) * WARP_TILE);
     const int grid = grid_for(c, 8);
-    if (n_tiles) {   // 8 L2-sized sweeps: (row, half-row)
-        for (uint32_t r = 0; r < CMS_DEPTH; r++)
-            for (uint32_t half = 0; half < 2; half++) {
-                occupancy_sweep_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(
-                    b.codes.p, n_tiles, c->k, c->k_mask, c->final_tab + (size_t(r) << CMS_WIDTH_LOG2), cms_seed(int(r)), half,
-                    r == 0 && half == 0, b.occ.p);
-                check_launch(c);
-            }
+    b.occ_narrow = n_tiles && narrow_table_for(c, min_needed);
+    if (b.occ_narrow) {   // 4 L2-sized sweeps over the narrow table: one per row
+        for (uint32_t r = 0; r < CMS_DEPTH; r++) {
+            occupancy_sweep8_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(
+                b.codes.p, n_tiles, c->k, c->k_mask, c->tab8.p + (size_t(r) << CMS_WIDTH_LOG2), cms_seed(int(r)), r == 0,
+                r + 1 == CMS_DEPTH, c->tab8_base, b.occ.p);
+            check_launch(c);
+        }
+    } else if (n_tiles) {
+        wide_occupancy_sweeps(c, b, n_tiles);
     }
     // reset positions -> segments
     const uint32_t n_ctiles = (b.n_codes + 4095) / 4096;
@@ -1175,6 +1224,7 @@ int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
             else if (m == "equal") c->h2d_mode = 2;
             else throw std::runtime_error("KMN_H2D_MODE must be adaptive, doubling or equal");
         }
+        c->scan_wide = std::getenv("KMN_SCAN_WIDE") != nullptr;
         if (const char* e = std::getenv("KMN_BLOOM_RUN_CAP")) {   // test knob
             const long v = std::strtol(e, nullptr, 10);
             if (v < 1 || v > long(RUN_CAP)) throw std::runtime_error("KMN_BLOOM_RUN_CAP must be in 1.." + std::to_string(RUN_CAP));
@@ -1283,7 +1333,7 @@ int kmn_reset_table(kmn_ctx* c) {
         c->tab_zero = true;   // zeroed lazily: by the first batch's apply pass, or by materialize_table
         c->finalized = false;
         c->widened = false;
-        c->final_tab = nullptr;
+        c->final_tab = nullptr; c->tab8_src = c->tab_max_src = nullptr;
     });
 }
 
@@ -1314,7 +1364,7 @@ int kmn_table_load(kmn_ctx* c, const uint16_t* table) {
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         c->tab_zero = false;
         c->widened = false;
-        c->final_tab = c->tab.p;
+        c->final_tab = c->tab.p; c->tab8_src = c->tab_max_src = nullptr;
         c->finalized = true;
     });
 }
@@ -1471,7 +1521,7 @@ static void launch_exchange(kmn_ctx* c) {
 static void finish_exchange(kmn_ctx* c) {
     check_exchange_error(c);   // synchronises the stream
     KMN_CUDA(cudaEventElapsedTime(&c->stage_ms[3], c->ev[0], c->ev[1]));
-    c->final_tab = c->xtab.p;
+    c->final_tab = c->xtab.p; c->tab8_src = c->tab_max_src = nullptr;
     c->finalized = true;       // valid once every rank's kernel has finished
 }
 
@@ -1673,6 +1723,10 @@ int kmn_fetch_occupancy(kmn_ctx* c, uint32_t batch_id, uint32_t sp, uint16_t* oc
         if (n) *n = n_res;
         if (!occ || n_res == 0) return;
         if (cap < n_res) throw std::runtime_error("occupancy buffer too small");
+        if (b.occ_narrow) {   // occ[] is exact only where >= min_needed: the estimates below it need the u16 table
+            wide_occupancy_sweeps(c, b, uint32_t((size_t(b.n_codes) + WARP_TILE - 1) / WARP_TILE));
+            b.occ_narrow = false;
+        }
         DevBuf<uint16_t> tmp;
         tmp.alloc(n_res);
         occupancy_gather_kernel<<<std::min<uint32_t>(r1 - r0, 4096u), 128, 0, c->stream>>>(b.occ.p, b.rec_cstart.p, r0, r1, tmp.p);

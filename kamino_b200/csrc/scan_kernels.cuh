@@ -61,6 +61,87 @@ occupancy_sweep_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int 
     }
 }
 
+// ---- narrow table: pass 2 in 4 sweeps instead of 8 ------------------------------------------------------------
+// Pass 2 only ever compares occupancies with min_needed and with each other, and only when at least one side is
+// shared (>= min_needed; group_extraction.rs:292-299: `previous.shared && previous.occupancy > current.occupancy`,
+// `current.shared && previous.occupancy < current.occupancy`; the start ranking of :151-175 sees shared hits only).
+// Any map that keeps the order of the values >= min_needed and sends everything below to something smaller
+// gives the same hits.  When the largest cell of the finalized table is <= min_needed + 253 the map
+// cell -> max(cell - (min_needed - 1), 0) fits a byte: the table shrinks to 256 MiB, ONE ROW (64 MiB) is an
+// L2-sized slice, and the occupancy takes 4 sweeps (a position that falls to 0 — below min_needed — in one row skips
+// the hash and the gather of the remaining rows: the sweeps run at the L2 gather rate, ~300 Gop/s).  The last sweep maps back (x ? x + min_needed - 1 : 0), so
+// occ[] holds the exact estimate wherever it is >= min_needed and 0 elsewhere; the kernels downstream do not change.
+// (kmn_fetch_occupancy, which also reports the estimates below min_needed, reruns the 8 wide sweeps.)
+__global__ void __launch_bounds__(256)
+table_max_kernel(const uint4* __restrict__ tab, size_t n_vec, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_vec; i += size_t(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldcs(tab + i);
+        m = __vmaxu2(__vmaxu2(m, v.x), __vmaxu2(__vmaxu2(v.y, v.z), v.w));
+    }
+    m = max(m & 0xFFFFu, m >> 16);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
+}
+
+// tab8[i] = min(max(tab[i] - base, 0), 255); 8 cells per thread
+__global__ void __launch_bounds__(256)
+narrow_table_kernel(const uint4* __restrict__ tab, uint2* __restrict__ tab8, size_t n_vec, uint32_t base) {
+    const uint32_t b2 = base | (base << 16);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_vec; i += size_t(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldcs(tab + i);
+        const uint32_t a = __vminu2(__vsubus2(v.x, b2), 0x00FF00FFu), b = __vminu2(__vsubus2(v.y, b2), 0x00FF00FFu);
+        const uint32_t c = __vminu2(__vsubus2(v.z, b2), 0x00FF00FFu), d = __vminu2(__vsubus2(v.w, b2), 0x00FF00FFu);
+        tab8[i] = make_uint2(__byte_perm(a, b, 0x6420), __byte_perm(c, d, 0x6420));
+    }
+}
+
+// One sweep per row over the narrow table (row8: 2^26 bytes).  `last`: map the running minimum back to estimates.
+__global__ void __launch_bounds__(SCAN_THREADS)
+occupancy_sweep8_kernel(const uint8_t* __restrict__ codes, uint32_t n_tiles, int k, uint64_t k_mask,
+                        const uint8_t* __restrict__ row8, uint64_t seed, bool first, bool last, uint32_t base,
+                        uint16_t* __restrict__ occ) {
+    const uint32_t warps_per_grid = gridDim.x * (SCAN_THREADS / 32);
+    const uint32_t warp_id = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t fseed = fold30_keep(seed);
+    for (uint32_t t = warp_id; t < n_tiles; t += warps_per_grid) {
+        const uint32_t c0 = t * WARP_TILE + lane * CHUNK;
+        uint64_t kmer[CHUNK];
+        const uint32_t valid = load_chunk_kmers<true>(codes, t * WARP_TILE, k, k_mask, kmer);
+        uint4* dst = reinterpret_cast<uint4*>(occ + c0);
+        uint32_t o[CHUNK / 2];
+        if (first) {
+#pragma unroll
+            for (int i = 0; i < CHUNK / 2; i++)
+                o[i] = (((valid >> (2 * i)) & 1u) ? 0xFFFFu : 0u) | (((valid >> (2 * i + 1)) & 1u) ? 0xFFFF0000u : 0u);
+        } else {
+            const uint4 a = __ldcs(dst), b = __ldcs(dst + 1);
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+            o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+        }
+        uint32_t v[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {   // all gathers of the chunk in flight together
+            v[j] = 0xFFFFu;
+            // a running minimum of 0 (below min_needed after an earlier row) cannot change any more: no hash, no gather
+            const uint32_t cur = (o[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+            if (((valid >> j) & 1u) && cur != 0u) v[j] = __ldg(row8 + cms_index_folded(fold30_keep(kmer[j]), fseed));
+        }
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; i++) {
+            uint32_t lo = min(o[i] & 0xFFFFu, v[2 * i]), hi = min(o[i] >> 16, v[2 * i + 1]);
+            if (last) {
+                lo = lo ? lo + base : 0u;
+                hi = hi ? hi + base : 0u;
+            }
+            o[i] = lo | (hi << 16);
+        }
+        __stcs(dst, make_uint4(o[0], o[1], o[2], o[3]));
+        __stcs(dst + 1, make_uint4(o[4], o[5], o[6], o[7]));
+    }
+}
+
 // ---- list of reset positions (0xFF codes) of a batch: count / scatter around exclusive_scan_kernel
 __global__ void __launch_bounds__(256)
 invalid_count_kernel(const uint8_t* __restrict__ codes, uint32_t n_codes, uint32_t* __restrict__ tile_cnt) {

@@ -816,3 +816,46 @@ def test_table_checksum_matches_the_snapshot(ffi, oracle):
     for i in nz.tolist():
         want = (want + int(t[i]) * oracle.mix64(i + 0x51)) & 0xFFFFFFFFFFFFFFFF
     assert h == want
+
+
+@pytest.mark.gpu
+def test_pass2_narrow_table_matches_oracle_and_wide_scan(ffi, oracle, monkeypatch):
+    """Pass 2 reads a one-byte-per-cell copy of the table (4 sweeps instead of 8) when every cell fits the byte window
+    above min_needed - 1, and the u16 table otherwise; both give the oracle's hits, occupancies and pairs
+    (group_extraction.rs:271-299: only comparisons with min_needed and between shared k-mers matter)."""
+    rng = np.random.default_rng(5)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    core = [aa[rng.integers(0, 20, 120)].tobytes() for _ in range(3)]
+    recs = []
+    for s in range(300):   # 300 small species: the core proteins' k-mers reach cells of ~300
+        own = [aa[rng.integers(0, 20, 150)].tobytes() for _ in range(2)]
+        mutated = bytearray(core[s % 3])
+        if s % 7 == 0:
+            mutated[40 + s % 30] = ord("W")
+        recs.append([core[0], own[0], bytes(mutated), core[2] if s % 2 else own[1]])
+    residues, rec_off, sp = _batch_from_records(recs)
+    k, scheme = 13, SR6
+    some = [0, 1, 7, 150, 299]
+    # min_needed = 1: base 0, largest cell ~300 > 255 -> the u16 table; 60 / 255: the narrow table
+    for min_needed in (1, 60, 255):
+        _check_pass1_and_pass2(ffi, oracle, residues, rec_off, sp, k, scheme, min_needed, scan_species=some)
+    # the narrow path is really taken, and equals the wide one on every species
+    def scan(env_wide):
+        if env_wide:
+            monkeypatch.setenv("KMN_SCAN_WIDE", "1")
+        else:
+            monkeypatch.delenv("KMN_SCAN_WIDE", raising=False)
+        with ffi.Context(k, scheme) as ctx:
+            bid, _ = ctx.count_batch(residues, rec_off, sp)
+            ctx.finalize_table()
+            before = ctx.launch_count()
+            ctx.scan_batch(bid, 60)
+            launches = ctx.launch_count() - before
+            hits = [ctx.fetch_hits(bid, s) for s in range(len(recs))]
+        return launches, hits
+    ln, hn = scan(False)
+    lw, hw = scan(True)
+    monkeypatch.delenv("KMN_SCAN_WIDE", raising=False)
+    assert lw - ln == 2, (ln, lw)   # 8 sweeps vs table max + narrow copy + 4 sweeps
+    for (sn, en), (sw, ew) in zip(hn, hw):
+        assert np.array_equal(sn, sw) and np.array_equal(en, ew)
