@@ -167,6 +167,7 @@ struct kmn_ctx {
     DevBuf<uint64_t> fa_file_off;          // scratch of kmn_count_fasta
     DevBuf<uint8_t> fa_tile_sum, fa_tile_in;
     DevBuf<uint32_t> fa_tile_hdr, fa_tile_base, fa_err;
+    DevBuf<kmn_pair> pair_scratch;        // kmn_pair_batch: pairs before compaction (one slot per start candidate)
     DevBuf<uint32_t> nj_valid, nj_mism;   // counts of the last pair_counts call (kmn_pair_counts_device)
     DevBuf<uint8_t> nj_mapped;            // scratch of the pair counts, kept between calls (no cudaMalloc per call)
     DevBuf<uint32_t> nj_planes;
@@ -898,20 +899,21 @@ void pair_batch(kmn_ctx* c, Batch& b, uint32_t length_middle, uint64_t* n_pairs)
         c->seg_s_cnt.ensure(size_t(n_seg) + 1);   // scratch: pairs per segment, then their offsets in seg_e_cnt
         c->seg_e_cnt.ensure(size_t(n_seg) + 2);
         const uint32_t blocks = (n_seg + 255) / 256;
-        pair_segments_kernel<false><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
-                                                                 uint32_t(c->k), length_middle, c->seg_s_cnt.p, nullptr, nullptr,
-                                                                 b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec, b.sp_cstart.p,
-                                                                 b.sp_rec_off.p, b.n_sp);
+        // one pass: pairs at the segments' start-hit offsets of a scratch array (pairs <= start candidates), then compaction
+        c->pair_scratch.ensure(std::max<uint32_t>(b.tot_starts, 1));
+        pair_segments_kernel<<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
+                                                                      uint32_t(c->k), length_middle, c->seg_s_cnt.p,
+                                                                      c->pair_scratch.p, b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec,
+                                                                      b.sp_cstart.p, b.sp_rec_off.p, b.n_sp);
         check_launch(c);
         device_exclusive_scan(c, c->seg_s_cnt.p, c->seg_e_cnt.p, n_seg);
         KMN_CUDA(cudaMemcpyAsync(&total, c->seg_e_cnt.p + n_seg, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         b.pairs.ensure(total);
-        pair_segments_kernel<true><<<blocks, 256, 0, c->stream>>>(b.starts.p, b.ends.p, b.seg_s_off.p, b.seg_e_off.p, n_seg,
-                                                                uint32_t(c->k), length_middle, nullptr, c->seg_e_cnt.p, b.pairs.p,
-                                                                b.codes.p, b.inv_pos.p, b.rec_cstart.p, b.n_rec, b.sp_cstart.p,
-                                                                b.sp_rec_off.p, b.n_sp);
-        check_launch(c);
+        if (total) {
+            pair_compact_kernel<<<grid_for(c, 8), 256, 0, c->stream>>>(c->pair_scratch.p, b.seg_s_off.p, c->seg_e_cnt.p, n_seg, b.pairs.p);
+            check_launch(c);
+        }
         species_hit_offsets_kernel<<<(b.n_sp + 1 + 255) / 256, 256, 0, c->stream>>>(
             b.inv_pos.p, n_seg, b.sp_cstart.p, b.n_sp, c->seg_e_cnt.p, c->seg_e_cnt.p, c->sp_s_off.p, c->sp_e_off.p);
         check_launch(c);

@@ -329,13 +329,14 @@ __global__ void species_hit_offsets_kernel(const uint32_t* __restrict__ inv_pos,
 // [first.start, first.start + 10); better = higher occupancy, then smaller start) and extract_bubble_pairs
 // (group_extraction.rs:178-242: best end anchor with left.end < right.start, right.start - left.end <=
 // length_middle; better = higher occupancy, then smaller start) on the segment's start / end hit lists.
-// EMIT == false: pairs per segment; EMIT == true: write them in (segment, left anchor) order.
-template <bool EMIT>
+// ONE pass: a segment has at most as many pairs as start candidates, so its pairs are written, in left-anchor order,
+// at seg_s_off[j] of a scratch array and counted (seg_p_cnt); pair_compact_kernel then moves them to their scanned
+// offsets (a separate count pass cost as much as the emit pass: both walk the hit lists one thread per segment;
+// 1.40 -> 1.08 ms per 100 proteomes).
 __global__ void __launch_bounds__(256)
 pair_segments_kernel(const uint2* __restrict__ starts, const uint2* __restrict__ ends,
                      const uint32_t* __restrict__ seg_s_off, const uint32_t* __restrict__ seg_e_off, uint32_t n_seg,
-                     uint32_t k, uint32_t length_middle, uint32_t* __restrict__ seg_p_cnt,
-                     const uint32_t* __restrict__ seg_p_off, kmn_pair* __restrict__ pairs,
+                     uint32_t k, uint32_t length_middle, uint32_t* __restrict__ seg_p_cnt, kmn_pair* __restrict__ pairs,
                      const uint8_t* __restrict__ codes, const uint32_t* __restrict__ inv_pos,
                      const uint32_t* __restrict__ rec_cstart, uint32_t n_rec, const uint32_t* __restrict__ sp_cstart,
                      const uint64_t* __restrict__ sp_rec_off, uint32_t n_sp) {
@@ -344,10 +345,10 @@ pair_segments_kernel(const uint2* __restrict__ starts, const uint2* __restrict__
     const uint32_t s0 = seg_s_off[j], s1 = seg_s_off[j + 1], e0 = seg_e_off[j], e1 = seg_e_off[j + 1];
     uint32_t n = 0;
     if (s1 > s0 && e1 > e0) {
-        const uint32_t out = EMIT ? seg_p_off[j] : 0u;
+        const uint32_t out = s0;
         const uint32_t seg_lo = j == 0 ? 0u : inv_pos[j - 1] + 1;
         SegCoords sc{0, 0};
-        if (EMIT && seg_p_off[j + 1] > out) sc = segment_coords(seg_lo, rec_cstart, n_rec, sp_cstart, sp_rec_off, n_sp);
+        bool have_sc = false;
         uint32_t first_end = e0;
         auto handle = [&](uint32_t lstart) {
             const uint32_t left_end = lstart + k;
@@ -361,16 +362,18 @@ pair_segments_kernel(const uint2* __restrict__ starts, const uint2* __restrict__
                 if (!have || r.y > bo || (r.y == bo && r.x < bs)) { have = true; bo = r.y; bs = r.x; }
             }
             if (!have) return;
-            if (EMIT) {
-                kmn_pair p;
-                p.left = kmer_ending_at(codes, seg_lo + lstart + k - 1, int(k));
-                p.right = kmer_ending_at(codes, seg_lo + bs + k - 1, int(k));
-                p.rec = sc.rec;
-                p.seg_start = sc.seg_start;
-                p.left_start = lstart;
-                p.len = bs + k - lstart;
-                pairs[out + n] = p;
+            if (!have_sc) {   // first pair of the segment
+                sc = segment_coords(seg_lo, rec_cstart, n_rec, sp_cstart, sp_rec_off, n_sp);
+                have_sc = true;
             }
+            kmn_pair p;
+            p.left = kmer_ending_at(codes, seg_lo + lstart + k - 1, int(k));
+            p.right = kmer_ending_at(codes, seg_lo + bs + k - 1, int(k));
+            p.rec = sc.rec;
+            p.seg_start = sc.seg_start;
+            p.left_start = lstart;
+            p.len = bs + k - lstart;
+            pairs[out + n] = p;
             n++;
         };
         const uint2 f = starts[s0];
@@ -386,7 +389,23 @@ pair_segments_kernel(const uint2* __restrict__ starts, const uint2* __restrict__
         }
         handle(best_start);
     }
-    if (!EMIT) seg_p_cnt[j] = n;
+    seg_p_cnt[j] = n;
+}
+
+// pairs of segment j: scratch[seg_s_off[j] ..] -> pairs[seg_p_off[j] ..]; one warp per segment, 16 pairs per step
+__global__ void __launch_bounds__(256)
+pair_compact_kernel(const kmn_pair* __restrict__ scratch, const uint32_t* __restrict__ seg_s_off,
+                    const uint32_t* __restrict__ seg_p_off, uint32_t n_seg, kmn_pair* __restrict__ pairs) {
+    static_assert(sizeof(kmn_pair) == 32, "two 16-byte vectors per pair");
+    const uint32_t warps_per_grid = gridDim.x * 8u;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t j = blockIdx.x * 8u + (threadIdx.x >> 5); j < n_seg; j += warps_per_grid) {
+        const uint32_t o0 = seg_p_off[j], n = seg_p_off[j + 1] - o0;
+        if (n == 0) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(scratch + seg_s_off[j]);
+        uint4* dst = reinterpret_cast<uint4*>(pairs + o0);
+        for (uint32_t i = lane; i < 2u * n; i += 32u) dst[i] = src[i];
+    }
 }
 
 // Parity helper: occupancy per stripped residue of one species (separators removed).
