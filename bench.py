@@ -410,6 +410,32 @@ def strong_scaling_c2(ctx, world, rank, local_rank, barrier, exchange_and_finali
             "table_hash": f"{h:016x}", "row_sums_equal_new_kmers": int(tot.item())}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """N > 1: run this rank (and so first-touch its pinned buffers) on the CPUs NVML reports as local to its GPU.
+    Without it every rank's pinned memory may sit on one socket and the per-GPU host-to-device rate of the e2e leg
+    drops from 55 to ~20 GB/s at N = 8 (round 1's SCALE record).  Returns the CPU list, None when nothing was done."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local_rank)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception as e:   # best effort: NVML missing, no permission, a container without the topology
+        log(f"[bench] no NUMA binding ({type(e).__name__}: {e})")
+        return None
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -421,6 +447,10 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the k-mer table build has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
+    if world > 1 and os.environ.get("KMN_BENCH_NUMA", "1") != "0":
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
+        log(f"[rank {rank}] bound to the {len(numa_cpus)} CPUs local to GPU {local_rank}" if numa_cpus else f"[rank {rank}] not bound to a NUMA node")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -642,6 +672,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_elapsed / args.steps},
             "gpu_launches": int(launches),
+            "host_binding": (f"rank 0 on the {len(numa_cpus)} CPUs NVML reports local to its GPU (every rank likewise)" if numa_cpus
+                             else "none"),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
