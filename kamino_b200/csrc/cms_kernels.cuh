@@ -254,6 +254,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same with an L2 evict-first hint (a stream that is read once and should not displace what else sits in L2)
+__device__ __forceinline__ void bulk_load_evict_first(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 
 // One CTA per bucket: histogram of the bucket's slots in 128 KiB of shared memory (two u16 counters per word),
 // then the saturating merge into the table.  The bucket's slot array is contiguous (ent[bucket][tile][32]); it is
@@ -282,6 +289,7 @@ struct ApplyRing {
     const uint4* src;
     uint32_t n_vec, n_chunks;
     uint32_t origin;              // slot_origin of the CTA's bucket
+    bool evict_first;             // merging into a live table: the prefetched cells should survive the slot stream in L2
     uint32_t issued;              // sequence number of the next chunk to issue (elected thread)
     uint32_t done;                // sequence number of the first chunk of the current pass
 };
@@ -292,7 +300,8 @@ __device__ __forceinline__ void apply_issue(ApplyRing& R) {   // elected thread 
     const uint32_t v0 = (g - R.done) * APPLY_STAGE_VEC;
     const uint32_t bytes = min(R.n_vec - v0, APPLY_STAGE_VEC) * 16u;
     mbar_expect_tx(R.full + 8 * st, bytes);
-    bulk_load(R.ring + st * APPLY_STAGE_BYTES, R.src + v0, bytes, R.full + 8 * st);
+    if (R.evict_first) bulk_load_evict_first(R.ring + st * APPLY_STAGE_BYTES, R.src + v0, bytes, R.full + 8 * st);
+    else bulk_load(R.ring + st * APPLY_STAGE_BYTES, R.src + v0, bytes, R.full + 8 * st);
 }
 
 // bump(c) for every live entry c of the bucket; returns this thread's number of live entries
@@ -367,6 +376,7 @@ cms_apply_kernel(CmsSlots L, uint16_t* __restrict__ tab, int force_exact, int fr
     R.n_vec = n_vec;
     R.n_chunks = (n_vec + APPLY_STAGE_VEC - 1) / APPLY_STAGE_VEC;
     R.origin = slot_origin(B & (CMS_BUCKETS_PER_ROW - 1));
+    R.evict_first = !fresh;   // (measured: 0.728 -> 0.711 ms when merging, 0.650 -> 0.665 ms on a fresh table)
     R.issued = 0;
     R.done = 0;
     if (threadIdx.x == 0) {
