@@ -82,7 +82,8 @@ void kmn_destroy(kmn_ctx* ctx);
 
 /* Page-locked host memory for the batch buffers handed to kmn_count_batch / kmn_stage_batch (io.rs side of
  * the pipeline: FASTA bytes are gunzipped straight into it).  Optional — any host pointer works — but only
- * pinned buffers let the host-to-device copies of kmn_count_batch overlap its kernels at full link speed. */
+ * pinned buffers let the host-to-device copies of kmn_count_batch overlap its kernels at full link speed
+ * (that holds for rec_off as well: it travels in slices with the residues, 8 bytes per record). */
 int  kmn_host_alloc(void** ptr, uint64_t bytes);
 void kmn_host_free(void* ptr);
 
@@ -228,7 +229,9 @@ int kmn_group_batches(kmn_ctx* ctx, const uint32_t* batch_ids, uint32_t n_batche
                       uint32_t sid_stride, uint32_t min_needed, uint32_t* perm, uint64_t cap_perm, kmn_group* groups,
                       uint64_t cap_groups, uint64_t* n_obs, uint64_t* n_groups);
 /* Occupancy per whitespace-stripped residue of species `sp` (records concatenated): estimate()
- * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues. */
+ * of the k-mer ENDING at that residue, 0 where none ends (roll shorter than k).  *n = residues.
+ * (A parity / debugging call: kmn_scan_batch keeps exact estimates only where they are >= min_needed when it can
+ * read the narrow table; this call then recomputes the batch's occupancies from the u16 table first.) */
 int kmn_fetch_occupancy(kmn_ctx* ctx, uint32_t batch_id, uint32_t sp, uint16_t* occ, uint64_t cap,
                         uint64_t* n);
 
