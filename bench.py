@@ -400,6 +400,8 @@ def strong_scaling_c2(ctx, world, rank, local_rank, barrier, exchange_and_finali
     dt = timed(job_resident, steps)
     ctx.release_batches()
     job_e2e()
+    rows_e, h_e = ctx.table_checksum()   # the job from host buffers (long range schedule) builds the same table
+    assert h_e == h and [int(x) for x in rows_e] == [int(x) for x in rows], "strong C2: the e2e job's table differs from the resident job's"
     dt_e2e = timed(job_e2e, steps)
     return {"workload": f"{C2_SPECIES} synthetic bacterial proteomes (~4k proteins x ~330 aa), k={K}, {SCHEME_NAME}, "
                         f"species round-robin over {world} GPU(s), one table exchange per job",
@@ -574,7 +576,13 @@ def run_gpu(args):
     e2e_steps = 0 if args.profile else args.steps
     if e2e_steps:
         job(step_e2e, 1, ctx.release_batches)
-    e2e_elapsed = timed_region(lambda: job(step_e2e, e2e_steps, ctx.release_batches)) if e2e_steps else 1e-9
+    link_gbs = []
+
+    def after_e2e_step():                                # host side only: the rate the library measured over the step's copies
+        link_gbs.append(ctx.stage_ms("h2d_gbs"))
+        ctx.release_batches()
+
+    e2e_elapsed = timed_region(lambda: job(step_e2e, e2e_steps, after_e2e_step)) if e2e_steps else 1e-9
     clocks = sampler.stop()
     e2e_value = n_res_total * args.steps / e2e_elapsed
     h2d = int(batch.residues.size + batch.rec_off.nbytes + batch.sp_rec_off.nbytes)
@@ -670,7 +678,11 @@ def run_gpu(args):
                             "fused NVLink peer kernel on u16 cells: reduce-scatter + saturate + all-gather, in-kernel rank sync") if fused
                            else "NCCL all-reduce of the u32 accumulators")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_elapsed / args.steps},
+                    "ms_per_step": 1e3 * e2e_elapsed / args.steps,
+                    "h2d_gbs": {"median": float(np.median(link_gbs)), "min": float(np.min(link_gbs)),
+                                "note": "host-to-device rate of rank 0's range copies as the library measured it per step "
+                                        "(its range schedule adapts to it; below 40 GB/s it switches to equal ranges)"}
+                    if link_gbs else None},
             "gpu_launches": int(launches),
             "host_binding": (f"rank 0 on the {len(numa_cpus)} CPUs NVML reports local to its GPU (every rank likewise)" if numa_cpus
                              else "none"),

@@ -260,7 +260,9 @@ int kmn_pair_counts_device(kmn_ctx* ctx, const uint32_t** valid, const uint32_t*
  * which: 0 frame, 1 bloom, 2 cms, 3 finalize (or exchange_reduce), 4 scan, 5 pair_counts,
  *        6 cms_partition_kernel alone, 7 bloom_bucket_kernel alone (single launches inside 2 / 1),
  *        8 pair_batch, 9 group_observations (kernels only),
- *        10 bloom_partition_kernel alone, 11 cms_apply_kernel (+ the idle spill / direct launches) alone. */
+ *        10 bloom_partition_kernel alone, 11 cms_apply_kernel (+ the idle spill / direct launches) alone;
+ *        12 is not a time: the host-to-device rate (GB/s) the last kmn_count_batch call measured over its range
+ *        copies (0 before the first such call; it steers the next call's range schedule). */
 int kmn_last_stage_ms(kmn_ctx* ctx, int which, float* ms);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t kmn_launch_count(kmn_ctx* ctx);

@@ -1766,8 +1766,8 @@ int kmn_pair_counts_device(kmn_ctx* c, const uint32_t** valid, const uint32_t** 
 
 int kmn_last_stage_ms(kmn_ctx* c, int which, float* ms) {
     return guarded(c, [&] {
-        if (which < 0 || which > 11 || !ms) throw std::runtime_error("invalid stage index");
-        *ms = c->stage_ms[which];
+        if (which < 0 || which > 12 || !ms) throw std::runtime_error("invalid stage index");
+        *ms = which == 12 ? c->h2d_gbs : c->stage_ms[which];
     });
 }
 

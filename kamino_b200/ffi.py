@@ -17,7 +17,7 @@ SCHEMES = {"dayhoff6": DAYHOFF6, "sr6": SR6, "kgb6": KGB6}
 CMS_CELLS = 4 << 26
 STAGES = {"frame": 0, "bloom": 1, "cms": 2, "finalize": 3, "scan": 4, "pair_counts": 5,
           "cms_partition_kernel": 6, "bloom_bucket_kernel": 7, "pair_batch": 8, "group_observations": 9,
-          "bloom_partition_kernel": 10, "cms_apply_kernel": 11}
+          "bloom_partition_kernel": 10, "cms_apply_kernel": 11, "h2d_gbs": 12}
 
 HIT_DTYPE = np.dtype(
     [("kmer", "<u8"), ("rec", "<u4"), ("seg_start", "<u4"), ("start", "<u4"), ("occ", "<u4")]

@@ -859,3 +859,42 @@ def test_pass2_narrow_table_matches_oracle_and_wide_scan(ffi, oracle, monkeypatc
     assert lw - ln == 2, (ln, lw)   # 8 sweeps vs table max + narrow copy + 4 sweeps
     for (sn, en), (sw, ew) in zip(hn, hw):
         assert np.array_equal(sn, sw) and np.array_equal(en, ew)
+
+
+@pytest.mark.gpu
+def test_host_batch_range_schedules_match_staged_count(ffi, monkeypatch):
+    """kmn_count_batch cuts a host batch into species ranges whose copies overlap the kernels (record offsets travel
+    in slices with them); batches over 160 MB take the long schedule (a ramp up to 48 MB ranges).  Whatever the
+    schedule, table and per-species counts equal those of the same batch staged first and counted in one range
+    (count_species_kmers is order-free across species: group_extraction.rs:558-567)."""
+    species = synth.bacterial(150, seed=77)          # ~180 MB: the long schedule
+    b = synth.stage(species)
+    assert b.residues.size > (160 << 20)
+    pin, h_res = ffi.PinnedBuffer.copy_of(b.residues)
+    pin_rec, h_rec = ffi.PinnedBuffer.copy_of(b.rec_off)
+    try:
+        with ffi.Context(13, SR6) as ctx:
+            bid = ctx.stage_batch(b.residues, b.rec_off, b.sp_rec_off)
+            want_new = ctx.count_staged(bid, b.n_sp)
+            ctx.finalize_table()
+            want_rows, want_hash = ctx.table_checksum()
+            assert [int(x) for x in want_rows] == [int(want_new.sum())] * 4
+        for chunks in (None, "1", "3", "32"):          # long schedule; one range; 3 and 32 geometric ranges
+            if chunks is None:
+                monkeypatch.delenv("KMN_H2D_CHUNKS", raising=False)
+            else:
+                monkeypatch.setenv("KMN_H2D_CHUNKS", chunks)
+            with ffi.Context(13, SR6) as ctx:
+                # pinned residues + pinned offsets, then pageable ones
+                for res, rec in ((h_res, h_rec), (b.residues, b.rec_off)):
+                    ctx.reset_table()
+                    _, new = ctx.count_batch(res, rec, b.sp_rec_off)
+                    ctx.finalize_table()
+                    rows, h = ctx.table_checksum()
+                    assert new.tolist() == want_new.tolist(), f"per-species counts differ (KMN_H2D_CHUNKS={chunks})"
+                    assert h == want_hash and [int(x) for x in rows] == [int(x) for x in want_rows], f"table differs (KMN_H2D_CHUNKS={chunks})"
+                    ctx.release_batches()
+    finally:
+        monkeypatch.delenv("KMN_H2D_CHUNKS", raising=False)
+        pin.free()
+        pin_rec.free()
