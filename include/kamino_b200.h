@@ -72,7 +72,7 @@ typedef struct kmn_group {
 
 const char* kmn_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-uint32_t kmn_abi_version(void);   /* currently 6 */
+uint32_t kmn_abi_version(void);   /* currently 7 */
 
 /* Context: owns the device, its stream, the count-min table (AtomicCountMinSketch::new,
  * proba_filter.rs:129-143), the scratch of the Bloom / count-min partition passes and all staged batches.
@@ -106,6 +106,15 @@ int kmn_count_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_o
  * HBM); each call adds the batch to the table again, so pair it with kmn_reset_table. */
 int kmn_stage_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
+/* kmn_stage_batch without the wait: the host-to-device copies are queued on the context's copy stream and the call
+ * returns; the first call that uses the batch (kmn_count_staged, kmn_scan_batch) makes the device wait for them.  In a
+ * job of several batches the copies of batch i+1 then overlap the kernels of batch i (the reference overlaps reading
+ * the next files with counting the current ones the same way: rayon over species, group_extraction.rs:558-567):
+ *     stage_async(b0); for i: { stage_async(b[i+1]); count_staged(b[i]); release_batch(b[i]); }
+ * The host buffers must stay valid and unchanged until a call that uses the batch has returned (or kmn_release_batch /
+ * kmn_release_batches / kmn_synchronize after it); pinned buffers (kmn_host_alloc) are needed for the overlap. */
+int kmn_stage_batch_async(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                          const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
 int kmn_count_staged(kmn_ctx* ctx, uint32_t batch_id, uint64_t* new_kmers_per_species);
 
 /* ---- FASTA framing on the device ("next" row 3 of SURVEY 8f) --------------------------------
@@ -135,6 +144,8 @@ int kmn_fetch_records(kmn_ctx* ctx, uint32_t batch_id, uint64_t* hdr_off, uint64
 int kmn_reset_table(kmn_ctx* ctx);
 /* Drop every staged batch (frees their HBM). */
 int kmn_release_batches(kmn_ctx* ctx);
+/* Release ONE staged batch (its buffers are recycled by the next stage / count call); its id is not reused. */
+int kmn_release_batch(kmn_ctx* ctx, uint32_t batch_id);
 
 /* AtomicCountMinSketch::snapshot (proba_filter.rs:171-177).  The device table is kept as the
  * reference's saturating u16 table at all times (every update is +1, so adding a batch's exact

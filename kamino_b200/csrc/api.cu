@@ -103,6 +103,10 @@ struct Batch {
     bool paired = false;
     DevBuf<kmn_pair> pairs;
     std::vector<uint32_t> h_sp_pairs_off;
+    // kmn_stage_batch_async: the batch's host-to-device copies were queued on the copy stream; the first consumer waits
+    cudaEvent_t staged_ev = nullptr;
+    bool staged_pending = false;
+    ~Batch() { if (staged_ev) cudaEventDestroy(staged_ev); }
 };
 
 }  // namespace
@@ -258,7 +262,7 @@ std::unique_ptr<Batch> take_batch(kmn_ctx* c) {
     if (!c->spare.empty()) {
         b = std::move(c->spare.back());
         c->spare.pop_back();
-        b->framed = b->scanned = b->paired = b->hits_expanded = b->from_fasta = false;
+        b->framed = b->scanned = b->paired = b->hits_expanded = b->from_fasta = b->occ_narrow = false;
         b->n_codes = b->n_inv = 0;
     } else {
         b = std::make_unique<Batch>();
@@ -313,6 +317,25 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
     KMN_CUDA(cudaMemcpyAsync(b->rec_off.p, rec_off, (n_rec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     KMN_CUDA(cudaStreamSynchronize(c->stream));  // the caller may free its buffers on return
+    c->batches.push_back(std::move(b));
+    if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
+}
+
+// kmn_stage_batch_async: the same copies on the copy stream, no wait.  The compute stream waits for them when the
+// batch is first used (run_pass1), so the copies of batch i+1 overlap the kernels of batch i in a multi-batch job.
+void stage_batch_async(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                       const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+    std::unique_ptr<Batch> b = new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp);
+    // a recycled batch's buffers may still be read by work queued on the compute stream
+    KMN_CUDA(cudaEventRecord(c->ev_copy[0], c->stream));
+    KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
+    KMN_CUDA(cudaMemcpyAsync(b->rec_off.p, rec_off, (n_rec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    KMN_CUDA(cudaMemcpyAsync(b->sp_rec_off.p, sp_rec_off, (size_t(n_sp) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (b->n_raw) KMN_CUDA(cudaMemcpyAsync(b->raw.p, residues, b->n_raw, cudaMemcpyHostToDevice, c->copy_stream));
+    KMN_CUDA(cudaMemsetAsync(b->raw.p + b->n_raw, 0x20, b->raw_pad - b->n_raw, c->copy_stream));
+    if (!b->staged_ev) KMN_CUDA(cudaEventCreateWithFlags(&b->staged_ev, cudaEventDisableTiming));
+    KMN_CUDA(cudaEventRecord(b->staged_ev, c->copy_stream));
+    b->staged_pending = true;
     c->batches.push_back(std::move(b));
     if (batch_id) *batch_id = uint32_t(c->batches.size() - 1);
 }
@@ -478,6 +501,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                const uint64_t* host_sp_rec_off, bool frame_only, uint64_t* new_kmers_per_species) {
     if (!frame_only && c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
     const bool from_host = host_rec_off != nullptr;
+    if (b.staged_pending) {   // kmn_stage_batch_async: the copies run on the copy stream
+        KMN_CUDA(cudaStreamWaitEvent(c->stream, b.staged_ev, 0));
+        b.staged_pending = false;
+    }
     // range schedule: doubling sizes while the link outruns the kernels (~27 GB/s of raw bytes), equal sizes and
     // more of them when the previous call measured a slower link
     // range schedule: growth ratio from the link rate the previous call measured (55 GB/s when none has been)
@@ -1156,7 +1183,7 @@ int guarded(kmn_ctx* c, F&& f) {
 extern "C" {
 
 const char* kmn_last_error(void) { return g_err.c_str(); }
-uint32_t kmn_abi_version(void) { return 6; }
+uint32_t kmn_abi_version(void) { return 7; }
 
 int kmn_create(kmn_ctx** out, int device, int k, int scheme) {
     try {
@@ -1288,6 +1315,11 @@ int kmn_stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off
     return guarded(c, [&] { stage_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, batch_id); });
 }
 
+int kmn_stage_batch_async(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
+                          const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
+    return guarded(c, [&] { stage_batch_async(c, residues, rec_off, n_rec, sp_rec_off, n_sp, batch_id); });
+}
+
 int kmn_count_staged(kmn_ctx* c, uint32_t batch_id, uint64_t* new_kmers_per_species) {
     return guarded(c, [&] { run_pass1(c, get_batch(c, batch_id), nullptr, nullptr, nullptr, false, new_kmers_per_species); });
 }
@@ -1342,9 +1374,26 @@ int kmn_reset_table(kmn_ctx* c) {
 int kmn_release_batches(kmn_ctx* c) {
     return guarded(c, [&] {
         KMN_CUDA(cudaStreamSynchronize(c->stream));
-        for (auto& b : c->batches)
+        KMN_CUDA(cudaStreamSynchronize(c->copy_stream));   // staged copies nobody consumed
+        for (auto& b : c->batches) {
+            if (b) b->staged_pending = false;
             if (b && c->spare.size() < 2) c->spare.push_back(std::move(b));
+        }
         c->batches.clear();
+    });
+}
+
+int kmn_release_batch(kmn_ctx* c, uint32_t batch_id) {
+    return guarded(c, [&] {
+        get_batch(c, batch_id);                                      // unknown ids are an error
+        std::unique_ptr<Batch>& b = c->batches[batch_id];
+        if (b->staged_pending) {                                     // never used: its copies may still read the caller's buffers
+            KMN_CUDA(cudaEventSynchronize(b->staged_ev));
+            b->staged_pending = false;
+        }
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->spare.size() < 2) c->spare.push_back(std::move(b));
+        b.reset();                                                   // the id stays taken until kmn_release_batches
     });
 }
 

@@ -35,7 +35,7 @@ GROUP_VALID, GROUP_HOST = 1, 2
 # every symbol declared in include/kamino_b200.h
 ABI_SYMBOLS = [
     "kmn_last_error", "kmn_abi_version", "kmn_create", "kmn_destroy", "kmn_host_alloc", "kmn_host_free", "kmn_count_batch",
-    "kmn_stage_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
+    "kmn_stage_batch", "kmn_stage_batch_async", "kmn_release_batch", "kmn_count_staged", "kmn_count_fasta", "kmn_fetch_records", "kmn_reset_table", "kmn_release_batches",
     "kmn_finalize_table", "kmn_table_snapshot", "kmn_table_load", "kmn_table_accum_device_ptr",
     "kmn_table_widen", "kmn_table_device_ptr", "kmn_exchange_export", "kmn_exchange_setup", "kmn_exchange_reduce", "kmn_exchange_setup_local", "kmn_exchange_reduce_all", "kmn_exchange_abort", "kmn_table_checksum", "kmn_synchronize", "kmn_stream", "kmn_scan_batch", "kmn_fetch_hits",
     "kmn_pair_batch", "kmn_fetch_pairs", "kmn_group_observations", "kmn_group_batches", "kmn_fetch_occupancy", "kmn_pair_counts", "kmn_pair_counts_rows", "kmn_pair_counts_device", "kmn_last_stage_ms", "kmn_launch_count",
@@ -78,6 +78,8 @@ def load_library() -> C.CDLL:
     lib.kmn_host_free.restype = None
     lib.kmn_count_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, vp, u32p]
     lib.kmn_stage_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, u32p]
+    lib.kmn_stage_batch_async.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, u32p]
+    lib.kmn_release_batch.argtypes = [vp, C.c_uint32]
     lib.kmn_count_staged.argtypes = [vp, C.c_uint32, vp]
     lib.kmn_reset_table.argtypes = [vp]
     lib.kmn_release_batches.argtypes = [vp]
@@ -209,6 +211,25 @@ class Context:
                                              _ptr(sp_rec_off), len(sp_rec_off) - 1, C.byref(bid)))
         return bid.value
 
+    def stage_batch_async(self, residues, rec_off, sp_rec_off) -> int:
+        """kmn_stage_batch_async: queues the copies and returns.  The arrays must be contiguous with the right dtype
+        already (no hidden temporary copy may be handed to an asynchronous copy) and are kept referenced until the
+        batch is released; pinned arrays (PinnedBuffer) are needed for the copies to overlap anything."""
+        for a, dt in ((residues, np.uint8), (rec_off, np.uint64), (sp_rec_off, np.uint64)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous):
+                raise KaminoError("stage_batch_async needs contiguous numpy arrays of uint8 / uint64 / uint64")
+        bid = C.c_uint32()
+        self._check(self.lib.kmn_stage_batch_async(self._h, _ptr(residues), _ptr(rec_off), len(rec_off) - 1,
+                                                   _ptr(sp_rec_off), len(sp_rec_off) - 1, C.byref(bid)))
+        if not hasattr(self, "_async_refs"):
+            self._async_refs = {}
+        self._async_refs[bid.value] = (residues, rec_off, sp_rec_off)
+        return bid.value
+
+    def release_batch(self, batch_id: int):
+        self._check(self.lib.kmn_release_batch(self._h, batch_id))
+        getattr(self, "_async_refs", {}).pop(batch_id, None)
+
     def count_staged(self, batch_id: int, n_sp: int | None = None) -> np.ndarray | None:
         out = np.zeros(n_sp, dtype=np.uint64) if n_sp is not None else None
         self._check(self.lib.kmn_count_staged(self._h, batch_id, _ptr(out)))
@@ -249,6 +270,7 @@ class Context:
 
     def release_batches(self):
         self._check(self.lib.kmn_release_batches(self._h))
+        getattr(self, "_async_refs", {}).clear()
 
     def finalize_table(self):
         self._check(self.lib.kmn_finalize_table(self._h))

@@ -898,3 +898,62 @@ def test_host_batch_range_schedules_match_staged_count(ffi, monkeypatch):
         monkeypatch.delenv("KMN_H2D_CHUNKS", raising=False)
         pin.free()
         pin_rec.free()
+
+
+@pytest.mark.gpu
+def test_stage_batch_async_pipeline_equals_oracle(ffi, oracle):
+    """kmn_stage_batch_async + kmn_count_staged + kmn_release_batch, driven the way a multi-batch job drives them (the
+    next batch is staged before the current one is counted, two device batches alternate): table and per-species
+    counts equal the oracle's for the concatenation of the batches (AtomicCountMinSketch::increment is commutative,
+    proba_filter.rs:146-166), and the staged batches can still be scanned."""
+    batches = [synth.stage(synth.bacterial(3, seed=300 + i, n_prot=120 + 40 * i, mean_len=150.0)) for i in range(5)]
+    pins = []
+    host = []
+    for b in batches:
+        triple = []
+        for a in (b.residues, b.rec_off, b.sp_rec_off):
+            p, v = ffi.PinnedBuffer.copy_of(a)
+            pins.append(p)
+            triple.append(v)
+        host.append(triple)
+    k, scheme = 13, SR6
+    h = oracle.cmsa_new()
+    try:
+        want_new = [oracle.count_batch(h, b.residues, b.rec_off, b.sp_rec_off, k, scheme, threads=4) for b in batches]
+        want = oracle.cmsa_table(h)
+        with ffi.Context(k, scheme) as ctx:
+            got_new = []
+            nxt = ctx.stage_batch_async(*host[0])
+            for i in range(len(batches)):
+                cur = nxt
+                if i + 1 < len(batches):
+                    nxt = ctx.stage_batch_async(*host[i + 1])
+                got_new.append(ctx.count_staged(cur, batches[i].n_sp))
+                if i != 2:
+                    ctx.release_batch(cur)
+                else:
+                    kept = cur
+            for g, w in zip(got_new, want_new):
+                assert g.tolist() == w.tolist()
+            ctx.finalize_table()
+            assert np.array_equal(ctx.table_snapshot(), want), "table of the pipelined job differs from the oracle"
+            # a batch that was kept can be scanned; a released id is an error; a staged batch nobody used can be released
+            ns, ne = ctx.scan_batch(kept, 2)
+            cms = oracle.cms_from_table(want)
+            try:
+                b = batches[2]
+                ws, we, _ = oracle.scan_species(cms, b.residues, b.rec_off, 0, int(b.sp_rec_off[1]), k, scheme, 2)
+                gs, ge = ctx.fetch_hits(kept, 0)
+                assert np.array_equal(gs, ws) and np.array_equal(ge, we)
+            finally:
+                oracle.cms_free(cms)
+            with pytest.raises(ffi.KaminoError):
+                ctx.count_staged(0)
+            unused = ctx.stage_batch_async(*host[1])
+            ctx.release_batch(unused)
+            with pytest.raises(ffi.KaminoError):
+                ctx.stage_batch_async(batches[0].residues.astype(np.int32), host[0][1], host[0][2])
+    finally:
+        oracle.cmsa_free(h)
+        for p in pins:
+            p.free()
