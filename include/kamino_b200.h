@@ -112,7 +112,10 @@ int kmn_stage_batch(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_o
  * the next files with counting the current ones the same way: rayon over species, group_extraction.rs:558-567):
  *     stage_async(b0); for i: { stage_async(b[i+1]); count_staged(b[i]); release_batch(b[i]); }
  * The host buffers must stay valid and unchanged until a call that uses the batch has returned (or kmn_release_batch /
- * kmn_release_batches / kmn_synchronize after it); pinned buffers (kmn_host_alloc) are needed for the overlap. */
+ * kmn_release_batches / kmn_synchronize after it); pinned buffers (kmn_host_alloc) are needed for the overlap.
+ * The order check of rec_off (one pass over 8 bytes per record) is deferred to the next count call of the context,
+ * where it runs under that call's kernels, or to the batch's own first use: an unsorted rec_off makes the call that
+ * first uses the batch fail ("rec_off must be non-decreasing"); all other argument errors are reported here. */
 int kmn_stage_batch_async(kmn_ctx* ctx, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                           const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id);
 int kmn_count_staged(kmn_ctx* ctx, uint32_t batch_id, uint64_t* new_kmers_per_species);

@@ -106,6 +106,8 @@ struct Batch {
     // kmn_stage_batch_async: the batch's host-to-device copies were queued on the copy stream; the first consumer waits
     cudaEvent_t staged_ev = nullptr;
     bool staged_pending = false;
+    const uint64_t* pending_rec_off = nullptr;   // the caller's rec_off, not yet checked for order (check_deferred_offsets)
+    bool bad_offsets = false;
     ~Batch() { if (staged_ev) cudaEventDestroy(staged_ev); }
 };
 
@@ -270,8 +272,25 @@ std::unique_ptr<Batch> take_batch(kmn_ctx* c) {
     return b;
 }
 
+// rec_off must be non-decreasing: one pass over 8 bytes per record (~0.15 ms per 100 proteomes from host memory).
+// Branch-free so that it vectorises.
+bool rec_off_sorted(const uint64_t* rec_off, uint64_t n_rec) {
+    uint64_t bad = 0;
+    for (uint64_t r = 0; r < n_rec; r++) bad |= uint64_t(rec_off[r + 1] < rec_off[r]);
+    return bad == 0;
+}
+
+// kmn_stage_batch_async defers that pass: it would run while the GPU idles between two counts.  It runs instead
+// inside the next count call of the context, after that call's kernels have been queued (run_pass1), or right
+// before the batch itself is used, whichever comes first; a batch that fails it refuses to be used.
+void check_deferred_offsets(Batch& b) {
+    if (!b.pending_rec_off) return;
+    b.bad_offsets = !rec_off_sorted(b.pending_rec_off, b.n_rec);
+    b.pending_rec_off = nullptr;
+}
+
 std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
-                                 const uint64_t* sp_rec_off, uint32_t n_sp) {
+                                 const uint64_t* sp_rec_off, uint32_t n_sp, bool defer_offset_check = false) {
     if (!rec_off || !sp_rec_off) throw std::runtime_error("rec_off / sp_rec_off must not be NULL");
     if (n_rec >= (1ull << 31)) throw std::runtime_error("too many records in one batch");
     if (n_sp > 65535) throw std::runtime_error("too many species in one batch (maximum 65535)");  // group_extraction.rs:538
@@ -279,11 +298,7 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     const uint64_t n_raw = rec_off[n_rec];
     if (n_raw + n_rec >= (1ull << 31)) throw std::runtime_error("batch too large: residues + records must stay below 2^31");
     if (n_raw && !residues) throw std::runtime_error("residues must not be NULL");
-    {   // branch-free so that it vectorises: this loop runs before any device work of kmn_count_batch is queued
-        uint64_t bad = 0;
-        for (uint64_t r = 0; r < n_rec; r++) bad |= uint64_t(rec_off[r + 1] < rec_off[r]);
-        if (bad) throw std::runtime_error("rec_off must be non-decreasing");
-    }
+    if (!defer_offset_check && !rec_off_sorted(rec_off, n_rec)) throw std::runtime_error("rec_off must be non-decreasing");
     if (sp_rec_off[0] != 0 || sp_rec_off[n_sp] != n_rec) throw std::runtime_error("sp_rec_off must span [0, n_rec]");
     for (uint32_t s = 0; s < n_sp; s++)
         if (sp_rec_off[s + 1] < sp_rec_off[s]) throw std::runtime_error("sp_rec_off must be non-decreasing");
@@ -294,6 +309,8 @@ std::unique_ptr<Batch> new_batch(kmn_ctx* c, const uint8_t* residues, const uint
     b->n_raw = n_raw;
     b->n_rec = uint32_t(n_rec);
     b->n_sp = n_sp;
+    b->pending_rec_off = defer_offset_check ? rec_off : nullptr;
+    b->bad_offsets = false;
     b->raw_pad = (size_t(n_raw) / FR_TILE + 1) * FR_TILE;   // at least one pad byte: offset n_raw has a chunk
     b->raw.ensure(b->raw_pad);
     b->rec_off.ensure(n_rec + 1);
@@ -325,7 +342,7 @@ void stage_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, u
 // batch is first used (run_pass1), so the copies of batch i+1 overlap the kernels of batch i in a multi-batch job.
 void stage_batch_async(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off, uint64_t n_rec,
                        const uint64_t* sp_rec_off, uint32_t n_sp, uint32_t* batch_id) {
-    std::unique_ptr<Batch> b = new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp);
+    std::unique_ptr<Batch> b = new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, /*defer_offset_check=*/true);
     // a recycled batch's buffers may still be read by work queued on the compute stream
     KMN_CUDA(cudaEventRecord(c->ev_copy[0], c->stream));
     KMN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0));
@@ -501,6 +518,8 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                const uint64_t* host_sp_rec_off, bool frame_only, uint64_t* new_kmers_per_species) {
     if (!frame_only && c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
     const bool from_host = host_rec_off != nullptr;
+    check_deferred_offsets(b);
+    if (b.bad_offsets) throw std::runtime_error("rec_off must be non-decreasing");
     if (b.staged_pending) {   // kmn_stage_batch_async: the copies run on the copy stream
         KMN_CUDA(cudaStreamWaitEvent(c->stream, b.staged_ev, 0));
         b.staged_pending = false;
@@ -729,6 +748,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
     }
     KMN_CUDA(cudaEventRecord(c->ev[3], c->stream));
     mark(c->stream, "apply done", 0);
+    // host work that fits under the kernels just queued (before the device-to-host copies below: into pageable memory
+    // they block until the stream has drained)
+    for (auto& other : c->batches)
+        if (other) check_deferred_offsets(*other);
     b.h_sp_cstart.resize(size_t(b.n_sp) + 1);
     KMN_CUDA(cudaMemcpyAsync(b.h_sp_cstart.data(), b.sp_cstart.p, (size_t(b.n_sp) + 1) * sizeof(uint32_t),
                              cudaMemcpyDeviceToHost, c->stream));
@@ -1376,7 +1399,7 @@ int kmn_release_batches(kmn_ctx* c) {
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         KMN_CUDA(cudaStreamSynchronize(c->copy_stream));   // staged copies nobody consumed
         for (auto& b : c->batches) {
-            if (b) b->staged_pending = false;
+            if (b) { b->staged_pending = false; b->pending_rec_off = nullptr; }
             if (b && c->spare.size() < 2) c->spare.push_back(std::move(b));
         }
         c->batches.clear();
@@ -1391,6 +1414,7 @@ int kmn_release_batch(kmn_ctx* c, uint32_t batch_id) {
             KMN_CUDA(cudaEventSynchronize(b->staged_ev));
             b->staged_pending = false;
         }
+        b->pending_rec_off = nullptr;
         KMN_CUDA(cudaStreamSynchronize(c->stream));
         if (c->spare.size() < 2) c->spare.push_back(std::move(b));
         b.reset();                                                   // the id stays taken until kmn_release_batches

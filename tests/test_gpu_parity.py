@@ -953,6 +953,15 @@ def test_stage_batch_async_pipeline_equals_oracle(ffi, oracle):
             ctx.release_batch(unused)
             with pytest.raises(ffi.KaminoError):
                 ctx.stage_batch_async(batches[0].residues.astype(np.int32), host[0][1], host[0][2])
+            # the order check of rec_off is deferred: an unsorted rec_off fails the first call that uses the batch
+            bad_rec = host[0][1].copy()
+            bad_rec[3], bad_rec[4] = bad_rec[4], bad_rec[3] + 0
+            if bad_rec[3] >= bad_rec[4]:
+                bad = ctx.stage_batch_async(host[0][0], bad_rec, host[0][2])
+                ctx.reset_table()
+                with pytest.raises(ffi.KaminoError, match="non-decreasing"):
+                    ctx.count_staged(bad)
+                ctx.release_batch(bad)
     finally:
         oracle.cmsa_free(h)
         for p in pins:
