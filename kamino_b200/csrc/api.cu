@@ -518,8 +518,10 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
                const uint64_t* host_sp_rec_off, bool frame_only, uint64_t* new_kmers_per_species) {
     if (!frame_only && c->finalized) throw std::runtime_error("table is finalized; call kmn_reset_table before counting again");
     const bool from_host = host_rec_off != nullptr;
-    check_deferred_offsets(b);
-    if (b.bad_offsets) throw std::runtime_error("rec_off must be non-decreasing");
+    if (!from_host) {   // (from host buffers: checked below, under the first range's copy)
+        check_deferred_offsets(b);
+        if (b.bad_offsets) throw std::runtime_error("rec_off must be non-decreasing");
+    }
     if (b.staged_pending) {   // kmn_stage_batch_async: the copies run on the copy stream
         KMN_CUDA(cudaStreamWaitEvent(c->stream, b.staged_ev, 0));
         b.staged_pending = false;
@@ -659,6 +661,13 @@ void run_pass1(kmn_ctx* c, Batch& b, const uint8_t* host_residues, const uint64_
             KMN_CUDA(cudaEventRecord(e, c->copy_stream));
             KMN_CUDA(cudaStreamWaitEvent(fs, e, 0));
             mark(c->copy_stream, "copy done", j);
+            if (j == 0) {   // the order check of rec_off runs while the first copy is in flight, before any kernel reads an offset
+                check_deferred_offsets(b);
+                if (b.bad_offsets) {
+                    KMN_CUDA(cudaStreamSynchronize(c->copy_stream));
+                    throw std::runtime_error("rec_off must be non-decreasing");
+                }
+            }
         }
         mark(fs, "frame begins", j);
         // ---- K0 frame on the range's tiles (running total of kept bytes carried on the device)
@@ -1351,7 +1360,7 @@ int kmn_count_batch(kmn_ctx* c, const uint8_t* residues, const uint64_t* rec_off
                     const uint64_t* sp_rec_off, uint32_t n_sp, uint64_t* new_kmers_per_species,
                     uint32_t* batch_id) {
     return guarded(c, [&] {
-        c->batches.push_back(new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp));
+        c->batches.push_back(new_batch(c, residues, rec_off, n_rec, sp_rec_off, n_sp, /*defer_offset_check=*/true));
         const uint32_t id = uint32_t(c->batches.size() - 1);
         if (batch_id) *batch_id = id;
         // host -> device copies of the species ranges overlap the kernels of the previous range
