@@ -158,7 +158,8 @@ cms_partition_kernel(const __grid_constant__ CUtensorMap slots_map, const uint8_
             const uint64_t seed = fold30_keep(cms_seed(r));   // (kept: ptxas otherwise re-folds the seed next to every use)
             // (Two branch-free forms of this loop were measured slower: all 16 hashes hoisted ahead of predicated atomics
             // and stores, 64 registers with spills: 1.27 ms; straight-line entries with a dummy bucket for dead lanes
-            // and min(rank, cap) stores, 64 registers: 1.03 ms; this branchy form, 56 registers: 0.92 ms.)
+            // and min(rank, cap) stores, 64 registers: 1.03 ms; the branchy form, 56 registers: 0.92 ms then, 0.84 ms with
+            // the hashes of two positions computed together and the addressing below.)
             // Entry index inside the staging buffer = b * 32 + ((b & 31) ^ rank) = Tq ^ rank with Tq one LOP3 of two
             // shifts of the index (idx < 2^26, so idx >> 16 is the bucket itself); explicit shared-memory addresses so
             // that neither the counter nor the store address is re-derived from generic pointers per entry.
