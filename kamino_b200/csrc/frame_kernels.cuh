@@ -226,7 +226,7 @@ __device__ __forceinline__ void fr_place(uint32_t a_stage, const uint32_t (&c)[4
 }
 
 #ifndef KMN_FRAME_CTAS
-#define KMN_FRAME_CTAS 4
+#define KMN_FRAME_CTAS 6   // measured: 3 / 4 / 5 / 6 CTAs per SM -> 0.240 / 0.216 / 0.207 / 0.200 ms per 100 proteomes
 #endif
 __global__ void __launch_bounds__(FRAME_THREADS, KMN_FRAME_CTAS)
 frame_kernel(const uint8_t* __restrict__ raw, uint64_t n_raw, RecodeLut lut, const uint64_t* __restrict__ rec_off,
