@@ -202,7 +202,8 @@ int kmn_exchange_abort(kmn_ctx* ctx);
  * sum of new_kmers_per_species over everything counted.  hash = sum over cells of cell * mix64(index + 0x51),
  * index = row * 2^26 + column, arithmetic modulo 2^64 (mix64 = proba_filter.rs:30-37). */
 int kmn_table_checksum(kmn_ctx* ctx, uint64_t* row_sums4, uint64_t* hash);
-/* Block until all work queued on the context's stream has finished. */
+/* Block until all work queued on the context's streams has finished (staged copies included; the caller's buffers
+ * of kmn_stage_batch_async calls are not touched afterwards). */
 int kmn_synchronize(kmn_ctx* ctx);
 /* CUDA stream of the context (cudaStream_t as void*), for event timing by the caller. */
 int kmn_stream(kmn_ctx* ctx, void** stream);

@@ -1316,6 +1316,7 @@ void kmn_destroy(kmn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);   // staged copies nobody consumed
     c->batches.clear();
     c->spare.clear();
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1722,7 +1723,14 @@ int kmn_table_checksum(kmn_ctx* c, uint64_t* row_sums4, uint64_t* hash) {
     });
 }
 
-int kmn_synchronize(kmn_ctx* c) { return guarded(c, [&] { KMN_CUDA(cudaStreamSynchronize(c->stream)); }); }
+int kmn_synchronize(kmn_ctx* c) {
+    return guarded(c, [&] {
+        KMN_CUDA(cudaStreamSynchronize(c->stream));
+        KMN_CUDA(cudaStreamSynchronize(c->copy_stream));   // copies of kmn_stage_batch_async nobody has consumed yet
+        for (auto& b : c->batches)                         // ... and nothing of the caller's buffers is needed afterwards
+            if (b) check_deferred_offsets(*b);
+    });
+}
 int kmn_stream(kmn_ctx* c, void** stream) { return guarded(c, [&] { *stream = c->stream; }); }
 
 int kmn_scan_batch(kmn_ctx* c, uint32_t batch_id, uint32_t min_needed, uint64_t* n_starts, uint64_t* n_ends) {
