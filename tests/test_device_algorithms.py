@@ -121,3 +121,25 @@ def test_pass2_needs_only_the_estimates_from_min_needed_up(oracle):
         finally:
             oracle.cms_free(full)
             oracle.cms_free(cut)
+
+
+def test_partition_slot_addresses_are_what_the_consumers_read():
+    """The staging-store addresses of the two partition kernels, exhaustively over (bucket, rank):
+    cms_partition_kernel writes entry index Tq ^ rank with Tq = ((idx >> 11) & 0x7FE0) | (bucket & ~0x7FE0) (one LOP3;
+    idx < 2^26, bucket = idx >> 16) where cms_apply_kernel reads rank r of slot b at b * 32 + (r ^ (b & 31));
+    bloom_partition_kernel<96> writes (stage + 384 b + 4 r) ^ 4 (b & 31) where bloom_bucket_kernel reads rank r of run b
+    at word 96 b + (r ^ (b & 31)) (stage 128-byte aligned, slots a multiple of 128 bytes)."""
+    rng = np.random.default_rng(1)
+    b = np.arange(1024, dtype=np.uint64)[:, None]
+    r = np.arange(32, dtype=np.uint64)[None, :]
+    low = rng.integers(0, 1 << 16, (1024, 1), dtype=np.uint64)       # the entry's low 16 index bits must not matter
+    idx = (b << np.uint64(16)) | low
+    tq = ((idx >> np.uint64(11)) & np.uint64(0x7FE0)) | (b & np.uint64(~0x7FE0 & 0xFFFFFFFF))
+    assert np.array_equal(tq ^ r, b * np.uint64(32) + (r ^ (b & np.uint64(31))))
+    assert np.unique(tq ^ r).size == 1024 * 32                       # a bijection onto the staging buffer's 32768 entries
+    for stage in (0x400, 0x12380, 0x30000):                          # 128-byte aligned shared-memory addresses
+        bb = np.arange(256, dtype=np.uint64)[:, None]
+        rr = np.arange(96, dtype=np.uint64)[None, :]
+        got = (np.uint64(stage) + np.uint64(384) * bb + np.uint64(4) * rr) ^ (np.uint64(4) * (bb & np.uint64(31)))
+        want = np.uint64(stage) + np.uint64(4) * (np.uint64(96) * bb + (rr ^ (bb & np.uint64(31))))
+        assert np.array_equal(got, want)
